@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LBDRN hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-encode]
+    torchrun ... bench.py --gpus N ...         (one rank per GPU; rank 0 prints ONE JSON line)
+
+Metric (BASELINE.json): decode throughput in Mpix/s at K=5 D=2 bc64 nl2; encode s/scene reported beside it.
+A "step" is one fused decode pass over one synthetic scene resident in HBM.  Workload at N=1: configs[1] of
+BASELINE.json, the 4-band 12-bit 8192x8192 scene.  At N>1 the scene grows to N*8192 rows and is row-stripe
+sharded (weak scaling: 8192 rows per GPU; per step one scalar max all-reduce + one D-row halo swap over NCCL).
+`e2e` is the same metric through the public host API (`lbdrn_fused.decode_image`) with pinned HOST buffers:
+H2D of the base layer and D2H of the reconstruction inside the timed region.
+`--impl reference` times the reference's CPU implementation of the path: the oracle port (oracle/lbdrn_oracle.py,
+a restatement pinned bit-exactly against the unmodified reference) on the box's host cores, on a bounded crop.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "lbdrn-msic_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+C_, SIDE, BITS, K_, D_, BC, NL = 4, 8192, 12, 5, 2, 64, 2
+DIM_IN = C_ * (2 * D_ + 1) ** 2
+FLOP_PER_PX = 2 * (DIM_IN * BC + (NL - 1) * BC * BC + BC * C_)          # 21 504
+TRAIN_FLOP_PER_PX = 3 * FLOP_PER_PX - 2 * DIM_IN * BC                    # 51 712
+HBM_BYTES_PER_PX = C_ * 1 + C_ * 2                                       # u8 MSB in, u16 out
+METRIC, UNIT = "decode_throughput_K5_D2_bc64_nl2", "Mpix/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(bf16_burst=j["bf16_tflops"], bf16_sustained=j["bf16_tflops_sustained"], hbm=j["hbm_gbs"],
+                    source="MEASURED_PEAKS.json")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def bench_params(device):
+    """Decode-only benchmark weights: reference init from the reference's seed, then the fpzip(prec=16) value map
+    (low 16 bits cleared) -- what a decoder would load."""
+    from LBDRNmodel import LBDRNModel
+    torch.manual_seed(19920517)
+    flat = LBDRNModel(DIM_IN, BC, C_, NL).flat_params()
+    flat = (flat.view(torch.int32) & -65536).view(torch.float32)
+    return flat.to(device)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_decode_sample(side, threads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lbdrn_oracle as O
+    from synth_scene import make_scene
+    torch.set_num_threads(threads)
+    img = make_scene(C_, side, side, BITS, seed=19920517)
+    msb, _ = O.split_msb_lsb(img, K_)
+    torch.manual_seed(19920517)
+    params = O.unflatten_params(O.fpzip_value_map(O.flatten_params(O.init_params(DIM_IN, BC, C_, NL)), 16),
+                                DIM_IN, BC, C_, NL)
+    t0 = time.perf_counter()
+    O.decode_image(msb, params, K_, D_)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    probe = cpu_decode_sample(256, threads)
+    per_px = probe / (256 * 256)
+    budget = 150.0 / max(1, args.steps + args.warmup)                 # whole run within a few minutes
+    side = int(min(2048, max(256, (budget / per_px) ** 0.5))) // 64 * 64
+    for _ in range(args.warmup):
+        cpu_decode_sample(side, threads)
+    ts = [cpu_decode_sample(side, threads) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    v = side * side / t / 1e6
+    sample = f"{C_}x{side}x{side} crop-sized synthetic scene per step (same generator/weights as the GPU arm)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[1]: synthetic 4-band 12-bit scene, K=5 D=2 bc64 nl2, decode; CPU sample {sample}"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes
+    import torch.distributed as dist
+    import lbdrn_cabi as cabi
+    import lbdrn_dist as LD
+    import lbdrn_fused as F
+    from synth_scene import make_scene_torch
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = cabi.load()
+    fl = F.Flags()
+    pk = peaks()
+
+    # ---- synthetic scene: this rank's 8192-row stripe of a (world*8192)-row scene -------------------------------
+    H_total = SIDE * world
+    own = make_scene_torch(C_, SIDE, SIDE, BITS, seed=19920517 + rank, device=dev)        # CHW uint16
+    scene = F.DeviceScene.from_image(own, K_)
+    del own
+    params = bench_params(dev)
+    r0, r1 = LD.stripe_bounds(H_total, world, rank)
+
+    def decode_step():
+        if world == 1:
+            d = scene.desc(D_, BC, NL, fl, path=cabi.PATH_AUTO)
+            cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(scene.msb), cabi.ptr(params), None, cabi.ptr(out),
+                                        cabi.stream_ptr()))
+            return out
+        mx = LD.global_max(torch.tensor([scene.msb_max], device=dev))
+        return LD.decode_stripe(scene.msb, H_total, params, K_, D_, BC, NL, fl, mx)
+
+    out = torch.empty((C_, SIDE, SIDE), dtype=torch.uint16, device=dev)
+    for _ in range(max(3, args.warmup)):
+        decode_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = lib.lbdrn_launch_count()
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev[0].record()
+        for i in range(args.steps):
+            decode_step()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lib.lbdrn_launch_count() - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    npx_step = SIDE * SIDE * world
+    value = npx_step * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- dominant kernel: measured alone with CUDA events on its stream (the decode kernel IS the step at N=1) ----
+    d = scene.desc(D_, BC, NL, fl, path=cabi.PATH_AUTO)
+    has_tc = bool(lib.lbdrn_has_tensor_path(ctypes.byref(d)))
+    kern_ms = min(step_ms) if world == 1 else None
+    if world > 1:
+        # local kernel time on this rank's stripe, without the collectives
+        buf = (scene.msb, 0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dd = cabi.make_desc(C_, SIDE, SIDE, K_, D_, BC, NL, fl.bits(), scene.msb_max, scene.msb_u16)
+        e0.record()
+        for _ in range(5):
+            cabi.check(lib.lbdrn_decode(ctypes.byref(dd), cabi.ptr(scene.msb), cabi.ptr(params), None, cabi.ptr(out),
+                                        cabi.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        kern_ms = e0.elapsed_time(e1) / 5
+    kern_avg_ms = (sum(step_ms) / len(step_ms)) if world == 1 else kern_ms
+    tflops = SIDE * SIDE * FLOP_PER_PX / (kern_avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                "frac": tflops / pk["bf16_burst"], "traffic": None,
+                "kernel": "tc_decode_kernel (tcgen05)" if has_tc else "infer_fp32_kernel<64,8,4,true,DECODE> (fp32 FFMA)",
+                "peak_source": pk["source"] + " bf16 dense burst",
+                "algorithmic_flop_per_pixel": FLOP_PER_PX,
+                "hbm": {"achieved_gbs": SIDE * SIDE * HBM_BYTES_PER_PX / (kern_avg_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
+                        "algorithmic_bytes_per_pixel": HBM_BYTES_PER_PX}}
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ------------------------------------
+    base_host = scene.msb.cpu().pin_memory()
+    out_host = torch.empty((C_, SIDE, SIDE), dtype=torch.uint16).pin_memory()
+    params_host = params.cpu()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        if world == 1:
+            F.decode_image(base_host, params_host, K_, D_, BC, NL, flags=fl, out_host=out_host, base_max=scene.msb_max)
+        else:
+            stripe = base_host.to(dev, non_blocking=True)
+            mx = LD.global_max(torch.tensor([scene.msb_max], device=dev))
+            o = LD.decode_stripe(stripe, H_total, params_host.to(dev), K_, D_, BC, NL, fl, mx)
+            out_host.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": npx_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
+           "h2d_bytes_per_step": int(base_host.numel() * base_host.element_size() * world + params_host.numel() * 4 * world),
+           "d2h_bytes_per_step": int(out_host.numel() * 2 * world), "steps": e2e_steps}
+    del base_host, out_host
+
+    # ---- encode s/scene (10 epochs, bs 8192, per-epoch eval + best-epoch select), scene-per-GPU replicas -----------
+    encode = None
+    if not args.no_encode:
+        from LBDRNmodel import LBDRNModel
+        torch.manual_seed(19920517)
+        model = LBDRNModel(DIM_IN, BC, C_, NL)
+        tr = F.FusedTrainer(model, scene, D_, 1e-3, 8192, args.encode_epochs, flags=fl, sampler=args.sampler)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = tr.run()
+        torch.cuda.synchronize()
+        enc_s = time.perf_counter() - t0
+        tr.close()
+        if world > 1:
+            t = torch.tensor([enc_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            enc_s = float(t.item())
+        n_steps = len(res["losses"])
+        flop = SIDE * SIDE * args.encode_epochs * (TRAIN_FLOP_PER_PX + FLOP_PER_PX)
+        encode = {"s_per_scene": enc_s, "scenes_per_s_all_gpus": world / enc_s, "mode": "scene-per-GPU replicas",
+                  "epochs": args.encode_epochs, "batch_size": 8192, "optimizer_steps": n_steps,
+                  "us_per_step_incl_eval": enc_s / n_steps * 1e6, "sampler": args.sampler,
+                  "final_val_mse": res["val_mse"][-1] if res["val_mse"] else None, "best_epoch": res["best_epoch"],
+                  "tensor_roofline_frac": flop / enc_s / 1e12 / pk["bf16_sustained"],
+                  "excludes": "GDAL read/write, JPEG-2000 base layer, fpzip (host, unchanged)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample ----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        side = 1024
+        t = cpu_decode_sample(side, threads)
+        cpu = {"value": side * side / t / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"one decode of a {C_}x{side}x{side} synthetic scene ({t:.1f} s) by oracle/lbdrn_oracle.py"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if not has_tc else "f16x2-split/f32-accum",
+                "data": "synthetic",
+                "config": {"workload": f"configs[1]: synthetic {C_}-band {BITS}-bit {SIDE}x{SIDE} scene per GPU "
+                                       f"(row stripes of a {H_total}x{SIDE} scene), K={K_} D={D_} bc{BC} nl{NL}, "
+                                       "Sine(w0=30) hidden / Sigmoid head, weights = seeded reference init after fpzip prec16",
+                           "l2": "inputs+outputs per step = 805 MB > 126 MB L2 (no flush needed)",
+                           "parallelism": f"stripe-sharded decode x{world}"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "encode": encode}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-encode", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encode-epochs", type=int, default=10)
+    ap.add_argument("--sampler", choices=["reference", "device"], default="device")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,444 @@
+// lbdrn_api.cu -- extern "C" entry points of liblbdrn_b200.so (see include/lbdrn.h for the contract).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "lbdrn_common.cuh"
+#include "lbdrn_infer_fp32.cuh"
+#include "lbdrn_train_fp32.cuh"
+#include "lbdrn_tc.cuh"
+
+using namespace lbdrn;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) return fail(LBDRN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---- descriptor -> Net ----------------------------------------------------------------------------------
+int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {
+  if (!d) return fail(LBDRN_E_INVALID, "null descriptor");
+  memset(&n, 0, sizeof n);
+  if (d->C < 1 || d->C > kMaxC) return fail(LBDRN_E_UNSUPPORTED, "C=%d bands (supported 1..%d)", d->C, kMaxC);
+  if (d->H < 1 || d->W < 1) return fail(LBDRN_E_INVALID, "bad image size %dx%d", d->H, d->W);
+  if (d->K < 1 || d->K > 15) return fail(LBDRN_E_INVALID, "K=%d outside 1..15 (4-bit header field)", d->K);
+  if (d->D < 0 || d->D > 15) return fail(LBDRN_E_INVALID, "D=%d outside 0..15", d->D);
+  if (d->nl < 1 || d->nl > kMaxLayers - 1) return fail(LBDRN_E_INVALID, "nl=%d outside 1..15", d->nl);
+  if (d->bc != 32 && d->bc != 64 && d->bc != 128 && d->bc != 256)
+    return fail(LBDRN_E_UNSUPPORTED, "bc=%d (kernels are built for 32/64/128/256)", d->bc);
+  const bool coords = d->flags & LBDRN_USE_COORDINATES, emb = d->flags & LBDRN_EMBEDDING;
+  const bool colors = d->flags & LBDRN_USE_COLORS;
+  n.C = d->C; n.H = d->H; n.W = d->W; n.K = d->K; n.D = d->D; n.n = 2 * d->D + 1;
+  n.bc = d->bc; n.nl = d->nl;
+  n.tabw = 2 * d->n_freq * (emb ? 1 : 0) + 1;                    // LBDRNdataset.py:105
+  n.nco = coords ? 2 * n.tabw : 0;
+  n.ncol = colors ? d->C * n.n * n.n : 0;                        // LBDRNdataset.py:104
+  n.dim_in = n.nco + n.ncol;
+  if (n.dim_in <= 0) return fail(LBDRN_E_INVALID, "feature set is empty (USE_COORDINATES and USE_COLORS both off)");
+  if (coords && (d->H < 2 || d->W < 2)) return fail(LBDRN_E_INVALID, "coordinates need H,W >= 2 (division by H-1)");
+  if (colors && (d->D >= d->H || d->D >= d->W)) return fail(LBDRN_E_INVALID, "reflect padding needs D < H,W");
+  n.relative = ((d->flags & LBDRN_RELATIVE) && d->D > 0) ? 1 : 0;  // LBDRNdataset.py:126
+  n.relu = (d->flags & LBDRN_ACT_RELU) ? 1 : 0;
+  n.w0 = d->w0;
+  if (colors && d->msb_max == 0)
+    return fail(LBDRN_E_INVALID, "MSB.max()==0: the reference's features are 0/0=NaN for this K (degenerate)");
+  n.maxv = (float)d->msb_max;
+  n.qmax = (float)((1 << d->K) - 1);
+  if (d->msb_dtype != LBDRN_U8 && d->msb_dtype != LBDRN_U16) return fail(LBDRN_E_INVALID, "bad msb_dtype");
+  n.msb_u16 = d->msb_dtype == LBDRN_U16;
+  n.lsb_u16 = d->K > 8;
+  n.row0 = d->row0; n.row1 = d->row1; n.buf_row0 = d->buf_row0; n.buf_rows = d->buf_rows;
+  if (need_rows) {
+    if (!(0 <= n.row0 && n.row0 < n.row1 && n.row1 <= n.H)) return fail(LBDRN_E_INVALID, "bad row range [%d,%d)", n.row0, n.row1);
+    const int lo = n.row0 - n.D > 0 ? n.row0 - n.D : 0, hi = n.row1 + n.D < n.H ? n.row1 + n.D : n.H;
+    if (n.buf_row0 > lo || n.buf_row0 + n.buf_rows < hi || n.buf_row0 < 0 || n.buf_row0 + n.buf_rows > n.H)
+      return fail(LBDRN_E_INVALID, "buffer rows [%d,%d) do not cover stripe+halo [%d,%d)", n.buf_row0,
+                  n.buf_row0 + n.buf_rows, lo, hi);
+  }
+  int off = 0, din = n.dim_in;
+  for (int l = 0; l <= n.nl; ++l) {                               // state_dict order, LBDRNmodel.py:62-77
+    const int out = l < n.nl ? n.bc : n.C;
+    n.woff[l] = off; off += out * din;
+    n.boff[l] = off; off += out;
+    din = n.bc;
+  }
+  n.P = off;
+  return LBDRN_OK;
+}
+
+// ---- per-device scratch (packed weights, SSE partials); grow-only, lives until process exit ----------------
+struct Scratch {
+  float* wpack = nullptr; size_t wpack_n = 0;
+  double* partials = nullptr; unsigned int* counter = nullptr;
+  int sms = 0, max_smem = 0;
+};
+std::mutex g_mu;
+Scratch g_scratch[64];
+
+int get_scratch(int P, Scratch*& out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  Scratch& s = g_scratch[dev];
+  if (!s.sms) {
+    CUDA_TRY(cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&s.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CUDA_TRY(cudaMalloc(&s.partials, 4096 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.counter, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(s.counter, 0, sizeof(unsigned int)));
+  }
+  if ((size_t)P > s.wpack_n) {
+    if (s.wpack) CUDA_TRY(cudaFree(s.wpack));
+    s.wpack = nullptr; s.wpack_n = 0;
+    CUDA_TRY(cudaMalloc(&s.wpack, ((size_t)P + 64) * sizeof(float)));
+    s.wpack_n = (size_t)P;
+  }
+  out = &s;
+  return LBDRN_OK;
+}
+
+// ---- fp32 inference dispatch ---------------------------------------------------------------------------
+template <int BC, int TM, int CP, bool WSMEM, int MODE>
+int launch_infer_t(const InferArgs& a, size_t smem, int sms, cudaStream_t st) {
+  auto kern = infer_fp32_kernel<BC, TM, CP, WSMEM, MODE>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "fp32 inference kernel does not fit (smem %zu B)", smem);
+  int grid = sms * occ;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (MODE == MODE_SSE && grid > 4096) grid = 4096;
+  kern<<<grid, kThreads, smem, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+template <int BC, int TM, int MODE>
+int launch_infer_bc(InferArgs& a, const Scratch& sc, cudaStream_t st) {
+  const Net& n = a.net;
+  constexpr int LDP = ldp_of<TM>(), TH = TM, TW = 16;
+  a.kmax = n.dim_in > BC ? n.dim_in : BC;
+  a.tiles_x = (n.W + TW - 1) / TW;
+  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TH - 1) / TH);
+  const size_t base = ((size_t)a.kmax * LDP + round4(n.C * (TH + 2 * n.D) * (TW + 2 * n.D))) * sizeof(float);
+  const size_t with_w = base + (size_t)round4(n.P) * sizeof(float);
+  const bool wsmem = with_w <= (size_t)sc.max_smem;
+  if (!wsmem && base > (size_t)sc.max_smem) return fail(LBDRN_E_UNSUPPORTED, "activation tile does not fit in shared memory");
+  if (n.C <= 4) {
+    return wsmem ? launch_infer_t<BC, TM, 4, true, MODE>(a, with_w, sc.sms, st)
+                 : launch_infer_t<BC, TM, 4, false, MODE>(a, base, sc.sms, st);
+  }
+  return wsmem ? launch_infer_t<BC, TM, 8, true, MODE>(a, with_w, sc.sms, st)
+               : launch_infer_t<BC, TM, 8, false, MODE>(a, base, sc.sms, st);
+}
+
+template <int MODE>
+int run_infer(const LbdrnDesc* d, const void* msb, const void* lsb, const float* params, const float* tab, void* out,
+              double* sse_out, void* stream) {
+  Net n;
+  int rc = resolve(d, n);
+  if (rc) return rc;
+  if (!msb || !params || (MODE != MODE_SSE && !out)) return fail(LBDRN_E_INVALID, "null device pointer");
+  if (n.nco && !tab) return fail(LBDRN_E_INVALID, "USE_COORDINATES set but coord_tab_dev is NULL");
+  if (MODE == MODE_SSE && (!lsb || !sse_out)) return fail(LBDRN_E_INVALID, "null lsb/sse pointer");
+  Scratch* sc = nullptr;
+  rc = get_scratch(n.P, sc);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  pack_params_kernel<<<(n.P + 255) / 256, 256, 0, st>>>(n, params, sc->wpack);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  InferArgs a;
+  memset(&a, 0, sizeof a);
+  a.net = n; a.msb = msb; a.lsb = lsb; a.wpack = sc->wpack; a.tab = tab; a.out = out;
+  a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
+  switch (n.bc) {
+    case 32: return launch_infer_bc<32, 8, MODE>(a, *sc, st);
+    case 64: return launch_infer_bc<64, 8, MODE>(a, *sc, st);
+    case 128: return launch_infer_bc<128, 4, MODE>(a, *sc, st);
+    default: return launch_infer_bc<256, 4, MODE>(a, *sc, st);
+  }
+}
+
+// ---- small elementwise kernels ----------------------------------------------------------------------------
+__global__ void split_kernel(const uint16_t* __restrict__ img, long long n, int K, int msb_u16, void* msb, void* lsb) {
+  const unsigned mask = (1u << K) - 1u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned v = img[i], m = v >> K, l = v & mask;                // MSB = img>>K; LSB = img-(MSB<<K)  (LBDRNdataset.py:95-96)
+    if (msb_u16) ((uint16_t*)msb)[i] = (uint16_t)m; else ((uint8_t*)msb)[i] = (uint8_t)m;
+    if (K > 8) ((uint16_t*)lsb)[i] = (uint16_t)l; else ((uint8_t*)lsb)[i] = (uint8_t)l;
+  }
+}
+
+__global__ void max_shifted_kernel(const uint16_t* __restrict__ img, long long n, int K, unsigned int* out) {
+  unsigned m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, (unsigned)img[i] >> K);
+  for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+}  // namespace
+
+// ---- training handle ------------------------------------------------------------------------------------
+struct LbdrnTrain {
+  Net net;
+  LbdrnTrainCfg cfg;
+  int dev = 0, sms = 0, grid = 0, pstride = 0, dimpad = 0;
+  size_t smem = 0;
+  bool wsmem = true;
+  float *params = nullptr, *wpack = nullptr, *m = nullptr, *v = nullptr, *partial = nullptr;
+  void* kernel = nullptr;
+};
+
+namespace {
+
+template <int BC, int CP>
+int pick_train_kernel(LbdrnTrain* t, int max_smem) {
+  const Net& n = t->net;
+  const size_t acts = ((size_t)t->dimpad + 2 * (size_t)n.nl * BC + 2 * CP) * kTrainLDP + kMaxC * kTrainNPIX;
+  const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
+  const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
+  if (with_w <= (size_t)max_smem) {
+    t->wsmem = true; t->smem = with_w; t->kernel = (void*)train_fp32_kernel<BC, CP, true>;
+  } else if (without <= (size_t)max_smem) {
+    t->wsmem = false; t->smem = without; t->kernel = (void*)train_fp32_kernel<BC, CP, false>;
+  } else {
+    return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
+                without, BC, n.nl, n.dim_in);
+  }
+  CUDA_TRY(cudaFuncSetAttribute(t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, kThreads, t->smem));
+  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "training kernel cannot be made resident");
+  const int cap = occ * t->sms;
+  int want = (t->cfg.batch_size + kTrainNPIX - 1) / kTrainNPIX;
+  if (want < 16) want = 16;
+  t->grid = want < cap ? want : cap;
+  return LBDRN_OK;
+}
+
+int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
+  a.net = t->net; a.params = t->params; a.wpack = t->wpack; a.m = t->m; a.v = t->v;
+  a.partial = t->partial; a.pstride = t->pstride; a.dimpad = t->dimpad;
+  a.beta1 = t->cfg.beta1; a.beta2 = t->cfg.beta2;
+  a.omb1 = (float)(1.0 - t->cfg.beta1); a.omb2 = (float)(1.0 - t->cfg.beta2);
+  a.beta2f = (float)t->cfg.beta2; a.eps = (float)t->cfg.eps;
+  void* kargs[] = {(void*)&a};
+  CUDA_TRY(cudaLaunchCooperativeKernel(t->kernel, dim3(t->grid), dim3(kThreads), kargs, t->smem, st));
+  ++g_launches;
+  return LBDRN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lbdrn_version(void) { return LBDRN_ABI_VERSION; }
+const char* lbdrn_last_error(void) { return g_err.c_str(); }
+int64_t lbdrn_launch_count(void) { return g_launches.load(); }
+
+int32_t lbdrn_dim_in(const LbdrnDesc* d) {
+  Net n;
+  int rc = resolve(d, n, false);
+  return rc ? rc : n.dim_in;
+}
+
+int64_t lbdrn_param_count(const LbdrnDesc* d) {
+  Net n;
+  int rc = resolve(d, n, false);
+  return rc ? rc : n.P;
+}
+
+int32_t lbdrn_has_tensor_path(const LbdrnDesc* d) {
+  Net n;
+  if (resolve(d, n, false)) return 0;
+  return tc_supported(n) ? 1 : 0;
+}
+
+int32_t lbdrn_split(const uint16_t* img_dev, int64_t n, int32_t K, int32_t msb_dtype, void* msb_dev, void* lsb_dev,
+                    void* stream) {
+  if (!img_dev || !msb_dev || !lsb_dev || n <= 0 || K < 1 || K > 15) return fail(LBDRN_E_INVALID, "lbdrn_split: bad argument");
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img_dev, n, K, msb_dtype == LBDRN_U16, msb_dev, lsb_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_t* max_dev, void* stream) {
+  if (!img_dev || !max_dev || n <= 0 || K < 0 || K > 15) return fail(LBDRN_E_INVALID, "lbdrn_max_shifted: bad argument");
+  long long blocks = (n + 2047) / 2048;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  max_shifted_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img_dev, n, K, max_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* params_dev, const float* coord_tab_dev,
+                     uint16_t* out_dev, void* stream) {
+  Net n;
+  int rc = resolve(d, n);
+  if (rc) return rc;
+  const bool tc_ok = tc_supported(n);
+  if (d->path == LBDRN_PATH_TENSOR && !tc_ok)
+    return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
+  if (tc_ok && d->path != LBDRN_PATH_PRECISE) {
+    if (!msb_dev || !params_dev || !out_dev) return fail(LBDRN_E_INVALID, "null device pointer");
+    std::string err;
+    long long launches = 0;
+    rc = tc_decode(n, msb_dev, params_dev, out_dev, (cudaStream_t)stream, err, launches);
+    g_launches += launches;
+    if (rc) return fail(rc, "%s", err.c_str());
+    return LBDRN_OK;
+  }
+  return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream);
+}
+
+int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev, const float* coord_tab_dev,
+                      float* y_dev, void* stream) {
+  return run_infer<MODE_PREDICT>(d, msb_dev, nullptr, params_dev, coord_tab_dev, y_dev, nullptr, stream);
+}
+
+int32_t lbdrn_eval_sse(const LbdrnDesc* d, const void* msb_dev, const void* lsb_dev, const float* params_dev,
+                       const float* coord_tab_dev, double* sse_dev, void* stream) {
+  return run_infer<MODE_SSE>(d, msb_dev, lsb_dev, params_dev, coord_tab_dev, nullptr, sse_dev, stream);
+}
+
+int32_t lbdrn_train_create(const LbdrnDesc* d, const LbdrnTrainCfg* cfg, LbdrnTrain** out) {
+  if (!cfg || !out) return fail(LBDRN_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->batch_size < 1) return fail(LBDRN_E_INVALID, "batch_size=%d", cfg->batch_size);
+  LbdrnTrain* t = new LbdrnTrain();
+  int rc = resolve(d, t->net);
+  if (rc) { delete t; return rc; }
+  t->cfg = *cfg;
+  int supports_coop = 0, max_smem = 0;
+  cudaError_t e = cudaGetDevice(&t->dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, t->dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&supports_coop, cudaDevAttrCooperativeLaunch, t->dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, t->dev);
+  if (e != cudaSuccess) { delete t; return fail(LBDRN_E_CUDA, "device query: %s", cudaGetErrorString(e)); }
+  if (!supports_coop) { delete t; return fail(LBDRN_E_UNSUPPORTED, "device lacks cooperative launch"); }
+  const Net& n = t->net;
+  t->dimpad = (n.dim_in + 7) & ~7;
+  t->pstride = round4(n.P + 1) + 28;   // keep CTAs' partials on distinct 128 B lines
+  t->pstride = (t->pstride + 31) & ~31;
+  const bool c4 = n.C <= 4;
+  switch (n.bc) {
+    case 32: rc = c4 ? pick_train_kernel<32, 4>(t, max_smem) : pick_train_kernel<32, 8>(t, max_smem); break;
+    case 64: rc = c4 ? pick_train_kernel<64, 4>(t, max_smem) : pick_train_kernel<64, 8>(t, max_smem); break;
+    case 128: rc = c4 ? pick_train_kernel<128, 4>(t, max_smem) : pick_train_kernel<128, 8>(t, max_smem); break;
+    default: rc = fail(LBDRN_E_UNSUPPORTED, "fused training is built for bc=32/64/128 (got %d)", n.bc);
+  }
+  if (rc) { delete t; return rc; }
+  const size_t pb = ((size_t)n.P + 64) * sizeof(float);
+  e = cudaMalloc(&t->params, pb);
+  if (e == cudaSuccess) e = cudaMalloc(&t->wpack, pb);
+  if (e == cudaSuccess) e = cudaMalloc(&t->m, pb);
+  if (e == cudaSuccess) e = cudaMalloc(&t->v, pb);
+  if (e == cudaSuccess) e = cudaMalloc(&t->partial, (size_t)t->grid * t->pstride * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(t->params, 0, pb);
+  if (e == cudaSuccess) e = cudaMemset(t->wpack, 0, pb);
+  if (e == cudaSuccess) e = cudaMemset(t->m, 0, pb);
+  if (e == cudaSuccess) e = cudaMemset(t->v, 0, pb);
+  if (e == cudaSuccess) e = cudaMemset(t->partial, 0, (size_t)t->grid * t->pstride * sizeof(float));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    lbdrn_train_destroy(t);
+    return fail(e == cudaErrorMemoryAllocation ? LBDRN_E_NOMEM : LBDRN_E_CUDA, "train_create: %s", cudaGetErrorString(e));
+  }
+  *out = t;
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_train_destroy(LbdrnTrain* t) {
+  if (!t) return LBDRN_OK;
+  cudaDeviceSynchronize();
+  cudaFree(t->params); cudaFree(t->wpack); cudaFree(t->m); cudaFree(t->v); cudaFree(t->partial);
+  delete t;
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_train_set_params(LbdrnTrain* t, const float* params_dev, void* stream) {
+  if (!t || !params_dev) return fail(LBDRN_E_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(t->params, params_dev, (size_t)t->net.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  pack_params_kernel<<<(t->net.P + 255) / 256, 256, 0, st>>>(t->net, t->params, t->wpack);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_train_get_params(LbdrnTrain* t, float* params_dev, void* stream) {
+  if (!t || !params_dev) return fail(LBDRN_E_INVALID, "null argument");
+  CUDA_TRY(cudaMemcpyAsync(params_dev, t->params, (size_t)t->net.P * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_train_steps(LbdrnTrain* t, const void* msb_dev, const void* lsb_dev, const float* coord_tab_dev,
+                          const int64_t* perm_dev, int64_t n_perm, int32_t n_steps, int64_t adam_t0, double lr,
+                          float* losses_dev, void* stream) {
+  if (!t || !msb_dev || !lsb_dev || !perm_dev || !losses_dev) return fail(LBDRN_E_INVALID, "null argument");
+  if (t->net.nco && !coord_tab_dev) return fail(LBDRN_E_INVALID, "USE_COORDINATES set but coord_tab_dev is NULL");
+  if (n_steps < 1 || (int64_t)(n_steps - 1) * t->cfg.batch_size >= n_perm)
+    return fail(LBDRN_E_INVALID, "n_steps=%d does not match n_perm=%lld at batch_size=%d", n_steps, (long long)n_perm,
+                t->cfg.batch_size);
+  TrainArgs a;
+  memset(&a, 0, sizeof a);
+  a.msb = msb_dev; a.lsb = lsb_dev; a.tab = coord_tab_dev; a.perm = perm_dev; a.n_perm = n_perm;
+  a.bs = t->cfg.batch_size; a.n_steps = n_steps; a.mode = TRAIN_FUSED; a.adam_t0 = adam_t0; a.lr = lr;
+  a.losses = losses_dev;
+  return launch_train(t, a, (cudaStream_t)stream);
+}
+
+int32_t lbdrn_train_grad(LbdrnTrain* t, const void* msb_dev, const void* lsb_dev, const float* coord_tab_dev,
+                         const int64_t* batch_dev, int32_t n_local, int32_t n_global, float* grad_dev, void* stream) {
+  if (!t || !msb_dev || !lsb_dev || !batch_dev || !grad_dev) return fail(LBDRN_E_INVALID, "null argument");
+  if (t->net.nco && !coord_tab_dev) return fail(LBDRN_E_INVALID, "USE_COORDINATES set but coord_tab_dev is NULL");
+  if (n_local < 1 || n_global < n_local || n_local > t->cfg.batch_size)
+    return fail(LBDRN_E_INVALID, "bad local/global batch %d/%d", n_local, n_global);
+  TrainArgs a;
+  memset(&a, 0, sizeof a);
+  a.msb = msb_dev; a.lsb = lsb_dev; a.tab = coord_tab_dev; a.perm = batch_dev; a.n_perm = n_local;
+  a.bs = n_local; a.n_steps = 1; a.mode = TRAIN_GRAD_ONLY; a.n_global = n_global; a.grad_out = grad_dev;
+  return launch_train(t, a, (cudaStream_t)stream);
+}
+
+int32_t lbdrn_train_apply(LbdrnTrain* t, const float* grad_dev, int64_t adam_t, double lr, void* stream) {
+  if (!t || !grad_dev || adam_t < 1) return fail(LBDRN_E_INVALID, "bad argument");
+  const double bc1 = 1.0 - std::pow(t->cfg.beta1, (double)adam_t), bc2 = 1.0 - std::pow(t->cfg.beta2, (double)adam_t);
+  adam_apply_kernel<<<(t->net.P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      t->net, grad_dev, t->params, t->wpack, t->m, t->v, (float)(1.0 - t->cfg.beta1), (float)(1.0 - t->cfg.beta2),
+      (float)t->cfg.beta2, (float)t->cfg.eps, (float)(lr / bc1), (float)std::sqrt(bc2));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+// lbdrn_train_fp32.cuh -- fused, persistent training kernel (fp32 FFMA): neighbourhood gather by pixel index,
+// forward, LBDRNLoss (MSE), backward, deterministic cross-CTA gradient reduction and Adam, for many consecutive
+// optimiser steps in ONE cooperative launch.  Replaces the per-step ~35-40 library launches + H2D + host sync of
+// the reference (modified_ignite_engine.py:18-27, encode.py:69-70,84-85,95).
+//
+// Per step:   [each CTA]  64-pixel chunks of the batch: gather -> fwd -> bwd -> gradient partial in HBM/L2
+//             grid.sync
+//             [all threads] fixed-order sum of the partials, Adam update of (param, m, v), refresh packed copy
+//             grid.sync ; reload weights into smem
+// Latency-bound by construction (81 920 dependent steps for an 8192^2 scene): the budget is the two grid syncs
+// plus the 43.5 KB weight reload, not flops.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "lbdrn_common.cuh"
+
+namespace lbdrn {
+namespace cg = cooperative_groups;
+
+constexpr int kTrainTM = 4;                 // pixels per thread group
+constexpr int kTrainNPIX = 16 * kTrainTM;   // 64 pixels per chunk
+constexpr int kTrainLDP = kTrainNPIX + 4;   // padded row stride: conflict-free LDS.128 down a column of rows
+
+enum { TRAIN_FUSED = 0, TRAIN_GRAD_ONLY = 1 };
+
+struct TrainArgs {
+  Net net;
+  const void* msb;
+  const void* lsb;
+  const float* tab;
+  const int64_t* perm;     // pixel indices; step s uses [s*bs, min((s+1)*bs, n_perm))
+  long long n_perm;
+  int bs, n_steps, mode;
+  long long adam_t0;
+  double lr, beta1, beta2;
+  float omb1, omb2, beta2f, eps;   // (float)(1-beta1), (float)(1-beta2), (float)beta2, (float)eps
+  int n_global;            // GRAD_ONLY: global batch size for the 2/(B*C) factor
+  float* params;           // master parameters, reference layout
+  float* wpack;            // packed copy (hidden W transposed) kept in sync by the Adam phase
+  float* m;
+  float* v;
+  float* partial;          // [gridDim.x][pstride]; slot P holds the chunk squared-error sum
+  int pstride;
+  float* losses;           // FUSED: [n_steps]
+  float* grad_out;         // GRAD_ONLY: [P+1]
+  int dimpad;              // dim_in rounded up to 8 (rows of the X buffer, padding rows are zero)
+};
+
+// out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin; dst is the natural [BC][Kin] gradient block.
+template <int BC>
+__device__ __forceinline__ void grad_weight_nt(const float* __restrict__ G, const float* __restrict__ A, int Kin,
+                                               int kpad8, float* __restrict__ dst, bool first) {
+  constexpr int LDP = kTrainLDP, RB = (BC < 64 ? BC : 64), RA = RB / 16;
+  const int tid = threadIdx.x, tc = tid & 7, tr = tid >> 3;
+  for (int r0 = 0; r0 < BC; r0 += RB) {
+    for (int q0 = 0; q0 < Kin; q0 += 64) {
+      float acc[RA][8];
+#pragma unroll
+      for (int x = 0; x < RA; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+      for (int p = 0; p < kTrainNPIX; p += 4) {
+        float4 gv[RA];
+#pragma unroll
+        for (int x = 0; x < RA; ++x) gv[x] = *reinterpret_cast<const float4*>(G + (size_t)(r0 + tr + 16 * x) * LDP + p);
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          if (q0 + 8 * y < kpad8) {
+            float4 av = *reinterpret_cast<const float4*>(A + (size_t)(q0 + tc + 8 * y) * LDP + p);
+#pragma unroll
+            for (int x = 0; x < RA; ++x) {
+              acc[x][y] = fmaf(gv[x].x, av.x, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].y, av.y, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].z, av.z, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].w, av.w, acc[x][y]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < RA; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          int q = q0 + tc + 8 * y;
+          if (q < Kin) {
+            float* d = dst + (size_t)(r0 + tr + 16 * x) * Kin + q;
+            *d = first ? acc[x][y] : *d + acc[x][y];
+          }
+        }
+    }
+  }
+}
+
+__device__ __forceinline__ float row_sum64(const float* __restrict__ row) {
+  float s = 0.f;
+#pragma unroll
+  for (int p = 0; p < kTrainNPIX; p += 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + p);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  return s;
+}
+
+__device__ __forceinline__ float row_dot64(const float* __restrict__ a, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int p = 0; p < kTrainNPIX; p += 4) {
+    float4 x = *reinterpret_cast<const float4*>(a + p), y = *reinterpret_cast<const float4*>(b + p);
+    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+  }
+  return s;
+}
+
+// index of parameter i inside the packed copy (hidden weights transposed)
+__device__ __forceinline__ int packed_index(const Net& net, int i) {
+  for (int l = 0; l < net.nl; ++l) {
+    int K = l == 0 ? net.dim_in : net.bc;
+    int o = i - net.woff[l];
+    if (o >= 0 && o < K * net.bc) {
+      int n = o / K, k = o - n * K;
+      return net.woff[l] + k * net.bc + n;
+    }
+  }
+  return i;
+}
+
+// torch.optim.Adam single-tensor update (lr, betas, eps; no weight decay / amsgrad), torch/optim/adam.py
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float omb1, float omb2,
+                                            float beta2, float eps, float step_size, float bc2_sqrt) {
+  m = fmaf(omb1, g - m, m);                              // exp_avg.lerp_(grad, 1-beta1)
+  v = fmaf(omb2, g * g, v * beta2);                      // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+  float denom = __fdiv_rn(__fsqrt_rn(v), bc2_sqrt) + eps;
+  p = p - step_size * __fdiv_rn(m, denom);               // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+template <int BC, int CP, bool WSMEM>
+__global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a) {
+  constexpr int TM = kTrainTM, NPIX = kTrainNPIX, LDP = kTrainLDP, TN = BC / 8;
+  cg::grid_group grid = cg::this_grid();
+  const Net& net = a.net;
+  const int tid = threadIdx.x, tn = tid & 7, pg = tid >> 3;
+  const int C = net.C, D = net.D, n = net.n, L = net.nl, P = net.P;
+
+  // ---- shared memory carve-up ----------------------------------------------------------------------------
+  extern __shared__ float4 smem4[];
+  float* X = reinterpret_cast<float*>(smem4);                   // [dimpad][LDP]   features
+  float* Hbuf = X + (size_t)a.dimpad * LDP;                     // [L][BC][LDP]    hidden outputs
+  float* Gbuf = Hbuf + (size_t)L * BC * LDP;                    // [L][BC][LDP]    act' then dz
+  float* dZo = Gbuf + (size_t)L * BC * LDP;                     // [CP][LDP]       output-layer dz
+  float* Tl = dZo + CP * LDP;                                   // [CP][LDP]       labels
+  float* ctr = Tl + CP * LDP;                                   // [kMaxC][NPIX]   normalised centre values
+  float* wsm = ctr + kMaxC * NPIX;                              // packed weights [P] (+pad) then natural hidden l>=1
+  float* wnat_sm = wsm + round4(P);
+  __shared__ int s_py[NPIX], s_px[NPIX], s_valid[NPIX];
+  __shared__ float s_red[kThreads / 32];
+  __shared__ float s_sse;
+  __shared__ float s_adam[2];
+
+  const float* w = WSMEM ? wsm : a.wpack;
+  // natural (untransposed) W_l for hidden layers l>=1, used as the k-major B operand of dh = W^T dz
+  auto wnat = [&](int l) -> const float* {
+    return WSMEM ? (wnat_sm + (size_t)(l - 1) * BC * BC) : (a.params + net.woff[l]);
+  };
+
+  for (int s = 0; s < a.n_steps; ++s) {
+    // ---- (re)load weights ----------------------------------------------------------------------------
+    if (WSMEM) {
+      const int P4 = P >> 2;
+      for (int i = tid; i < P4; i += kThreads)
+        reinterpret_cast<float4*>(wsm)[i] = __ldcg(reinterpret_cast<const float4*>(a.wpack) + i);
+      for (int i = (P4 << 2) + tid; i < P; i += kThreads) wsm[i] = __ldcg(a.wpack + i);
+      for (int l = 1; l < L; ++l) {
+        const float4* src = reinterpret_cast<const float4*>(a.params + net.woff[l]);
+        float4* dst = reinterpret_cast<float4*>(wnat_sm + (size_t)(l - 1) * BC * BC);
+        for (int i = tid; i < BC * BC / 4; i += kThreads) dst[i] = __ldcg(src + i);
+      }
+    }
+    if (tid == 0) s_sse = 0.f;
+    __syncthreads();
+
+    const long long b0 = a.mode == TRAIN_FUSED ? (long long)s * a.bs : 0;
+    long long rem = a.n_perm - b0;
+    const int B = (int)(rem < a.bs ? rem : a.bs);                 // last batch of an epoch may be partial
+    const int Bglobal = a.mode == TRAIN_FUSED ? B : a.n_global;
+    const float gscale = 2.0f / ((float)Bglobal * (float)C);       // d(mean((y-t)^2))/dy = 2 (y-t) / (B*C)
+    const int n_chunks = (B + NPIX - 1) / NPIX;
+    float* mypart = a.partial + (size_t)blockIdx.x * a.pstride;
+    bool first = true;
+
+    for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+      __syncthreads();
+      // ---- gather: pixel coordinates, centres, labels, features (LBDRNdataset.py:104-131,151-155) --------
+      const int nvalid = min(NPIX, B - ch * NPIX);
+      if (tid < NPIX) {
+        long long idx = tid < nvalid ? a.perm[b0 + (long long)ch * NPIX + tid] : 0;
+        int y = (int)(idx / net.W);
+        s_py[tid] = y;
+        s_px[tid] = (int)(idx - (long long)y * net.W);
+        s_valid[tid] = tid < nvalid;
+      }
+      __syncthreads();
+      for (int e = tid; e < C * NPIX; e += kThreads) {
+        int c = e / NPIX, pp = e - c * NPIX;
+        size_t off = ((size_t)c * net.buf_rows + (s_py[pp] - net.buf_row0)) * net.W + s_px[pp];
+        ctr[c * NPIX + pp] = load_msb_norm(a.msb, net.msb_u16, off, net.maxv);
+        uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+        Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);
+      }
+      __syncthreads();
+      for (int idx = tid; idx < a.dimpad * NPIX; idx += kThreads) {
+        int k = idx / NPIX, pp = idx - k * NPIX;
+        float v = 0.f;
+        if (k < net.dim_in && s_valid[pp]) {
+          int gy = s_py[pp], gx = s_px[pp];
+          if (k < net.nco) {
+            int half = k / net.tabw, i = k - half * net.tabw;
+            v = half == 0 ? a.tab[(size_t)gy * net.tabw + i] : a.tab[(size_t)(net.H + gx) * net.tabw + i];
+          } else {
+            int kk = k - net.nco;
+            int c = kk / (n * n), r2 = kk - c * n * n;
+            int dy = r2 / n, dx = r2 - dy * n;
+            int yy = reflect_clamp(gy + dy - D, net.H), xx = reflect_clamp(gx + dx - D, net.W);
+            v = load_msb_norm(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (yy - net.buf_row0)) * net.W + xx, net.maxv);
+            if (net.relative) v -= ctr[c * NPIX + pp];
+          }
+        }
+        X[(size_t)k * LDP + pp] = v;
+      }
+      __syncthreads();
+
+      // ---- forward (LBDRNmodel.py:79-82), keeping h_l and act'(z_l) per layer ------------------------------
+      float h[TM][TN];
+      for (int l = 0; l < L; ++l) {
+        const int K = l == 0 ? net.dim_in : BC;
+        const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
+        float* Hl = Hbuf + (size_t)l * BC * LDP;
+        float* Gl = Gbuf + (size_t)l * BC * LDP;
+        float acc[TM][TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          float b = w[net.boff[l] + unit_of<TN>(j, tn)];
+#pragma unroll
+          for (int i = 0; i < TM; ++i) acc[i][j] = b;
+        }
+        gemm_kmajor<TM, TN, BC>(acc, in, LDP, w + net.woff[l], K, pg, tn);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          float g4[TM];
+#pragma unroll
+          for (int i = 0; i < TM; ++i) {
+            if (net.relu) {
+              h[i][j] = fmaxf(acc[i][j], 0.f);
+              g4[i] = acc[i][j] > 0.f ? 1.f : 0.f;
+            } else {
+              float sn, cs;
+              sincosf(net.w0 * acc[i][j], &sn, &cs);   // d sin(w0 z)/dz = w0 cos(w0 z)
+              h[i][j] = sn;
+              g4[i] = cs * net.w0;
+            }
+          }
+          size_t o = (size_t)unit_of<TN>(j, tn) * LDP + pg * TM;
+          *reinterpret_cast<float4*>(Hl + o) = make_float4(h[0][j], h[1][j], h[2][j], h[3][j]);
+          *reinterpret_cast<float4*>(Gl + o) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+        }
+        __syncwarp();   // next layer reads only this warp's pixel columns
+      }
+
+      // ---- output layer + loss (LBDRNloss.py:9) ---------------------------------------------------------
+      float part[TM * CP];
+      const float* wo = w + net.woff[L];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) part[i * CP + c] = 0.f;
+        if (c < C) {
+#pragma unroll
+          for (int j = 0; j < TN; ++j) {
+            float wv = wo[c * BC + unit_of<TN>(j, tn)];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) part[i * CP + c] = fmaf(wv, h[i][j], part[i * CP + c]);
+          }
+        }
+      }
+      group8_allreduce<TM * CP>(part);
+      float sse = 0.f;
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        if (i == tn) {
+          int pp = pg * TM + i;
+          bool ok = s_valid[pp] != 0;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            if (c < C) {
+              float y = sigmoidf_rn(part[i * CP + c] + w[net.boff[L] + c]);
+              float d = y - Tl[c * LDP + pp];
+              float dz = ok ? (gscale * d) * ((1.0f - y) * y) : 0.f;   // mse backward then sigmoid backward
+              dZo[c * LDP + pp] = dz;
+              if (ok) sse += d * d;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
+      if ((tid & 31) == 0) s_red[tid >> 5] = sse;
+      __syncthreads();
+      if (tid == 0) s_sse += (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+
+      // ---- backward --------------------------------------------------------------------------------------
+      // output layer: dW_o[c][n] = sum_p dz_o[c][p] h_L[n][p];  db_o[c] = sum_p dz_o[c][p]
+      {
+        const float* HL = Hbuf + (size_t)(L - 1) * BC * LDP;
+        for (int o = tid; o < C * BC; o += kThreads) {
+          int c = o / BC, u = o - c * BC;
+          float g = row_dot64(dZo + c * LDP, HL + (size_t)u * LDP);
+          float* d = mypart + net.woff[L] + o;
+          *d = first ? g : *d + g;
+        }
+        if (tid < C) {
+          float g = row_sum64(dZo + tid * LDP);
+          float* d = mypart + net.boff[L] + tid;
+          *d = first ? g : *d + g;
+        }
+      }
+      for (int l = L - 1; l >= 0; --l) {
+        float* Gl = Gbuf + (size_t)l * BC * LDP;
+        float acc[TM][TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        if (l == L - 1) {
+          // dh_L[u][p] = sum_c W_o[c][u] dz_o[c][p]
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            if (c < C) {
+              float4 dv = *reinterpret_cast<const float4*>(dZo + c * LDP + pg * TM);
+#pragma unroll
+              for (int j = 0; j < TN; ++j) {
+                float wv = wo[c * BC + unit_of<TN>(j, tn)];
+                acc[0][j] = fmaf(wv, dv.x, acc[0][j]);
+                acc[1][j] = fmaf(wv, dv.y, acc[1][j]);
+                acc[2][j] = fmaf(wv, dv.z, acc[2][j]);
+                acc[3][j] = fmaf(wv, dv.w, acc[3][j]);
+              }
+            }
+          }
+        } else {
+          // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p]   (k-major in m on both operands)
+          gemm_kmajor<TM, TN, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, LDP, wnat(l + 1), BC, pg, tn);
+        }
+        // dz_l = dh_l * act'(z_l): thread-private read-modify-write of its own (unit, pixel) entries
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          float4* gp = reinterpret_cast<float4*>(Gl + (size_t)unit_of<TN>(j, tn) * LDP + pg * TM);
+          float4 g = *gp;
+          g.x *= acc[0][j]; g.y *= acc[1][j]; g.z *= acc[2][j]; g.w *= acc[3][j];
+          *gp = g;
+        }
+        __syncthreads();
+        // dW_l = dz_l . in_l^T ; db_l = row sums
+        const int K = l == 0 ? net.dim_in : BC;
+        const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
+        grad_weight_nt<BC>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
+        for (int u = tid; u < BC; u += kThreads) {
+          float g = row_sum64(Gl + (size_t)u * LDP);
+          float* d = mypart + net.boff[l] + u;
+          *d = first ? g : *d + g;
+        }
+      }
+      first = false;
+    }
+    __syncthreads();
+    if (tid == 0 && !first) mypart[P] = s_sse;
+    __threadfence();
+    grid.sync();
+
+    // ---- fixed-order reduction over the CTAs that produced partials, then Adam ----------------------------
+    const int n_act = min((int)gridDim.x, n_chunks);
+    if (tid == 0 && a.mode == TRAIN_FUSED) {
+      double t = (double)(a.adam_t0 + s + 1);
+      double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
+      s_adam[0] = (float)(a.lr / bc1);              // step_size
+      s_adam[1] = (float)sqrt(bc2);                 // bias_correction2_sqrt
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * kThreads + tid; i <= P; i += gridDim.x * kThreads) {
+      float g = 0.f;
+      for (int c = 0; c < n_act; ++c) g += __ldcg(a.partial + (size_t)c * a.pstride + i);
+      if (a.mode == TRAIN_GRAD_ONLY) {
+        a.grad_out[i] = g;
+      } else if (i == P) {
+        a.losses[s] = g / ((float)B * (float)C);
+      } else {
+        float p = a.params[i], m = a.m[i], v = a.v[i];
+        adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
+        a.params[i] = p; a.m[i] = m; a.v[i] = v;
+        a.wpack[packed_index(net, i)] = p;
+      }
+    }
+    __threadfence();
+    grid.sync();
+  }
+}
+
+// Adam on an externally reduced gradient (data-parallel mode) + packed-copy refresh.
+__global__ void adam_apply_kernel(Net net, const float* __restrict__ grad, float* params, float* wpack, float* m,
+                                  float* v, float omb1, float omb2, float beta2, float eps, float step_size,
+                                  float bc2_sqrt) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < net.P; i += gridDim.x * blockDim.x) {
+    float p = params[i], mm = m[i], vv = v[i];
+    adam_update(p, mm, vv, grad[i], omb1, omb2, beta2, eps, step_size, bc2_sqrt);
+    params[i] = p; m[i] = mm; v[i] = vv;
+    wpack[packed_index(net, i)] = p;
+  }
+}
+
+}  // namespace lbdrn

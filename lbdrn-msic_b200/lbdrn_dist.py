@@ -1,0 +1,114 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): row-stripe sharded decode and data-parallel /
+scene-parallel encode.  The reference has no distributed code at all; this is the B200-side design.
+
+Decode shards naturally: an output pixel depends on its (2D+1)^2 MSB neighbourhood, the global scalar MSB.max() and the
+shared weights.  Each rank owns a contiguous row stripe; the only exchanges are a scalar max all-reduce and a ONE-OFF
+D-row halo swap of the static MSB planes with the two neighbouring stripes (<= D*W*C*2 bytes per edge).  Reflect padding
+is applied only at the true image border, never at stripe seams, so the result is bit-identical to the 1-GPU decode.
+
+Encode, data-parallel: every rank holds the whole scene and takes a contiguous 1/G slice of every batch; one all-reduce
+of the flat gradient vector (P+1 floats) per step, identical Adam update on every rank.  Latency-bound at bs=8192.
+Encode, scene-parallel: independent scenes / tiles per rank, no communication (replicas only).
+"""
+import ctypes
+import math
+
+import torch
+import torch.distributed as dist
+
+import lbdrn_cabi as cabi
+
+
+def stripe_bounds(H, world, rank):
+    """Rows [r0, r1) of rank `rank` when H rows are cut into `world` contiguous, near-equal stripes."""
+    base, extra = divmod(H, world)
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+def global_max(local_max, group=None):
+    """MSB.max() over all stripes (LBDRNdataset.py:120 takes it over the whole image)."""
+    t = local_max.clone().reshape(1) if torch.is_tensor(local_max) else torch.tensor([int(local_max)])
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.to(torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def exchange_halos(stripe, D, group=None):
+    """stripe: [C, rows, W] tensor holding this rank's own rows.  Returns ([C, rows + top + bottom, W], top) where
+    `top` halo rows came from rank-1 and the bottom ones from rank+1 (none at the image border).  Works on CUDA
+    (NCCL send/recv over NVLink) and CPU (gloo) tensors; uint16 planes travel as int16 views."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if D == 0 or world == 1:
+        return stripe, 0
+    if stripe.shape[1] < D:
+        raise ValueError("stripe thinner than the halo")
+    wire = stripe.view(torch.int16) if stripe.dtype == torch.uint16 else stripe
+    C, rows, W = wire.shape
+    up = torch.empty((C, D, W), dtype=wire.dtype, device=wire.device) if rank > 0 else None
+    down = torch.empty((C, D, W), dtype=wire.dtype, device=wire.device) if rank + 1 < world else None
+    ops = []
+    if rank > 0:
+        ops += [dist.P2POp(dist.isend, wire[:, :D].contiguous(), rank - 1, group),
+                dist.P2POp(dist.irecv, up, rank - 1, group)]
+    if rank + 1 < world:
+        ops += [dist.P2POp(dist.isend, wire[:, rows - D:].contiguous(), rank + 1, group),
+                dist.P2POp(dist.irecv, down, rank + 1, group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    parts = ([up] if up is not None else []) + [wire] + ([down] if down is not None else [])
+    buf = torch.cat(parts, dim=1).contiguous()
+    return (buf.view(torch.uint16) if stripe.dtype == torch.uint16 else buf), (D if up is not None else 0)
+
+
+def decode_stripe(stripe_msb, H, flat_params_dev, K, D, bc, nl, flags, msb_max, group=None, relu=False, w0=30.0,
+                  path=cabi.PATH_AUTO, tab=None, halo=None):
+    """Decode this rank's stripe of an H-row scene.  stripe_msb: [C, rows, W] CUDA tensor of the rank's OWN rows.
+    Returns the [C, rows, W] uint16 reconstruction of those rows.  `halo`: a cached (buffer, top) from
+    `exchange_halos` when the same scene is decoded repeatedly."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    r0, r1 = stripe_bounds(H, world, rank)
+    buf, top = exchange_halos(stripe_msb, D, group) if halo is None else halo
+    C, brows, W = buf.shape
+    d = cabi.make_desc(C, H, W, K, D, bc, nl, flags.bits(relu), msb_max, buf.dtype == torch.uint16, row0=r0, row1=r1,
+                       buf_row0=r0 - top, buf_rows=brows, w0=w0, n_freq=flags.n_freq, path=path)
+    out = torch.empty((C, brows, W), dtype=torch.uint16, device=buf.device)
+    cabi.check(cabi.load().lbdrn_decode(ctypes.byref(d), cabi.ptr(buf), cabi.ptr(flat_params_dev), cabi.ptr(tab),
+                                        cabi.ptr(out), cabi.stream_ptr()))
+    return out.view(torch.int16)[:, top:top + (r1 - r0)].contiguous().view(torch.uint16)
+
+
+def batch_slice(n, world, rank):
+    """Contiguous share [a, b) of an n-pixel batch for `rank` (same rule as stripe_bounds)."""
+    return stripe_bounds(n, world, rank)
+
+
+class DataParallelTrainer:
+    """Data-parallel encode: identical replicas, each computing the gradient of its slice of every batch; one
+    all-reduce(sum) of P+1 floats per step (NCCL over NVLink/NVSwitch), then the same Adam step everywhere."""
+
+    def __init__(self, fused_trainer, group=None):
+        self.t, self.group = fused_trainer, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        n = fused_trainer.model.flat_params().numel()
+        self.grad = torch.zeros(n + 1, dtype=torch.float32, device=fused_trainer.dev)
+
+    def train_epoch(self, perm_dev, lr):
+        t, lib = self.t, self.t.lib
+        n, bs, C = perm_dev.numel(), t.bs, t.scene.C
+        losses = []
+        for s in range(math.ceil(n / bs)):
+            b0, b1 = s * bs, min(n, (s + 1) * bs)
+            a, b = batch_slice(b1 - b0, self.world, self.rank)
+            if b > a:
+                cabi.check(lib.lbdrn_train_grad(t.handle, cabi.ptr(t.scene.msb), cabi.ptr(t.scene.lsb), cabi.ptr(t.tab),
+                                                ctypes.c_void_p(perm_dev.data_ptr() + 8 * (b0 + a)), b - a, b1 - b0,
+                                                cabi.ptr(self.grad), cabi.stream_ptr()))
+            else:
+                self.grad.zero_()
+            dist.all_reduce(self.grad, group=self.group)
+            t.adam_t += 1
+            cabi.check(lib.lbdrn_train_apply(t.handle, cabi.ptr(self.grad), t.adam_t, float(lr), cabi.stream_ptr()))
+            losses.append(self.grad[-1:] / ((b1 - b0) * C))
+        return torch.cat(losses)

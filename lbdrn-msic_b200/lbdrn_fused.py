@@ -1,0 +1,355 @@
+"""Host side of the fused LBDRN path: keeps the scene resident on the GPU as integer MSB/LSB planes and drives the
+C-ABI kernels of liblbdrn_b200 (decode, predict, full-scene MSE, fused training).  Never materialises the
+(H*W, dim_in) feature matrix the reference builds on the host (LBDRNdataset.py:104-130, decode.py:77-102).
+
+There is no CPU fallback here: every function needs a CUDA device and the native library.
+"""
+import ctypes
+import math
+import threading
+
+import numpy as np
+import torch
+
+import lbdrn_cabi as cabi
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# feature flags
+# ----------------------------------------------------------------------------------------------------------------
+class Flags:
+    """Snapshot of the codec's feature switches (module globals of constants.py)."""
+
+    def __init__(self, use_coordinates=False, embedding=False, sigma=1.4, n_freq=12, use_colors=True, relative=True):
+        self.use_coordinates, self.embedding = bool(use_coordinates), bool(embedding)
+        self.sigma, self.n_freq = float(sigma), int(n_freq)
+        self.use_colors, self.relative = bool(use_colors), bool(relative)
+
+    @classmethod
+    def from_constants(cls):
+        import constants as k
+        return cls(k.USE_COORDINATES, k.EMBEDDING, k.SIGMA, k.N_FREQ, k.USE_COLORS, k.RELATIVE)
+
+    @property
+    def tabw(self):
+        return 2 * self.n_freq * int(self.embedding) + 1
+
+    def num_coords(self):
+        return self.tabw * 2 * int(self.use_coordinates)
+
+    def dim_in(self, C, D):
+        """Feature count (LBDRNdataset.py:104-106)."""
+        return self.num_coords() + C * (2 * D + 1) ** 2 * int(self.use_colors)
+
+    def bits(self, relu=False):
+        return cabi.flag_bits(self.use_coordinates, self.embedding, self.use_colors, self.relative, relu)
+
+
+def _flags(flags):
+    return Flags.from_constants() if flags is None else flags
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise cabi.LbdrnError(cabi.E_CUDA, "no CUDA device: the LBDRN fused path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def coord_table(H, W, flags):
+    """float32 [(H+W), tabw]: per-row then per-column coordinate / positional-encoding entries.
+
+    The reference evaluates, per pixel, v = float32(2*i/(n-1) - 1) and [v, sin(sigma^k pi v), cos(sigma^k pi v)] in
+    float64, stored as float32 (LBDRNdataset.py:108-118).  Each entry depends only on the row or only on the column,
+    so an (H+W) x tabw table carries exactly the same values."""
+    def axis(n):
+        v = (2 * np.arange(n) / (n - 1) - 1).astype(np.float32)
+        if not flags.embedding:
+            return v[:, None]
+        arg = (flags.sigma ** np.arange(flags.n_freq) * np.pi) * v[:, None]      # float64
+        return np.concatenate([v[:, None], np.sin(arg), np.cos(arg)], axis=1).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([axis(H), axis(W)], axis=0), dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# scene residency
+# ----------------------------------------------------------------------------------------------------------------
+class DeviceScene:
+    """MSB / LSB planes of one scene on the GPU (a1 of the hot path: LBDRNdataset.py:93-100)."""
+
+    def __init__(self, msb, lsb, K, msb_max):
+        self.msb, self.lsb, self.K, self.msb_max = msb, lsb, K, int(msb_max)
+        self.C, self.H, self.W = msb.shape
+
+    @property
+    def msb_u16(self):
+        return self.msb.dtype == torch.uint16
+
+    @classmethod
+    def from_image(cls, img, K, device=None):
+        """img: CHW (or HW) uint16/uint8 numpy array or torch tensor; the split runs on the device."""
+        dev = _device(device)
+        lib = cabi.load()
+        if isinstance(img, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(img.astype(np.uint16, copy=False)))
+        else:
+            t = img if img.dtype == torch.uint16 else img.to(torch.int32).to(torch.uint16)
+        t = t.reshape((-1,) + tuple(t.shape[-2:])).to(dev).contiguous()
+        n = t.numel()
+        mx = torch.zeros(1, dtype=torch.int32, device=dev)
+        cabi.check(lib.lbdrn_max_shifted(cabi.ptr(t), n, K, cabi.ptr(mx), cabi.stream_ptr()))
+        msb_max = int(mx.item())
+        u16 = msb_max > 255                                   # LBDRNdataset.py:100
+        msb = torch.empty(t.shape, dtype=torch.uint16 if u16 else torch.uint8, device=dev)
+        lsb = torch.empty(t.shape, dtype=torch.uint16 if K > 8 else torch.uint8, device=dev)
+        cabi.check(lib.lbdrn_split(cabi.ptr(t), n, K, cabi.U16 if u16 else cabi.U8, cabi.ptr(msb), cabi.ptr(lsb),
+                                   cabi.stream_ptr()))
+        return cls(msb, lsb, K, msb_max)
+
+    def desc(self, D, bc, nl, flags, relu=False, w0=30.0, path=cabi.PATH_AUTO, row0=0, row1=None):
+        return cabi.make_desc(self.C, self.H, self.W, self.K, D, bc, nl, flags.bits(relu), self.msb_max, self.msb_u16,
+                              row0=row0, row1=row1, w0=w0, n_freq=flags.n_freq, path=path)
+
+
+def _base_to_device(base, dev, known_max=None):
+    """CHW base layer (numpy u8/u16 or tensor) -> device tensor keeping u8 when it is u8, else u16, and its max."""
+    if isinstance(base, np.ndarray):
+        base = base.reshape((-1,) + base.shape[-2:])
+        if base.dtype not in (np.uint8, np.uint16):
+            base = base.astype(np.uint16)
+        t = torch.from_numpy(np.ascontiguousarray(base))
+    else:
+        t = base.reshape((-1,) + tuple(base.shape[-2:]))
+        if t.dtype not in (torch.uint8, torch.uint16):
+            t = t.to(torch.int32).to(torch.uint16)
+    t = t.to(dev, non_blocking=True).contiguous()
+    if known_max is not None:
+        return t, int(known_max)
+    if t.dtype == torch.uint8:
+        return t, int(t.max().item())
+    mx = torch.zeros(1, dtype=torch.int32, device=dev)
+    cabi.check(cabi.load().lbdrn_max_shifted(cabi.ptr(t), t.numel(), 0, cabi.ptr(mx), cabi.stream_ptr()))
+    return t, int(mx.item())
+
+
+_PATHS = {"auto": cabi.PATH_AUTO, "precise": cabi.PATH_PRECISE, "tensor": cabi.PATH_TENSOR}
+
+
+def _tab_tensor(H, W, flags, dev):
+    if not flags.use_coordinates:
+        return None
+    return torch.from_numpy(coord_table(H, W, flags)).to(dev)
+
+
+def decode_image(base, flat_params, K, D, bc, nl, flags=None, relu=False, w0=30.0, path="auto", device=None,
+                 return_tensor=False, out_host=None, base_max=None):
+    """Fused decode of one scene: uint16 CHW = (base << K) + round_half_even(net(features(base)) * (2^K-1)).
+    Replaces decode.py:77-134.  `base` may be a numpy array / CPU tensor (copied to the device; pinned memory makes
+    the copy asynchronous) or a CUDA tensor.  `out_host`: optional pinned uint16 CPU tensor receiving the result.
+    `base_max`: the global `base.max()` if the caller already knows it (saves a reduction + sync)."""
+    flags, dev, lib = _flags(flags), _device(device), cabi.load()
+    msb, mx = _base_to_device(base, dev, base_max)
+    C, H, W = msb.shape
+    params = torch.as_tensor(flat_params, dtype=torch.float32).to(dev).contiguous()
+    d = cabi.make_desc(C, H, W, K, D, bc, nl, flags.bits(relu), mx, msb.dtype == torch.uint16, w0=w0,
+                       n_freq=flags.n_freq, path=_PATHS[path])
+    if params.numel() != lib.lbdrn_param_count(ctypes.byref(d)):
+        raise ValueError(f"parameter vector has {params.numel()} values, network needs "
+                         f"{lib.lbdrn_param_count(ctypes.byref(d))}")
+    tab = _tab_tensor(H, W, flags, dev)
+    out = torch.empty((C, H, W), dtype=torch.uint16, device=dev)
+    cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(msb), cabi.ptr(params), cabi.ptr(tab), cabi.ptr(out),
+                                cabi.stream_ptr()))
+    if out_host is not None:
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+    return out if return_tensor else out.cpu().numpy()
+
+
+def predict_image(base, flat_params, D, bc, nl, flags=None, relu=False, w0=30.0, device=None):
+    """Network output y [H*W, C] (float32 CUDA tensor) for every pixel of the base layer."""
+    flags, dev, lib = _flags(flags), _device(device), cabi.load()
+    msb, mx = _base_to_device(base, dev)
+    C, H, W = msb.shape
+    params = torch.as_tensor(flat_params, dtype=torch.float32).to(dev).contiguous()
+    d = cabi.make_desc(C, H, W, 1, D, bc, nl, flags.bits(relu), mx, msb.dtype == torch.uint16, w0=w0,
+                       n_freq=flags.n_freq)
+    tab = _tab_tensor(H, W, flags, dev)
+    y = torch.empty((H * W, C), dtype=torch.float32, device=dev)
+    cabi.check(lib.lbdrn_predict(ctypes.byref(d), cabi.ptr(msb), cabi.ptr(params), cabi.ptr(tab), cabi.ptr(y),
+                                 cabi.stream_ptr()))
+    return y
+
+
+def eval_mse(scene, flat_params_dev, D, bc, nl, flags=None, relu=False, w0=30.0, tab=None):
+    """Full-scene MSE of the network against the LSB labels (encode.py:105-108 / LBDRNperformance.py:18-21)."""
+    flags, lib = _flags(flags), cabi.load()
+    dev = scene.msb.device
+    d = scene.desc(D, bc, nl, flags, relu, w0)
+    if tab is None:
+        tab = _tab_tensor(scene.H, scene.W, flags, dev)
+    sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    cabi.check(lib.lbdrn_eval_sse(ctypes.byref(d), cabi.ptr(scene.msb), cabi.ptr(scene.lsb), cabi.ptr(flat_params_dev),
+                                  cabi.ptr(tab), cabi.ptr(sse), cabi.stream_ptr()))
+    return float(sse.item()) / (scene.C * scene.H * scene.W)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# schedule and sampling (encode.py:69-70,85,98)
+# ----------------------------------------------------------------------------------------------------------------
+def lr_for_epoch(lr, epoch, epochs):
+    """StepLR(step_size=max(1,int(E/3)), gamma=0.1) stepped once per finished epoch; `epoch` is 1-based."""
+    v = lr
+    for _ in range((epoch - 1) // max(1, int(epochs / 3))):
+        v = v * 0.1
+    return v
+
+
+def draw_loader_seeds():
+    """Consume torch's default generator exactly as one `iter(DataLoader(shuffle=True))` does: an int64 draw for the
+    loader's base seed, then one for the RandomSampler's seed.  Returns the sampler seed."""
+    torch.empty((), dtype=torch.int64).random_()
+    return int(torch.empty((), dtype=torch.int64).random_().item())
+
+
+def permutation_from_seed(n, seed):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
+class FusedTrainer:
+    """The encoder's optimisation loop on the device (replaces trainer.run / evaluator.run of encode.py:84-117,157).
+
+    sampler="reference": every epoch's batch order is the permutation the reference's DataLoader would produce from
+    the same torch seed (host randperm, generated one epoch ahead on a worker thread, uploaded as int64 indices).
+    sampler="device": permutation drawn on the GPU (statistically equivalent, no host work).
+    Adam(lr, betas=(0.9,0.999), eps=1e-8), StepLR, per-epoch full-scene MSE and best-epoch selection follow
+    encode.py:84-85,96-117 (including the epochs==1 special case, which skips evaluation)."""
+
+    def __init__(self, model, scene, D, lr, batch_size, epochs, val_duration=1, flags=None, sampler="reference",
+                 on_epoch=None):
+        self.model, self.scene, self.D = model, scene, D
+        self.lr, self.bs, self.epochs, self.val_duration = float(lr), int(batch_size), int(epochs), int(val_duration)
+        self.flags = _flags(flags)
+        self.sampler, self.on_epoch = sampler, on_epoch
+        self.bc, self.nl = model.dim_hidden, model.num_layers
+        model._require_fused()
+        self.relu, self.w0 = model._relu, model.w0
+        if model.dim_in != self.flags.dim_in(scene.C, D) or model.dim_out != scene.C:
+            raise ValueError("model shape does not match the scene / feature flags")
+        self.lib = cabi.load()
+        self.dev = scene.msb.device
+        self.desc = scene.desc(D, self.bc, self.nl, self.flags, self.relu, self.w0)
+        cfg = cabi.LbdrnTrainCfg()
+        cfg.batch_size, cfg.world_size, cfg.rank = self.bs, 1, 0
+        cfg.beta1, cfg.beta2, cfg.eps = 0.9, 0.999, 1e-8
+        self.cfg = cfg
+        self.handle = ctypes.c_void_p()
+        cabi.check(self.lib.lbdrn_train_create(ctypes.byref(self.desc), ctypes.byref(cfg), ctypes.byref(self.handle)))
+        self.tab = _tab_tensor(scene.H, scene.W, self.flags, self.dev)
+        self.losses, self.val_mse, self.best_epoch, self.best_mse = [], [], -1, 1e6
+        self.best_params = None
+
+    def close(self):
+        if self.handle:
+            self.lib.lbdrn_train_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ----------------------------------------------------------------------------------------------
+    def _plan_seeds(self):
+        """All default-generator draws of the run, in the reference's order: train iterator of epoch e, then (when the
+        epoch is evaluated) the evaluator's iterator over the same shuffled loader."""
+        seeds = []
+        for e in range(1, self.epochs + 1):
+            seeds.append(draw_loader_seeds())
+            if self.epochs != 1 and e % min(self.val_duration, self.epochs) == 0:
+                draw_loader_seeds()
+        return seeds
+
+    def begin(self):
+        """Upload the model's current parameters into the training handle and reset the step counter."""
+        self.params_dev = self.model.flat_params().to(self.dev).contiguous()
+        cabi.check(self.lib.lbdrn_train_set_params(self.handle, cabi.ptr(self.params_dev), cabi.stream_ptr()))
+        self.adam_t = 0
+
+    def train_epoch(self, perm_dev, lr):
+        """One pass over `perm_dev` (int64 pixel indices on the device) in batches of `bs`; returns the per-step
+        losses (device tensor).  One persistent kernel launch."""
+        n = perm_dev.numel()
+        steps = math.ceil(n / self.bs)
+        losses = torch.empty(steps, dtype=torch.float32, device=self.dev)
+        sc = self.scene
+        cabi.check(self.lib.lbdrn_train_steps(self.handle, cabi.ptr(sc.msb), cabi.ptr(sc.lsb), cabi.ptr(self.tab),
+                                              cabi.ptr(perm_dev), n, steps, self.adam_t, float(lr), cabi.ptr(losses),
+                                              cabi.stream_ptr()))
+        self.adam_t += steps
+        return losses
+
+    def current_params(self):
+        """Flat parameter vector after the steps taken so far (new device tensor)."""
+        cur = torch.empty_like(self.params_dev)
+        cabi.check(self.lib.lbdrn_train_get_params(self.handle, cabi.ptr(cur), cabi.stream_ptr()))
+        return cur
+
+    def scene_mse(self, params_dev):
+        return eval_mse(self.scene, params_dev, self.D, self.bc, self.nl, self.flags, self.relu, self.w0, self.tab)
+
+    def run(self):
+        """Train; returns dict(params=best flat params (CPU tensor), losses, val_mse, best_epoch)."""
+        N = self.scene.H * self.scene.W
+        self.begin()
+        seeds = self._plan_seeds()
+        host_perm, pinned, uploaded = {}, [None, None], [None, None]
+
+        def make_host_perm(e):
+            g = torch.Generator()
+            g.manual_seed(seeds[e - 1])
+            if pinned[e % 2] is None:
+                pinned[e % 2] = torch.empty(N, dtype=torch.int64).pin_memory()
+            host_perm[e] = torch.randperm(N, generator=g, out=pinned[e % 2])
+
+        if self.sampler == "reference":
+            make_host_perm(1)
+        for e in range(1, self.epochs + 1):
+            th = None
+            if self.sampler == "reference":
+                perm = host_perm.pop(e).to(self.dev, non_blocking=True)
+                uploaded[e % 2] = torch.cuda.Event()
+                uploaded[e % 2].record()
+                if e < self.epochs:
+                    if uploaded[(e + 1) % 2] is not None:
+                        uploaded[(e + 1) % 2].synchronize()      # that pinned buffer is free again
+                    th = threading.Thread(target=make_host_perm, args=(e + 1,))
+                    th.start()
+            else:
+                g = torch.Generator(device=self.dev)
+                g.manual_seed(seeds[e - 1] & 0x7FFFFFFFFFFFFFFF)
+                perm = torch.randperm(N, generator=g, device=self.dev)
+            self.losses.append(self.train_epoch(perm, lr_for_epoch(self.lr, e, self.epochs)))
+            if self.epochs == 1:                                        # encode.py:100-103
+                self.best_epoch, self.best_params = e, self.current_params()
+            elif e % min(self.val_duration, self.epochs) == 0:          # encode.py:104-117
+                cur = self.current_params()
+                mse = self.scene_mse(cur)
+                self.val_mse.append(mse)
+                improved = mse < self.best_mse
+                if improved:
+                    self.best_mse, self.best_epoch, self.best_params = mse, e, cur
+                if self.on_epoch:
+                    self.on_epoch(e, mse, improved)
+            del perm
+            if th is not None:
+                th.join()
+        if self.best_params is None:                                    # never evaluated (val_duration > epochs)
+            raise RuntimeError("no epoch was evaluated; choose val_duration <= epochs")
+        losses = torch.cat(self.losses).cpu()
+        best = self.best_params.cpu()
+        self.model.load_flat_params(best)
+        return dict(params=best, losses=losses.tolist(), val_mse=self.val_mse, best_epoch=self.best_epoch)

@@ -64,5 +64,6 @@ def make_scene_torch(C, H, W, bits=12, seed=SEED, device="cuda", peak_frac=0.9):
         gain = 0.55 + 0.45 * float(torch.rand((), generator=g, device=device))
         v = 0.08 + gain * (0.50 * low + 0.22 * mid + 0.10 * fine + 0.06 * field(6))
         v = v * top + torch.randn((H, W), generator=g, device=device) * (top * 0.0025)
-        out[c] = v.round_().clamp_(0, 2 ** bits - 1).to(torch.int32).to(torch.uint16)
+        q = v.round_().clamp_(0, 2 ** bits - 1).to(torch.int32)
+        out[c] = ((q + 32768) % 65536 - 32768).to(torch.int16).view(torch.uint16)   # int16 bit pattern == uint16 value
     return out

@@ -252,7 +252,7 @@ def train(msb, lsb, D, bc, nl, lr, bs, epochs, flags=DEFAULT_FLAGS, val_duration
             loss = torch.nn.functional.mse_loss(forward(params, X[idx]), T[idx])   # LBDRNloss.py:9
             loss.backward()
             opt.step()
-            losses.append(float(loss))
+            losses.append(float(loss.detach()))
             if max_steps is not None and len(losses) >= max_steps:
                 return dict(params=[p.detach().clone() for p in params], losses=losses, mses=mses,
                             best_epoch=epoch)

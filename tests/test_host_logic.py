@@ -1,0 +1,161 @@
+"""CPU: host-side product logic (container, model module, schedule, sampling, cold feature path, ABI surface)."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, ROOT
+import lbdrn_cabi as cabi
+import lbdrn_container as box
+import lbdrn_fused as F
+import lbdrn_oracle as O
+from LBDRNmodel import LBDRNModel
+
+
+def test_container_header_kat_and_roundtrip():
+    for k in json.load(open(os.path.join(GOLD, "header_kat.json"))):
+        a = k["args"]
+        b = box.pack_header(**a)
+        assert b.hex() == k["hex"]
+        assert list(box.read_image_header(b + b"payload")) == k["parsed"]
+    with pytest.raises(ValueError):
+        box.pack_header(1, 8, 8, 5, 96, 2, 2, [1], [1])           # bc not a power of two
+    with pytest.raises(OverflowError):
+        box.pack_header(6, 8, 8, 5, 64, 2, 2, [1] * 36, [1] * 36)  # 8+7*36 > 255: header length byte overflows
+    with pytest.raises(OverflowError):
+        box.pack_header(1, 8, 8, 16, 64, 2, 2, [1], [1])          # K is a 4-bit field
+
+
+def test_model_module_matches_reference_init_and_keys():
+    for k in json.load(open(os.path.join(GOLD, "init_kat.json"))):
+        torch.manual_seed(19920517)
+        m = LBDRNModel(**k["args"])
+        assert list(m.state_dict().keys()) == k["keys"]
+        flat = m.flat_params().numpy()
+        assert hashlib.sha256(flat.tobytes()).hexdigest() == k["sha256"]
+        assert [int(torch.empty((), dtype=torch.int64).random_()) for _ in range(2)] == k["next_draws"]
+        # flat <-> state_dict round trip
+        m2 = LBDRNModel(**k["args"])
+        m2.load_flat_params(flat)
+        assert torch.equal(m2.flat_params(), m.flat_params())
+        with pytest.raises(ValueError):
+            m2.load_flat_params(flat[:-1])
+
+
+def test_model_forward_cold_path_matches_reference():
+    g = np.load(os.path.join(GOLD, "forward_d100_bc64.npz"))
+    m = LBDRNModel(100, 64, 4, 2)
+    m.load_flat_params(g["params"])
+    with torch.no_grad():
+        assert np.array_equal(m(torch.from_numpy(g["x"])).numpy(), g["y"])
+
+
+def test_cold_feature_path_matches_reference(monkeypatch):
+    from synth_scene import make_scene
+    import constants
+    import LBDRNdataset
+    idx = json.load(open(os.path.join(GOLD, "features_index.json")))
+    for name, meta in idx.items():
+        fl = O.Flags(**meta["flags"])
+        for attr, val in (("USE_COORDINATES", fl.use_coordinates), ("EMBEDDING", fl.embedding),
+                          ("USE_COLORS", fl.use_colors), ("RELATIVE", fl.relative)):
+            monkeypatch.setattr(constants, attr, val)
+        g = np.load(os.path.join(GOLD, f"features_{name}.npz"))
+        assert np.array_equal(LBDRNdataset.host_features(g["base"], meta["D"]), g["features"]), name
+
+
+def test_coord_table_matches_oracle_block():
+    for emb in (False, True):
+        fl = F.Flags(use_coordinates=True, embedding=emb)
+        tab = F.coord_table(7, 9, fl)
+        blk = O.coordinate_block(7, 9, O.Flags(use_coordinates=True, embedding=emb))
+        w = fl.tabw
+        assert tab.shape == (16, w)
+        assert np.array_equal(blk[:, :, :w], np.broadcast_to(tab[:7][:, None, :], (7, 9, w)))
+        assert np.array_equal(blk[:, :, w:], np.broadcast_to(tab[7:][None, :, :], (7, 9, w)))
+
+
+def test_lr_schedule_equals_torch_steplr():
+    for E in (1, 2, 5, 10, 15):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=1e-3)
+        sch = torch.optim.lr_scheduler.StepLR(opt, step_size=max(1, int(E / 3)), gamma=0.1)
+        for e in range(1, E + 1):
+            assert F.lr_for_epoch(1e-3, e, E) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12)
+            opt.step()
+            sch.step()
+
+
+def test_sampler_reproduces_dataloader_permutation():
+    from torch.utils.data import DataLoader, TensorDataset
+    n = 1000
+    ds = TensorDataset(torch.arange(n))
+    torch.manual_seed(123)
+    ref = [torch.cat([b[0] for b in DataLoader(ds, batch_size=64, shuffle=True)]) for _ in range(3)]
+    torch.manual_seed(123)
+    for r in ref:
+        assert torch.equal(F.permutation_from_seed(n, F.draw_loader_seeds()), r)
+
+
+def test_flags_dim_in_table():
+    # feature counts the reference tabulates (BD_metrics.py:176)
+    f = F.Flags
+    assert f(use_coordinates=True, use_colors=False).dim_in(4, 2) == 2
+    assert f(use_coordinates=True, embedding=True, use_colors=False).dim_in(4, 2) == 50
+    assert f(relative=False).dim_in(4, 0) == 4
+    assert f().dim_in(4, 1) == 36 and f().dim_in(4, 2) == 100 and f().dim_in(4, 3) == 196
+    assert f(use_coordinates=True).dim_in(4, 2) == 102
+    assert f().dim_in(8, 2) == 200
+
+
+# ---- the C-ABI library loads on a CPU-only box and exports exactly what include/lbdrn.h declares -----------------
+def test_cabi_exports_every_declared_symbol():
+    lib = cabi.load()
+    hdr = open(os.path.join(ROOT, "include", "lbdrn.h")).read()
+    declared = sorted(set(re.findall(r"\b(lbdrn_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(cabi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.lbdrn_version() == 1
+
+
+def test_cabi_struct_layout_matches_header():
+    assert ctypes.sizeof(cabi.LbdrnDesc) == 20 * 4
+    assert ctypes.sizeof(cabi.LbdrnTrainCfg) == 4 * 4 + 3 * 8 + 4 * 4
+
+
+def test_cabi_geometry_queries_and_validation():
+    lib = cabi.load()
+    bits = cabi.flag_bits(False, False, True, True)
+    for (C, D, bc, nl, fl, din, P) in [(4, 2, 64, 2, bits, 100, 10884), (4, 3, 256, 2, bits, 196, 117252),
+                                      (8, 2, 64, 2, bits, 200, 17544), (4, 2, 128, 1, bits, 100, 13444),
+                                      (4, 2, 128, 2, bits, 100, 29956), (4, 2, 256, 2, bits, 100, 92676),
+                                      (4, 2, 64, 2, cabi.flag_bits(True, True, False, True), 50, 7684),
+                                      (4, 2, 64, 2, cabi.flag_bits(True, True, True, True), 150, 14084)]:
+        d = cabi.make_desc(C, 64, 64, 5, D, bc, nl, fl, 100, False)
+        assert lib.lbdrn_dim_in(ctypes.byref(d)) == din
+        assert lib.lbdrn_param_count(ctypes.byref(d)) == P == O.n_params(din, bc, C, nl)
+    bad = cabi.make_desc(4, 64, 64, 5, 2, 48, 2, bits, 100, False)
+    assert lib.lbdrn_dim_in(ctypes.byref(bad)) == cabi.E_UNSUPPORTED
+    assert b"bc=48" in lib.lbdrn_last_error()
+    deg = cabi.make_desc(4, 64, 64, 12, 2, 64, 2, bits, 0, False)   # MSB.max()==0: the reference divides 0/0
+    assert lib.lbdrn_param_count(ctypes.byref(deg)) == cabi.E_INVALID
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    with pytest.raises(cabi.LbdrnError):
+        F.decode_image(np.zeros((4, 8, 8), np.uint8), np.zeros(10884, np.float32), 5, 2, 64, 2, flags=F.Flags())
+    m = LBDRNModel(100, 64, 4, 2)
+    with pytest.raises(cabi.LbdrnError):
+        m.decode_image(np.zeros((4, 8, 8), np.uint8), 5, 2, flags=F.Flags())
+    # and the raw ABI reports a CUDA error instead of computing anything on the host
+    lib = cabi.load()
+    d = cabi.make_desc(4, 8, 8, 5, 2, 64, 2, cabi.flag_bits(False, False, True, True), 100, False)
+    rc = lib.lbdrn_decode(ctypes.byref(d), ctypes.c_void_p(16), ctypes.c_void_p(16), None, ctypes.c_void_p(16), None)
+    assert rc == cabi.E_CUDA
