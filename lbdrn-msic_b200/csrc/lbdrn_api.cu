@@ -7,18 +7,16 @@
 #include <mutex>
 #include <string>
 
-#include "lbdrn_common.cuh"
 #include "lbdrn_infer_fp32.cuh"
+#include "lbdrn_internal.h"
 #include "lbdrn_train_fp32.cuh"
-#include "lbdrn_tc.cuh"
 
 using namespace lbdrn;
 
-namespace {
-
-thread_local std::string g_err;
+namespace lbdrn {
 std::atomic<long long> g_launches{0};
-
+static thread_local std::string g_err;
+const char* last_error() { return g_err.c_str(); }
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -28,12 +26,9 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+}  // namespace lbdrn
 
-#define CUDA_TRY(expr)                                                                        \
-  do {                                                                                        \
-    cudaError_t e__ = (expr);                                                                 \
-    if (e__ != cudaSuccess) return fail(LBDRN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
-  } while (0)
+namespace {
 
 // ---- descriptor -> Net ----------------------------------------------------------------------------------
 int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {
@@ -86,12 +81,7 @@ int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {
   return LBDRN_OK;
 }
 
-// ---- per-device scratch (packed weights, SSE partials); grow-only, lives until process exit ----------------
-struct Scratch {
-  float* wpack = nullptr; size_t wpack_n = 0;
-  double* partials = nullptr; unsigned int* counter = nullptr;
-  int sms = 0, max_smem = 0;
-};
+// ---- per-device scratch (struct Scratch in lbdrn_internal.h) ----------------------------------------------
 std::mutex g_mu;
 Scratch g_scratch[64];
 
@@ -118,42 +108,6 @@ int get_scratch(int P, Scratch*& out) {
   return LBDRN_OK;
 }
 
-// ---- fp32 inference dispatch ---------------------------------------------------------------------------
-template <int BC, int TM, int CP, bool WSMEM, int MODE>
-int launch_infer_t(const InferArgs& a, size_t smem, int sms, cudaStream_t st) {
-  auto kern = infer_fp32_kernel<BC, TM, CP, WSMEM, MODE>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "fp32 inference kernel does not fit (smem %zu B)", smem);
-  int grid = sms * occ;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  if (MODE == MODE_SSE && grid > 4096) grid = 4096;
-  kern<<<grid, kThreads, smem, st>>>(a);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
-  return LBDRN_OK;
-}
-
-template <int BC, int TM, int MODE>
-int launch_infer_bc(InferArgs& a, const Scratch& sc, cudaStream_t st) {
-  const Net& n = a.net;
-  constexpr int LDP = ldp_of<TM>(), TH = TM, TW = 16;
-  a.kmax = n.dim_in > BC ? n.dim_in : BC;
-  a.tiles_x = (n.W + TW - 1) / TW;
-  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TH - 1) / TH);
-  const size_t base = ((size_t)a.kmax * LDP + round4(n.C * (TH + 2 * n.D) * (TW + 2 * n.D))) * sizeof(float);
-  const size_t with_w = base + (size_t)round4(n.P) * sizeof(float);
-  const bool wsmem = with_w <= (size_t)sc.max_smem;
-  if (!wsmem && base > (size_t)sc.max_smem) return fail(LBDRN_E_UNSUPPORTED, "activation tile does not fit in shared memory");
-  if (n.C <= 4) {
-    return wsmem ? launch_infer_t<BC, TM, 4, true, MODE>(a, with_w, sc.sms, st)
-                 : launch_infer_t<BC, TM, 4, false, MODE>(a, base, sc.sms, st);
-  }
-  return wsmem ? launch_infer_t<BC, TM, 8, true, MODE>(a, with_w, sc.sms, st)
-               : launch_infer_t<BC, TM, 8, false, MODE>(a, base, sc.sms, st);
-}
-
 template <int MODE>
 int run_infer(const LbdrnDesc* d, const void* msb, const void* lsb, const float* params, const float* tab, void* out,
               double* sse_out, void* stream) {
@@ -167,19 +121,15 @@ int run_infer(const LbdrnDesc* d, const void* msb, const void* lsb, const float*
   rc = get_scratch(n.P, sc);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  pack_params_kernel<<<(n.P + 255) / 256, 256, 0, st>>>(n, params, sc->wpack);
-  ++g_launches;
+  launch_pack_params(n, params, sc->wpack, st);
   CUDA_TRY(cudaGetLastError());
   InferArgs a;
   memset(&a, 0, sizeof a);
   a.net = n; a.msb = msb; a.lsb = lsb; a.wpack = sc->wpack; a.tab = tab; a.out = out;
   a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
-  switch (n.bc) {
-    case 32: return launch_infer_bc<32, 8, MODE>(a, *sc, st);
-    case 64: return launch_infer_bc<64, 8, MODE>(a, *sc, st);
-    case 128: return launch_infer_bc<128, 4, MODE>(a, *sc, st);
-    default: return launch_infer_bc<256, 4, MODE>(a, *sc, st);
-  }
+  if (MODE == MODE_DECODE) return infer_fp32_decode(a, *sc, st);
+  if (MODE == MODE_PREDICT) return infer_fp32_predict(a, *sc, st);
+  return infer_fp32_sse(a, *sc, st);
 }
 
 // ---- small elementwise kernels ----------------------------------------------------------------------------
@@ -206,50 +156,20 @@ __global__ void max_shifted_kernel(const uint16_t* __restrict__ img, long long n
 struct LbdrnTrain {
   Net net;
   LbdrnTrainCfg cfg;
-  int dev = 0, sms = 0, grid = 0, pstride = 0, dimpad = 0;
-  size_t smem = 0;
-  bool wsmem = true;
+  TrainPlan plan;
+  int dev = 0, sms = 0;
   float *params = nullptr, *wpack = nullptr, *m = nullptr, *v = nullptr, *partial = nullptr;
-  void* kernel = nullptr;
 };
 
 namespace {
 
-template <int BC, int CP>
-int pick_train_kernel(LbdrnTrain* t, int max_smem) {
-  const Net& n = t->net;
-  const size_t acts = ((size_t)t->dimpad + 2 * (size_t)n.nl * BC + 2 * CP) * kTrainLDP + kMaxC * kTrainNPIX;
-  const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
-  const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
-  if (with_w <= (size_t)max_smem) {
-    t->wsmem = true; t->smem = with_w; t->kernel = (void*)train_fp32_kernel<BC, CP, true>;
-  } else if (without <= (size_t)max_smem) {
-    t->wsmem = false; t->smem = without; t->kernel = (void*)train_fp32_kernel<BC, CP, false>;
-  } else {
-    return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
-                without, BC, n.nl, n.dim_in);
-  }
-  CUDA_TRY(cudaFuncSetAttribute(t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, kThreads, t->smem));
-  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "training kernel cannot be made resident");
-  const int cap = occ * t->sms;
-  int want = (t->cfg.batch_size + kTrainNPIX - 1) / kTrainNPIX;
-  if (want < 16) want = 16;
-  t->grid = want < cap ? want : cap;
-  return LBDRN_OK;
-}
-
 int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
   a.net = t->net; a.params = t->params; a.wpack = t->wpack; a.m = t->m; a.v = t->v;
-  a.partial = t->partial; a.pstride = t->pstride; a.dimpad = t->dimpad;
+  a.partial = t->partial; a.pstride = t->plan.pstride; a.dimpad = t->plan.dimpad;
   a.beta1 = t->cfg.beta1; a.beta2 = t->cfg.beta2;
   a.omb1 = (float)(1.0 - t->cfg.beta1); a.omb2 = (float)(1.0 - t->cfg.beta2);
   a.beta2f = (float)t->cfg.beta2; a.eps = (float)t->cfg.eps;
-  void* kargs[] = {(void*)&a};
-  CUDA_TRY(cudaLaunchCooperativeKernel(t->kernel, dim3(t->grid), dim3(kThreads), kargs, t->smem, st));
-  ++g_launches;
-  return LBDRN_OK;
+  return train_fp32_launch(t->plan, a, st);
 }
 
 }  // namespace
@@ -257,7 +177,7 @@ int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
 extern "C" {
 
 int32_t lbdrn_version(void) { return LBDRN_ABI_VERSION; }
-const char* lbdrn_last_error(void) { return g_err.c_str(); }
+const char* lbdrn_last_error(void) { return lbdrn::last_error(); }
 int64_t lbdrn_launch_count(void) { return g_launches.load(); }
 
 int32_t lbdrn_dim_in(const LbdrnDesc* d) {
@@ -309,12 +229,7 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
     return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
   if (tc_ok && d->path != LBDRN_PATH_PRECISE) {
     if (!msb_dev || !params_dev || !out_dev) return fail(LBDRN_E_INVALID, "null device pointer");
-    std::string err;
-    long long launches = 0;
-    rc = tc_decode(n, msb_dev, params_dev, out_dev, (cudaStream_t)stream, err, launches);
-    g_launches += launches;
-    if (rc) return fail(rc, "%s", err.c_str());
-    return LBDRN_OK;
+    return tc_decode(n, msb_dev, params_dev, out_dev, (cudaStream_t)stream);
   }
   return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream);
 }
@@ -345,28 +260,19 @@ int32_t lbdrn_train_create(const LbdrnDesc* d, const LbdrnTrainCfg* cfg, LbdrnTr
   if (e != cudaSuccess) { delete t; return fail(LBDRN_E_CUDA, "device query: %s", cudaGetErrorString(e)); }
   if (!supports_coop) { delete t; return fail(LBDRN_E_UNSUPPORTED, "device lacks cooperative launch"); }
   const Net& n = t->net;
-  t->dimpad = (n.dim_in + 7) & ~7;
-  t->pstride = round4(n.P + 1) + 28;   // keep CTAs' partials on distinct 128 B lines
-  t->pstride = (t->pstride + 31) & ~31;
-  const bool c4 = n.C <= 4;
-  switch (n.bc) {
-    case 32: rc = c4 ? pick_train_kernel<32, 4>(t, max_smem) : pick_train_kernel<32, 8>(t, max_smem); break;
-    case 64: rc = c4 ? pick_train_kernel<64, 4>(t, max_smem) : pick_train_kernel<64, 8>(t, max_smem); break;
-    case 128: rc = c4 ? pick_train_kernel<128, 4>(t, max_smem) : pick_train_kernel<128, 8>(t, max_smem); break;
-    default: rc = fail(LBDRN_E_UNSUPPORTED, "fused training is built for bc=32/64/128 (got %d)", n.bc);
-  }
+  rc = train_fp32_plan(n, cfg->batch_size, t->sms, max_smem, t->plan);
   if (rc) { delete t; return rc; }
   const size_t pb = ((size_t)n.P + 64) * sizeof(float);
   e = cudaMalloc(&t->params, pb);
   if (e == cudaSuccess) e = cudaMalloc(&t->wpack, pb);
   if (e == cudaSuccess) e = cudaMalloc(&t->m, pb);
   if (e == cudaSuccess) e = cudaMalloc(&t->v, pb);
-  if (e == cudaSuccess) e = cudaMalloc(&t->partial, (size_t)t->grid * t->pstride * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t->partial, (size_t)t->plan.grid * t->plan.pstride * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(t->params, 0, pb);
   if (e == cudaSuccess) e = cudaMemset(t->wpack, 0, pb);
   if (e == cudaSuccess) e = cudaMemset(t->m, 0, pb);
   if (e == cudaSuccess) e = cudaMemset(t->v, 0, pb);
-  if (e == cudaSuccess) e = cudaMemset(t->partial, 0, (size_t)t->grid * t->pstride * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(t->partial, 0, (size_t)t->plan.grid * t->plan.pstride * sizeof(float));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     lbdrn_train_destroy(t);
@@ -388,8 +294,7 @@ int32_t lbdrn_train_set_params(LbdrnTrain* t, const float* params_dev, void* str
   if (!t || !params_dev) return fail(LBDRN_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaMemcpyAsync(t->params, params_dev, (size_t)t->net.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  pack_params_kernel<<<(t->net.P + 255) / 256, 256, 0, st>>>(t->net, t->params, t->wpack);
-  ++g_launches;
+  launch_pack_params(t->net, t->params, t->wpack, st);
   CUDA_TRY(cudaGetLastError());
   return LBDRN_OK;
 }
@@ -433,10 +338,9 @@ int32_t lbdrn_train_grad(LbdrnTrain* t, const void* msb_dev, const void* lsb_dev
 int32_t lbdrn_train_apply(LbdrnTrain* t, const float* grad_dev, int64_t adam_t, double lr, void* stream) {
   if (!t || !grad_dev || adam_t < 1) return fail(LBDRN_E_INVALID, "bad argument");
   const double bc1 = 1.0 - std::pow(t->cfg.beta1, (double)adam_t), bc2 = 1.0 - std::pow(t->cfg.beta2, (double)adam_t);
-  adam_apply_kernel<<<(t->net.P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      t->net, grad_dev, t->params, t->wpack, t->m, t->v, (float)(1.0 - t->cfg.beta1), (float)(1.0 - t->cfg.beta2),
-      (float)t->cfg.beta2, (float)t->cfg.eps, (float)(lr / bc1), (float)std::sqrt(bc2));
-  ++g_launches;
+  launch_adam_apply(t->net, grad_dev, t->params, t->wpack, t->m, t->v, (float)(1.0 - t->cfg.beta1),
+                    (float)(1.0 - t->cfg.beta2), (float)t->cfg.beta2, (float)t->cfg.eps, (float)(lr / bc1),
+                    (float)std::sqrt(bc2), (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return LBDRN_OK;
 }

@@ -31,7 +31,7 @@ struct InferArgs {
 };
 
 // Transpose hidden-layer weights W_l [bc][K_l] -> [K_l][bc]; copy biases and the output layer unchanged.
-__global__ void pack_params_kernel(Net net, const float* __restrict__ params, float* __restrict__ wpack) {
+static __global__ void pack_params_kernel(Net net, const float* __restrict__ params, float* __restrict__ wpack) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < net.P; i += gridDim.x * blockDim.x) {
     int dst = i;
     for (int l = 0; l < net.nl; ++l) {
@@ -75,35 +75,45 @@ __global__ void __launch_bounds__(kThreads) infer_fp32_kernel(const InferArgs a)
   for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int ty0 = net.row0 + (t / a.tiles_x) * TH, tx0 = (t % a.tiles_x) * TW;
 
-    // ---- 1. normalised tile + halo (reflect at true image borders only) -------------------------------
+    // ---- 1. normalised tile + halo (reflect at true image borders only); one warp per tile row ---------------
     if (net.ncol) {
-      for (int e = tid; e < C * trows * twp; e += kThreads) {
-        int c = e / (trows * twp), rem = e - c * trows * twp;
-        int r = rem / twp, x = rem - r * twp;
-        int gy = reflect_clamp(ty0 - D + r, net.H), gx = reflect_clamp(tx0 - D + x, net.W);
-        tile[e] = load_msb_norm(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx,
-                                net.maxv);
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int c = 0; c < C; ++c) {
+        for (int r = warp; r < trows; r += kThreads / 32) {
+          const int gy = reflect_clamp(ty0 - D + r, net.H);
+          const size_t rowoff = ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W;
+          for (int x = lane; x < twp; x += 32)
+            tile[(c * trows + r) * twp + x] =
+                load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(tx0 - D + x, net.W), net.maxv);
+        }
       }
     }
     __syncthreads();   // also orders the previous tile's compute before act[] is overwritten below
 
-    // ---- 2. feature rows (LBDRNdataset.py:104-130): [coords | colours(c, dy, dx)] ----------------------
-    for (int idx = tid; idx < net.dim_in * NPIX; idx += kThreads) {
-      int k = idx / NPIX, p = idx - k * NPIX;
-      int r = p >> 4, x = p & 15;
-      float v;
-      if (k < net.nco) {
-        int half = k / net.tabw, i = k - half * net.tabw;
-        int gy = min(ty0 + r, net.H - 1), gx = min(tx0 + x, net.W - 1);
-        v = half == 0 ? a.tab[(size_t)gy * net.tabw + i] : a.tab[(size_t)(net.H + gx) * net.tabw + i];
-      } else {
-        int kk = k - net.nco;
-        int c = kk / (n * n), rem = kk - c * n * n;
-        int dy = rem / n, dx = rem - dy * n;
-        v = tile[(c * trows + r + dy) * twp + x + dx];
-        if (net.relative) v -= tile[(c * trows + r + D) * twp + x + D];
+    // ---- 2. feature rows (LBDRNdataset.py:104-130): [coords | colours(c, dy, dx)]; thread = (pixel, band share) ----
+    {
+      constexpr int SHARE = kThreads / NPIX;               // threads cooperating on one pixel (1 or 2)
+      const int p = tid % NPIX, share = tid / NPIX;
+      const int r = p >> 4, x = p & 15;
+      float* dst = act + p;
+      if (net.nco && share == 0) {
+        const int gy = min(ty0 + r, net.H - 1), gx = min(tx0 + x, net.W - 1);
+        const float* trow = a.tab + (size_t)gy * net.tabw;
+        const float* tcol = a.tab + (size_t)(net.H + gx) * net.tabw;
+        for (int i = 0; i < net.tabw; ++i) {
+          dst[(size_t)i * LDP] = trow[i];
+          dst[(size_t)(net.tabw + i) * LDP] = tcol[i];
+        }
       }
-      act[(size_t)k * LDP + p] = v;
+      if (net.ncol) {
+        for (int c = share; c < C; c += SHARE) {
+          const float* tc = tile + (c * trows + r) * twp + x;
+          const float ctr = net.relative ? tc[D * twp + D] : 0.f;
+          float* d = dst + (size_t)(net.nco + c * n * n) * LDP;
+          for (int dy = 0; dy < n; ++dy)
+            for (int dx = 0; dx < n; ++dx, d += LDP) *d = tc[dy * twp + dx] - ctr;
+        }
+      }
     }
     __syncthreads();
 

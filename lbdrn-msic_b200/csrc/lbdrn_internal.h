@@ -1,0 +1,52 @@
+// lbdrn_internal.h -- declarations shared by the translation units of liblbdrn_b200 (not part of the ABI).
+#pragma once
+#include <atomic>
+#include <string>
+
+#include "lbdrn_common.cuh"
+
+namespace lbdrn {
+
+int fail(int code, const char* fmt, ...);          // records the thread-local message, returns `code`
+extern std::atomic<long long> g_launches;
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) return ::lbdrn::fail(LBDRN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// per-device scratch (packed weights, SSE partials); grow-only, lives until process exit
+struct Scratch {
+  float* wpack = nullptr;
+  size_t wpack_n = 0;
+  double* partials = nullptr;
+  unsigned int* counter = nullptr;
+  int sms = 0, max_smem = 0;
+};
+
+struct InferArgs;
+// fp32 inference launchers, one translation unit per mode (MODE_DECODE / MODE_PREDICT / MODE_SSE)
+int infer_fp32_decode(InferArgs& a, const Scratch& sc, cudaStream_t st);
+int infer_fp32_predict(InferArgs& a, const Scratch& sc, cudaStream_t st);
+int infer_fp32_sse(InferArgs& a, const Scratch& sc, cudaStream_t st);
+void launch_pack_params(const Net& n, const float* params, float* wpack, cudaStream_t st);
+
+// fused training: kernel selection + launch (lbdrn_train_fp32.cu)
+struct TrainPlan {
+  void* kernel = nullptr;
+  size_t smem = 0;
+  bool wsmem = true;
+  int grid = 0, dimpad = 0, pstride = 0;
+};
+struct TrainArgs;
+int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& plan);
+int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st);
+void launch_adam_apply(const Net& n, const float* grad, float* params, float* wpack, float* m, float* v, float omb1,
+                       float omb2, float beta2, float eps, float step_size, float bc2_sqrt, cudaStream_t st);
+
+// tcgen05 tensor-core decode (lbdrn_tc.cu)
+bool tc_supported(const Net& n);
+int tc_decode(const Net& n, const void* msb, const float* params, uint16_t* out, cudaStream_t st);
+
+}  // namespace lbdrn

@@ -1,0 +1,60 @@
+// lbdrn_train_fp32.cu -- instantiations, planning and launch of the fused fp32 training kernel.
+#include "lbdrn_train_fp32.cuh"
+#include "lbdrn_internal.h"
+
+namespace lbdrn {
+namespace {
+
+template <int BC, int CP>
+int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
+  const size_t acts = ((size_t)t.dimpad + 2 * (size_t)n.nl * BC + 2 * CP) * kTrainLDP;
+  const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
+  const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
+  if (with_w <= (size_t)max_smem) {
+    t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true>;
+  } else if (without <= (size_t)max_smem) {
+    t.wsmem = false; t.smem = without; t.kernel = (void*)train_fp32_kernel<BC, CP, false>;
+  } else {
+    return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
+                without, BC, n.nl, n.dim_in);
+  }
+  CUDA_TRY(cudaFuncSetAttribute(t.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t.kernel, kThreads, t.smem));
+  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "training kernel cannot be made resident");
+  const int cap = occ * sms;                  // cooperative launch: every CTA must be co-resident
+  int want = (batch_size + kTrainNPIX - 1) / kTrainNPIX;
+  if (want < 16) want = 16;
+  t.grid = want < cap ? want : cap;
+  return LBDRN_OK;
+}
+
+}  // namespace
+
+int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
+  t.dimpad = (n.dim_in + 7) & ~7;
+  t.pstride = (round4(n.P + 1) + 28 + 31) & ~31;   // keep CTAs' partials on distinct 128 B lines
+  const bool c4 = n.C <= 4;
+  switch (n.bc) {
+    case 32: return c4 ? plan_t<32, 4>(n, batch_size, sms, max_smem, t) : plan_t<32, 8>(n, batch_size, sms, max_smem, t);
+    case 64: return c4 ? plan_t<64, 4>(n, batch_size, sms, max_smem, t) : plan_t<64, 8>(n, batch_size, sms, max_smem, t);
+    case 128: return c4 ? plan_t<128, 4>(n, batch_size, sms, max_smem, t) : plan_t<128, 8>(n, batch_size, sms, max_smem, t);
+    default: return fail(LBDRN_E_UNSUPPORTED, "fused training is built for bc=32/64/128 (got %d)", n.bc);
+  }
+}
+
+int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
+  void* kargs[] = {(void*)&a};
+  CUDA_TRY(cudaLaunchCooperativeKernel(plan.kernel, dim3(plan.grid), dim3(kThreads), kargs, plan.smem, st));
+  ++g_launches;
+  return LBDRN_OK;
+}
+
+void launch_adam_apply(const Net& n, const float* grad, float* params, float* wpack, float* m, float* v, float omb1,
+                       float omb2, float beta2, float eps, float step_size, float bc2_sqrt, cudaStream_t st) {
+  adam_apply_kernel<<<(n.P + 255) / 256, 256, 0, st>>>(n, grad, params, wpack, m, v, omb1, omb2, beta2, eps, step_size,
+                                                      bc2_sqrt);
+  ++g_launches;
+}
+
+}  // namespace lbdrn

@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
   float* Gbuf = Hbuf + (size_t)L * BC * LDP;                    // [L][BC][LDP]    act' then dz
   float* dZo = Gbuf + (size_t)L * BC * LDP;                     // [CP][LDP]       output-layer dz
   float* Tl = dZo + CP * LDP;                                   // [CP][LDP]       labels
-  float* ctr = Tl + CP * LDP;                                   // [kMaxC][NPIX]   normalised centre values
-  float* wsm = ctr + kMaxC * NPIX;                              // packed weights [P] (+pad) then natural hidden l>=1
+  float* wsm = Tl + CP * LDP;                                   // packed weights [P] (+pad) then natural hidden l>=1
   float* wnat_sm = wsm + round4(P);
   __shared__ int s_py[NPIX], s_px[NPIX], s_valid[NPIX];
   __shared__ float s_red[kThreads / 32];
@@ -161,6 +160,8 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
   auto wnat = [&](int l) -> const float* {
     return WSMEM ? (wnat_sm + (size_t)(l - 1) * BC * BC) : (a.params + net.woff[l]);
   };
+
+  for (int i = net.dim_in * LDP + tid; i < a.dimpad * LDP; i += kThreads) X[i] = 0.f;   // padding rows stay zero
 
   for (int s = 0; s < a.n_steps; ++s) {
     // ---- (re)load weights ----------------------------------------------------------------------------
@@ -199,32 +200,37 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
         s_valid[tid] = tid < nvalid;
       }
       __syncthreads();
-      for (int e = tid; e < C * NPIX; e += kThreads) {
-        int c = e / NPIX, pp = e - c * NPIX;
-        size_t off = ((size_t)c * net.buf_rows + (s_py[pp] - net.buf_row0)) * net.W + s_px[pp];
-        ctr[c * NPIX + pp] = load_msb_norm(a.msb, net.msb_u16, off, net.maxv);
-        uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
-        Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);
-      }
-      __syncthreads();
-      for (int idx = tid; idx < a.dimpad * NPIX; idx += kThreads) {
-        int k = idx / NPIX, pp = idx - k * NPIX;
-        float v = 0.f;
-        if (k < net.dim_in && s_valid[pp]) {
-          int gy = s_py[pp], gx = s_px[pp];
-          if (k < net.nco) {
-            int half = k / net.tabw, i = k - half * net.tabw;
-            v = half == 0 ? a.tab[(size_t)gy * net.tabw + i] : a.tab[(size_t)(net.H + gx) * net.tabw + i];
-          } else {
-            int kk = k - net.nco;
-            int c = kk / (n * n), r2 = kk - c * n * n;
-            int dy = r2 / n, dx = r2 - dy * n;
-            int yy = reflect_clamp(gy + dy - D, net.H), xx = reflect_clamp(gx + dx - D, net.W);
-            v = load_msb_norm(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (yy - net.buf_row0)) * net.W + xx, net.maxv);
-            if (net.relative) v -= ctr[c * NPIX + pp];
+      {
+        // thread = (pixel, band parity): labels, centre, neighbourhood straight from the resident planes
+        const int pp = tid & (NPIX - 1), share = tid >> 6;
+        const int gy = s_py[pp], gx = s_px[pp];
+        const bool ok = s_valid[pp] != 0;
+        float* dst = X + pp;
+        if (net.nco && share == 0) {
+          const float* trow = a.tab + (size_t)gy * net.tabw;
+          const float* tcol = a.tab + (size_t)(net.H + gx) * net.tabw;
+          for (int i = 0; i < net.tabw; ++i) {
+            dst[(size_t)i * LDP] = ok ? trow[i] : 0.f;
+            dst[(size_t)(net.tabw + i) * LDP] = ok ? tcol[i] : 0.f;
           }
         }
-        X[(size_t)k * LDP + pp] = v;
+        for (int c = share; c < C; c += kThreads / NPIX) {
+          const size_t plane = (size_t)c * net.buf_rows;
+          const size_t off = (plane + (gy - net.buf_row0)) * net.W + gx;
+          const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+          Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);          // label = LSB/(2^K-1)
+          if (net.ncol) {
+            const float ctr = net.relative ? load_msb_norm(a.msb, net.msb_u16, off, net.maxv) : 0.f;
+            float* d = dst + (size_t)(net.nco + c * n * n) * LDP;
+            for (int dy = 0; dy < n; ++dy) {
+              const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
+              for (int dx = 0; dx < n; ++dx, d += LDP) {
+                float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), net.maxv) - ctr;
+                *d = ok ? v : 0.f;
+              }
+            }
+          }
+        }
       }
       __syncthreads();
 
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
               g4[i] = acc[i][j] > 0.f ? 1.f : 0.f;
             } else {
               float sn, cs;
-              sincosf(net.w0 * acc[i][j], &sn, &cs);   // d sin(w0 z)/dz = w0 cos(w0 z)
+              sincos_cw(net.w0 * acc[i][j], sn, cs);   // d sin(w0 z)/dz = w0 cos(w0 z)
               h[i][j] = sn;
               g4[i] = cs * net.w0;
             }
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
 }
 
 // Adam on an externally reduced gradient (data-parallel mode) + packed-copy refresh.
-__global__ void adam_apply_kernel(Net net, const float* __restrict__ grad, float* params, float* wpack, float* m,
+static __global__ void adam_apply_kernel(Net net, const float* __restrict__ grad, float* params, float* wpack, float* m,
                                   float* v, float omb1, float omb2, float beta2, float eps, float step_size,
                                   float bc2_sqrt) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < net.P; i += gridDim.x * blockDim.x) {
