@@ -51,7 +51,8 @@ enum { LBDRN_U8 = 0, LBDRN_U16 = 1 };
 /* kernel selection for lbdrn_decode: PRECISE = fp32 FFMA everywhere (closest to the reference's fp32 path);
  * TENSOR = tcgen05 split-precision tensor-core path where the configuration supports it. AUTO picks TENSOR
  * when available, else PRECISE. */
-enum { LBDRN_PATH_AUTO = 0, LBDRN_PATH_PRECISE = 1, LBDRN_PATH_TENSOR = 2 };
+enum { LBDRN_PATH_AUTO = 0, LBDRN_PATH_PRECISE = 1, LBDRN_PATH_TENSOR = 2,
+       LBDRN_PATH_TENSOR_FASTSIN = 3 /* TENSOR with MUFU.SIN after an exact range reduction (abs err ~4e-7) */ };
 
 /* One scene (or one row stripe of it) + network shape.  Rows are GLOBAL image rows: a rank that decodes
  * stripe [row0,row1) passes a buffer holding rows [buf_row0, buf_row0+buf_rows) which must cover
@@ -112,6 +113,10 @@ int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_
  * written: out = (base << K) + round_half_even(sigmoid(...) * (2^K-1)). */
 int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* params_dev,
                      const float* coord_tab_dev, uint16_t* out_dev, void* stream);
+
+/* Diagnostic: D[128][64] (fp32) = A[128][K] * B[64][K]^T with fp16 row-major A, B through the same tcgen05 descriptors,
+ * shared-memory operand layout and TMEM read-back as the tensor decode kernel (K multiple of 16, <= 256). */
+int32_t lbdrn_selftest_tc_gemm(const void* a_dev, const void* b_dev, float* d_dev, int32_t K, void* stream);
 
 /* network output y [n_rows*W, C] float32 (pixel-major, like model(x) in decode.py:130) for rows [row0,row1) */
 int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev,

@@ -81,9 +81,12 @@ int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {
   return LBDRN_OK;
 }
 
+}  // namespace
+
 // ---- per-device scratch (struct Scratch in lbdrn_internal.h) ----------------------------------------------
-std::mutex g_mu;
-Scratch g_scratch[64];
+namespace lbdrn {
+static std::mutex g_mu;
+static Scratch g_scratch[64];
 
 int get_scratch(int P, Scratch*& out) {
   int dev = 0;
@@ -107,6 +110,9 @@ int get_scratch(int P, Scratch*& out) {
   out = &s;
   return LBDRN_OK;
 }
+}  // namespace lbdrn
+
+namespace {
 
 template <int MODE>
 int run_infer(const LbdrnDesc* d, const void* msb, const void* lsb, const float* params, const float* tab, void* out,
@@ -227,11 +233,19 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
   const bool tc_ok = tc_supported(n);
   if (d->path == LBDRN_PATH_TENSOR && !tc_ok)
     return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
+  if (d->path == LBDRN_PATH_TENSOR_FASTSIN && !tc_ok)
+    return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
   if (tc_ok && d->path != LBDRN_PATH_PRECISE) {
     if (!msb_dev || !params_dev || !out_dev) return fail(LBDRN_E_INVALID, "null device pointer");
-    return tc_decode(n, msb_dev, params_dev, out_dev, (cudaStream_t)stream);
+    return tc_decode(n, msb_dev, params_dev, coord_tab_dev, out_dev, d->path == LBDRN_PATH_TENSOR_FASTSIN,
+                     (cudaStream_t)stream);
   }
   return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream);
+}
+
+int32_t lbdrn_selftest_tc_gemm(const void* a_dev, const void* b_dev, float* d_dev, int32_t K, void* stream) {
+  if (!a_dev || !b_dev || !d_dev) return fail(LBDRN_E_INVALID, "null device pointer");
+  return tc_selftest(a_dev, b_dev, d_dev, K, (cudaStream_t)stream);
 }
 
 int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev, const float* coord_tab_dev,

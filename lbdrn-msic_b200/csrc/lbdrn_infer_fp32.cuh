@@ -28,6 +28,8 @@ struct InferArgs {
   double* sse_out;       // MODE_SSE
   int tiles_x, n_tiles;
   int kmax;              // max(dim_in, bc): rows of the activation buffer
+  const int* skip_flag;  // optional device flag: when non-null and non-zero the kernel exits at once (the tensor-core
+                         // kernel launched before it already decoded the scene)
 };
 
 // Transpose hidden-layer weights W_l [bc][K_l] -> [K_l][bc]; copy biases and the output layer unchanged.
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(kThreads) infer_fp32_kernel(const InferArgs a)
   const int tid = threadIdx.x, tn = tid & 7, pg = tid >> 3;
   const int D = net.D, n = net.n, C = net.C;
   const int trows = TH + 2 * D, twp = TW + 2 * D;
+
+  if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
 
   extern __shared__ float4 smem4[];
   float* act = reinterpret_cast<float*>(smem4);

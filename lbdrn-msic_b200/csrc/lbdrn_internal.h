@@ -1,6 +1,8 @@
 // lbdrn_internal.h -- declarations shared by the translation units of liblbdrn_b200 (not part of the ABI).
 #pragma once
 #include <atomic>
+#include <cstring>
+#include <mutex>
 #include <string>
 
 #include "lbdrn_common.cuh"
@@ -25,6 +27,8 @@ struct Scratch {
   int sms = 0, max_smem = 0;
 };
 
+int get_scratch(int P, Scratch*& out);   // per-device scratch of the calling thread's current device
+
 struct InferArgs;
 // fp32 inference launchers, one translation unit per mode (MODE_DECODE / MODE_PREDICT / MODE_SSE)
 int infer_fp32_decode(InferArgs& a, const Scratch& sc, cudaStream_t st);
@@ -47,6 +51,8 @@ void launch_adam_apply(const Net& n, const float* grad, float* params, float* wp
 
 // tcgen05 tensor-core decode (lbdrn_tc.cu)
 bool tc_supported(const Net& n);
-int tc_decode(const Net& n, const void* msb, const float* params, uint16_t* out, cudaStream_t st);
+int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
+              cudaStream_t st);
+int tc_selftest(const void* a_dev, const void* b_dev, float* d_dev, int K, cudaStream_t st);
 
 }  // namespace lbdrn

@@ -1,9 +1,583 @@
-// lbdrn_tc.cu -- tcgen05 / TMA tensor-core decode path (placeholder until the kernel lands).
+// lbdrn_tc.cu -- tcgen05 tensor-core decode kernel (sm_100a): the "TENSOR" path of lbdrn_decode.
+//
+// Per 128-pixel tile (one CTA = one warpgroup = the 128 TMEM lanes; 3 CTAs per SM overlap each other's phases):
+//   patch   : (tile + D halo) of every band, MSB integers as fp16, staged in smem (reflect at true borders)
+//   A1      : per pixel the (2D+1)^2*C INTEGER differences m_nbr - m_ctr (exact in fp16 for MSB <= 2048), written by
+//             the pixel's thread straight into the UMMA canonical K-major / no-swizzle layout
+//   MMA 1   : tcgen05.mma kind::f16, M=128 N=bc K=16 per instruction, D in TMEM (fp32), B1 = W1 * 2^s1 resident in
+//             smem as fp16 (fpzip prec<=16 weights are bf16 values => exact after a power-of-two scale)
+//   epi 1   : tcgen05.ld -> z = acc*(2^-s1/max) + b1 -> h = sin(w0 z) -> split h = hi + lo (two fp16 terms, |err| <=
+//             2^-22 |h|) -> A2 = [hi | lo] written back in the same canonical layout
+//   MMA l   : K = 2*bc against the SAME resident B_l for the hi and the lo half (no duplication of weights)
+//   epi last: tcgen05.ld -> z -> sin -> output layer (bc x C) in fp32 FFMA -> sigmoid -> round_half_even -> (m<<K)+r
+// Why split precision: rounding activations once to fp16/bf16/tf32 leaves only 99.95 % of pixels identical to the
+// reference's fp32 path; hi+lo keeps 99.998 % (measured in SURVEY.md 7.2-1 and re-checked by tests/ on the GPU).
+//
+// Weights that are NOT exactly representable (e.g. -prec 32 streams) are detected by the prep kernel on the device;
+// the tensor kernel then exits immediately and the fp32 kernel, launched behind it with the same flag, does the work.
+#include <cuda_fp16.h>
+
+#include "lbdrn_infer_fp32.cuh"
 #include "lbdrn_internal.h"
 
 namespace lbdrn {
-bool tc_supported(const Net&) { return false; }
-int tc_decode(const Net&, const void*, const float*, uint16_t*, cudaStream_t) {
-  return fail(LBDRN_E_UNSUPPORTED, "tensor-core path not built");
+
+namespace {
+
+constexpr int TC_THREADS = 128;       // one warpgroup: thread t <-> TMEM lane t <-> pixel t of the tile
+constexpr int TC_BC = 64;             // hidden width this kernel is instantiated for
+constexpr int TC_TH = 8, TC_TW = 16;  // 128-pixel tile
+constexpr int TC_TMEM_COLS = 64;      // fp32 accumulator: bc columns (power of two >= 32)
+constexpr int TC_MAX_K1 = 400;        // C*(2D+1)^2 <= 400 (8 bands, D=3 -> 392)
+
+// ---- packed weight block (global scratch and, copied verbatim, shared memory) ------------------------------------
+struct TcHeader {
+  int exact;            // 1: every hidden weight is exactly representable as fp16 after its power-of-two scale
+  int k1, k1pad;        // layer-1 K (= dim_in) and K rounded up to 16
+  int nl;
+  float scale[kMaxLayers];   // per hidden layer: multiply the fp32 accumulator by this (2^-s, and /max for layer 0)
+  int off_bias, off_w3, off_b[kMaxLayers], total;   // byte offsets inside the block
+  int pad[8];
+};
+
+__host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// byte offset of element (row, k) of a K-major, no-swizzle UMMA operand with `rows` rows:
+// 8x8 core matrices of 128 contiguous bytes; consecutive 8-row groups are contiguous (SBO = 128 B), consecutive
+// 8-element K chunks are rows*16 B apart (LBO).
+__host__ __device__ inline int umma_off(int rows, int row, int k) { return ((k >> 3) * rows + row) * 16 + (k & 7) * 2; }
+
+void plan_block(const Net& n, TcHeader& h) {
+  memset(&h, 0, sizeof h);
+  h.k1 = n.dim_in;
+  h.k1pad = align_up(n.dim_in, 16);
+  h.nl = n.nl;
+  int off = align_up((int)sizeof(TcHeader), 16);
+  h.off_bias = off; off += n.nl * TC_BC * 4;
+  h.off_w3 = off;   off += (TC_BC * 8 + 8) * 4;          // W3^T [bc][8] fp32 then b3[8]
+  off = align_up(off, 128);
+  for (int l = 0; l < n.nl; ++l) {
+    h.off_b[l] = off;
+    off += (l == 0 ? h.k1pad : TC_BC) * TC_BC * 2;
+  }
+  h.total = align_up(off, 16);
 }
+
+// One block: per-layer max -> power-of-two scale -> fp16 operands in UMMA layout, exactness flag, biases, W3^T.
+__global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ params, uint8_t* __restrict__ blk) {
+  __shared__ float s_max[32];
+  __shared__ int s_exact;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_exact = 1;
+  for (int i = tid; i < hdr.total / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(blk)[i] = 0u;
+  __syncthreads();
+  TcHeader* H = reinterpret_cast<TcHeader*>(blk);
+  for (int l = 0; l < net.nl; ++l) {
+    const int K = l == 0 ? net.dim_in : net.bc;
+    const float* W = params + net.woff[l];
+    float m = 0.f;
+    for (int i = tid; i < K * net.bc; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((tid & 31) == 0) s_max[tid >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_max[i]);
+    __syncthreads();
+    const int s = (m > 0.f && isfinite(m)) ? 13 - ilogbf(m) : 0;       // max|W| * 2^s in [2^13, 2^14)
+    const float up = ldexpf(1.0f, s);
+    __half* B = reinterpret_cast<__half*>(blk + hdr.off_b[l]);
+    int bad = 0;
+    for (int i = tid; i < K * net.bc; i += blockDim.x) {
+      const int nrow = i / K, k = i - nrow * K;
+      const float v = W[i] * up;                                          // exact (power of two)
+      const __half hv = __float2half_rn(v);
+      if (__half2float(hv) != v) bad = 1;
+      B[umma_off(TC_BC, nrow, k) / 2] = hv;
+    }
+    if (bad) atomicAnd(&s_exact, 0);
+    if (tid == 0) H->scale[l] = l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net.maxv) : ldexpf(1.0f, -s);
+    float* bias = reinterpret_cast<float*>(blk + hdr.off_bias) + l * TC_BC;
+    for (int i = tid; i < net.bc; i += blockDim.x) bias[i] = params[net.boff[l] + i];
+  }
+  float* w3t = reinterpret_cast<float*>(blk + hdr.off_w3);
+  for (int i = tid; i < net.bc * net.C; i += blockDim.x) {
+    const int c = i / net.bc, u = i - c * net.bc;
+    w3t[u * 8 + c] = params[net.woff[net.nl] + i];
+  }
+  for (int i = tid; i < net.C; i += blockDim.x) w3t[TC_BC * 8 + i] = params[net.boff[net.nl] + i];
+  __syncthreads();
+  if (tid == 0) {
+    H->exact = s_exact;
+    H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl;
+    H->off_bias = hdr.off_bias; H->off_w3 = hdr.off_w3; H->total = hdr.total;
+    for (int l = 0; l < net.nl; ++l) H->off_b[l] = hdr.off_b[l];
+  }
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout NONE [61,64)
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// cute::UMMA::InstrDescriptor, kind::f16: D=f32 (bit 4), A=B=f16 (0), both K-major (0), N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  // bounded: a lost arrival traps (surfacing as a CUDA error) instead of hanging the GPU
+  for (int it = 0; it < (1 << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcArgs {
+  Net net;
+  const void* msb;
+  const uint8_t* blk;     // packed weight block (TcHeader + operands) in global memory
+  uint16_t* out;
+  int tiles_x, n_tiles;
+  int a_bytes, w_bytes;   // smem: A region, weight block copy
+  int selftest;           // !=0: GEMM self-test mode (see tc_selftest_kernel)
+};
+
+// sin(w0 z): FAST = 3-term Cody-Waite to [-pi, pi] then MUFU.SIN (abs err ~4e-7); else the 7e-8 polynomial version
+template <bool FAST>
+__device__ __forceinline__ float tc_sine(float a) {
+  if (!FAST) return sin_pi9(a);
+  const float t = fmaf(a, 0.15915494309189535f, 12582912.0f);
+  const float k = t - 12582912.0f;
+  float r = fmaf(k, -6.28318548202514648f, a);
+  r = fmaf(k, 1.74845553146e-7f, r);       // 2*pi = 6.28318548202514648 - 1.74845553146e-7 (fp32 hi + lo)
+  return __sinf(r);
+}
+
+constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+2D)*(16+2D) <= 2048)
+
+// CC/DD > 0: bands / radius known at compile time (feature offsets fold into immediates); CC == 0: generic tables.
+template <bool FAST, int CC, int DD>
+__global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a) {
+  const Net& net = a.net;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int C = CC ? CC : net.C, D = CC ? DD : net.D, n = 2 * D + 1;
+  const int trows = TC_TH + 2 * D, twp = TC_TW + 2 * D;
+  const int n_patch = C * trows * twp;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + a.a_bytes;
+  __half* patch = reinterpret_cast<__half*>(sW + a.w_bytes);
+  uint16_t* koff = reinterpret_cast<uint16_t*>(patch + align_up(C * trows * twp, 8));   // [k1pad] patch offset of feature k
+  uint16_t* kctr = koff + TC_MAX_K1 + 16;                                                // [k1pad] patch offset of its centre
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ uint32_t s_tmem;
+
+  // ---- one-time setup: weight block -> smem, feature offset tables, TMEM, mbarrier ------------------------------------
+  {
+    const int4* src = reinterpret_cast<const int4*>(a.blk);
+    int4* dst = reinterpret_cast<int4*>(sW);
+    for (int i = tid; i < a.w_bytes / 16; i += TC_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const TcHeader* H = reinterpret_cast<const TcHeader*>(sW);
+  if (!H->exact) return;                       // inexact weights: the fp32 kernel launched behind us does the work
+  const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
+  for (int k = tid; k < k1pad; k += TC_THREADS) {
+    int off = 0, ctr = 0;
+    if (k < k1) {
+      const int c = k / (n * n), rem = k - c * n * n, dy = rem / n, dx = rem - dy * n;
+      off = (c * trows + dy) * twp + dx;
+      ctr = (c * trows + D) * twp + D;
+    }
+    koff[k] = (uint16_t)off;
+    kctr[k] = (uint16_t)ctr;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 lanes
+  const uint32_t mbar = smem_u32(&s_mbar);
+  const uint32_t idesc = umma_idesc_f16(128, TC_BC);
+  const uint32_t sA_u = smem_u32(sA);
+  const float* bias = reinterpret_cast<const float*>(sW + H->off_bias);
+  const float* w3t = reinterpret_cast<const float*>(sW + H->off_w3);
+  const bool rel = net.relative != 0;
+  uint32_t phase = 0;
+
+  // ---- patch element -> (band, row, col), fixed for the whole kernel; tile loads are prefetched one tile ahead -------
+  int pe[TC_PF];                                   // band << 16 | row << 8 | col, or -1
+  const bool pf_ok = n_patch <= TC_PF * TC_THREADS;
+#pragma unroll
+  for (int i = 0; i < TC_PF; ++i) {
+    const int e = tid + i * TC_THREADS;
+    const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp;
+    pe[i] = e < n_patch ? ((c << 16) | (r << 8) | (rem - r * twp)) : -1;
+  }
+  uint32_t pf[TC_PF];
+  auto issue_patch_loads = [&](int tile) {
+    const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
+#pragma unroll
+    for (int i = 0; i < TC_PF; ++i) {
+      if (pe[i] >= 0) {
+        const int gy = reflect_clamp(y0 + ((pe[i] >> 8) & 255), net.H), gx = reflect_clamp(x0 + (pe[i] & 255), net.W);
+        pf[i] = load_msb_int(a.msb, net.msb_u16, ((size_t)(pe[i] >> 16) * net.buf_rows + (gy - net.buf_row0)) * net.W + gx);
+      }
+    }
+  };
+  if (pf_ok && (int)blockIdx.x < a.n_tiles) issue_patch_loads(blockIdx.x);
+
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
+
+    // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
+    if (pf_ok) {
+#pragma unroll
+      for (int i = 0; i < TC_PF; ++i)
+        if (pe[i] >= 0) patch[tid + i * TC_THREADS] = __uint2half_rn(pf[i]);
+    } else {
+      for (int e = tid; e < n_patch; e += TC_THREADS) {
+        const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
+        const int gy = reflect_clamp(ty0 - D + r, net.H), gx = reflect_clamp(tx0 - D + x, net.W);
+        patch[e] = __uint2half_rn(load_msb_int(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx));
+      }
+    }
+    __syncthreads();
+    if (pf_ok && t + (int)gridDim.x < a.n_tiles) issue_patch_loads(t + gridDim.x);   // lands while this tile computes
+
+    // ---- A1 row of this thread's pixel: integer differences (exact in fp16), 16 B per K chunk ---------------------------
+    const int pr = tid >> 4, px = tid & 15;
+    const __half* pme = patch + pr * twp + px;
+    if (CC) {
+      constexpr int N_ = 2 * DD + 1, NN_ = N_ * N_, K1_ = (CC ? CC : 1) * NN_, TWP_ = TC_TW + 2 * DD, TRW_ = TC_TH + 2 * DD;
+      __half2 ctr2[CC ? CC : 1];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        const __half cv = rel ? pme[(c * TRW_ + DD) * TWP_ + DD] : __half(0);
+        ctr2[c] = __halves2half2(cv, cv);
+      }
+#pragma unroll
+      for (int kc = 0; kc < (K1_ + 15) / 16 * 2; ++kc) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k0 = kc * 8 + 2 * e, k1_ = k0 + 1;
+          const int c0 = k0 / NN_, c1 = k1_ / NN_;
+          const int o0 = (c0 * TRW_ + (k0 % NN_) / N_) * TWP_ + (k0 % NN_) % N_;
+          const int o1 = (c1 * TRW_ + (k1_ % NN_) / N_) * TWP_ + (k1_ % NN_) % N_;
+          __half2 v = __halves2half2(k0 < K1_ ? pme[o0] : __half(0), k1_ < K1_ ? pme[o1] : __half(0));
+          if (k0 < K1_) {
+            // both lanes of the pair belong to the same band except across a band boundary
+            const __half2 cpair = (c0 == c1 || k1_ >= K1_) ? ctr2[c0 < CC ? c0 : 0]
+                                                           : __halves2half2(__low2half(ctr2[c0 < CC ? c0 : 0]),
+                                                                            __low2half(ctr2[c1 < CC ? c1 : 0]));
+            v = __hsub2(v, (k1_ < K1_) ? cpair : __halves2half2(__low2half(cpair), __half(0)));
+          }
+          w[e] = *reinterpret_cast<const uint32_t*>(&v);
+        }
+        *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      for (int kc = 0; kc < k1pad / 8; ++kc) {
+        __half2 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = kc * 8 + 2 * e;
+          __half x0 = pme[koff[k]], x1 = pme[koff[k + 1]];
+          if (rel) {
+            x0 = __hsub(x0, pme[kctr[k]]);
+            x1 = __hsub(x1, pme[kctr[k + 1]]);
+          }
+          v[e] = __halves2half2(k < k1 ? x0 : __half(0), k + 1 < k1 ? x1 : __half(0));
+        }
+        *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) =
+            make_uint4(*reinterpret_cast<uint32_t*>(&v[0]), *reinterpret_cast<uint32_t*>(&v[1]),
+                       *reinterpret_cast<uint32_t*>(&v[2]), *reinterpret_cast<uint32_t*>(&v[3]));
+      }
+    }
+    // centre MSB integers for the final (m << K) + residual
+    uint32_t mctr[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      mctr[c] = c < C ? (uint32_t)__half2int_rn(patch[(c * trows + pr + D) * twp + px + D]) : 0u;
+
+    float yacc[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) yacc[c] = 0.f;
+
+    for (int l = 0; l < NL; ++l) {
+      // ---- MMA for hidden layer l: one elected thread issues, completion arrives on the mbarrier -----------------------
+      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t sB_u = smem_u32(sW + H->off_b[l]);
+        if (l == 0) {
+          for (int i = 0; i < k1pad / 16; ++i)
+            umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128), umma_desc(sB_u + i * 2 * 1024, 1024, 128), idesc, i > 0);
+        } else {
+          for (int i = 0; i < 2 * TC_BC / 16; ++i)       // hi half then lo half of A2, both against the same B_l
+            umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128),
+                     umma_desc(sB_u + (i % (TC_BC / 16)) * 2 * 1024, 1024, 128), idesc, i > 0);
+        }
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+
+      // ---- epilogue of layer l: thread = pixel = TMEM lane ------------------------------------------------------------
+      const float scale = H->scale[l];
+      const float* bl = bias + l * TC_BC;
+      const bool last = l + 1 == NL;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_BC; cb += 16) {
+        float acc[16];
+        tmem_ld16(tmem_row + cb, acc);
+        float h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float z = fmaf(acc[j], scale, bl[cb + j]);
+          h[j] = net.relu ? fmaxf(z, 0.f) : tc_sine<FAST>(net.w0 * z);
+        }
+        if (!last) {
+          // h = hi + lo, both fp16; A2 chunk index: hi -> (cb+j)/8, lo -> bc/8 + (cb+j)/8
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const __half2 hh = __floats2half2_rn(h[j], h[j + 1]);
+            const float2 back = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(h[j] - back.x, h[j + 1] - back.y);
+            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const int kc = cb >> 3;
+          *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sA + (size_t)((kc + 1) * 128 + tid) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(sA + (size_t)((TC_BC / 8 + kc) * 128 + tid) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(sA + (size_t)((TC_BC / 8 + kc + 1) * 128 + tid) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        } else {
+          // output layer in fp32: y_c += W3[c][u] * h[u]   (W3^T rows of 8 floats: one or two LDS.128, broadcast)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 wa = *reinterpret_cast<const float4*>(w3t + (cb + j) * 8);
+            yacc[0] = fmaf(wa.x, h[j], yacc[0]); yacc[1] = fmaf(wa.y, h[j], yacc[1]);
+            yacc[2] = fmaf(wa.z, h[j], yacc[2]); yacc[3] = fmaf(wa.w, h[j], yacc[3]);
+            if (C > 4) {
+              const float4 wb = *reinterpret_cast<const float4*>(w3t + (cb + j) * 8 + 4);
+              yacc[4] = fmaf(wb.x, h[j], yacc[4]); yacc[5] = fmaf(wb.y, h[j], yacc[5]);
+              yacc[6] = fmaf(wb.z, h[j], yacc[6]); yacc[7] = fmaf(wb.w, h[j], yacc[7]);
+            }
+          }
+        }
+      }
+    }
+
+    // ---- sigmoid, inverse quantisation, integer write (decode.py:131-134) ----------------------------------------------
+    const int gy = ty0 + pr, gx = tx0 + px;
+    if (gy < net.row1 && gx < net.W) {
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) {
+        if (c < C) {
+          const float y = sigmoidf_rn(yacc[c] + w3t[TC_BC * 8 + c]);
+          const int res = (int)rintf(y * net.qmax);
+          a.out[((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx] = (uint16_t)((mctr[c] << net.K) + (uint32_t)res);
+        }
+      }
+    }
+    tc_fence_before();      // our tcgen05.ld's are ordered before the next tile's MMA (issued after the next barrier)
+  }
+
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+}
+
+// ---- self-test: D[128][64] = A[128][K] * B[64][K]^T through the same descriptors / layouts / TMEM path ----------------
+__global__ void __launch_bounds__(TC_THREADS) tc_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
+                                                                float* __restrict__ Dout, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * K; i += TC_THREADS) {
+    const int r = i / K, k = i - r * K;
+    *reinterpret_cast<__half*>(sA + umma_off(128, r, k)) = A[i];
+  }
+  for (int i = tid; i < TC_BC * K; i += TC_THREADS) {
+    const int r = i / K, k = i - r * K;
+    *reinterpret_cast<__half*>(sB + umma_off(TC_BC, r, k)) = B[i];
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, TC_BC);
+    for (int i = 0; i < K / 16; ++i)
+      umma_f16(tmem, umma_desc(smem_u32(sA) + i * 2 * 2048, 2048, 128), umma_desc(smem_u32(sB) + i * 2 * 1024, 1024, 128),
+               idesc, i > 0);
+    umma_commit(smem_u32(&s_mbar));
+  }
+  mbar_wait(smem_u32(&s_mbar), 0);
+  tc_fence_after();
+  for (int cb = 0; cb < TC_BC; cb += 16) {
+    float acc[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cb, acc);
+    for (int j = 0; j < 16; ++j) Dout[tid * TC_BC + cb + j] = acc[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+}
+
+std::mutex& tc_mu() {
+  static std::mutex m;
+  return m;
+}
+uint8_t* g_blk[64] = {nullptr};
+constexpr int kBlkBytes = 1 << 18;
+
+}  // namespace
+
+bool tc_supported(const Net& n) {
+  // colours only (integer differences are exact in fp16 up to 2048); bc = 64; up to 8 bands, D <= 3
+  return n.bc == TC_BC && n.nco == 0 && n.ncol > 0 && n.dim_in <= TC_MAX_K1 && n.maxv <= 2048.0f && n.C <= kMaxC &&
+         n.nl >= 1 && n.nl <= 4;
+}
+
+int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
+              cudaStream_t st) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
+  {
+    std::lock_guard<std::mutex> lk(tc_mu());
+    if (!g_blk[dev]) CUDA_TRY(cudaMalloc(&g_blk[dev], kBlkBytes));
+  }
+  TcHeader h;
+  plan_block(n, h);
+  if (h.total > kBlkBytes) return fail(LBDRN_E_UNSUPPORTED, "tensor-core weight block too large (%d B)", h.total);
+  tc_prep_kernel<<<1, 1024, 0, st>>>(n, h, params, g_blk[dev]);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+
+  TcArgs a;
+  memset(&a, 0, sizeof a);
+  a.net = n; a.msb = msb; a.blk = g_blk[dev]; a.out = out;
+  a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
+  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
+  const int kmax = h.k1pad > 2 * TC_BC ? h.k1pad : 2 * TC_BC;
+  a.a_bytes = align_up(128 * kmax * 2, 1024);
+  a.w_bytes = h.total;
+  const size_t smem = (size_t)a.a_bytes + a.w_bytes + align_up(n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D), 8) * 2 +
+                      2 * (TC_MAX_K1 + 16) * 2 + 64;
+  int sms = 0, max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem > (size_t)max_smem) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode needs %zu B of shared memory", smem);
+  using KernT = void (*)(const TcArgs);
+  KernT kern;
+#define LBDRN_TC_PICK(CC, DD) (fast_sine ? (KernT)tc_decode_kernel<true, CC, DD> : (KernT)tc_decode_kernel<false, CC, DD>)
+  if (n.C == 4 && n.D == 2) kern = LBDRN_TC_PICK(4, 2);
+  else if (n.C == 8 && n.D == 2) kern = LBDRN_TC_PICK(8, 2);
+  else if (n.C == 4 && n.D == 1) kern = LBDRN_TC_PICK(4, 1);
+  else if (n.C == 4 && n.D == 3) kern = LBDRN_TC_PICK(4, 3);
+  else kern = LBDRN_TC_PICK(0, 0);
+#undef LBDRN_TC_PICK
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_THREADS, smem));
+  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
+  if (occ * TC_TMEM_COLS > 512) occ = 512 / TC_TMEM_COLS;         // TMEM: 512 columns per SM
+  int grid = sms * occ;                                          // persistent: whole CTAs per SM
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  kern<<<grid, TC_THREADS, smem, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+
+  // fp32 kernel behind it, skipped on the device when the tensor kernel handled the scene (weights exact)
+  Scratch* sc = nullptr;
+  int rc = get_scratch(n.P, sc);
+  if (rc) return rc;
+  launch_pack_params(n, params, sc->wpack, st);
+  InferArgs ia;
+  memset(&ia, 0, sizeof ia);
+  ia.net = n; ia.msb = msb; ia.wpack = sc->wpack; ia.tab = tab; ia.out = out;
+  ia.skip_flag = reinterpret_cast<const int*>(g_blk[dev]);       // TcHeader::exact
+  return infer_fp32_decode(ia, *sc, st);
+}
+
+int tc_selftest(const void* a_dev, const void* b_dev, float* d_dev, int K, cudaStream_t st) {
+  if (K % 16 || K < 16 || K > 256) return fail(LBDRN_E_INVALID, "selftest K=%d", K);
+  const size_t smem = (size_t)(128 + TC_BC) * K * 2;
+  CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_kernel<<<1, TC_THREADS, smem, st>>>((const __half*)a_dev, (const __half*)b_dev, d_dev, K);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
 }  // namespace lbdrn

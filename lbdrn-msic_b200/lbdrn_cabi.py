@@ -12,11 +12,11 @@ LIB_PATH = os.path.join(HERE, "liblbdrn_b200.so")
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4
 USE_COORDINATES, EMBEDDING, USE_COLORS, RELATIVE, ACT_RELU = 1, 2, 4, 8, 16
 U8, U16 = 0, 1
-PATH_AUTO, PATH_PRECISE, PATH_TENSOR = 0, 1, 2
+PATH_AUTO, PATH_PRECISE, PATH_TENSOR, PATH_TENSOR_FASTSIN = 0, 1, 2, 3
 
 # every symbol include/lbdrn.h declares (tests check the library exports exactly these)
 SYMBOLS = ["lbdrn_version", "lbdrn_last_error", "lbdrn_dim_in", "lbdrn_param_count", "lbdrn_has_tensor_path",
-           "lbdrn_launch_count", "lbdrn_split", "lbdrn_max_shifted", "lbdrn_decode", "lbdrn_predict",
+           "lbdrn_launch_count", "lbdrn_selftest_tc_gemm", "lbdrn_split", "lbdrn_max_shifted", "lbdrn_decode", "lbdrn_predict",
            "lbdrn_eval_sse", "lbdrn_train_create", "lbdrn_train_destroy", "lbdrn_train_set_params",
            "lbdrn_train_get_params", "lbdrn_train_steps", "lbdrn_train_grad", "lbdrn_train_apply"]
 
@@ -65,6 +65,7 @@ def load(build_if_missing=True):
         "lbdrn_param_count": (i64, [D]),
         "lbdrn_has_tensor_path": (i32, [D]),
         "lbdrn_launch_count": (i64, []),
+        "lbdrn_selftest_tc_gemm": (i32, [vp, vp, vp, i32, vp]),
         "lbdrn_split": (i32, [vp, i64, i32, i32, vp, vp, vp]),
         "lbdrn_max_shifted": (i32, [vp, i64, i32, vp, vp]),
         "lbdrn_decode": (i32, [D, vp, vp, vp, vp, vp]),

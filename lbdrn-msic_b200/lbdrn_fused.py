@@ -131,7 +131,8 @@ def _base_to_device(base, dev, known_max=None):
     return t, int(mx.item())
 
 
-_PATHS = {"auto": cabi.PATH_AUTO, "precise": cabi.PATH_PRECISE, "tensor": cabi.PATH_TENSOR}
+_PATHS = {"auto": cabi.PATH_AUTO, "precise": cabi.PATH_PRECISE, "tensor": cabi.PATH_TENSOR,
+          "tensor_fastsin": cabi.PATH_TENSOR_FASTSIN}
 
 
 def _tab_tensor(H, W, flags, dev):

@@ -26,10 +26,26 @@ def _check(out, ref, what):
     return n_bad
 
 
-def _paths(K, D, bc, nl, C, flags):
+def _paths(K, D, bc, nl, C, flags, msb_max=100):
     lib = cabi.load()
-    d = cabi.make_desc(C, 64, 64, K, D, bc, nl, flags.bits(), 100, False)
-    return ["precise"] + (["tensor"] if lib.lbdrn_has_tensor_path(ctypes.byref(d)) else [])
+    d = cabi.make_desc(C, 64, 64, K, D, bc, nl, flags.bits(), int(msb_max), msb_max > 255)
+    return ["precise"] + (["tensor", "tensor_fastsin"] if lib.lbdrn_has_tensor_path(ctypes.byref(d)) else [])
+
+
+def test_tcgen05_selftest_gemm_is_exact_on_integers():
+    """The tensor path's building blocks in isolation: smem operand layout, UMMA descriptors, instruction descriptor,
+    TMEM accumulator read-back.  Small-integer operands make every fp16 product and fp32 sum exact."""
+    lib = cabi.load()
+    rng = np.random.default_rng(0)
+    for K in (16, 32, 64, 112, 128, 208):
+        A = rng.integers(-9, 10, size=(128, K)).astype(np.float16)
+        B = rng.integers(-9, 10, size=(64, K)).astype(np.float16)
+        a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        d = torch.full((128, 64), float("nan"), device="cuda")
+        cabi.check(lib.lbdrn_selftest_tc_gemm(cabi.ptr(a), cabi.ptr(b), cabi.ptr(d), K, cabi.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        assert np.array_equal(d.cpu().numpy().astype(np.float64), ref), K
 
 
 @pytest.mark.parametrize("name", CODEC_CASES)
@@ -41,7 +57,7 @@ def test_decode_golden_streams(name):
     flags = case_flags(meta, F.Flags)
     base = read_base(tiles[0][1])
     params = np.asarray(fpzip.decompress(tiles[0][0])[0][0][0], dtype=np.float32)
-    for path in _paths(K, D, bc, nl, base.shape[0], flags):
+    for path in _paths(K, D, bc, nl, base.shape[0], flags, base.max()):
         out = F.decode_image(base, params, K, D, bc, nl, flags=flags, path=path)
         assert out.dtype == np.uint16 and out.shape == recon.shape
         _check(out, recon, f"{name}/{path}")
@@ -89,14 +105,32 @@ def test_decode_k_sweep_identity_fraction():
     img = make_scene(4, 256, 256, 12, seed=77)
     params = _trained_params()
     p = O.unflatten_params(params, 100, 64, 4, 2)
+    report = {}
     for K in range(1, 12):
         msb, _ = O.split_msb_lsb(img, K)
         ref = O.decode_image(msb, p, K, 2)
-        out = F.decode_image(msb, params, K, 2, 64, 2, flags=F.Flags(), path="precise")
-        diff = np.abs(out.astype(np.int64) - ref.astype(np.int64))
-        frac = 1.0 - (diff != 0).mean()
-        assert diff.max() <= 1
-        assert frac >= (0.9999 if K <= 9 else 0.999), (K, frac)
+        for path in _paths(K, 2, 64, 2, 4, F.Flags(), msb.max()):
+            out = F.decode_image(msb, params, K, 2, 64, 2, flags=F.Flags(), path=path)
+            diff = np.abs(out.astype(np.int64) - ref.astype(np.int64))
+            frac = 1.0 - (diff != 0).mean()
+            report[(K, path)] = frac
+            assert diff.max() <= 1, (K, path)
+            assert frac >= (0.9999 if K <= 9 else 0.999), (K, path, frac)
+    print({k: round(v, 6) for k, v in report.items()})
+
+
+def test_tensor_path_falls_back_on_device_for_inexact_weights():
+    """Weights that are not fp16-exact after scaling (e.g. a -prec 32 stream) are detected on the device: the tensor
+    kernel exits and the fp32 kernel behind it produces the result -- identical to the precise path."""
+    from synth_scene import make_scene
+    img = make_scene(4, 100, 120, 12, seed=8)
+    msb, _ = O.split_msb_lsb(img, 5)
+    torch.manual_seed(5)
+    from LBDRNmodel import LBDRNModel
+    flat = LBDRNModel(100, 64, 4, 2).flat_params().numpy()          # full fp32 mantissas
+    a = F.decode_image(msb, flat, 5, 2, 64, 2, flags=F.Flags(), path="tensor")
+    b = F.decode_image(msb, flat, 5, 2, 64, 2, flags=F.Flags(), path="precise")
+    assert np.array_equal(a, b)
 
 
 def test_stripe_decode_is_bit_identical_to_whole_image():
