@@ -17,6 +17,9 @@
 // the tensor kernel then exits immediately and the fp32 kernel, launched behind it with the same flag, does the work.
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "lbdrn_infer_fp32.cuh"
 #include "lbdrn_internal.h"
 
@@ -95,9 +98,11 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
       B[umma_off(TC_BC, nrow, k) / 2] = hv;
     }
     if (bad) atomicAnd(&s_exact, 0);
-    if (tid == 0) H->scale[l] = l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net.maxv) : ldexpf(1.0f, -s);
+    // sine path: a = w0*(acc*scale + b) is evaluated as one FFMA, acc*(w0*scale) + w0*b (w0 folded here)
+    const float fold = net.relu ? 1.0f : net.w0;
+    if (tid == 0) H->scale[l] = fold * (l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net.maxv) : ldexpf(1.0f, -s));
     float* bias = reinterpret_cast<float*>(blk + hdr.off_bias) + l * TC_BC;
-    for (int i = tid; i < net.bc; i += blockDim.x) bias[i] = params[net.boff[l] + i];
+    for (int i = tid; i < net.bc; i += blockDim.x) bias[i] = fold * params[net.boff[l] + i];
   }
   float* w3t = reinterpret_cast<float*>(blk + hdr.off_w3);
   for (int i = tid; i < net.bc * net.C; i += blockDim.x) {
@@ -189,7 +194,7 @@ struct TcArgs {
 // sin(w0 z): FAST = 3-term Cody-Waite to [-pi, pi] then MUFU.SIN (abs err ~4e-7); else the 7e-8 polynomial version
 template <bool FAST>
 __device__ __forceinline__ float tc_sine(float a) {
-  if (!FAST) return sin_pi9(a);
+  if (!FAST) return sin_pi9_core(a);
   const float t = fmaf(a, 0.15915494309189535f, 12582912.0f);
   const float k = t - 12582912.0f;
   float r = fmaf(k, -6.28318548202514648f, a);
@@ -266,8 +271,19 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a
     pe[i] = e < n_patch ? ((c << 16) | (r << 8) | (rem - r * twp)) : -1;
   }
   uint32_t pf[TC_PF];
+  long long pe_off[TC_PF];                         // element offset relative to the patch origin (interior tiles)
+#pragma unroll
+  for (int i = 0; i < TC_PF; ++i)
+    pe_off[i] = pe[i] >= 0 ? ((long long)(pe[i] >> 16) * net.buf_rows + ((pe[i] >> 8) & 255)) * net.W + (pe[i] & 255) : 0;
   auto issue_patch_loads = [&](int tile) {
     const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
+    if (y0 >= 0 && x0 >= 0 && y0 + trows <= net.H && x0 + twp <= net.W) {      // no reflection needed
+      const long long origin = (long long)(y0 - net.buf_row0) * net.W + x0;
+#pragma unroll
+      for (int i = 0; i < TC_PF; ++i)
+        if (pe[i] >= 0) pf[i] = load_msb_int(a.msb, net.msb_u16, (size_t)(origin + pe_off[i]));
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < TC_PF; ++i) {
       if (pe[i] >= 0) {
@@ -387,10 +403,21 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a
         float acc[16];
         tmem_ld16(tmem_row + cb, acc);
         float h[16];
+        if (net.relu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float z = fmaf(acc[j], scale, bl[cb + j]);
-          h[j] = net.relu ? fmaxf(z, 0.f) : tc_sine<FAST>(net.w0 * z);
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bl[cb + j]), 0.f);
+        } else {
+          float amax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            acc[j] = fmaf(acc[j], scale, bl[cb + j]);          // = w0 * z (w0 folded into scale and bias)
+            amax = fmaxf(amax, fabsf(acc[j]));
+            h[j] = tc_sine<FAST>(acc[j]);
+          }
+          if (__builtin_expect(!(amax <= 20000.0f), 0)) {       // huge or NaN argument: library slow path, out of line
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = sin_slow(acc[j]);
+          }
         }
         if (!last) {
           // h = hi + lo, both fp16; A2 chunk index: hi -> (cb+j)/8, lo -> bc/8 + (cb+j)/8
@@ -548,10 +575,24 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
   else kern = LBDRN_TC_PICK(0, 0);
 #undef LBDRN_TC_PICK
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_THREADS, smem));
-  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
+  // Resident CTAs per SM.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate tensor
+  // memory (measured on B200 / CUDA 12.9) although the hardware co-schedules as many CTAs as shared memory, registers
+  // and the 512 TMEM columns allow (3 here: 4.3 vs 1.7 Gpix/s), so the limit is computed from the kernel's attributes.
+  cudaFuncAttributes fa;
+  CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+  int smem_sm = 0, regs_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+  int occ = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));   // +1 KB: per-CTA reservation of the driver
+  const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS;
+  if (regs_cta > 0 && regs_sm / regs_cta < occ) occ = regs_sm / regs_cta;
   if (occ * TC_TMEM_COLS > 512) occ = 512 / TC_TMEM_COLS;         // TMEM: 512 columns per SM
+  if (occ > 3) occ = 3;                                           // measured optimum (4 CTAs: 3.0 vs 4.3 Gpix/s)
+  if (const char* e = getenv("LBDRN_TC_OCC")) occ = atoi(e);
+  if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
+  if (getenv("LBDRN_DEBUG"))
+    fprintf(stderr, "[lbdrn] tc_decode: smem dyn %zu static %zu regs %d occ %d sms %d tiles %d\n", smem,
+            fa.sharedSizeBytes, fa.numRegs, occ, sms, a.n_tiles);
   int grid = sms * occ;                                          // persistent: whole CTAs per SM
   if (grid > a.n_tiles) grid = a.n_tiles;
   kern<<<grid, TC_THREADS, smem, st>>>(a);
