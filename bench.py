@@ -227,7 +227,8 @@ def run_ours(args):
     tflops = SIDE * SIDE * FLOP_PER_PX / (kern_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
                 "frac": tflops / pk["bf16_burst"], "traffic": None,
-                "kernel": "tc_decode_kernel (tcgen05)" if has_tc else "infer_fp32_kernel<64,8,4,true,DECODE> (fp32 FFMA)",
+                "kernel": "tc_decode_kernel<fast,4,2> (tcgen05 kind::f16, fp16 hi+lo split activations, fp32 TMEM accumulators)"
+                if has_tc else "infer_fp32_kernel<64,8,4,true,DECODE> (fp32 FFMA)",
                 "peak_source": pk["source"] + " bf16 dense burst",
                 "algorithmic_flop_per_pixel": FLOP_PER_PX,
                 "hbm": {"achieved_gbs": SIDE * SIDE * HBM_BYTES_PER_PX / (kern_avg_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
@@ -241,7 +242,8 @@ def run_ours(args):
 
     def e2e_step():
         if world == 1:
-            F.decode_image(base_host, params_host, K_, D_, BC, NL, flags=fl, out_host=out_host, base_max=scene.msb_max)
+            # the call a user of decode.py makes: host base layer in, host reconstruction out, base.max() NOT known
+            F.decode_image_streamed(base_host, params_host, K_, D_, BC, NL, flags=fl, out_host=out_host)
         else:
             stripe = base_host.to(dev, non_blocking=True)
             mx = LD.global_max(torch.tensor([scene.msb_max], device=dev))
@@ -264,7 +266,9 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e = {"value": npx_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
            "h2d_bytes_per_step": int(base_host.numel() * base_host.element_size() * world + params_host.numel() * 4 * world),
-           "d2h_bytes_per_step": int(out_host.numel() * 2 * world), "steps": e2e_steps}
+           "d2h_bytes_per_step": int(out_host.numel() * 2 * world), "steps": e2e_steps,
+           "api": "lbdrn_fused.decode_image_streamed (pinned host in/out, stripe-pipelined H2D | kernel | D2H, "
+                  "base.max() reduced on the device)" if world == 1 else "lbdrn_dist.decode_stripe per rank"}
     del base_host, out_host
 
     # ---- encode s/scene (10 epochs, bs 8192, per-epoch eval + best-epoch select), scene-per-GPU replicas -----------

@@ -167,6 +167,83 @@ def decode_image(base, flat_params, K, D, bc, nl, flags=None, relu=False, w0=30.
     return out if return_tensor else out.cpu().numpy()
 
 
+_streams = {}
+
+
+def _get_streams(dev):
+    key = (dev.type, dev.index)
+    if key not in _streams:
+        _streams[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _streams[key]
+
+
+def decode_image_streamed(base_host, flat_params, K, D, bc, nl, flags=None, relu=False, w0=30.0, path="auto", device=None,
+                          out_host=None, base_max=None, stripe_rows=1024):
+    """End-to-end decode from HOST memory to HOST memory with the copies overlapped with the kernel (N1 of SURVEY.md 8f).
+
+    The base layer is uploaded stripe by stripe on a copy stream; each stripe is decoded on a compute stream as soon as
+    it and its lower halo are resident, and downloaded on a third stream while the next stripe computes.  The global
+    normaliser `base.max()` is a property of the whole image: when the caller does not pass it, the upload is finished
+    first and the maximum is reduced on the device (4-byte read-back) before the first stripe is decoded.
+    base_host / out_host: CHW CPU tensors (pinned memory makes the copies asynchronous); returns out_host."""
+    flags, dev, lib = _flags(flags), _device(device), cabi.load()
+    if isinstance(base_host, np.ndarray):
+        base_host = torch.from_numpy(np.ascontiguousarray(base_host))
+    base_host = base_host.reshape((-1,) + tuple(base_host.shape[-2:]))
+    if base_host.dtype not in (torch.uint8, torch.uint16):
+        base_host = base_host.to(torch.int32).to(torch.uint16)
+    C, H, W = base_host.shape
+    if out_host is None:
+        out_host = torch.empty((C, H, W), dtype=torch.uint16).pin_memory()
+    s_in, s_cmp, s_out = _get_streams(dev)
+    cur = torch.cuda.current_stream(dev)
+    params = torch.as_tensor(flat_params, dtype=torch.float32).to(dev, non_blocking=True).contiguous()
+    msb = torch.empty((C, H, W), dtype=base_host.dtype, device=dev)
+    out = torch.empty((C, H, W), dtype=torch.uint16, device=dev)
+    tab = _tab_tensor(H, W, flags, dev)
+    bounds = list(range(0, H, stripe_rows)) + [H]
+    n = len(bounds) - 1
+    up = [torch.cuda.Event() for _ in range(n)]
+    done = [torch.cuda.Event() for _ in range(n)]
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    for st in (s_in, s_cmp, s_out):
+        st.wait_event(ready)
+    with torch.cuda.stream(s_in):
+        for i in range(n):
+            r0, r1 = bounds[i], bounds[i + 1]
+            for c in range(C):
+                msb[c, r0:r1].copy_(base_host[c, r0:r1], non_blocking=True)
+            up[i].record(s_in)
+        if base_max is None:
+            if msb.dtype == torch.uint8:
+                mx = msb.max()
+            else:
+                mx = torch.zeros(1, dtype=torch.int32, device=dev)
+                cabi.check(lib.lbdrn_max_shifted(cabi.ptr(msb), msb.numel(), 0, cabi.ptr(mx), cabi.stream_ptr()))
+            base_max = int(mx.item())                       # waits for the upload: max is a whole-image property
+    for i in range(n):
+        r0, r1 = bounds[i], bounds[i + 1]
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(up[min(i + 1, n - 1)])         # stripe i and the halo rows of stripe i+1 are resident
+            d = cabi.make_desc(C, H, W, K, D, bc, nl, flags.bits(relu), base_max, msb.dtype == torch.uint16, row0=r0,
+                               row1=r1, w0=w0, n_freq=flags.n_freq, path=_PATHS[path])
+            cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(msb), cabi.ptr(params), cabi.ptr(tab), cabi.ptr(out),
+                                        cabi.stream_ptr()))
+            done[i].record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done[i])
+            for c in range(C):
+                out_host[c, r0:r1].copy_(out[c, r0:r1], non_blocking=True)
+    fin = torch.cuda.Event()
+    fin.record(s_out)
+    fin.synchronize()
+    cur.wait_stream(s_cmp)
+    for t in (msb, out, params):
+        t.record_stream(s_cmp)
+    return out_host
+
+
 def predict_image(base, flat_params, D, bc, nl, flags=None, relu=False, w0=30.0, device=None):
     """Network output y [H*W, C] (float32 CUDA tensor) for every pixel of the base layer."""
     flags, dev, lib = _flags(flags), _device(device), cabi.load()

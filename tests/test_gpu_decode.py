@@ -200,3 +200,17 @@ def test_relu_variant_matches_torch_module():
         y_ref = m(torch.from_numpy(O.features(msb, 2))).numpy()
     y = m.predict_image(msb, 2, flags=F.Flags()).cpu().numpy()
     assert np.max(np.abs(y - y_ref)) < 2e-6
+
+
+def test_streamed_host_to_host_decode_matches_resident_decode():
+    """decode_image_streamed (stripe-pipelined copies, device-side max) is bit-identical to the one-shot decode."""
+    from synth_scene import make_scene
+    img = make_scene(4, 333, 200, 12, seed=21)
+    msb, _ = O.split_msb_lsb(img, 5)
+    params = _trained_params()
+    whole = F.decode_image(msb, params, 5, 2, 64, 2, flags=F.Flags())
+    host = torch.from_numpy(msb).pin_memory()
+    out = F.decode_image_streamed(host, params, 5, 2, 64, 2, flags=F.Flags(), stripe_rows=64)
+    assert np.array_equal(out.numpy(), whole)
+    out2 = F.decode_image_streamed(msb, params, 5, 2, 64, 2, flags=F.Flags(), stripe_rows=1000, base_max=int(msb.max()))
+    assert np.array_equal(out2.numpy(), whole)
