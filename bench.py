@@ -171,14 +171,22 @@ def run_ours(args):
     params = bench_params(dev)
     r0, r1 = LD.stripe_bounds(H_total, world, rank)
 
+    sbuf = None
+    if world > 1:
+        sbuf = LD.StripeBuffer(H_total, SIDE, C_, D_, scene.msb.dtype, dev)
+        sbuf.load(scene.msb)
+        local_max = torch.tensor([scene.msb_max], device=dev)
+
     def decode_step():
         if world == 1:
             d = scene.desc(D_, BC, NL, fl, path=cabi.PATH_AUTO)
             cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(scene.msb), cabi.ptr(params), None, cabi.ptr(out),
                                         cabi.stream_ptr()))
             return out
-        mx = LD.global_max(torch.tensor([scene.msb_max], device=dev))
-        return LD.decode_stripe(scene.msb, H_total, params, K_, D_, BC, NL, fl, mx)
+        # per scene: scalar max all-reduce + one D-row halo swap with each neighbour, then the local kernel
+        mx = LD.global_max(local_max)
+        sbuf.exchange()
+        return sbuf.decode(params, K_, BC, NL, fl, mx)[0]
 
     out = torch.empty((C_, SIDE, SIDE), dtype=torch.uint16, device=dev)
     for _ in range(max(3, args.warmup)):
@@ -245,10 +253,12 @@ def run_ours(args):
             # the call a user of decode.py makes: host base layer in, host reconstruction out, base.max() NOT known
             F.decode_image_streamed(base_host, params_host, K_, D_, BC, NL, flags=fl, out_host=out_host)
         else:
-            stripe = base_host.to(dev, non_blocking=True)
-            mx = LD.global_max(torch.tensor([scene.msb_max], device=dev))
-            o = LD.decode_stripe(stripe, H_total, params_host.to(dev), K_, D_, BC, NL, fl, mx)
-            out_host.copy_(o, non_blocking=True)
+            sbuf.own.copy_(base_host.view(torch.int16) if base_host.dtype == torch.uint16 else base_host, non_blocking=True)
+            mx = LD.global_max(sbuf.own.max() if sbuf.buf.dtype == torch.uint8 else local_max)
+            sbuf.exchange()
+            o, rows = sbuf.decode(params_host.to(dev, non_blocking=True), K_, BC, NL, fl, mx)
+            for c in range(C_):
+                out_host[c].copy_(o[c, rows], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     e2e_step()
@@ -268,7 +278,7 @@ def run_ours(args):
            "h2d_bytes_per_step": int(base_host.numel() * base_host.element_size() * world + params_host.numel() * 4 * world),
            "d2h_bytes_per_step": int(out_host.numel() * 2 * world), "steps": e2e_steps,
            "api": "lbdrn_fused.decode_image_streamed (pinned host in/out, stripe-pipelined H2D | kernel | D2H, "
-                  "base.max() reduced on the device)" if world == 1 else "lbdrn_dist.decode_stripe per rank"}
+                  "base.max() reduced on the device)" if world == 1 else "lbdrn_dist.StripeBuffer per rank (H2D, max all-reduce, halo swap, kernel, D2H)"}
     del base_host, out_host
 
     # ---- encode s/scene (10 epochs, bs 8192, per-epoch eval + best-epoch select), scene-per-GPU replicas -----------

@@ -111,6 +111,26 @@ __device__ __forceinline__ float row_dot64(const float* __restrict__ a, const fl
   return s;
 }
 
+// One band's (2D+1)^2 neighbourhood of one pixel: all loads are issued before the first use so their latencies overlap
+// (the naive dependent loop cost ~25 serialized global round trips per band).
+template <int N_>
+__device__ __forceinline__ void gather_band(const void* msb, int u16, size_t plane, int gy, int gx, const Net& net,
+                                            float ctr, bool ok, float* d) {
+  constexpr int D_ = N_ / 2;
+  uint32_t raw[N_ * N_];
+#pragma unroll
+  for (int dy = 0; dy < N_; ++dy) {
+    const size_t rowoff = (plane + (reflect_clamp(gy + dy - D_, net.H) - net.buf_row0)) * net.W;
+#pragma unroll
+    for (int dx = 0; dx < N_; ++dx) raw[dy * N_ + dx] = load_msb_int(msb, u16, rowoff + reflect_clamp(gx + dx - D_, net.W));
+  }
+#pragma unroll
+  for (int i = 0; i < N_ * N_; ++i) {
+    const float v = __fdiv_rn((float)raw[i], net.maxv) - ctr;
+    d[(size_t)i * kTrainLDP] = ok ? v : 0.f;
+  }
+}
+
 // index of parameter i inside the packed copy (hidden weights transposed)
 __device__ __forceinline__ int packed_index(const Net& net, int i) {
   for (int l = 0; l < net.nl; ++l) {
@@ -222,12 +242,19 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
           if (net.ncol) {
             const float ctr = net.relative ? load_msb_norm(a.msb, net.msb_u16, off, net.maxv) : 0.f;
             float* d = dst + (size_t)(net.nco + c * n * n) * LDP;
-            for (int dy = 0; dy < n; ++dy) {
-              const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
-              for (int dx = 0; dx < n; ++dx, d += LDP) {
-                float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), net.maxv) - ctr;
-                *d = ok ? v : 0.f;
-              }
+            switch (n) {
+              case 1: gather_band<1>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
+              case 3: gather_band<3>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
+              case 5: gather_band<5>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
+              case 7: gather_band<7>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
+              default:
+                for (int dy = 0; dy < n; ++dy) {
+                  const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
+                  for (int dx = 0; dx < n; ++dx, d += LDP) {
+                    float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), net.maxv) - ctr;
+                    *d = ok ? v : 0.f;
+                  }
+                }
             }
           }
         }
@@ -391,8 +418,18 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
     }
     __syncthreads();
     for (int i = blockIdx.x * kThreads + tid; i <= P; i += gridDim.x * kThreads) {
-      float g = 0.f;
-      for (int c = 0; c < n_act; ++c) g += __ldcg(a.partial + (size_t)c * a.pstride + i);
+      // fixed summation order (deterministic), 8 independent loads in flight
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
+      const float* pp = a.partial + i;
+      int c = 0;
+      for (; c + 8 <= n_act; c += 8) {
+        g0 += __ldcg(pp + (size_t)(c + 0) * a.pstride); g1 += __ldcg(pp + (size_t)(c + 1) * a.pstride);
+        g2 += __ldcg(pp + (size_t)(c + 2) * a.pstride); g3 += __ldcg(pp + (size_t)(c + 3) * a.pstride);
+        g4 += __ldcg(pp + (size_t)(c + 4) * a.pstride); g5 += __ldcg(pp + (size_t)(c + 5) * a.pstride);
+        g6 += __ldcg(pp + (size_t)(c + 6) * a.pstride); g7 += __ldcg(pp + (size_t)(c + 7) * a.pstride);
+      }
+      for (; c < n_act; ++c) g0 += __ldcg(pp + (size_t)c * a.pstride);
+      const float g = ((g0 + g1) + (g2 + g3)) + ((g4 + g5) + (g6 + g7));
       if (a.mode == TRAIN_GRAD_ONLY) {
         a.grad_out[i] = g;
       } else if (i == P) {

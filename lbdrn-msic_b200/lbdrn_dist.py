@@ -62,6 +62,69 @@ def exchange_halos(stripe, D, group=None):
     return (buf.view(torch.uint16) if stripe.dtype == torch.uint16 else buf), (D if up is not None else 0)
 
 
+class StripeBuffer:
+    """This rank's stripe of the MSB image resident INSIDE a buffer that already has room for the halo rows, so a halo
+    swap moves only 2*D*W*C elements (no re-assembly of the stripe)."""
+
+    def __init__(self, H, W, C, D, dtype, device, group=None):
+        self.group, self.D, self.H = group, D, H
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.r0, self.r1 = stripe_bounds(H, self.world, self.rank)
+        self.top = D if (self.rank > 0 and D > 0) else 0
+        self.bot = D if (self.rank + 1 < self.world and D > 0) else 0
+        rows = self.r1 - self.r0
+        if self.world > 1 and rows < D:
+            raise ValueError("stripe thinner than the halo")
+        self.buf = torch.empty((C, self.top + rows + self.bot, W), dtype=dtype, device=device)
+        self.out = torch.empty_like(self.buf, dtype=torch.uint16)
+        wire_dtype = torch.int16 if dtype == torch.uint16 else dtype
+        mk = lambda: torch.empty((C, D, W), dtype=wire_dtype, device=device)
+        self._send_up, self._send_dn, self._recv_up, self._recv_dn = (mk() if self.top else None, mk() if self.bot else None,
+                                                                      mk() if self.top else None, mk() if self.bot else None)
+
+    def _wire(self, t):
+        return t.view(torch.int16) if t.dtype == torch.uint16 else t
+
+    @property
+    def own(self):
+        """[C, rows, W] view of this rank's own rows (fill it with the stripe, e.g. own.copy_(...))."""
+        return self._wire(self.buf)[:, self.top:self.top + (self.r1 - self.r0)]
+
+    def load(self, stripe):
+        self.own.copy_(self._wire(stripe), non_blocking=True)
+
+    def exchange(self):
+        """One D-row halo swap with each neighbouring stripe (NCCL send/recv over NVLink, or gloo on CPU)."""
+        if not (self.top or self.bot):
+            return
+        w, D, rows = self._wire(self.buf), self.D, self.r1 - self.r0
+        ops = []
+        if self.top:
+            self._send_up.copy_(w[:, self.top:self.top + D])
+            ops += [dist.P2POp(dist.isend, self._send_up, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, self._recv_up, self.rank - 1, self.group)]
+        if self.bot:
+            self._send_dn.copy_(w[:, self.top + rows - D:self.top + rows])
+            ops += [dist.P2POp(dist.isend, self._send_dn, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, self._recv_dn, self.rank + 1, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if self.top:
+            w[:, :D].copy_(self._recv_up)
+        if self.bot:
+            w[:, self.top + rows:].copy_(self._recv_dn)
+
+    def decode(self, flat_params_dev, K, bc, nl, flags, msb_max, relu=False, w0=30.0, path=cabi.PATH_AUTO, tab=None):
+        """Decode the stripe (halos must be current); returns the [C, buf_rows, W] output buffer and the slice of own rows."""
+        C, brows, W = self.buf.shape
+        d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), msb_max, self.buf.dtype == torch.uint16,
+                           row0=self.r0, row1=self.r1, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0,
+                           n_freq=flags.n_freq, path=path)
+        cabi.check(cabi.load().lbdrn_decode(ctypes.byref(d), cabi.ptr(self.buf), cabi.ptr(flat_params_dev), cabi.ptr(tab),
+                                            cabi.ptr(self.out), cabi.stream_ptr()))
+        return self.out, slice(self.top, self.top + (self.r1 - self.r0))
+
+
 def decode_stripe(stripe_msb, H, flat_params_dev, K, D, bc, nl, flags, msb_max, group=None, relu=False, w0=30.0,
                   path=cabi.PATH_AUTO, tab=None, halo=None):
     """Decode this rank's stripe of an H-row scene.  stripe_msb: [C, rows, W] CUDA tensor of the rank's OWN rows.

@@ -70,6 +70,12 @@ def _stripe_decode(rank, world):
     for name, path in (("precise", 1), ("auto", 0)):
         o = LD.decode_stripe(own, H, torch.from_numpy(params).cuda(), 5, 2, 64, 2, F.Flags(), mx, path=path)
         out[name] = o.cpu().numpy()
+    # the persistent-buffer variant used by bench.py produces the same rows
+    sb = LD.StripeBuffer(H, msb.shape[2], 4, 2, own.dtype, own.device)
+    sb.load(own)
+    sb.exchange()
+    o, rows = sb.decode(torch.from_numpy(params).cuda(), 5, 64, 2, F.Flags(), mx, path=1)
+    assert np.array_equal(o.cpu().numpy()[:, rows], out["precise"])
     return r0, r1, out, mx
 
 

@@ -1,0 +1,31 @@
+"""Time the fused training kernel: us/step for bs=8192 on a resident scene. usage: time_train.py side [epochs]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lbdrn-msic_b200"))
+import torch
+import lbdrn_fused as F
+from LBDRNmodel import LBDRNModel
+from synth_scene import make_scene_torch
+side = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+img = make_scene_torch(4, side, side, 12, device="cuda")
+scene = F.DeviceScene.from_image(img, 5)
+torch.manual_seed(19920517)
+model = LBDRNModel(100, 64, 4, 2)
+tr = F.FusedTrainer(model, scene, 2, 1e-3, 8192, 10, flags=F.Flags(), sampler="device")
+tr.begin()
+perm = torch.randperm(side * side, device="cuda")
+tr.train_epoch(perm, 1e-3)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+losses = tr.train_epoch(perm, 1e-3)
+e1.record()
+torch.cuda.synchronize()
+n = losses.numel()
+print(f"side={side} steps={n} {e0.elapsed_time(e1) * 1e3 / n:.2f} us/step  loss {losses[0].item():.5f} -> {losses[-1].item():.5f}")
+e0.record()
+mse = tr.scene_mse(tr.current_params())
+e1.record()
+torch.cuda.synchronize()
+print(f"eval pass {e0.elapsed_time(e1):.2f} ms  mse {mse:.5f}")
+tr.close()
