@@ -1,26 +1,34 @@
 // lbdrn_train_fp32.cu -- instantiations, planning and launch of the fused fp32 training kernel.
+#include <cstdio>
+#include <cstdlib>
+
 #include "lbdrn_train_fp32.cuh"
 #include "lbdrn_internal.h"
 
 namespace lbdrn {
 namespace {
 
+#ifndef LBDRN_TRAIN_THREADS
+#define LBDRN_TRAIN_THREADS 512
+#endif
+constexpr int kTT = LBDRN_TRAIN_THREADS;     // threads per CTA = 4*US warps working on one 64-pixel chunk
+
 template <int BC, int CP>
 int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
-  const size_t acts = ((size_t)t.dimpad + 2 * (size_t)n.nl * BC + 2 * CP) * kTrainLDP;
+  const size_t acts = ((size_t)t.dimpad + 2 * (size_t)n.nl * BC + (2 + kTT / 128) * CP) * kTrainLDP;
   const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
   const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
   if (with_w <= (size_t)max_smem) {
-    t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true>;
+    t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT>;
   } else if (without <= (size_t)max_smem) {
-    t.wsmem = false; t.smem = without; t.kernel = (void*)train_fp32_kernel<BC, CP, false>;
+    t.wsmem = false; t.smem = without; t.kernel = (void*)train_fp32_kernel<BC, CP, false, kTT>;
   } else {
     return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
                 without, BC, n.nl, n.dim_in);
   }
   CUDA_TRY(cudaFuncSetAttribute(t.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t.kernel, kThreads, t.smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t.kernel, kTT, t.smem));
   if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "training kernel cannot be made resident");
   const int cap = occ * sms;                  // cooperative launch: every CTA must be co-resident
   int want = (batch_size + kTrainNPIX - 1) / kTrainNPIX;
@@ -44,9 +52,25 @@ int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPl
 }
 
 int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
+  static long long* prof_dev = nullptr;
+  const bool prof = getenv("LBDRN_TRAIN_PROF") != nullptr;
+  if (prof) {
+    if (!prof_dev) CUDA_TRY(cudaMalloc(&prof_dev, 16 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), st));
+    a.prof = prof_dev;
+  }
   void* kargs[] = {(void*)&a};
-  CUDA_TRY(cudaLaunchCooperativeKernel(plan.kernel, dim3(plan.grid), dim3(kThreads), kargs, plan.smem, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel(plan.kernel, dim3(plan.grid), dim3(kTT), kargs, plan.smem, st));
   ++g_launches;
+  if (prof) {
+    long long h[16];
+    CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    static const char* names[8] = {"reload", "gather", "fwd", "out+loss", "bwd", "sync1", "reduce+adam", "sync2"};
+    fprintf(stderr, "[lbdrn] train phases (cycles/step on CTA 0, %d steps, grid %d x %d thr):", a.n_steps, plan.grid, kTT);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
+    fprintf(stderr, "\n");
+  }
   return LBDRN_OK;
 }
 

@@ -44,52 +44,8 @@ struct TrainArgs {
   float* losses;           // FUSED: [n_steps]
   float* grad_out;         // GRAD_ONLY: [P+1]
   int dimpad;              // dim_in rounded up to 8 (rows of the X buffer, padding rows are zero)
+  long long* prof;         // optional (LBDRN_TRAIN_PROF=1): clock64 cycles per phase accumulated by CTA 0 / thread 0
 };
-
-// out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin; dst is the natural [BC][Kin] gradient block.
-template <int BC>
-__device__ __forceinline__ void grad_weight_nt(const float* __restrict__ G, const float* __restrict__ A, int Kin,
-                                               int kpad8, float* __restrict__ dst, bool first) {
-  constexpr int LDP = kTrainLDP, RB = (BC < 64 ? BC : 64), RA = RB / 16;
-  const int tid = threadIdx.x, tc = tid & 7, tr = tid >> 3;
-  for (int r0 = 0; r0 < BC; r0 += RB) {
-    for (int q0 = 0; q0 < Kin; q0 += 64) {
-      float acc[RA][8];
-#pragma unroll
-      for (int x = 0; x < RA; ++x)
-#pragma unroll
-        for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
-      for (int p = 0; p < kTrainNPIX; p += 4) {
-        float4 gv[RA];
-#pragma unroll
-        for (int x = 0; x < RA; ++x) gv[x] = *reinterpret_cast<const float4*>(G + (size_t)(r0 + tr + 16 * x) * LDP + p);
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          if (q0 + 8 * y < kpad8) {
-            float4 av = *reinterpret_cast<const float4*>(A + (size_t)(q0 + tc + 8 * y) * LDP + p);
-#pragma unroll
-            for (int x = 0; x < RA; ++x) {
-              acc[x][y] = fmaf(gv[x].x, av.x, acc[x][y]);
-              acc[x][y] = fmaf(gv[x].y, av.y, acc[x][y]);
-              acc[x][y] = fmaf(gv[x].z, av.z, acc[x][y]);
-              acc[x][y] = fmaf(gv[x].w, av.w, acc[x][y]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int x = 0; x < RA; ++x)
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          int q = q0 + tc + 8 * y;
-          if (q < Kin) {
-            float* d = dst + (size_t)(r0 + tr + 16 * x) * Kin + q;
-            *d = first ? acc[x][y] : *d + acc[x][y];
-          }
-        }
-    }
-  }
-}
 
 __device__ __forceinline__ float row_sum64(const float* __restrict__ row) {
   float s = 0.f;
@@ -109,26 +65,6 @@ __device__ __forceinline__ float row_dot64(const float* __restrict__ a, const fl
     s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
   }
   return s;
-}
-
-// One band's (2D+1)^2 neighbourhood of one pixel: all loads are issued before the first use so their latencies overlap
-// (the naive dependent loop cost ~25 serialized global round trips per band).
-template <int N_>
-__device__ __forceinline__ void gather_band(const void* msb, int u16, size_t plane, int gy, int gx, const Net& net,
-                                            float ctr, bool ok, float* d) {
-  constexpr int D_ = N_ / 2;
-  uint32_t raw[N_ * N_];
-#pragma unroll
-  for (int dy = 0; dy < N_; ++dy) {
-    const size_t rowoff = (plane + (reflect_clamp(gy + dy - D_, net.H) - net.buf_row0)) * net.W;
-#pragma unroll
-    for (int dx = 0; dx < N_; ++dx) raw[dy * N_ + dx] = load_msb_int(msb, u16, rowoff + reflect_clamp(gx + dx - D_, net.W));
-  }
-#pragma unroll
-  for (int i = 0; i < N_ * N_; ++i) {
-    const float v = __fdiv_rn((float)raw[i], net.maxv) - ctr;
-    d[(size_t)i * kTrainLDP] = ok ? v : 0.f;
-  }
 }
 
 // index of parameter i inside the packed copy (hidden weights transposed)
@@ -153,12 +89,107 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
   p = p - step_size * __fdiv_rn(m, denom);               // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-template <int BC, int CP, bool WSMEM>
-__global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a) {
-  constexpr int TM = kTrainTM, NPIX = kTrainNPIX, LDP = kTrainLDP, TN = BC / 8;
+// load VEC consecutive floats
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float* out) {
+  if (VEC == 4) { float4 v = *reinterpret_cast<const float4*>(p); out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+  else if (VEC == 2) { float2 v = *reinterpret_cast<const float2*>(p); out[0] = v.x; out[1] = v.y; }
+  else out[0] = *p;
+}
+
+// acc[i][j] += sum_k act[k*LDP + pg*4 + i] * wt[k*BC + ubase + (j/VEC)*8*VEC + j%VEC]   (both operands k-major)
+template <int TN, int VEC, int BC>
+__device__ __forceinline__ void gemm_kmajor_v(float (&acc)[kTrainTM][TN], const float* __restrict__ act, const float* wt,
+                                              int K, int pg, int ubase) {
+  const float* a = act + pg * kTrainTM;
+  const float* b = wt + ubase;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    float av[4], bv[TN];
+    load_vec<4>(a + (size_t)k * kTrainLDP, av);
+#pragma unroll
+    for (int j = 0; j < TN; j += VEC) load_vec<VEC>(b + (size_t)k * BC + (j / VEC) * 8 * VEC, bv + j);
+#pragma unroll
+    for (int i = 0; i < kTrainTM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+// One row (fixed dy) of one band's neighbourhood of one pixel; loads issued before first use.
+template <int N_>
+__device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowoff, int gx, const Net& net, float ctr,
+                                           bool ok, float* d) {
+  constexpr int D_ = N_ / 2;
+  uint32_t raw[N_];
+#pragma unroll
+  for (int dx = 0; dx < N_; ++dx) raw[dx] = load_msb_int(msb, u16, rowoff + reflect_clamp(gx + dx - D_, net.W));
+#pragma unroll
+  for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? __fdiv_rn((float)raw[dx], net.maxv) - ctr : 0.f;
+}
+
+// out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin (dst = natural [BC][Kin] gradient block); THREADS/8 row
+// lanes x 8 column lanes, 64 rows x 64 columns per pass.
+template <int BC, int THREADS>
+__device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, const float* __restrict__ A, int Kin,
+                                                 int kpad8, float* __restrict__ dst, bool first) {
+  constexpr int LDP = kTrainLDP, NR = THREADS / 8, RA = 64 / NR;
+  const int tid = threadIdx.x, tc = tid & 7, tr = tid >> 3;
+  for (int r0 = 0; r0 < BC; r0 += 64) {
+    for (int q0 = 0; q0 < Kin; q0 += 64) {
+      float acc[RA][8];
+#pragma unroll
+      for (int x = 0; x < RA; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+      for (int p = 0; p < kTrainNPIX; p += 4) {
+        float4 gv[RA];
+#pragma unroll
+        for (int x = 0; x < RA; ++x) {
+          const int r = r0 + tr + NR * x;
+          gv[x] = r < BC ? *reinterpret_cast<const float4*>(G + (size_t)r * LDP + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          if (q0 + 8 * y < kpad8) {
+            float4 av = *reinterpret_cast<const float4*>(A + (size_t)(q0 + tc + 8 * y) * LDP + p);
+#pragma unroll
+            for (int x = 0; x < RA; ++x) {
+              acc[x][y] = fmaf(gv[x].x, av.x, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].y, av.y, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].z, av.z, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].w, av.w, acc[x][y]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < RA; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          const int q = q0 + tc + 8 * y, r = r0 + tr + NR * x;
+          if (q < Kin && r < BC) {
+            float* d = dst + (size_t)r * Kin + q;
+            *d = first ? acc[x][y] : *d + acc[x][y];
+          }
+        }
+    }
+  }
+}
+
+// THREADS = 128 * US: the chunk's 64 pixels x BC units are tiled as 16 pixel groups (4 px) x 8 lanes x US unit splits,
+// so one 64-pixel chunk is worked on by 4*US warps.  The step time is the latency of ONE chunk on ONE SM (every CTA
+// has at most one chunk per step at bs <= 64*grid), so more warps per chunk is what shortens the step.
+template <int BC, int CP, bool WSMEM, int THREADS>
+__global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) {
+  constexpr int TM = kTrainTM, NPIX = kTrainNPIX, LDP = kTrainLDP, US = THREADS / 128, TN = BC / 8 / US;
+  constexpr int VEC = TN >= 4 ? 4 : TN;
+  static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
   cg::grid_group grid = cg::this_grid();
   const Net& net = a.net;
-  const int tid = threadIdx.x, tn = tid & 7, pg = tid >> 3;
+  const int tid = threadIdx.x, us = tid >> 7, t128 = tid & 127, tn = t128 & 7, pg = t128 >> 3;
+  const int ubase = us * (BC / US) + tn * VEC;
+  auto unit = [&](int j) { return ubase + (j / VEC) * 8 * VEC + (j % VEC); };
   const int C = net.C, D = net.D, n = net.n, L = net.nl, P = net.P;
 
   // ---- shared memory carve-up ----------------------------------------------------------------------------
@@ -168,10 +199,11 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
   float* Gbuf = Hbuf + (size_t)L * BC * LDP;                    // [L][BC][LDP]    act' then dz
   float* dZo = Gbuf + (size_t)L * BC * LDP;                     // [CP][LDP]       output-layer dz
   float* Tl = dZo + CP * LDP;                                   // [CP][LDP]       labels
-  float* wsm = Tl + CP * LDP;                                   // packed weights [P] (+pad) then natural hidden l>=1
+  float* Pp = Tl + CP * LDP;                                    // [US][CP][LDP]   output-layer partial sums per unit split
+  float* wsm = Pp + US * CP * LDP;                              // packed weights [P] (+pad) then natural hidden l>=1
   float* wnat_sm = wsm + round4(P);
   __shared__ int s_py[NPIX], s_px[NPIX], s_valid[NPIX];
-  __shared__ float s_red[kThreads / 32];
+  __shared__ float s_red[THREADS / 32];
   __shared__ float s_sse;
   __shared__ float s_adam[2];
 
@@ -180,24 +212,38 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
   auto wnat = [&](int l) -> const float* {
     return WSMEM ? (wnat_sm + (size_t)(l - 1) * BC * BC) : (a.params + net.woff[l]);
   };
+  auto layer_sync = [&]() {
+    if (US == 1) __syncwarp();       // a pixel group's columns are private to its warp
+    else __syncthreads();            // columns are shared by the US warps holding different units
+  };
 
-  for (int i = net.dim_in * LDP + tid; i < a.dimpad * LDP; i += kThreads) X[i] = 0.f;   // padding rows stay zero
+  for (int i = net.dim_in * LDP + tid; i < a.dimpad * LDP; i += THREADS) X[i] = 0.f;   // padding rows stay zero
+  long long t_prev = 0;
+  const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  if (prof) t_prev = clock64();
+#define LBDRN_PHASE(idx)                                   \
+  if (prof) {                                              \
+    const long long t_now = clock64();                     \
+    a.prof[idx] += t_now - t_prev;                         \
+    t_prev = t_now;                                        \
+  }
 
   for (int s = 0; s < a.n_steps; ++s) {
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (WSMEM) {
       const int P4 = P >> 2;
-      for (int i = tid; i < P4; i += kThreads)
+      for (int i = tid; i < P4; i += THREADS)
         reinterpret_cast<float4*>(wsm)[i] = __ldcg(reinterpret_cast<const float4*>(a.wpack) + i);
-      for (int i = (P4 << 2) + tid; i < P; i += kThreads) wsm[i] = __ldcg(a.wpack + i);
+      for (int i = (P4 << 2) + tid; i < P; i += THREADS) wsm[i] = __ldcg(a.wpack + i);
       for (int l = 1; l < L; ++l) {
         const float4* src = reinterpret_cast<const float4*>(a.params + net.woff[l]);
         float4* dst = reinterpret_cast<float4*>(wnat_sm + (size_t)(l - 1) * BC * BC);
-        for (int i = tid; i < BC * BC / 4; i += kThreads) dst[i] = __ldcg(src + i);
+        for (int i = tid; i < BC * BC / 4; i += THREADS) dst[i] = __ldcg(src + i);
       }
     }
     if (tid == 0) s_sse = 0.f;
     __syncthreads();
+    LBDRN_PHASE(0)   // weight reload
 
     const long long b0 = a.mode == TRAIN_FUSED ? (long long)s * a.bs : 0;
     long long rem = a.n_perm - b0;
@@ -221,12 +267,13 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
       }
       __syncthreads();
       {
-        // thread = (pixel, band parity): labels, centre, neighbourhood straight from the resident planes
-        const int pp = tid & (NPIX - 1), share = tid >> 6;
+        // thread = (pixel, share); a share takes (band, window-row) items straight from the resident planes
+        constexpr int NSH = THREADS / NPIX;
+        const int pp = tid & (NPIX - 1), share = tid / NPIX;
         const int gy = s_py[pp], gx = s_px[pp];
         const bool ok = s_valid[pp] != 0;
         float* dst = X + pp;
-        if (net.nco && share == 0) {
+        if (net.nco && share == NSH - 1) {
           const float* trow = a.tab + (size_t)gy * net.tabw;
           const float* tcol = a.tab + (size_t)(net.H + gx) * net.tabw;
           for (int i = 0; i < net.tabw; ++i) {
@@ -234,32 +281,35 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
             dst[(size_t)(net.tabw + i) * LDP] = ok ? tcol[i] : 0.f;
           }
         }
-        for (int c = share; c < C; c += kThreads / NPIX) {
+        const int n_items = net.ncol ? C * n : C;
+        for (int it = share; it < n_items; it += NSH) {
+          const int c = net.ncol ? it / n : it, dy = net.ncol ? it - c * n : 0;
           const size_t plane = (size_t)c * net.buf_rows;
           const size_t off = (plane + (gy - net.buf_row0)) * net.W + gx;
-          const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
-          Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);          // label = LSB/(2^K-1)
+          if (dy == 0) {
+            const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+            Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);          // label = LSB/(2^K-1)
+          }
           if (net.ncol) {
             const float ctr = net.relative ? load_msb_norm(a.msb, net.msb_u16, off, net.maxv) : 0.f;
-            float* d = dst + (size_t)(net.nco + c * n * n) * LDP;
+            float* d = dst + (size_t)(net.nco + (c * n + dy) * n) * LDP;
+            const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
             switch (n) {
-              case 1: gather_band<1>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
-              case 3: gather_band<3>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
-              case 5: gather_band<5>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
-              case 7: gather_band<7>(a.msb, net.msb_u16, plane, gy, gx, net, ctr, ok, d); break;
+              case 1: gather_row<1>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
+              case 3: gather_row<3>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
+              case 5: gather_row<5>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
+              case 7: gather_row<7>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
               default:
-                for (int dy = 0; dy < n; ++dy) {
-                  const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
-                  for (int dx = 0; dx < n; ++dx, d += LDP) {
-                    float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), net.maxv) - ctr;
-                    *d = ok ? v : 0.f;
-                  }
+                for (int dx = 0; dx < n; ++dx, d += LDP) {
+                  float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), net.maxv) - ctr;
+                  *d = ok ? v : 0.f;
                 }
             }
           }
         }
       }
       __syncthreads();
+      LBDRN_PHASE(1)   // gather
 
       // ---- forward (LBDRNmodel.py:79-82), keeping h_l and act'(z_l) per layer ------------------------------
       float h[TM][TN];
@@ -271,11 +321,11 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
         float acc[TM][TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          float b = w[net.boff[l] + unit_of<TN>(j, tn)];
+          float b = w[net.boff[l] + unit(j)];
 #pragma unroll
           for (int i = 0; i < TM; ++i) acc[i][j] = b;
         }
-        gemm_kmajor<TM, TN, BC>(acc, in, LDP, w + net.woff[l], K, pg, tn);
+        gemm_kmajor_v<TN, VEC, BC>(acc, in, w + net.woff[l], K, pg, ubase);
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
           float g4[TM];
@@ -291,13 +341,14 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
               g4[i] = cs * net.w0;
             }
           }
-          size_t o = (size_t)unit_of<TN>(j, tn) * LDP + pg * TM;
+          size_t o = (size_t)unit(j) * LDP + pg * TM;
           *reinterpret_cast<float4*>(Hl + o) = make_float4(h[0][j], h[1][j], h[2][j], h[3][j]);
           *reinterpret_cast<float4*>(Gl + o) = make_float4(g4[0], g4[1], g4[2], g4[3]);
         }
-        __syncwarp();   // next layer reads only this warp's pixel columns
+        layer_sync();
       }
 
+      LBDRN_PHASE(2)   // hidden layers forward
       // ---- output layer + loss (LBDRNloss.py:9) ---------------------------------------------------------
       float part[TM * CP];
       const float* wo = w + net.woff[L];
@@ -308,27 +359,44 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
         if (c < C) {
 #pragma unroll
           for (int j = 0; j < TN; ++j) {
-            float wv = wo[c * BC + unit_of<TN>(j, tn)];
+            float wv = wo[c * BC + unit(j)];
 #pragma unroll
             for (int i = 0; i < TM; ++i) part[i * CP + c] = fmaf(wv, h[i][j], part[i * CP + c]);
           }
         }
       }
       group8_allreduce<TM * CP>(part);
+      if (US > 1) {
+        // cross-split sum through smem: lane tn == i publishes pixel i of its group
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+          if (i == tn)
+#pragma unroll
+            for (int c = 0; c < CP; ++c) Pp[(us * CP + c) * LDP + pg * TM + i] = part[i * CP + c];
+        __syncthreads();
+      }
       float sse = 0.f;
+      if (us == 0) {
 #pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        if (i == tn) {
-          int pp = pg * TM + i;
-          bool ok = s_valid[pp] != 0;
+        for (int i = 0; i < TM; ++i) {
+          if (i == tn) {
+            int pp = pg * TM + i;
+            bool ok = s_valid[pp] != 0;
 #pragma unroll
-          for (int c = 0; c < CP; ++c) {
-            if (c < C) {
-              float y = sigmoidf_rn(part[i * CP + c] + w[net.boff[L] + c]);
-              float d = y - Tl[c * LDP + pp];
-              float dz = ok ? (gscale * d) * ((1.0f - y) * y) : 0.f;   // mse backward then sigmoid backward
-              dZo[c * LDP + pp] = dz;
-              if (ok) sse += d * d;
+            for (int c = 0; c < CP; ++c) {
+              if (c < C) {
+                float z = part[i * CP + c];
+                if (US > 1) {
+                  z = 0.f;
+#pragma unroll
+                  for (int u2 = 0; u2 < US; ++u2) z += Pp[(u2 * CP + c) * LDP + pp];
+                }
+                float y = sigmoidf_rn(z + w[net.boff[L] + c]);
+                float d = y - Tl[c * LDP + pp];
+                float dz = ok ? (gscale * d) * ((1.0f - y) * y) : 0.f;   // mse backward then sigmoid backward
+                dZo[c * LDP + pp] = dz;
+                if (ok) sse += d * d;
+              }
             }
           }
         }
@@ -337,13 +405,18 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
       for (int off = 16; off > 0; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
       if ((tid & 31) == 0) s_red[tid >> 5] = sse;
       __syncthreads();
-      if (tid == 0) s_sse += (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+      if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < THREADS / 32; ++i) t += s_red[i];
+        s_sse += t;
+      }
 
+      LBDRN_PHASE(3)   // output layer + loss
       // ---- backward --------------------------------------------------------------------------------------
       // output layer: dW_o[c][n] = sum_p dz_o[c][p] h_L[n][p];  db_o[c] = sum_p dz_o[c][p]
       {
         const float* HL = Hbuf + (size_t)(L - 1) * BC * LDP;
-        for (int o = tid; o < C * BC; o += kThreads) {
+        for (int o = tid; o < C * BC; o += THREADS) {
           int c = o / BC, u = o - c * BC;
           float g = row_dot64(dZo + c * LDP, HL + (size_t)u * LDP);
           float* d = mypart + net.woff[L] + o;
@@ -370,7 +443,7 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
               float4 dv = *reinterpret_cast<const float4*>(dZo + c * LDP + pg * TM);
 #pragma unroll
               for (int j = 0; j < TN; ++j) {
-                float wv = wo[c * BC + unit_of<TN>(j, tn)];
+                float wv = wo[c * BC + unit(j)];
                 acc[0][j] = fmaf(wv, dv.x, acc[0][j]);
                 acc[1][j] = fmaf(wv, dv.y, acc[1][j]);
                 acc[2][j] = fmaf(wv, dv.z, acc[2][j]);
@@ -380,12 +453,12 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
           }
         } else {
           // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p]   (k-major in m on both operands)
-          gemm_kmajor<TM, TN, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, LDP, wnat(l + 1), BC, pg, tn);
+          gemm_kmajor_v<TN, VEC, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, pg, ubase);
         }
         // dz_l = dh_l * act'(z_l): thread-private read-modify-write of its own (unit, pixel) entries
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          float4* gp = reinterpret_cast<float4*>(Gl + (size_t)unit_of<TN>(j, tn) * LDP + pg * TM);
+          float4* gp = reinterpret_cast<float4*>(Gl + (size_t)unit(j) * LDP + pg * TM);
           float4 g = *gp;
           g.x *= acc[0][j]; g.y *= acc[1][j]; g.z *= acc[2][j]; g.w *= acc[3][j];
           *gp = g;
@@ -394,19 +467,21 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
         // dW_l = dz_l . in_l^T ; db_l = row sums
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
-        grad_weight_nt<BC>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
-        for (int u = tid; u < BC; u += kThreads) {
+        grad_weight_nt_t<BC, THREADS>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
+        for (int u = tid; u < BC; u += THREADS) {
           float g = row_sum64(Gl + (size_t)u * LDP);
           float* d = mypart + net.boff[l] + u;
           *d = first ? g : *d + g;
         }
       }
       first = false;
+      LBDRN_PHASE(4)   // backward
     }
     __syncthreads();
     if (tid == 0 && !first) mypart[P] = s_sse;
     __threadfence();
     grid.sync();
+    LBDRN_PHASE(5)   // fence + grid sync 1
 
     // ---- fixed-order reduction over the CTAs that produced partials, then Adam ----------------------------
     const int n_act = min((int)gridDim.x, n_chunks);
@@ -417,33 +492,49 @@ __global__ void __launch_bounds__(kThreads) train_fp32_kernel(const TrainArgs a)
       s_adam[1] = (float)sqrt(bc2);                 // bias_correction2_sqrt
     }
     __syncthreads();
-    for (int i = blockIdx.x * kThreads + tid; i <= P; i += gridDim.x * kThreads) {
-      // fixed summation order (deterministic), 8 independent loads in flight
-      float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
-      const float* pp = a.partial + i;
-      int c = 0;
-      for (; c + 8 <= n_act; c += 8) {
-        g0 += __ldcg(pp + (size_t)(c + 0) * a.pstride); g1 += __ldcg(pp + (size_t)(c + 1) * a.pstride);
-        g2 += __ldcg(pp + (size_t)(c + 2) * a.pstride); g3 += __ldcg(pp + (size_t)(c + 3) * a.pstride);
-        g4 += __ldcg(pp + (size_t)(c + 4) * a.pstride); g5 += __ldcg(pp + (size_t)(c + 5) * a.pstride);
-        g6 += __ldcg(pp + (size_t)(c + 6) * a.pstride); g7 += __ldcg(pp + (size_t)(c + 7) * a.pstride);
-      }
-      for (; c < n_act; ++c) g0 += __ldcg(pp + (size_t)c * a.pstride);
-      const float g = ((g0 + g1) + (g2 + g3)) + ((g4 + g5) + (g6 + g7));
-      if (a.mode == TRAIN_GRAD_ONLY) {
-        a.grad_out[i] = g;
-      } else if (i == P) {
-        a.losses[s] = g / ((float)B * (float)C);
-      } else {
-        float p = a.params[i], m = a.m[i], v = a.v[i];
-        adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
-        a.params[i] = p; a.m[i] = m; a.v[i] = v;
-        a.wpack[packed_index(net, i)] = p;
+    {
+      // 4 lanes per parameter: lane `sub` sums partials sub, sub+4, ... (8 loads in flight), then a fixed-order shuffle
+      // tree combines them -- deterministic, and every thread of the grid takes part.
+      const int gt = blockIdx.x * THREADS + tid, sub = gt & 3, stride = (gridDim.x * THREADS) >> 2;
+      const int iters = (P + 1 + stride - 1) / stride;
+      for (int it = 0; it < iters; ++it) {
+        const int i = (gt >> 2) + it * stride;
+        const bool in = i <= P;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
+        if (in) {
+          const float* pp = a.partial + i;
+          int c = sub;
+          for (; c + 28 < n_act; c += 32) {
+            g0 += __ldcg(pp + (size_t)(c + 0) * a.pstride);  g1 += __ldcg(pp + (size_t)(c + 4) * a.pstride);
+            g2 += __ldcg(pp + (size_t)(c + 8) * a.pstride);  g3 += __ldcg(pp + (size_t)(c + 12) * a.pstride);
+            g4 += __ldcg(pp + (size_t)(c + 16) * a.pstride); g5 += __ldcg(pp + (size_t)(c + 20) * a.pstride);
+            g6 += __ldcg(pp + (size_t)(c + 24) * a.pstride); g7 += __ldcg(pp + (size_t)(c + 28) * a.pstride);
+          }
+          for (; c < n_act; c += 4) g0 += __ldcg(pp + (size_t)c * a.pstride);
+        }
+        float g = ((g0 + g1) + (g2 + g3)) + ((g4 + g5) + (g6 + g7));
+        g += __shfl_xor_sync(0xffffffffu, g, 1);
+        g += __shfl_xor_sync(0xffffffffu, g, 2);
+        if (in && sub == 0) {
+          if (a.mode == TRAIN_GRAD_ONLY) {
+            a.grad_out[i] = g;
+          } else if (i == P) {
+            a.losses[s] = g / ((float)B * (float)C);
+          } else {
+            float p = a.params[i], m = a.m[i], v = a.v[i];
+            adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
+            a.params[i] = p; a.m[i] = m; a.v[i] = v;
+            a.wpack[packed_index(net, i)] = p;
+          }
+        }
       }
     }
+    LBDRN_PHASE(6)   // reduce + Adam
     __threadfence();
     grid.sync();
+    LBDRN_PHASE(7)   // fence + grid sync 2
   }
+#undef LBDRN_PHASE
 }
 
 // Adam on an externally reduced gradient (data-parallel mode) + packed-copy refresh.

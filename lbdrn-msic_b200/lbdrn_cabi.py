@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblbdrn_b200.so")
+LIB_PATH = os.environ.get("LBDRN_LIB", os.path.join(HERE, "liblbdrn_b200.so"))
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4
 USE_COORDINATES, EMBEDDING, USE_COLORS, RELATIVE, ACT_RELU = 1, 2, 4, 8, 16

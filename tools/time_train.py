@@ -7,11 +7,12 @@ import lbdrn_fused as F
 from LBDRNmodel import LBDRNModel
 from synth_scene import make_scene_torch
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+bs = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 img = make_scene_torch(4, side, side, 12, device="cuda")
 scene = F.DeviceScene.from_image(img, 5)
 torch.manual_seed(19920517)
 model = LBDRNModel(100, 64, 4, 2)
-tr = F.FusedTrainer(model, scene, 2, 1e-3, 8192, 10, flags=F.Flags(), sampler="device")
+tr = F.FusedTrainer(model, scene, 2, 1e-3, bs, 10, flags=F.Flags(), sampler="device")
 tr.begin()
 perm = torch.randperm(side * side, device="cuda")
 tr.train_epoch(perm, 1e-3)
@@ -22,7 +23,7 @@ losses = tr.train_epoch(perm, 1e-3)
 e1.record()
 torch.cuda.synchronize()
 n = losses.numel()
-print(f"side={side} steps={n} {e0.elapsed_time(e1) * 1e3 / n:.2f} us/step  loss {losses[0].item():.5f} -> {losses[-1].item():.5f}")
+print(f"side={side} bs={bs} steps={n} {e0.elapsed_time(e1) * 1e3 / n:.2f} us/step  loss {losses[0].item():.5f} -> {losses[-1].item():.5f}")
 e0.record()
 mse = tr.scene_mse(tr.current_params())
 e1.record()
