@@ -40,7 +40,9 @@ struct TcHeader {
   int nl;
   float scale[kMaxLayers];   // per hidden layer: multiply the fp32 accumulator by this (2^-s, and /max for layer 0)
   int off_bias, off_w3, off_b[kMaxLayers], total;   // byte offsets inside the block
-  int pad[8];
+  int off_blo[kMaxLayers];   // low-order fp16 term of the weights (W*2^s = hi + lo); all zero when `exact`
+  int hi_bytes;              // block size without the lo operands (what the exact-weights kernel copies)
+  int pad[7];
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -61,6 +63,12 @@ void plan_block(const Net& n, TcHeader& h) {
   off = align_up(off, 128);
   for (int l = 0; l < n.nl; ++l) {
     h.off_b[l] = off;
+    off += (l == 0 ? h.k1pad : TC_BC) * TC_BC * 2;
+  }
+  h.hi_bytes = align_up(off, 16);
+  off = h.hi_bytes;
+  for (int l = 0; l < n.nl; ++l) {
+    h.off_blo[l] = off;
     off += (l == 0 ? h.k1pad : TC_BC) * TC_BC * 2;
   }
   h.total = align_up(off, 16);
@@ -89,13 +97,16 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
     const int s = (m > 0.f && isfinite(m)) ? 13 - ilogbf(m) : 0;       // max|W| * 2^s in [2^13, 2^14)
     const float up = ldexpf(1.0f, s);
     __half* B = reinterpret_cast<__half*>(blk + hdr.off_b[l]);
+    __half* Blo = reinterpret_cast<__half*>(blk + hdr.off_blo[l]);
     int bad = 0;
     for (int i = tid; i < K * net.bc; i += blockDim.x) {
       const int nrow = i / K, k = i - nrow * K;
       const float v = W[i] * up;                                          // exact (power of two)
       const __half hv = __float2half_rn(v);
-      if (__half2float(hv) != v) bad = 1;
+      const float rem = v - __half2float(hv);                             // exact in fp32
+      if (rem != 0.f) bad = 1;
       B[umma_off(TC_BC, nrow, k) / 2] = hv;
+      Blo[umma_off(TC_BC, nrow, k) / 2] = __float2half_rn(rem);           // second term: |err| <= 2^-22 |v|
     }
     if (bad) atomicAnd(&s_exact, 0);
     // sine path: a = w0*(acc*scale + b) is evaluated as one FFMA, acc*(w0*scale) + w0*b (w0 folded here)
@@ -114,8 +125,8 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
   if (tid == 0) {
     H->exact = s_exact;
     H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl;
-    H->off_bias = hdr.off_bias; H->off_w3 = hdr.off_w3; H->total = hdr.total;
-    for (int l = 0; l < net.nl; ++l) H->off_b[l] = hdr.off_b[l];
+    H->off_bias = hdr.off_bias; H->off_w3 = hdr.off_w3; H->total = hdr.total; H->hi_bytes = hdr.hi_bytes;
+    for (int l = 0; l < net.nl; ++l) { H->off_b[l] = hdr.off_b[l]; H->off_blo[l] = hdr.off_blo[l]; }
   }
 }
 
@@ -188,8 +199,14 @@ struct TcArgs {
   uint16_t* out;
   int tiles_x, n_tiles;
   int a_bytes, w_bytes;   // smem: A region, weight block copy
-  int selftest;           // !=0: GEMM self-test mode (see tc_selftest_kernel)
+  int run_if_exact;       // 1: run only when the weights are fp16-exact; 0: only when they are not; -1: always
+  const void* lsb;        // SSE mode: LSB codes
+  double* partials;       // SSE mode: [gridDim.x]
+  unsigned int* counter;  // SSE mode: zero on entry / exit
+  double* sse_out;        // SSE mode
 };
+
+enum { TC_DECODE = 0, TC_SSE = 1 };
 
 // sin(w0 z): FAST = 3-term Cody-Waite to [-pi, pi] then MUFU.SIN (abs err ~4e-7); else the 7e-8 polynomial version
 template <bool FAST>
@@ -205,8 +222,10 @@ __device__ __forceinline__ float tc_sine(float a) {
 constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+2D)*(16+2D) <= 2048)
 
 // CC/DD > 0: bands / radius known at compile time (feature offsets fold into immediates); CC == 0: generic tables.
-template <bool FAST, int CC, int DD>
-__global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a) {
+// WLO: the weights carry a low-order fp16 term (fp32 weights during training / -prec 32 streams): extra MMAs against
+// the lo operands.  MODE: TC_DECODE writes the reconstruction, TC_SSE accumulates sum((y - label)^2) (encode.py:105-108).
+template <bool FAST, int CC, int DD, bool WLO, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(const TcArgs a) {
   const Net& net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = CC ? CC : net.C, D = CC ? DD : net.D, n = 2 * D + 1;
@@ -230,7 +249,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a
   }
   __syncthreads();
   const TcHeader* H = reinterpret_cast<const TcHeader*>(sW);
-  if (!H->exact) return;                       // inexact weights: the fp32 kernel launched behind us does the work
+  if (a.run_if_exact >= 0 && (H->exact != 0) != (a.run_if_exact != 0)) return;   // the sibling launch handles this scene
+  __shared__ double s_red[TC_THREADS / 32];
+  double sse_local = 0.0;
   const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
   for (int k = tid; k < k1pad; k += TC_THREADS) {
     int off = 0, ctr = 0;
@@ -380,13 +401,20 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a
       if (tid == 0) {
         tc_fence_after();
         const uint32_t sB_u = smem_u32(sW + H->off_b[l]);
+        const uint32_t sBlo_u = smem_u32(sW + H->off_blo[l]);
         if (l == 0) {
           for (int i = 0; i < k1pad / 16; ++i)
             umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128), umma_desc(sB_u + i * 2 * 1024, 1024, 128), idesc, i > 0);
+          if (WLO)
+            for (int i = 0; i < k1pad / 16; ++i)
+              umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128), umma_desc(sBlo_u + i * 2 * 1024, 1024, 128), idesc, 1);
         } else {
           for (int i = 0; i < 2 * TC_BC / 16; ++i)       // hi half then lo half of A2, both against the same B_l
             umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128),
                      umma_desc(sB_u + (i % (TC_BC / 16)) * 2 * 1024, 1024, 128), idesc, i > 0);
+          if (WLO)                                       // hi half of A2 against the low-order weight term
+            for (int i = 0; i < TC_BC / 16; ++i)
+              umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128), umma_desc(sBlo_u + i * 2 * 1024, 1024, 128), idesc, 1);
         }
         umma_commit(mbar);
       }
@@ -459,15 +487,41 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_decode_kernel(const TcArgs a
       for (int c = 0; c < kMaxC; ++c) {
         if (c < C) {
           const float y = sigmoidf_rn(yacc[c] + w3t[TC_BC * 8 + c]);
-          const int res = (int)rintf(y * net.qmax);
-          a.out[((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx] = (uint16_t)((mctr[c] << net.K) + (uint32_t)res);
+          const size_t off = ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx;
+          if (MODE == TC_DECODE) {
+            const int res = (int)rintf(y * net.qmax);
+            a.out[off] = (uint16_t)((mctr[c] << net.K) + (uint32_t)res);
+          } else {
+            const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+            const float d = y - __fdiv_rn((float)code, net.qmax);
+            sse_local += (double)(d * d);
+          }
         }
       }
     }
     tc_fence_before();      // our tcgen05.ld's are ordered before the next tile's MMA (issued after the next barrier)
   }
 
+  if (MODE == TC_SSE) {
+    // deterministic: lanes -> warp -> CTA partial -> the last CTA sums the partials in index order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sse_local += __shfl_xor_sync(0xffffffffu, sse_local, off);
+    if ((tid & 31) == 0) s_red[warp] = sse_local;
+  }
   __syncthreads();
+  if (MODE == TC_SSE && tid == 0) {
+    double sum = 0.0;
+    for (int i = 0; i < TC_THREADS / 32; ++i) sum += s_red[i];
+    a.partials[blockIdx.x] = sum;
+    __threadfence();
+    if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {
+      __threadfence();
+      double tot = 0.0;
+      for (unsigned int i = 0; i < gridDim.x; ++i) tot += ((volatile double*)a.partials)[i];
+      *a.sse_out = tot;
+      *a.counter = 0u;
+    }
+  }
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
 }
@@ -535,54 +589,39 @@ bool tc_supported(const Net& n) {
          n.nl >= 1 && n.nl <= 4;
 }
 
-int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
-              cudaStream_t st) {
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
-  {
-    std::lock_guard<std::mutex> lk(tc_mu());
-    if (!g_blk[dev]) CUDA_TRY(cudaMalloc(&g_blk[dev], kBlkBytes));
-  }
-  TcHeader h;
-  plan_block(n, h);
-  if (h.total > kBlkBytes) return fail(LBDRN_E_UNSUPPORTED, "tensor-core weight block too large (%d B)", h.total);
-  tc_prep_kernel<<<1, 1024, 0, st>>>(n, h, params, g_blk[dev]);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+namespace {
 
-  TcArgs a;
-  memset(&a, 0, sizeof a);
-  a.net = n; a.msb = msb; a.blk = g_blk[dev]; a.out = out;
-  a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
-  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
+using KernT = void (*)(const TcArgs);
+
+template <bool FAST, bool WLO, int MODE>
+KernT pick_kernel(const Net& n) {
+  if (n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE>;
+  if (n.C == 8 && n.D == 2) return tc_decode_kernel<FAST, 8, 2, WLO, MODE>;
+  if (n.C == 4 && n.D == 1) return tc_decode_kernel<FAST, 4, 1, WLO, MODE>;
+  if (n.C == 4 && n.D == 3) return tc_decode_kernel<FAST, 4, 3, WLO, MODE>;
+  return tc_decode_kernel<FAST, 0, 0, WLO, MODE>;
+}
+
+// one launch of the tensor kernel family (wlo: smem holds the low-order weight operands too)
+int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int dev, cudaStream_t st) {
+  const Net& n = a.net;
   const int kmax = h.k1pad > 2 * TC_BC ? h.k1pad : 2 * TC_BC;
   a.a_bytes = align_up(128 * kmax * 2, 1024);
-  a.w_bytes = h.total;
+  a.w_bytes = wlo ? h.total : h.hi_bytes;
   const size_t smem = (size_t)a.a_bytes + a.w_bytes + align_up(n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D), 8) * 2 +
                       2 * (TC_MAX_K1 + 16) * 2 + 64;
-  int sms = 0, max_smem = 0;
+  int sms = 0, max_smem = 0, smem_sm = 0, regs_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
   if (smem > (size_t)max_smem) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode needs %zu B of shared memory", smem);
-  using KernT = void (*)(const TcArgs);
-  KernT kern;
-#define LBDRN_TC_PICK(CC, DD) (fast_sine ? (KernT)tc_decode_kernel<true, CC, DD> : (KernT)tc_decode_kernel<false, CC, DD>)
-  if (n.C == 4 && n.D == 2) kern = LBDRN_TC_PICK(4, 2);
-  else if (n.C == 8 && n.D == 2) kern = LBDRN_TC_PICK(8, 2);
-  else if (n.C == 4 && n.D == 1) kern = LBDRN_TC_PICK(4, 1);
-  else if (n.C == 4 && n.D == 3) kern = LBDRN_TC_PICK(4, 3);
-  else kern = LBDRN_TC_PICK(0, 0);
-#undef LBDRN_TC_PICK
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // Resident CTAs per SM.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that allocate tensor
   // memory (measured on B200 / CUDA 12.9) although the hardware co-schedules as many CTAs as shared memory, registers
   // and the 512 TMEM columns allow (3 here: 4.3 vs 1.7 Gpix/s), so the limit is computed from the kernel's attributes.
   cudaFuncAttributes fa;
   CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
-  int smem_sm = 0, regs_sm = 0;
-  CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
   int occ = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));   // +1 KB: per-CTA reservation of the driver
   const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS;
   if (regs_cta > 0 && regs_sm / regs_cta < occ) occ = regs_sm / regs_cta;
@@ -590,25 +629,69 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
   if (occ > 3) occ = 3;                                           // measured optimum (4 CTAs: 3.0 vs 4.3 Gpix/s)
   if (const char* e = getenv("LBDRN_TC_OCC")) occ = atoi(e);
   if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
-  if (getenv("LBDRN_DEBUG"))
-    fprintf(stderr, "[lbdrn] tc_decode: smem dyn %zu static %zu regs %d occ %d sms %d tiles %d\n", smem,
-            fa.sharedSizeBytes, fa.numRegs, occ, sms, a.n_tiles);
+  a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
+  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
   int grid = sms * occ;                                          // persistent: whole CTAs per SM
   if (grid > a.n_tiles) grid = a.n_tiles;
+  if (getenv("LBDRN_DEBUG"))
+    fprintf(stderr, "[lbdrn] tc kernel: smem dyn %zu static %zu regs %d occ %d grid %d tiles %d wlo %d\n", smem,
+            fa.sharedSizeBytes, fa.numRegs, occ, grid, a.n_tiles, (int)wlo);
   kern<<<grid, TC_THREADS, smem, st>>>(a);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
 
-  // fp32 kernel behind it, skipped on the device when the tensor kernel handled the scene (weights exact)
-  Scratch* sc = nullptr;
-  int rc = get_scratch(n.P, sc);
+int tc_prepare(const Net& n, const float* params, TcHeader& h, uint8_t*& blk, int& dev, cudaStream_t st) {
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
+  {
+    std::lock_guard<std::mutex> lk(tc_mu());
+    if (!g_blk[dev]) CUDA_TRY(cudaMalloc(&g_blk[dev], kBlkBytes));
+  }
+  blk = g_blk[dev];
+  plan_block(n, h);
+  if (h.total > kBlkBytes) return fail(LBDRN_E_UNSUPPORTED, "tensor-core weight block too large (%d B)", h.total);
+  tc_prep_kernel<<<1, 1024, 0, st>>>(n, h, params, blk);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+}  // namespace
+
+int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
+              cudaStream_t st) {
+  (void)tab;
+  TcHeader h;
+  uint8_t* blk = nullptr;
+  int dev = 0, rc = tc_prepare(n, params, h, blk, dev, st);
   if (rc) return rc;
-  launch_pack_params(n, params, sc->wpack, st);
-  InferArgs ia;
-  memset(&ia, 0, sizeof ia);
-  ia.net = n; ia.msb = msb; ia.wpack = sc->wpack; ia.tab = tab; ia.out = out;
-  ia.skip_flag = reinterpret_cast<const int*>(g_blk[dev]);       // TcHeader::exact
-  return infer_fp32_decode(ia, *sc, st);
+  TcArgs a;
+  memset(&a, 0, sizeof a);
+  a.net = n; a.msb = msb; a.blk = blk; a.out = out;
+  // two sibling launches; the exactness flag computed by tc_prep_kernel decides ON THE DEVICE which one does the work
+  a.run_if_exact = 1;
+  rc = tc_launch(fast_sine ? pick_kernel<true, false, TC_DECODE>(n) : pick_kernel<false, false, TC_DECODE>(n), a, h, false, dev, st);
+  if (rc) return rc;
+  a.run_if_exact = 0;
+  return tc_launch(fast_sine ? pick_kernel<true, true, TC_DECODE>(n) : pick_kernel<false, true, TC_DECODE>(n), a, h, true, dev, st);
+}
+
+int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st) {
+  TcHeader h;
+  uint8_t* blk = nullptr;
+  int dev = 0, rc = tc_prepare(n, params, h, blk, dev, st);
+  if (rc) return rc;
+  Scratch* sc = nullptr;
+  rc = get_scratch(n.P, sc);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof a);
+  a.net = n; a.msb = msb; a.blk = blk; a.lsb = lsb;
+  a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
+  a.run_if_exact = -1;
+  return tc_launch(pick_kernel<true, true, TC_SSE>(n), a, h, true, dev, st);
 }
 
 int tc_selftest(const void* a_dev, const void* b_dev, float* d_dev, int K, cudaStream_t st) {

@@ -119,18 +119,25 @@ def test_decode_k_sweep_identity_fraction():
     print({k: round(v, 6) for k, v in report.items()})
 
 
-def test_tensor_path_falls_back_on_device_for_inexact_weights():
-    """Weights that are not fp16-exact after scaling (e.g. a -prec 32 stream) are detected on the device: the tensor
-    kernel exits and the fp32 kernel behind it produces the result -- identical to the precise path."""
+def test_tensor_path_with_full_precision_weights():
+    """Weights that are not fp16-exact after scaling (a -prec 32 stream, or the fp32 weights evaluated during training)
+    are detected on the device; the sibling launch with the low-order weight term (W = hi + lo) does the work and meets
+    the same parity bar against the oracle.  Full-scene MSE through the tensor path matches the oracle too."""
     from synth_scene import make_scene
-    img = make_scene(4, 100, 120, 12, seed=8)
-    msb, _ = O.split_msb_lsb(img, 5)
-    torch.manual_seed(5)
     from LBDRNmodel import LBDRNModel
-    flat = LBDRNModel(100, 64, 4, 2).flat_params().numpy()          # full fp32 mantissas
-    a = F.decode_image(msb, flat, 5, 2, 64, 2, flags=F.Flags(), path="tensor")
-    b = F.decode_image(msb, flat, 5, 2, 64, 2, flags=F.Flags(), path="precise")
-    assert np.array_equal(a, b)
+    img = make_scene(4, 200, 240, 12, seed=8)
+    msb, lsb = O.split_msb_lsb(img, 5)
+    flat = _trained_params().astype(np.float64)
+    rng = np.random.default_rng(3)
+    flat = (flat * (1.0 + 1e-4 * rng.standard_normal(flat.size))).astype(np.float32)     # full fp32 mantissas
+    p = O.unflatten_params(flat, 100, 64, 4, 2)
+    ref = O.decode_image(msb, p, 5, 2)
+    for path in ("tensor", "tensor_fastsin", "precise"):
+        _check(F.decode_image(msb, flat, 5, 2, 64, 2, flags=F.Flags(), path=path), ref, f"fp32-weights/{path}")
+    scene = F.DeviceScene.from_image(img, 5)
+    mse = F.eval_mse(scene, torch.from_numpy(flat).cuda(), 2, 64, 2, flags=F.Flags())
+    assert mse == pytest.approx(O.eval_mse(msb, lsb, p, 2), rel=1e-5)
+    assert mse == F.eval_mse(scene, torch.from_numpy(flat).cuda(), 2, 64, 2, flags=F.Flags())   # deterministic
 
 
 def test_stripe_decode_is_bit_identical_to_whole_image():

@@ -24,9 +24,11 @@ e1.record()
 torch.cuda.synchronize()
 n = losses.numel()
 print(f"side={side} bs={bs} steps={n} {e0.elapsed_time(e1) * 1e3 / n:.2f} us/step  loss {losses[0].item():.5f} -> {losses[-1].item():.5f}")
-e0.record()
-mse = tr.scene_mse(tr.current_params())
-e1.record()
-torch.cuda.synchronize()
-print(f"eval pass {e0.elapsed_time(e1):.2f} ms  mse {mse:.5f}")
+cur = tr.current_params()
+for _ in range(3):
+    e0.record()
+    mse = tr.scene_mse(cur)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"eval pass {e0.elapsed_time(e1):.2f} ms  mse {mse:.7f}")
 tr.close()
