@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
                 sys.stderr.write(f"[build_ext] {name} failed:\n{out[-6000:]}\n")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not failed:
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs      # cudart is linked statically; no libcuda dependency
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log.append("### link\n" + " ".join(cmd) + "\n" + r.stdout)
         failed = r.returncode != 0

@@ -15,6 +15,7 @@
 //
 // Weights that are NOT exactly representable (e.g. -prec 32 streams) are detected by the prep kernel on the device;
 // the tensor kernel then exits immediately and the fp32 kernel, launched behind it with the same flag, does the work.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -161,9 +162,11 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+__device__ int g_tc_timeout[4];   // diagnostics: {which barrier, tile, block, count}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity, int what = 0, int tile = -1, int no_trap = 0) {
   // bounded: a lost arrival traps (surfacing as a CUDA error) instead of hanging the GPU
-  for (int it = 0; it < (1 << 24); ++it) {
+  for (int it = 0; it < (1 << 22); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -172,7 +175,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         : "memory");
     if (ok) return;
   }
+  if (threadIdx.x == 0) {
+    g_tc_timeout[0] = what; g_tc_timeout[1] = tile; g_tc_timeout[2] = blockIdx.x;
+    atomicAdd(&g_tc_timeout[3], 1);
+    __threadfence_system();
+  }
+  if (no_trap) return;      // LBDRN_DEBUG: let the kernel finish (garbage output) so the host can read the diagnostics
+  __nanosleep(1000000);
   __trap();
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+
+// TMA: one 3-D box (x, y, band) of the MSB planes -> shared memory; out-of-range elements are zero-filled
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar)
+      : "memory");
 }
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -193,6 +215,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 struct TcArgs {
+  const CUtensorMap* tmap_dev;  // 3-D tiled map of the MSB buffer (W, buf_rows, C) in global memory; valid when use_tma
+  int no_trap;            // debug: do not trap on a barrier timeout
+  int use_tma, box_w, box_lead;  // TMA patch staging for interior tiles: the box starts `box_lead` elements left of the
+                                 // tile (a multiple of 16 B: the innermost TMA coordinate must be 16 B-aligned --
+                                 // measured: an unaligned start raises "illegal instruction") and is box_w wide
   Net net;
   const void* msb;
   const uint8_t* blk;     // packed weight block (TcHeader + operands) in global memory
@@ -238,6 +265,8 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
   __half* patch = reinterpret_cast<__half*>(sW + a.w_bytes);
   uint16_t* koff = reinterpret_cast<uint16_t*>(patch + align_up(C * trows * twp, 8));   // [k1pad] patch offset of feature k
   uint16_t* kctr = koff + TC_MAX_K1 + 16;                                                // [k1pad] patch offset of its centre
+  uint8_t* raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(kctr + TC_MAX_K1 + 16) + 127) & ~(uintptr_t)127);  // TMA box
+  __shared__ __align__(8) uint64_t s_mbar_tma;
   __shared__ __align__(8) uint64_t s_mbar;
   __shared__ uint32_t s_tmem;
 
@@ -268,7 +297,10 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_mbar), 1);
+    mbar_init(smem_u32(&s_mbar_tma), 1);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -313,13 +345,58 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
       }
     }
   };
-  if (pf_ok && (int)blockIdx.x < a.n_tiles) issue_patch_loads(blockIdx.x);
+  // TMA staging of interior tiles: one elected thread issues the box load for the NEXT tile; it lands in `raw` while
+  // this tile computes and is converted to fp16 at the top of the next iteration.  Border tiles (reflection needed) and
+  // buffers TMA cannot address (row pitch not a multiple of 16 B) use the per-thread prefetch above.
+  const uint32_t mbar_tma = smem_u32(&s_mbar_tma), raw_u = smem_u32(raw);
+  const int es = net.msb_u16 ? 2 : 1, box_w = a.box_w;
+  const uint32_t box_bytes = (uint32_t)(box_w * trows * C * es);
+  auto tile_uses_tma = [&](int tile) {
+    if (!a.use_tma) return false;
+    const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
+    return y0 >= 0 && x0 >= 0 && y0 + trows <= net.H && x0 + twp <= net.W;
+  };
+  auto stage_next = [&](int tile) {            // called by all threads; exactly one of the two mechanisms is used
+    if (tile >= a.n_tiles) return;
+    if (tile_uses_tma(tile)) {
+      if (tid == 0) {
+        const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
+        mbar_expect_tx(mbar_tma, box_bytes);
+        tma_load_3d(raw_u, a.tmap_dev, x0 + D - a.box_lead, y0 - net.buf_row0, 0, mbar_tma);
+      }
+    } else if (pf_ok) {
+      issue_patch_loads(tile);
+    }
+  };
+  uint32_t phase_tma = 0;
+  stage_next(blockIdx.x);
 
   for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
 
     // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
-    if (pf_ok) {
+    if (tile_uses_tma(t)) {
+      mbar_wait(mbar_tma, phase_tma, 2, t, a.no_trap);
+      phase_tma ^= 1;
+      if (pf_ok) {                                                   // element -> (band,row,col) precomputed in pe[]
+#pragma unroll
+        for (int i = 0; i < TC_PF; ++i) {
+          if (pe[i] >= 0) {
+            const int src = ((pe[i] >> 16) * trows + ((pe[i] >> 8) & 255)) * box_w + (a.box_lead - D) + (pe[i] & 255);
+            const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[src] : (uint32_t)raw[src];
+            patch[tid + i * TC_THREADS] = __uint2half_rn(v);
+          }
+        }
+      } else {
+        for (int e = tid; e < n_patch; e += TC_THREADS) {
+          const int row = e / twp, x = e - row * twp;               // row = band * trows + patch row
+          const int src = row * box_w + (a.box_lead - D) + x;
+          const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[src] : (uint32_t)raw[src];
+          patch[e] = __uint2half_rn(v);
+        }
+      }
+      fence_async_smem();      // our generic-proxy reads of `raw` are ordered before the next TMA write into it
+    } else if (pf_ok) {
 #pragma unroll
       for (int i = 0; i < TC_PF; ++i)
         if (pe[i] >= 0) patch[tid + i * TC_THREADS] = __uint2half_rn(pf[i]);
@@ -331,7 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
       }
     }
     __syncthreads();
-    if (pf_ok && t + (int)gridDim.x < a.n_tiles) issue_patch_loads(t + gridDim.x);   // lands while this tile computes
+    stage_next(t + gridDim.x);                                                       // lands while this tile computes
 
     // ---- A1 row of this thread's pixel: integer differences (exact in fp16), 16 B per K chunk ---------------------------
     const int pr = tid >> 4, px = tid & 15;
@@ -418,7 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
         }
         umma_commit(mbar);
       }
-      mbar_wait(mbar, phase);
+      mbar_wait(mbar, phase, 1, t, a.no_trap);
       phase ^= 1;
       tc_fence_after();
 
@@ -608,8 +685,10 @@ int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int dev, cudaS
   const int kmax = h.k1pad > 2 * TC_BC ? h.k1pad : 2 * TC_BC;
   a.a_bytes = align_up(128 * kmax * 2, 1024);
   a.w_bytes = wlo ? h.total : h.hi_bytes;
+  const int es_ = n.msb_u16 ? 2 : 1, al_ = 16 / es_, lead_ = (n.D + al_ - 1) / al_ * al_;
+  const int raw_bytes = (2 * lead_ + TC_TW) * es_ * (TC_TH + 2 * n.D) * n.C;
   const size_t smem = (size_t)a.a_bytes + a.w_bytes + align_up(n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D), 8) * 2 +
-                      2 * (TC_MAX_K1 + 16) * 2 + 64;
+                      2 * (TC_MAX_K1 + 16) * 2 + 64 + 128 + raw_bytes;
   int sms = 0, max_smem = 0, smem_sm = 0, regs_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -631,14 +710,65 @@ int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int dev, cudaS
   if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
   a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
   a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
+  // TMA descriptor of the MSB planes: dims (W, buf_rows, C); needs 16 B-aligned base and row / plane pitches
+  {
+    const int es = n.msb_u16 ? 2 : 1, trows = TC_TH + 2 * n.D;
+    const int al = 16 / es, lead = (n.D + al - 1) / al * al, box_w = lead + TC_TW + lead;
+    a.box_lead = lead;
+    const size_t pitch = (size_t)n.W * es, plane = pitch * n.buf_rows;
+    a.use_tma = 0;
+    a.box_w = box_w;
+    if (!getenv("LBDRN_NO_TMA") && ((uintptr_t)a.msb % 16) == 0 && pitch % 16 == 0 && plane % 16 == 0 && box_w <= 256 &&
+        trows <= 256 && n.W >= box_w) {
+      cuuint64_t dims[3] = {(cuuint64_t)n.W, (cuuint64_t)n.buf_rows, (cuuint64_t)n.C};
+      cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
+      cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)trows, (cuuint32_t)n.C};
+      cuuint32_t estr[3] = {1, 1, 1};
+      // resolved through the runtime so the library has no link-time dependency on libcuda (it must load on CPU-only boxes)
+      using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      static EncodeFn encode = nullptr;
+      if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+          encode = reinterpret_cast<EncodeFn>(fn);
+      }
+      alignas(64) CUtensorMap tm;
+      CUresult r = !encode ? CUDA_ERROR_NOT_SUPPORTED : encode(&tm, n.msb_u16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                          const_cast<void*>(a.msb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      a.use_tma = r == CUDA_SUCCESS;
+      if (a.use_tma) {
+        // the descriptor lives in global memory (a slot per launch in a small ring, so sibling launches do not race)
+        static CUtensorMap* ring[64] = {nullptr};
+        static unsigned slot[64] = {0};
+        if (!ring[dev]) CUDA_TRY(cudaMalloc(&ring[dev], 64 * sizeof(CUtensorMap)));
+        CUtensorMap* dst = ring[dev] + (slot[dev]++ % 64);
+        CUDA_TRY(cudaMemcpyAsync(dst, &tm, sizeof tm, cudaMemcpyHostToDevice, st));
+        a.tmap_dev = dst;
+      }
+      if (getenv("LBDRN_DEBUG")) fprintf(stderr, "[lbdrn] tensor map encode rc=%d use_tma=%d\n", (int)r, a.use_tma);
+    }
+  }
   int grid = sms * occ;                                          // persistent: whole CTAs per SM
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (getenv("LBDRN_DEBUG"))
-    fprintf(stderr, "[lbdrn] tc kernel: smem dyn %zu static %zu regs %d occ %d grid %d tiles %d wlo %d\n", smem,
-            fa.sharedSizeBytes, fa.numRegs, occ, grid, a.n_tiles, (int)wlo);
+    fprintf(stderr, "[lbdrn] tc kernel: smem dyn %zu static %zu regs %d occ %d grid %d tiles %d wlo %d tma %d box_w %d\n", smem,
+            fa.sharedSizeBytes, fa.numRegs, occ, grid, a.n_tiles, (int)wlo, a.use_tma, a.box_w);
+  a.no_trap = getenv("LBDRN_DEBUG") != nullptr;
   kern<<<grid, TC_THREADS, smem, st>>>(a);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
+  if (a.no_trap) {
+    int h4[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpyFromSymbol(h4, g_tc_timeout, sizeof h4));
+    if (h4[3]) fprintf(stderr, "[lbdrn] tc kernel: %d barrier timeouts; last: barrier %d (1=mma 2=tma) tile %d block %d\n", h4[3], h4[0], h4[1], h4[2]);
+  }
   return LBDRN_OK;
 }
 
