@@ -369,21 +369,25 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
     }
   };
   uint32_t phase_tma = 0;
+  int pe_src[TC_PF];                               // offset of patch element i inside the TMA box (fixed per kernel)
+#pragma unroll
+  for (int i = 0; i < TC_PF; ++i)
+    pe_src[i] = pe[i] >= 0 ? ((pe[i] >> 16) * trows + ((pe[i] >> 8) & 255)) * box_w + (a.box_lead - D) + (pe[i] & 255) : 0;
+  bool cur_tma = tile_uses_tma(blockIdx.x);        // staging mechanism of the tile about to be consumed
   stage_next(blockIdx.x);
 
   for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
 
     // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
-    if (tile_uses_tma(t)) {
+    if (cur_tma) {
       mbar_wait(mbar_tma, phase_tma, 2, t, a.no_trap);
       phase_tma ^= 1;
       if (pf_ok) {                                                   // element -> (band,row,col) precomputed in pe[]
 #pragma unroll
         for (int i = 0; i < TC_PF; ++i) {
           if (pe[i] >= 0) {
-            const int src = ((pe[i] >> 16) * trows + ((pe[i] >> 8) & 255)) * box_w + (a.box_lead - D) + (pe[i] & 255);
-            const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[src] : (uint32_t)raw[src];
+            const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[pe_src[i]] : (uint32_t)raw[pe_src[i]];
             patch[tid + i * TC_THREADS] = __uint2half_rn(v);
           }
         }
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
       }
     }
     __syncthreads();
+    cur_tma = t + (int)gridDim.x < a.n_tiles && tile_uses_tma(t + gridDim.x);
     stage_next(t + gridDim.x);                                                       // lands while this tile computes
 
     // ---- A1 row of this thread's pixel: integer differences (exact in fp16), 16 B per K chunk ---------------------------
