@@ -256,10 +256,7 @@ def run_ours(args):
             sbuf.own.copy_(base_host.view(torch.int16) if base_host.dtype == torch.uint16 else base_host, non_blocking=True)
             mx = LD.global_max(sbuf.own.max() if sbuf.buf.dtype == torch.uint8 else local_max)
             sbuf.exchange()
-            o, rows = sbuf.decode(params_host.to(dev, non_blocking=True), K_, BC, NL, fl, mx)
-            for c in range(C_):
-                out_host[c].copy_(o[c, rows], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            sbuf.decode_to_host(out_host, params_host.to(dev, non_blocking=True), K_, BC, NL, fl, mx)
 
     e2e_step()
     torch.cuda.synchronize()
@@ -278,7 +275,7 @@ def run_ours(args):
            "h2d_bytes_per_step": int(base_host.numel() * base_host.element_size() * world + params_host.numel() * 4 * world),
            "d2h_bytes_per_step": int(out_host.numel() * 2 * world), "steps": e2e_steps,
            "api": "lbdrn_fused.decode_image_streamed (pinned host in/out, stripe-pipelined H2D | kernel | D2H, "
-                  "base.max() reduced on the device)" if world == 1 else "lbdrn_dist.StripeBuffer per rank (H2D, max all-reduce, halo swap, kernel, D2H)"}
+                  "base.max() reduced on the device)" if world == 1 else "lbdrn_dist.StripeBuffer per rank (H2D, max all-reduce, halo swap, sub-stripe kernels overlapped with D2H)"}
     del base_host, out_host
 
     # ---- encode s/scene (10 epochs, bs 8192, per-epoch eval + best-epoch select), scene-per-GPU replicas -----------

@@ -125,6 +125,39 @@ class StripeBuffer:
         return self.out, slice(self.top, self.top + (self.r1 - self.r0))
 
 
+    def decode_to_host(self, out_host, flat_params_dev, K, bc, nl, flags, msb_max, sub_rows=1024, relu=False, w0=30.0,
+                       path=cabi.PATH_AUTO, tab=None):
+        """Decode this rank's rows in sub-stripes and download each one on a side stream while the next computes.
+        out_host: [C, rows, W] uint16 CPU tensor (pinned for asynchronous copies) receiving this rank's own rows."""
+        C, brows, W = self.buf.shape
+        dev = self.buf.device
+        side = getattr(self, "_side", None)
+        if side is None:
+            side = self._side = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        lib = cabi.load()
+        last = None
+        for a in range(self.r0, self.r1, sub_rows):
+            b = min(self.r1, a + sub_rows)
+            d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), msb_max, self.buf.dtype == torch.uint16,
+                               row0=a, row1=b, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0, n_freq=flags.n_freq,
+                               path=path)
+            cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(self.buf), cabi.ptr(flat_params_dev), cabi.ptr(tab),
+                                        cabi.ptr(self.out), cabi.stream_ptr()))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                lo, hi = self.top + (a - self.r0), self.top + (b - self.r0)
+                for c in range(C):
+                    out_host[c, a - self.r0:b - self.r0].copy_(self.out[c, lo:hi], non_blocking=True)
+                last = torch.cuda.Event()
+                last.record(side)
+        if last is not None:
+            last.synchronize()
+        return out_host
+
+
 def decode_stripe(stripe_msb, H, flat_params_dev, K, D, bc, nl, flags, msb_max, group=None, relu=False, w0=30.0,
                   path=cabi.PATH_AUTO, tab=None, halo=None):
     """Decode this rank's stripe of an H-row scene.  stripe_msb: [C, rows, W] CUDA tensor of the rank's OWN rows.

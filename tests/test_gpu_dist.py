@@ -76,6 +76,9 @@ def _stripe_decode(rank, world):
     sb.exchange()
     o, rows = sb.decode(torch.from_numpy(params).cuda(), 5, 64, 2, F.Flags(), mx, path=1)
     assert np.array_equal(o.cpu().numpy()[:, rows], out["precise"])
+    host = torch.empty((4, r1 - r0, msb.shape[2]), dtype=torch.uint16).pin_memory()
+    sb.decode_to_host(host, torch.from_numpy(params).cuda(), 5, 64, 2, F.Flags(), mx, sub_rows=37, path=1)
+    assert np.array_equal(host.numpy(), out["precise"])
     return r0, r1, out, mx
 
 
