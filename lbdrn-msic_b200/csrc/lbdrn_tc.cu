@@ -225,7 +225,8 @@ struct TcArgs {
   const uint8_t* blk;     // packed weight block (TcHeader + operands) in global memory
   uint16_t* out;
   int tiles_x, n_tiles;
-  int a_bytes, w_bytes;   // smem: A region, weight block copy
+  int a_bytes, w_bytes;   // smem: A region (per warpgroup), weight block copy
+  int wg_bytes;           // smem: per-warpgroup staging region (fp16 patch + TMA landing box)
   int run_if_exact;       // 1: run only when the weights are fp16-exact; 0: only when they are not; -1: always
   const void* lsb;        // SSE mode: LSB codes
   double* partials;       // SSE mode: [gridDim.x]
@@ -251,94 +252,116 @@ constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+
 // CC/DD > 0: bands / radius known at compile time (feature offsets fold into immediates); CC == 0: generic tables.
 // WLO: the weights carry a low-order fp16 term (fp32 weights during training / -prec 32 streams): extra MMAs against
 // the lo operands.  MODE: TC_DECODE writes the reconstruction, TC_SSE accumulates sum((y - label)^2) (encode.py:105-108).
-template <bool FAST, int CC, int DD, bool WLO, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(const TcArgs a) {
+// NWG: warpgroups per CTA.  NWG=1: one tile in flight per CTA, 3 CTAs/SM, register-prefetched patches (any input).
+// NWG=2 (TMA-addressable inputs, exact weights): two independent warpgroups share ONE copy of the weights, 2 CTAs/SM
+// = 16 resident warps per SM instead of 12; each warpgroup has its own A region, staging buffers, mbarriers and TMEM
+// columns and synchronises on its own named barrier.
+template <bool FAST, int CC, int DD, bool WLO, int MODE, int NWG>
+__global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)) tc_decode_kernel(const TcArgs a) {
+  constexpr int THREADS = TC_THREADS * NWG;
   const Net& net = a.net;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int gtid = threadIdx.x, wg = gtid >> 7, tid = gtid & 127, warp = tid >> 5;
   const int C = CC ? CC : net.C, D = CC ? DD : net.D, n = 2 * D + 1;
   const int trows = TC_TH + 2 * D, twp = TC_TW + 2 * D;
   const int n_patch = C * trows * twp;
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sW = smem + a.a_bytes;
-  __half* patch = reinterpret_cast<__half*>(sW + a.w_bytes);
-  uint16_t* koff = reinterpret_cast<uint16_t*>(patch + align_up(C * trows * twp, 8));   // [k1pad] patch offset of feature k
+  uint8_t* sA = smem + (size_t)wg * a.a_bytes;
+  uint8_t* sW = smem + (size_t)NWG * a.a_bytes;
+  uint8_t* region = sW + a.w_bytes + (size_t)wg * a.wg_bytes;
+  __half* patch = reinterpret_cast<__half*>(region);
+  uint8_t* raw = region + align_up(n_patch * 2, 128);                                    // TMA landing box (128 B aligned)
+  uint16_t* koff = reinterpret_cast<uint16_t*>(sW + a.w_bytes + (size_t)NWG * a.wg_bytes);  // [k1pad] patch offset of feature k
   uint16_t* kctr = koff + TC_MAX_K1 + 16;                                                // [k1pad] patch offset of its centre
-  uint8_t* raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(kctr + TC_MAX_K1 + 16) + 127) & ~(uintptr_t)127);  // TMA box
-  __shared__ __align__(8) uint64_t s_mbar_tma;
-  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ __align__(8) uint64_t s_mbar_tma[NWG];
+  __shared__ __align__(8) uint64_t s_mbar[NWG];
   __shared__ uint32_t s_tmem;
+  auto wg_sync = [&]() {
+    if (NWG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "r"(TC_THREADS) : "memory");
+  };
 
   // ---- one-time setup: weight block -> smem, feature offset tables, TMEM, mbarrier ------------------------------------
   {
     const int4* src = reinterpret_cast<const int4*>(a.blk);
     int4* dst = reinterpret_cast<int4*>(sW);
-    for (int i = tid; i < a.w_bytes / 16; i += TC_THREADS) dst[i] = src[i];
+    for (int i = gtid; i < a.w_bytes / 16; i += THREADS) dst[i] = src[i];
   }
   __syncthreads();
   const TcHeader* H = reinterpret_cast<const TcHeader*>(sW);
   if (a.run_if_exact >= 0 && (H->exact != 0) != (a.run_if_exact != 0)) return;   // the sibling launch handles this scene
-  __shared__ double s_red[TC_THREADS / 32];
+  __shared__ double s_red[THREADS / 32];
   double sse_local = 0.0;
   const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
-  for (int k = tid; k < k1pad; k += TC_THREADS) {
-    int off = 0, ctr = 0;
-    if (k < k1) {
-      const int c = k / (n * n), rem = k - c * n * n, dy = rem / n, dx = rem - dy * n;
-      off = (c * trows + dy) * twp + dx;
-      ctr = (c * trows + D) * twp + D;
+  if (CC == 0) {
+    for (int k = gtid; k < k1pad; k += THREADS) {
+      int off = 0, ctr = 0;
+      if (k < k1) {
+        const int c = k / (n * n), rem = k - c * n * n, dy = rem / n, dx = rem - dy * n;
+        off = (c * trows + dy) * twp + dx;
+        ctr = (c * trows + D) * twp + D;
+      }
+      koff[k] = (uint16_t)off;
+      kctr[k] = (uint16_t)ctr;
     }
-    koff[k] = (uint16_t)off;
-    kctr[k] = (uint16_t)ctr;
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS)
+  if (gtid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(TC_TMEM_COLS * NWG)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 0) {
-    mbar_init(smem_u32(&s_mbar), 1);
-    mbar_init(smem_u32(&s_mbar_tma), 1);
+  if (gtid == 0) {
+    for (int g = 0; g < NWG; ++g) {
+      mbar_init(smem_u32(&s_mbar[g]), 1);
+      mbar_init(smem_u32(&s_mbar_tma[g]), 1);
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = s_tmem;
+  const uint32_t tmem = s_tmem + (uint32_t)(wg * TC_TMEM_COLS);       // this warpgroup's accumulator columns
   const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 lanes
-  const uint32_t mbar = smem_u32(&s_mbar);
+  const uint32_t mbar = smem_u32(&s_mbar[wg]);
   const uint32_t idesc = umma_idesc_f16(128, TC_BC);
   const uint32_t sA_u = smem_u32(sA);
   const float* bias = reinterpret_cast<const float*>(sW + H->off_bias);
   const float* w3t = reinterpret_cast<const float*>(sW + H->off_w3);
   const bool rel = net.relative != 0;
   uint32_t phase = 0;
+  const int tile0 = blockIdx.x * NWG + wg, tile_step = gridDim.x * NWG;
 
   // ---- patch element -> (band, row, col), fixed for the whole kernel; tile loads are prefetched one tile ahead -------
-  int pe[TC_PF];                                   // band << 16 | row << 8 | col, or -1
-  const bool pf_ok = n_patch <= TC_PF * TC_THREADS;
+  constexpr int PFN = (CC == 4 && DD <= 2) ? 8 : TC_PF;   // patch elements per thread
+  constexpr bool REGPF = NWG == 1;                        // per-thread register prefetch of non-TMA tiles
+  const bool pf_ok = n_patch <= PFN * TC_THREADS;
+  const int es = net.msb_u16 ? 2 : 1, box_w = a.box_w;
+  int pe[REGPF ? PFN : 1];                         // band << 16 | row << 8 | col, or -1
+  uint32_t pf[REGPF ? PFN : 1];
+  long long pe_off[REGPF ? PFN : 1];               // element offset relative to the patch origin (interior tiles)
+  int pe_src[PFN];                                 // offset of patch element i inside the TMA box (fixed per kernel), or -1
 #pragma unroll
-  for (int i = 0; i < TC_PF; ++i) {
+  for (int i = 0; i < PFN; ++i) {
     const int e = tid + i * TC_THREADS;
-    const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp;
-    pe[i] = e < n_patch ? ((c << 16) | (r << 8) | (rem - r * twp)) : -1;
+    const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
+    pe_src[i] = e < n_patch ? (c * trows + r) * box_w + (a.box_lead - D) + x : -1;
+    if (REGPF) {
+      pe[i] = e < n_patch ? ((c << 16) | (r << 8) | x) : -1;
+      pe_off[i] = e < n_patch ? ((long long)c * net.buf_rows + r) * net.W + x : 0;
+    }
   }
-  uint32_t pf[TC_PF];
-  long long pe_off[TC_PF];                         // element offset relative to the patch origin (interior tiles)
-#pragma unroll
-  for (int i = 0; i < TC_PF; ++i)
-    pe_off[i] = pe[i] >= 0 ? ((long long)(pe[i] >> 16) * net.buf_rows + ((pe[i] >> 8) & 255)) * net.W + (pe[i] & 255) : 0;
   auto issue_patch_loads = [&](int tile) {
+    if (!REGPF) return;
     const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
     if (y0 >= 0 && x0 >= 0 && y0 + trows <= net.H && x0 + twp <= net.W) {      // no reflection needed
       const long long origin = (long long)(y0 - net.buf_row0) * net.W + x0;
 #pragma unroll
-      for (int i = 0; i < TC_PF; ++i)
+      for (int i = 0; i < (REGPF ? PFN : 1); ++i)
         if (pe[i] >= 0) pf[i] = load_msb_int(a.msb, net.msb_u16, (size_t)(origin + pe_off[i]));
       return;
     }
 #pragma unroll
-    for (int i = 0; i < TC_PF; ++i) {
+    for (int i = 0; i < (REGPF ? PFN : 1); ++i) {
       if (pe[i] >= 0) {
         const int gy = reflect_clamp(y0 + ((pe[i] >> 8) & 255), net.H), gx = reflect_clamp(x0 + (pe[i] & 255), net.W);
         pf[i] = load_msb_int(a.msb, net.msb_u16, ((size_t)(pe[i] >> 16) * net.buf_rows + (gy - net.buf_row0)) * net.W + gx);
@@ -347,9 +370,9 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
   };
   // TMA staging of interior tiles: one elected thread issues the box load for the NEXT tile; it lands in `raw` while
   // this tile computes and is converted to fp16 at the top of the next iteration.  Border tiles (reflection needed) and
-  // buffers TMA cannot address (row pitch not a multiple of 16 B) use the per-thread prefetch above.
-  const uint32_t mbar_tma = smem_u32(&s_mbar_tma), raw_u = smem_u32(raw);
-  const int es = net.msb_u16 ? 2 : 1, box_w = a.box_w;
+  // buffers TMA cannot address (row pitch not a multiple of 16 B) use the per-thread prefetch above (NWG=1) or plain
+  // loads (NWG=2: border tiles only, <1 % of a scene).
+  const uint32_t mbar_tma = smem_u32(&s_mbar_tma[wg]), raw_u = smem_u32(raw);
   const uint32_t box_bytes = (uint32_t)(box_w * trows * C * es);
   auto tile_uses_tma = [&](int tile) {
     if (!a.use_tma) return false;
@@ -364,29 +387,25 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
         mbar_expect_tx(mbar_tma, box_bytes);
         tma_load_3d(raw_u, a.tmap_dev, x0 + D - a.box_lead, y0 - net.buf_row0, 0, mbar_tma);
       }
-    } else if (pf_ok) {
+    } else if (REGPF && pf_ok) {
       issue_patch_loads(tile);
     }
   };
   uint32_t phase_tma = 0;
-  int pe_src[TC_PF];                               // offset of patch element i inside the TMA box (fixed per kernel)
-#pragma unroll
-  for (int i = 0; i < TC_PF; ++i)
-    pe_src[i] = pe[i] >= 0 ? ((pe[i] >> 16) * trows + ((pe[i] >> 8) & 255)) * box_w + (a.box_lead - D) + (pe[i] & 255) : 0;
-  bool cur_tma = tile_uses_tma(blockIdx.x);        // staging mechanism of the tile about to be consumed
-  stage_next(blockIdx.x);
+  bool cur_tma = tile0 < a.n_tiles && tile_uses_tma(tile0);   // staging mechanism of the tile about to be consumed
+  stage_next(tile0);
 
-  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+  for (int t = tile0; t < a.n_tiles; t += tile_step) {
     const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
 
     // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
     if (cur_tma) {
       mbar_wait(mbar_tma, phase_tma, 2, t, a.no_trap);
       phase_tma ^= 1;
-      if (pf_ok) {                                                   // element -> (band,row,col) precomputed in pe[]
+      if (pf_ok) {                                                   // box offsets precomputed in pe_src[]
 #pragma unroll
-        for (int i = 0; i < TC_PF; ++i) {
-          if (pe[i] >= 0) {
+        for (int i = 0; i < PFN; ++i) {
+          if (pe_src[i] >= 0) {
             const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[pe_src[i]] : (uint32_t)raw[pe_src[i]];
             patch[tid + i * TC_THREADS] = __uint2half_rn(v);
           }
@@ -400,9 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
         }
       }
       fence_async_smem();      // our generic-proxy reads of `raw` are ordered before the next TMA write into it
-    } else if (pf_ok) {
+    } else if (REGPF && pf_ok) {
 #pragma unroll
-      for (int i = 0; i < TC_PF; ++i)
+      for (int i = 0; i < (REGPF ? PFN : 1); ++i)
         if (pe[i] >= 0) patch[tid + i * TC_THREADS] = __uint2half_rn(pf[i]);
     } else {
       for (int e = tid; e < n_patch; e += TC_THREADS) {
@@ -411,9 +430,9 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
         patch[e] = __uint2half_rn(load_msb_int(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx));
       }
     }
-    __syncthreads();
-    cur_tma = t + (int)gridDim.x < a.n_tiles && tile_uses_tma(t + gridDim.x);
-    stage_next(t + gridDim.x);                                                       // lands while this tile computes
+    wg_sync();
+    cur_tma = t + tile_step < a.n_tiles && tile_uses_tma(t + tile_step);
+    stage_next(t + tile_step);                                                       // lands while this tile computes
 
     // ---- A1 row of this thread's pixel: integer differences (exact in fp16), 16 B per K chunk ---------------------------
     const int pr = tid >> 4, px = tid & 15;
@@ -479,7 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
       // ---- MMA for hidden layer l: one elected thread issues, completion arrives on the mbarrier -----------------------
       fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
-      __syncthreads();
+      wg_sync();
       if (tid == 0) {
         tc_fence_after();
         const uint32_t sB_u = smem_u32(sW + H->off_b[l]);
@@ -588,12 +607,12 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
     // deterministic: lanes -> warp -> CTA partial -> the last CTA sums the partials in index order
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sse_local += __shfl_xor_sync(0xffffffffu, sse_local, off);
-    if ((tid & 31) == 0) s_red[warp] = sse_local;
+    if ((gtid & 31) == 0) s_red[gtid >> 5] = sse_local;
   }
   __syncthreads();
-  if (MODE == TC_SSE && tid == 0) {
+  if (MODE == TC_SSE && gtid == 0) {
     double sum = 0.0;
-    for (int i = 0; i < TC_THREADS / 32; ++i) sum += s_red[i];
+    for (int i = 0; i < THREADS / 32; ++i) sum += s_red[i];
     a.partials[blockIdx.x] = sum;
     __threadfence();
     if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {
@@ -604,8 +623,8 @@ __global__ void __launch_bounds__(TC_THREADS, WLO ? 2 : 3) tc_decode_kernel(cons
       *a.counter = 0u;
     }
   }
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+  if (gtid < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(TC_TMEM_COLS * NWG) : "memory");
 }
 
 // ---- self-test: D[128][64] = A[128][K] * B[64][K]^T through the same descriptors / layouts / TMEM path ----------------
@@ -675,25 +694,71 @@ namespace {
 
 using KernT = void (*)(const TcArgs);
 
-template <bool FAST, bool WLO, int MODE>
+template <bool FAST, bool WLO, int MODE, int NWG>
 KernT pick_kernel(const Net& n) {
-  if (n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE>;
-  if (n.C == 8 && n.D == 2) return tc_decode_kernel<FAST, 8, 2, WLO, MODE>;
-  if (n.C == 4 && n.D == 1) return tc_decode_kernel<FAST, 4, 1, WLO, MODE>;
-  if (n.C == 4 && n.D == 3) return tc_decode_kernel<FAST, 4, 3, WLO, MODE>;
-  return tc_decode_kernel<FAST, 0, 0, WLO, MODE>;
+  if (n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE, NWG>;
+  if (n.C == 8 && n.D == 2) return tc_decode_kernel<FAST, 8, 2, WLO, MODE, NWG>;
+  if (n.C == 4 && n.D == 1) return tc_decode_kernel<FAST, 4, 1, WLO, MODE, NWG>;
+  if (n.C == 4 && n.D == 3) return tc_decode_kernel<FAST, 4, 3, WLO, MODE, NWG>;
+  return tc_decode_kernel<FAST, 0, 0, WLO, MODE, NWG>;
 }
 
-// one launch of the tensor kernel family (wlo: smem holds the low-order weight operands too)
-int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int dev, cudaStream_t st) {
+// TMA descriptor of the MSB planes: dims (W, buf_rows, C); needs a 16 B-aligned base and row / plane pitches.
+int tc_setup_tma(TcArgs& a, int dev, cudaStream_t st) {
+  const Net& n = a.net;
+  const int es = n.msb_u16 ? 2 : 1, trows = TC_TH + 2 * n.D;
+  const int al = 16 / es, lead = (n.D + al - 1) / al * al, box_w = lead + TC_TW + lead;
+  const size_t pitch = (size_t)n.W * es, plane = pitch * n.buf_rows;
+  a.use_tma = 0;
+  a.box_w = box_w;
+  a.box_lead = lead;
+  if (getenv("LBDRN_NO_TMA") || ((uintptr_t)a.msb % 16) != 0 || pitch % 16 != 0 || plane % 16 != 0 || box_w > 256 ||
+      trows > 256 || n.W < box_w)
+    return LBDRN_OK;
+  // resolved through the runtime so the library has no link-time dependency on libcuda (it must load on CPU-only boxes)
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  if (!encode) return LBDRN_OK;
+  cuuint64_t dims[3] = {(cuuint64_t)n.W, (cuuint64_t)n.buf_rows, (cuuint64_t)n.C};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)trows, (cuuint32_t)n.C};
+  cuuint32_t estr[3] = {1, 1, 1};
+  alignas(64) CUtensorMap tm;
+  CUresult r = encode(&tm, n.msb_u16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                      const_cast<void*>(a.msb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return LBDRN_OK;
+  // the descriptor lives in global memory (a slot per call in a small ring, so queued launches do not race)
+  static CUtensorMap* ring[64] = {nullptr};
+  static unsigned slot[64] = {0};
+  if (!ring[dev]) CUDA_TRY(cudaMalloc(&ring[dev], 64 * sizeof(CUtensorMap)));
+  CUtensorMap* dst = ring[dev] + (slot[dev]++ % 64);
+  CUDA_TRY(cudaMemcpyAsync(dst, &tm, sizeof tm, cudaMemcpyHostToDevice, st));
+  a.tmap_dev = dst;
+  a.use_tma = 1;
+  return LBDRN_OK;
+}
+
+// one launch of the tensor kernel family (wlo: smem holds the low-order weight operands too; nwg: warpgroups per CTA)
+int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int dev, cudaStream_t st) {
   const Net& n = a.net;
   const int kmax = h.k1pad > 2 * TC_BC ? h.k1pad : 2 * TC_BC;
   a.a_bytes = align_up(128 * kmax * 2, 1024);
   a.w_bytes = wlo ? h.total : h.hi_bytes;
-  const int es_ = n.msb_u16 ? 2 : 1, al_ = 16 / es_, lead_ = (n.D + al_ - 1) / al_ * al_;
-  const int raw_bytes = (2 * lead_ + TC_TW) * es_ * (TC_TH + 2 * n.D) * n.C;
-  const size_t smem = (size_t)a.a_bytes + a.w_bytes + align_up(n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D), 8) * 2 +
-                      2 * (TC_MAX_K1 + 16) * 2 + 64 + 128 + raw_bytes;
+  const int n_patch = n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D);
+  const int raw_bytes = a.box_w * (n.msb_u16 ? 2 : 1) * (TC_TH + 2 * n.D) * n.C;
+  a.wg_bytes = align_up(n_patch * 2, 128) + align_up(raw_bytes, 128);
+  const int threads = TC_THREADS * nwg;
+  const size_t smem = (size_t)nwg * a.a_bytes + a.w_bytes + (size_t)nwg * a.wg_bytes + 2 * (TC_MAX_K1 + 16) * 2 + 64;
   int sms = 0, max_smem = 0, smem_sm = 0, regs_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -707,65 +772,22 @@ int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int dev, cudaS
   cudaFuncAttributes fa;
   CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
   int occ = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));   // +1 KB: per-CTA reservation of the driver
-  const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS;
+  const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
   if (regs_cta > 0 && regs_sm / regs_cta < occ) occ = regs_sm / regs_cta;
-  if (occ * TC_TMEM_COLS > 512) occ = 512 / TC_TMEM_COLS;         // TMEM: 512 columns per SM
-  if (occ > 3) occ = 3;                                           // measured optimum (4 CTAs: 3.0 vs 4.3 Gpix/s)
+  if (occ * TC_TMEM_COLS * nwg > 512) occ = 512 / (TC_TMEM_COLS * nwg);   // TMEM: 512 columns per SM
+  const int occ_max = nwg == 2 ? 2 : 3;                           // measured optimum for NWG=1 (4 CTAs: 3.0 vs 4.3 Gpix/s)
+  if (occ > occ_max) occ = occ_max;
   if (const char* e = getenv("LBDRN_TC_OCC")) occ = atoi(e);
   if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
   a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
   a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
-  // TMA descriptor of the MSB planes: dims (W, buf_rows, C); needs 16 B-aligned base and row / plane pitches
-  {
-    const int es = n.msb_u16 ? 2 : 1, trows = TC_TH + 2 * n.D;
-    const int al = 16 / es, lead = (n.D + al - 1) / al * al, box_w = lead + TC_TW + lead;
-    a.box_lead = lead;
-    const size_t pitch = (size_t)n.W * es, plane = pitch * n.buf_rows;
-    a.use_tma = 0;
-    a.box_w = box_w;
-    if (!getenv("LBDRN_NO_TMA") && ((uintptr_t)a.msb % 16) == 0 && pitch % 16 == 0 && plane % 16 == 0 && box_w <= 256 &&
-        trows <= 256 && n.W >= box_w) {
-      cuuint64_t dims[3] = {(cuuint64_t)n.W, (cuuint64_t)n.buf_rows, (cuuint64_t)n.C};
-      cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
-      cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)trows, (cuuint32_t)n.C};
-      cuuint32_t estr[3] = {1, 1, 1};
-      // resolved through the runtime so the library has no link-time dependency on libcuda (it must load on CPU-only boxes)
-      using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-      static EncodeFn encode = nullptr;
-      if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-          encode = reinterpret_cast<EncodeFn>(fn);
-      }
-      alignas(64) CUtensorMap tm;
-      CUresult r = !encode ? CUDA_ERROR_NOT_SUPPORTED : encode(&tm, n.msb_u16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
-                                          const_cast<void*>(a.msb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      a.use_tma = r == CUDA_SUCCESS;
-      if (a.use_tma) {
-        // the descriptor lives in global memory (a slot per launch in a small ring, so sibling launches do not race)
-        static CUtensorMap* ring[64] = {nullptr};
-        static unsigned slot[64] = {0};
-        if (!ring[dev]) CUDA_TRY(cudaMalloc(&ring[dev], 64 * sizeof(CUtensorMap)));
-        CUtensorMap* dst = ring[dev] + (slot[dev]++ % 64);
-        CUDA_TRY(cudaMemcpyAsync(dst, &tm, sizeof tm, cudaMemcpyHostToDevice, st));
-        a.tmap_dev = dst;
-      }
-      if (getenv("LBDRN_DEBUG")) fprintf(stderr, "[lbdrn] tensor map encode rc=%d use_tma=%d\n", (int)r, a.use_tma);
-    }
-  }
   int grid = sms * occ;                                          // persistent: whole CTAs per SM
-  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid * nwg > a.n_tiles) grid = (a.n_tiles + nwg - 1) / nwg;
   if (getenv("LBDRN_DEBUG"))
-    fprintf(stderr, "[lbdrn] tc kernel: smem dyn %zu static %zu regs %d occ %d grid %d tiles %d wlo %d tma %d box_w %d\n", smem,
-            fa.sharedSizeBytes, fa.numRegs, occ, grid, a.n_tiles, (int)wlo, a.use_tma, a.box_w);
+    fprintf(stderr, "[lbdrn] tc kernel: smem dyn %zu static %zu regs %d occ %d grid %d x %d thr tiles %d wlo %d tma %d box_w %d\n",
+            smem, fa.sharedSizeBytes, fa.numRegs, occ, grid, threads, a.n_tiles, (int)wlo, a.use_tma, a.box_w);
   a.no_trap = getenv("LBDRN_DEBUG") != nullptr;
-  kern<<<grid, TC_THREADS, smem, st>>>(a);
+  kern<<<grid, threads, smem, st>>>(a);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (a.no_trap) {
@@ -805,12 +827,21 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
   TcArgs a;
   memset(&a, 0, sizeof a);
   a.net = n; a.msb = msb; a.blk = blk; a.out = out;
+  rc = tc_setup_tma(a, dev, st);
+  if (rc) return rc;
   // two sibling launches; the exactness flag computed by tc_prep_kernel decides ON THE DEVICE which one does the work
   a.run_if_exact = 1;
-  rc = tc_launch(fast_sine ? pick_kernel<true, false, TC_DECODE>(n) : pick_kernel<false, false, TC_DECODE>(n), a, h, false, dev, st);
+  const bool two = a.use_tma && !getenv("LBDRN_TC_NWG1");     // TMA-addressable input: two warpgroups per CTA
+  if (two)
+    rc = tc_launch(fast_sine ? pick_kernel<true, false, TC_DECODE, 2>(n) : pick_kernel<false, false, TC_DECODE, 2>(n), a, h,
+                   false, 2, dev, st);
+  else
+    rc = tc_launch(fast_sine ? pick_kernel<true, false, TC_DECODE, 1>(n) : pick_kernel<false, false, TC_DECODE, 1>(n), a, h,
+                   false, 1, dev, st);
   if (rc) return rc;
   a.run_if_exact = 0;
-  return tc_launch(fast_sine ? pick_kernel<true, true, TC_DECODE>(n) : pick_kernel<false, true, TC_DECODE>(n), a, h, true, dev, st);
+  return tc_launch(fast_sine ? pick_kernel<true, true, TC_DECODE, 1>(n) : pick_kernel<false, true, TC_DECODE, 1>(n), a, h, true,
+                   1, dev, st);
 }
 
 int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st) {
@@ -826,7 +857,9 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
   a.net = n; a.msb = msb; a.blk = blk; a.lsb = lsb;
   a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
   a.run_if_exact = -1;
-  return tc_launch(pick_kernel<true, true, TC_SSE>(n), a, h, true, dev, st);
+  rc = tc_setup_tma(a, dev, st);
+  if (rc) return rc;
+  return tc_launch(pick_kernel<true, true, TC_SSE, 1>(n), a, h, true, 1, dev, st);
 }
 
 int tc_selftest(const void* a_dev, const void* b_dev, float* d_dev, int K, cudaStream_t st) {
