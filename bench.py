@@ -46,46 +46,58 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms on a thread (the timed
+    region of a decode benchmark is only tens of ms, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop, self.th, self.h = index, [], False, None, None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.h = None
         return self
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(mhz), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop = True
+        if self.th:
             self.th.join(timeout=2)
 
     def summary(self):
-        sm, reasons, mx = [], set(), None
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        seen = 0
+        for _, r in self.rows:
+            seen |= r
+        return dict(sm_mhz=statistics.median(m for m, _ in self.rows), sm_max_mhz=self.max_mhz,
+                    reasons=sorted(k for k, bit in names.items() if seen & bit), samples=len(self.rows))
 
 
 def bench_params(device):
@@ -175,7 +187,8 @@ def run_ours(args):
     if world > 1:
         sbuf = LD.StripeBuffer(H_total, SIDE, C_, D_, scene.msb.dtype, dev)
         sbuf.load(scene.msb)
-        local_max = torch.tensor([scene.msb_max], device=dev)
+        local_max = torch.tensor([scene.msb_max], dtype=torch.int32, device=dev)
+        gmax = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def decode_step():
         if world == 1:
@@ -183,10 +196,12 @@ def run_ours(args):
             cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(scene.msb), cabi.ptr(params), None, cabi.ptr(out),
                                         cabi.stream_ptr()))
             return out
-        # per scene: scalar max all-reduce + one D-row halo swap with each neighbour, then the local kernel
-        mx = LD.global_max(local_max)
+        # per scene: scalar max all-reduce (result stays on the device: LbdrnDesc.msb_max_dev) + one D-row halo swap with
+        # each neighbour, then the local kernel -- no host synchronisation inside a step
+        gmax.copy_(local_max)
+        LD.global_max_dev(gmax)
         sbuf.exchange()
-        return sbuf.decode(params, K_, BC, NL, fl, mx)[0]
+        return sbuf.decode(params, K_, BC, NL, fl, gmax)[0]
 
     out = torch.empty((C_, SIDE, SIDE), dtype=torch.uint16, device=dev)
     for _ in range(max(3, args.warmup)):
@@ -254,9 +269,10 @@ def run_ours(args):
             F.decode_image_streamed(base_host, params_host, K_, D_, BC, NL, flags=fl, out_host=out_host)
         else:
             sbuf.own.copy_(base_host.view(torch.int16) if base_host.dtype == torch.uint16 else base_host, non_blocking=True)
-            mx = LD.global_max(sbuf.own.max() if sbuf.buf.dtype == torch.uint8 else local_max)
+            gmax.copy_(sbuf.own.max().to(torch.int32).reshape(1) if sbuf.buf.dtype == torch.uint8 else local_max)
+            LD.global_max_dev(gmax)
             sbuf.exchange()
-            sbuf.decode_to_host(out_host, params_host.to(dev, non_blocking=True), K_, BC, NL, fl, mx)
+            sbuf.decode_to_host(out_host, params_host.to(dev, non_blocking=True), K_, BC, NL, fl, gmax)
 
     e2e_step()
     torch.cuda.synchronize()
@@ -286,10 +302,11 @@ def run_ours(args):
         model = LBDRNModel(DIM_IN, BC, C_, NL)
         tr = F.FusedTrainer(model, scene, D_, 1e-3, 8192, args.encode_epochs, flags=fl, sampler=args.sampler)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = tr.run()
-        torch.cuda.synchronize()
-        enc_s = time.perf_counter() - t0
+        with ClockSampler(local) as enc_clk:
+            t0 = time.perf_counter()
+            res = tr.run()
+            torch.cuda.synchronize()
+            enc_s = time.perf_counter() - t0
         tr.close()
         if world > 1:
             t = torch.tensor([enc_s], device=dev)
@@ -301,7 +318,7 @@ def run_ours(args):
                   "epochs": args.encode_epochs, "batch_size": 8192, "optimizer_steps": n_steps,
                   "us_per_step_incl_eval": enc_s / n_steps * 1e6, "sampler": args.sampler,
                   "final_val_mse": res["val_mse"][-1] if res["val_mse"] else None, "best_epoch": res["best_epoch"],
-                  "tensor_roofline_frac": flop / enc_s / 1e12 / pk["bf16_sustained"],
+                  "tensor_roofline_frac": flop / enc_s / 1e12 / pk["bf16_sustained"], "clocks": enc_clk.summary(),
                   "excludes": "GDAL read/write, JPEG-2000 base layer, fpzip (host, unchanged)"}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample ----------------------------

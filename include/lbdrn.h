@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LBDRN_ABI_VERSION 1
+#define LBDRN_ABI_VERSION 2
 
 enum {
   LBDRN_OK = 0,
@@ -71,6 +71,9 @@ typedef struct LbdrnDesc {
   int32_t buf_rows;       /* rows present in the buffers (plane stride = buf_rows*W) */
   int32_t path;           /* LBDRN_PATH_* */
   int32_t reserved[3];
+  const uint32_t* msb_max_dev; /* optional DEVICE word holding MSB.max(): when non-NULL the kernels read the normaliser
+                                  from it (no host round trip after a device-side reduction / all-reduce) and `msb_max`
+                                  only has to be an upper bound (it still selects uint8/uint16-safe kernels) */
 } LbdrnDesc;
 
 /* Optimiser / loop settings of the encoder (encode.py:84-85, -lr -bs -e flags). */

@@ -58,6 +58,7 @@ int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {
   if (colors && d->msb_max == 0)
     return fail(LBDRN_E_INVALID, "MSB.max()==0: the reference's features are 0/0=NaN for this K (degenerate)");
   n.maxv = (float)d->msb_max;
+  n.maxv_dev = d->msb_max_dev;
   n.qmax = (float)((1 << d->K) - 1);
   if (d->msb_dtype != LBDRN_U8 && d->msb_dtype != LBDRN_U16) return fail(LBDRN_E_INVALID, "bad msb_dtype");
   n.msb_u16 = d->msb_dtype == LBDRN_U16;

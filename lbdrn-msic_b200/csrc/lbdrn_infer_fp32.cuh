@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kThreads) infer_fp32_kernel(const InferArgs a)
   const int trows = TH + 2 * D, twp = TW + 2 * D;
 
   if (a.skip_flag != nullptr && *a.skip_flag != 0) return;
+  const float maxv = net_maxv(net);
 
   extern __shared__ float4 smem4[];
   float* act = reinterpret_cast<float*>(smem4);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) infer_fp32_kernel(const InferArgs a)
           const size_t rowoff = ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W;
           for (int x = lane; x < twp; x += 32)
             tile[(c * trows + r) * twp + x] =
-                load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(tx0 - D + x, net.W), net.maxv);
+                load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(tx0 - D + x, net.W), maxv);
         }
       }
     }

@@ -112,7 +112,7 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
     if (bad) atomicAnd(&s_exact, 0);
     // sine path: a = w0*(acc*scale + b) is evaluated as one FFMA, acc*(w0*scale) + w0*b (w0 folded here)
     const float fold = net.relu ? 1.0f : net.w0;
-    if (tid == 0) H->scale[l] = fold * (l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net.maxv) : ldexpf(1.0f, -s));
+    if (tid == 0) H->scale[l] = fold * (l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net_maxv(net)) : ldexpf(1.0f, -s));
     float* bias = reinterpret_cast<float*>(blk + hdr.off_bias) + l * TC_BC;
     for (int i = tid; i < net.bc; i += blockDim.x) bias[i] = fold * params[net.boff[l] + i];
   }

@@ -118,14 +118,14 @@ __device__ __forceinline__ void gemm_kmajor_v(float (&acc)[kTrainTM][TN], const 
 
 // One row (fixed dy) of one band's neighbourhood of one pixel; loads issued before first use.
 template <int N_>
-__device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowoff, int gx, const Net& net, float ctr,
-                                           bool ok, float* d) {
+__device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowoff, int gx, const Net& net, float maxv,
+                                           float ctr, bool ok, float* d) {
   constexpr int D_ = N_ / 2;
   uint32_t raw[N_];
 #pragma unroll
   for (int dx = 0; dx < N_; ++dx) raw[dx] = load_msb_int(msb, u16, rowoff + reflect_clamp(gx + dx - D_, net.W));
 #pragma unroll
-  for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? __fdiv_rn((float)raw[dx], net.maxv) - ctr : 0.f;
+  for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? __fdiv_rn((float)raw[dx], maxv) - ctr : 0.f;
 }
 
 // out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin (dst = natural [BC][Kin] gradient block); THREADS/8 row
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   const int ubase = us * (BC / US) + tn * VEC;
   auto unit = [&](int j) { return ubase + (j / VEC) * 8 * VEC + (j % VEC); };
   const int C = net.C, D = net.D, n = net.n, L = net.nl, P = net.P;
+  const float maxv = net_maxv(net);
 
   // ---- shared memory carve-up ----------------------------------------------------------------------------
   extern __shared__ float4 smem4[];
@@ -291,17 +292,17 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);          // label = LSB/(2^K-1)
           }
           if (net.ncol) {
-            const float ctr = net.relative ? load_msb_norm(a.msb, net.msb_u16, off, net.maxv) : 0.f;
+            const float ctr = net.relative ? load_msb_norm(a.msb, net.msb_u16, off, maxv) : 0.f;
             float* d = dst + (size_t)(net.nco + (c * n + dy) * n) * LDP;
             const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
             switch (n) {
-              case 1: gather_row<1>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
-              case 3: gather_row<3>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
-              case 5: gather_row<5>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
-              case 7: gather_row<7>(a.msb, net.msb_u16, rowoff, gx, net, ctr, ok, d); break;
+              case 1: gather_row<1>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 3: gather_row<3>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 5: gather_row<5>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 7: gather_row<7>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
               default:
                 for (int dx = 0; dx < n; ++dx, d += LDP) {
-                  float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), net.maxv) - ctr;
+                  float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), maxv) - ctr;
                   *d = ok ? v : 0.f;
                 }
             }

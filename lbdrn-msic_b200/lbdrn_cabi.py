@@ -32,7 +32,7 @@ class LbdrnDesc(C.Structure):
                 ("bc", C.c_int32), ("nl", C.c_int32), ("flags", C.c_uint32), ("w0", C.c_float),
                 ("n_freq", C.c_int32), ("msb_max", C.c_uint32), ("msb_dtype", C.c_int32),
                 ("row0", C.c_int32), ("row1", C.c_int32), ("buf_row0", C.c_int32), ("buf_rows", C.c_int32),
-                ("path", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("path", C.c_int32), ("reserved", C.c_int32 * 3), ("msb_max_dev", C.c_void_p)]
 
 
 class LbdrnTrainCfg(C.Structure):
@@ -98,7 +98,8 @@ def flag_bits(use_coordinates, embedding, use_colors, relative, relu=False):
 
 
 def make_desc(C_, H, W, K, D, bc, nl, flags, msb_max, msb_u16, row0=0, row1=None, buf_row0=0, buf_rows=None,
-              w0=30.0, n_freq=12, path=PATH_AUTO):
+              w0=30.0, n_freq=12, path=PATH_AUTO, msb_max_dev=None):
+    """msb_max_dev: optional int32/uint32 CUDA tensor holding the exact MSB.max(); `msb_max` is then an upper bound."""
     d = LbdrnDesc()
     d.C, d.H, d.W, d.K, d.D, d.bc, d.nl = C_, H, W, K, D, bc, nl
     d.flags, d.w0, d.n_freq = flags, w0, n_freq
@@ -106,6 +107,7 @@ def make_desc(C_, H, W, K, D, bc, nl, flags, msb_max, msb_u16, row0=0, row1=None
     d.row0, d.row1 = row0, (H if row1 is None else row1)
     d.buf_row0, d.buf_rows = buf_row0, (H if buf_rows is None else buf_rows)
     d.path = path
+    d.msb_max_dev = None if msb_max_dev is None else msb_max_dev.data_ptr()
     return d
 
 

@@ -35,6 +35,13 @@ def global_max(local_max, group=None):
     return int(t.item())
 
 
+def global_max_dev(local_max_dev, group=None):
+    """Device-side variant: all-reduce(max) of a 1-element int32 CUDA tensor in place, NO host read-back; pass the
+    tensor to the kernels through LbdrnDesc.msb_max_dev."""
+    dist.all_reduce(local_max_dev, op=dist.ReduceOp.MAX, group=group)
+    return local_max_dev
+
+
 def exchange_halos(stripe, D, group=None):
     """stripe: [C, rows, W] tensor holding this rank's own rows.  Returns ([C, rows + top + bottom, W], top) where
     `top` halo rows came from rank-1 and the bottom ones from rank+1 (none at the image border).  Works on CUDA
@@ -114,12 +121,20 @@ class StripeBuffer:
         if self.bot:
             w[:, self.top + rows:].copy_(self._recv_dn)
 
+    def _max_args(self, msb_max):
+        """msb_max may be an int (host value) or a 1-element int32 CUDA tensor (device value, e.g. fresh from an
+        all-reduce): then the descriptor carries the dtype's upper bound and the device pointer."""
+        if torch.is_tensor(msb_max):
+            return (255 if self.buf.dtype == torch.uint8 else 2048), msb_max
+        return int(msb_max), None
+
     def decode(self, flat_params_dev, K, bc, nl, flags, msb_max, relu=False, w0=30.0, path=cabi.PATH_AUTO, tab=None):
         """Decode the stripe (halos must be current); returns the [C, buf_rows, W] output buffer and the slice of own rows."""
         C, brows, W = self.buf.shape
-        d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), msb_max, self.buf.dtype == torch.uint16,
+        bound, mdev = self._max_args(msb_max)
+        d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), bound, self.buf.dtype == torch.uint16,
                            row0=self.r0, row1=self.r1, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0,
-                           n_freq=flags.n_freq, path=path)
+                           n_freq=flags.n_freq, path=path, msb_max_dev=mdev)
         cabi.check(cabi.load().lbdrn_decode(ctypes.byref(d), cabi.ptr(self.buf), cabi.ptr(flat_params_dev), cabi.ptr(tab),
                                             cabi.ptr(self.out), cabi.stream_ptr()))
         return self.out, slice(self.top, self.top + (self.r1 - self.r0))
@@ -137,11 +152,12 @@ class StripeBuffer:
         cur = torch.cuda.current_stream(dev)
         lib = cabi.load()
         last = None
+        bound, mdev = self._max_args(msb_max)
         for a in range(self.r0, self.r1, sub_rows):
             b = min(self.r1, a + sub_rows)
-            d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), msb_max, self.buf.dtype == torch.uint16,
+            d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), bound, self.buf.dtype == torch.uint16,
                                row0=a, row1=b, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0, n_freq=flags.n_freq,
-                               path=path)
+                               path=path, msb_max_dev=mdev)
             cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(self.buf), cabi.ptr(flat_params_dev), cabi.ptr(tab),
                                         cabi.ptr(self.out), cabi.stream_ptr()))
             ev = torch.cuda.Event()

@@ -170,6 +170,11 @@ def decode_image(base, flat_params, K, D, bc, nl, flags=None, relu=False, w0=30.
 _streams = {}
 
 
+def _assume_tensor_range(K):
+    """uint16 base layers: the exact max decides whether the tensor kernel (MSB <= 2048) applies, so it is read back."""
+    return False
+
+
 def _get_streams(dev):
     key = (dev.type, dev.index)
     if key not in _streams:
@@ -215,19 +220,26 @@ def decode_image_streamed(base_host, flat_params, K, D, bc, nl, flags=None, relu
             for c in range(C):
                 msb[c, r0:r1].copy_(base_host[c, r0:r1], non_blocking=True)
             up[i].record(s_in)
+        max_dev = None
         if base_max is None:
+            # max is a whole-image property: reduced on the device once the upload is complete and handed to the kernels
+            # through LbdrnDesc.msb_max_dev -- no host round trip; the descriptor carries the dtype's upper bound
+            max_dev = torch.zeros(1, dtype=torch.int32, device=dev)
             if msb.dtype == torch.uint8:
-                mx = msb.max()
+                max_dev.copy_(msb.max().to(torch.int32).reshape(1))
+                base_max = 255
             else:
-                mx = torch.zeros(1, dtype=torch.int32, device=dev)
-                cabi.check(lib.lbdrn_max_shifted(cabi.ptr(msb), msb.numel(), 0, cabi.ptr(mx), cabi.stream_ptr()))
-            base_max = int(mx.item())                       # waits for the upload: max is a whole-image property
+                cabi.check(lib.lbdrn_max_shifted(cabi.ptr(msb), msb.numel(), 0, cabi.ptr(max_dev), cabi.stream_ptr()))
+                base_max = int(max_dev.item()) if not _assume_tensor_range(K) else 2048
+        up_all = torch.cuda.Event()
+        up_all.record(s_in)
     for i in range(n):
         r0, r1 = bounds[i], bounds[i + 1]
         with torch.cuda.stream(s_cmp):
-            s_cmp.wait_event(up[min(i + 1, n - 1)])         # stripe i and the halo rows of stripe i+1 are resident
+            # stripe i and the halo rows of stripe i+1 are resident (and, with a device-side max, the whole upload)
+            s_cmp.wait_event(up[min(i + 1, n - 1)] if max_dev is None else up_all)
             d = cabi.make_desc(C, H, W, K, D, bc, nl, flags.bits(relu), base_max, msb.dtype == torch.uint16, row0=r0,
-                               row1=r1, w0=w0, n_freq=flags.n_freq, path=_PATHS[path])
+                               row1=r1, w0=w0, n_freq=flags.n_freq, path=_PATHS[path], msb_max_dev=max_dev)
             cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(msb), cabi.ptr(params), cabi.ptr(tab), cabi.ptr(out),
                                         cabi.stream_ptr()))
             done[i].record(s_cmp)
@@ -239,7 +251,7 @@ def decode_image_streamed(base_host, flat_params, K, D, bc, nl, flags=None, relu
     fin.record(s_out)
     fin.synchronize()
     cur.wait_stream(s_cmp)
-    for t in (msb, out, params):
+    for t in (msb, out, params) + ((max_dev,) if max_dev is not None else ()):
         t.record_stream(s_cmp)
     return out_host
 

@@ -79,6 +79,12 @@ def _stripe_decode(rank, world):
     host = torch.empty((4, r1 - r0, msb.shape[2]), dtype=torch.uint16).pin_memory()
     sb.decode_to_host(host, torch.from_numpy(params).cuda(), 5, 64, 2, F.Flags(), mx, sub_rows=37, path=1)
     assert np.array_equal(host.numpy(), out["precise"])
+    # device-side max (no host read-back): same result for both kernel families
+    gmax = torch.tensor([int(msb[:, r0:r1].max())], dtype=torch.int32, device="cuda")
+    LD.global_max_dev(gmax)
+    for name, path in (("precise", 1), ("auto", 0)):
+        o2, rows2 = sb.decode(torch.from_numpy(params).cuda(), 5, 64, 2, F.Flags(), gmax, path=path)
+        assert np.array_equal(o2.cpu().numpy()[:, rows2], out[name]), name
     return r0, r1, out, mx
 
 

@@ -121,11 +121,11 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == sorted(cabi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lbdrn_version() == 1
+    assert lib.lbdrn_version() == 2
 
 
 def test_cabi_struct_layout_matches_header():
-    assert ctypes.sizeof(cabi.LbdrnDesc) == 20 * 4
+    assert ctypes.sizeof(cabi.LbdrnDesc) == 20 * 4 + 8
     assert ctypes.sizeof(cabi.LbdrnTrainCfg) == 4 * 4 + 3 * 8 + 4 * 4
 
 
