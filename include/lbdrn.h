@@ -109,6 +109,10 @@ int32_t lbdrn_split(const uint16_t* img_dev, int64_t n, int32_t K, int32_t msb_d
  * result written to *max_dev (device uint32, must be zero-initialised by the caller). */
 int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_t* max_dev, void* stream);
 
+/* ---- a16: quality read-out (decode.py:216): *sse_dev (device uint64, zero-initialised by the caller) += sum over n
+ * elements of (a-b)^2 for two uint16 images.  Integer accumulation: exact and order-independent. */
+int32_t lbdrn_sse_u16(const uint16_t* a_dev, const uint16_t* b_dev, int64_t n, uint64_t* sse_dev, void* stream);
+
 /* ---- a14+a15: fused decode (decode.py:77-134) -----------------------------------------------------------
  * msb_dev: base layer, CHW per desc (rows buf_row0..).  params_dev: flat fp32 [P].  coord_tab_dev: float32
  * [(H + W) * tabw] row table then column table, tabw = 2*n_freq*EMBEDDING+1, or NULL when USE_COORDINATES is

@@ -157,6 +157,17 @@ __global__ void max_shifted_kernel(const uint16_t* __restrict__ img, long long n
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
+__global__ void sse_u16_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, long long n,
+                               unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long d = (long long)a[i] - (long long)b[i];
+    acc += (unsigned long long)(d * d);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);      // integer sum: exact, order-independent
+}
+
 }  // namespace
 
 // ---- training handle ------------------------------------------------------------------------------------
@@ -221,6 +232,16 @@ int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_
   long long blocks = (n + 2047) / 2048;
   if (blocks > 148 * 8) blocks = 148 * 8;
   max_shifted_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img_dev, n, K, max_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_sse_u16(const uint16_t* a_dev, const uint16_t* b_dev, int64_t n, uint64_t* sse_dev, void* stream) {
+  if (!a_dev || !b_dev || !sse_dev || n <= 0) return fail(LBDRN_E_INVALID, "lbdrn_sse_u16: bad argument");
+  long long blocks = (n + 4095) / 4096;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sse_u16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a_dev, b_dev, n, (unsigned long long*)sse_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return LBDRN_OK;

@@ -169,9 +169,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity, int wh
   for (int it = 0; it < (1 << 22); ++it) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(mbar), "r"(parity)
+        : "r"(mbar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware instead of re-polling
         : "memory");
     if (ok) return;
   }

@@ -97,7 +97,11 @@ def main(argv=None):
         org = gdal.Open(args.org_path).ReadAsArray()
         rec = gdal.Open(recon_path).ReadAsArray()
         n_bytes = os.path.getsize(args.bin_path)
-        mse = np.mean((org.astype(np.float32) - rec.astype(np.float32)) ** 2)
+        if org.dtype == np.uint16 and rec.dtype == np.uint16 and torch.cuda.is_available():
+            import lbdrn_fused
+            mse = np.float32(lbdrn_fused.image_mse(org, rec))            # exact integer sum on the device
+        else:
+            mse = np.mean((org.astype(np.float32) - rec.astype(np.float32)) ** 2)
         logger.log.info(f"MSE: {mse}")
         logger.log.info(f"PSNR: {10 * np.log10(10000 ** 2 / mse)}")       # peak fixed at 10000 (decode.py:218)
         logger.log.info(f"Total size: {n_bytes} bytes, bpsp={n_bytes * 8 / np.prod(org.shape)}")

@@ -256,6 +256,21 @@ def decode_image_streamed(base_host, flat_params, K, D, bc, nl, flags=None, relu
     return out_host
 
 
+def image_mse(a, b, device=None):
+    """mean((a-b)^2) of two uint16 images on the device (quality read-out of decode.py:216); exact integer sum."""
+    dev, lib = _device(device), cabi.load()
+    def up(x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x.astype(np.uint16, copy=False)))
+        return x.to(dev).contiguous()
+    ta, tb = up(a), up(b)
+    if ta.numel() != tb.numel():
+        raise ValueError("image sizes differ")
+    acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    cabi.check(lib.lbdrn_sse_u16(cabi.ptr(ta), cabi.ptr(tb), ta.numel(), cabi.ptr(acc), cabi.stream_ptr()))
+    return float(acc.item()) / ta.numel()
+
+
 def predict_image(base, flat_params, D, bc, nl, flags=None, relu=False, w0=30.0, device=None):
     """Network output y [H*W, C] (float32 CUDA tensor) for every pixel of the base layer."""
     flags, dev, lib = _flags(flags), _device(device), cabi.load()

@@ -221,3 +221,12 @@ def test_streamed_host_to_host_decode_matches_resident_decode():
     assert np.array_equal(out.numpy(), whole)
     out2 = F.decode_image_streamed(msb, params, 5, 2, 64, 2, flags=F.Flags(), stripe_rows=1000, base_max=int(msb.max()))
     assert np.array_equal(out2.numpy(), whole)
+
+
+def test_device_quality_readout_matches_numpy():
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 65536, size=(4, 301, 257), dtype=np.uint16)
+    b = (a.astype(np.int64) + rng.integers(-40, 41, size=a.shape)).clip(0, 65535).astype(np.uint16)
+    ref = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    assert F.image_mse(a, b) == pytest.approx(ref, rel=1e-12)
+    assert F.image_mse(a, a) == 0.0

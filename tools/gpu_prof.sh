@@ -7,7 +7,7 @@ $CMD > gpurun_out/plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"
 python tools/prof_decode.py decode 4096 auto > gpurun_out/plain_decode.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:tc_decode -s 1 -c 1 -f -o /tmp/prof_decode \
+ncu --set full --clock-control none --import-source on -k regex:tc_decode_kernel -s 2 -c 1 -f -o /tmp/prof_decode \
     python tools/prof_decode.py decode 4096 auto > gpurun_out/ncu_decode.log 2>&1
 echo "decode capture rc=$?"
 python tools/prof_decode.py train 1024 > gpurun_out/plain_train.log 2>&1 &&
