@@ -256,6 +256,78 @@ def decode_image_streamed(base_host, flat_params, K, D, bc, nl, flags=None, relu
     return out_host
 
 
+class StreamedDecoder:
+    """Throughput-oriented host->host decoder for a sequence of same-shaped scenes (base-layer hand-off, N1 of
+    SURVEY.md 8f).  `submit()` queues upload, device-side max, stripe kernels and download of one scene on three streams
+    and returns immediately; with two buffer slots the upload of scene i+1 overlaps the kernels and the download of scene
+    i, so a steady stream of scenes runs at the slowest of (H2D, kernel, D2H) instead of their sum.  `wait()` blocks until
+    a submitted scene's reconstruction is complete in its host buffer."""
+
+    def __init__(self, C, H, W, msb_dtype, K, D, bc, nl, flat_params, flags=None, relu=False, w0=30.0, path="auto",
+                 device=None, stripe_rows=1024, slots=2):
+        self.flags, self.dev, self.lib = _flags(flags), _device(device), cabi.load()
+        self.C, self.H, self.W, self.K, self.D, self.bc, self.nl = C, H, W, K, D, bc, nl
+        self.relu, self.w0, self.path = relu, w0, _PATHS[path]
+        self.u16 = msb_dtype == torch.uint16
+        self.params = torch.as_tensor(flat_params, dtype=torch.float32).to(self.dev).contiguous()
+        self.tab = _tab_tensor(H, W, self.flags, self.dev)
+        self.s_in, self.s_cmp, self.s_out = _get_streams(self.dev)
+        self.bounds = list(range(0, H, stripe_rows)) + [H]
+        self.slots = [dict(msb=torch.empty((C, H, W), dtype=msb_dtype, device=self.dev),
+                           out=torch.empty((C, H, W), dtype=torch.uint16, device=self.dev),
+                           mx=torch.zeros(1, dtype=torch.int32, device=self.dev), cmp_done=None, out_done=None)
+                      for _ in range(slots)]
+        self.n = 0
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def submit(self, base_host, out_host):
+        """base_host: [C,H,W] uint8/uint16 CPU tensor (pinned); out_host: [C,H,W] uint16 CPU tensor (pinned)."""
+        sl = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        C, lib = self.C, self.lib
+        with torch.cuda.stream(self.s_in):
+            if sl["cmp_done"] is not None:
+                self.s_in.wait_event(sl["cmp_done"])           # the kernels that read this slot's planes are done
+            for c in range(C):
+                sl["msb"][c].copy_(base_host[c], non_blocking=True)
+            if self.u16:
+                sl["mx"].zero_()
+                cabi.check(lib.lbdrn_max_shifted(cabi.ptr(sl["msb"]), sl["msb"].numel(), 0, cabi.ptr(sl["mx"]),
+                                                 cabi.stream_ptr()))
+            else:
+                sl["mx"].copy_(sl["msb"].max().to(torch.int32).reshape(1))
+            up = torch.cuda.Event()
+            up.record(self.s_in)
+        bound = 2048 if self.u16 else 255                      # msb_max_dev carries the exact value
+        last = None
+        for i in range(len(self.bounds) - 1):
+            r0, r1 = self.bounds[i], self.bounds[i + 1]
+            with torch.cuda.stream(self.s_cmp):
+                if i == 0:
+                    self.s_cmp.wait_event(up)
+                    if sl["out_done"] is not None:
+                        self.s_cmp.wait_event(sl["out_done"])  # the previous download from this slot's output is done
+                d = cabi.make_desc(C, self.H, self.W, self.K, self.D, self.bc, self.nl, self.flags.bits(self.relu), bound,
+                                   self.u16, row0=r0, row1=r1, w0=self.w0, n_freq=self.flags.n_freq, path=self.path,
+                                   msb_max_dev=sl["mx"])
+                cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(sl["msb"]), cabi.ptr(self.params), cabi.ptr(self.tab),
+                                            cabi.ptr(sl["out"]), cabi.stream_ptr()))
+                ev = torch.cuda.Event()
+                ev.record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev)
+                for c in range(C):
+                    out_host[c, r0:r1].copy_(sl["out"][c, r0:r1], non_blocking=True)
+                last = torch.cuda.Event()
+                last.record(self.s_out)
+        sl["cmp_done"], sl["out_done"] = ev, last
+        return last
+
+    @staticmethod
+    def wait(ticket):
+        ticket.synchronize()
+
+
 def image_mse(a, b, device=None):
     """mean((a-b)^2) of two uint16 images on the device (quality read-out of decode.py:216); exact integer sum."""
     dev, lib = _device(device), cabi.load()

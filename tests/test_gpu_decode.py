@@ -230,3 +230,18 @@ def test_device_quality_readout_matches_numpy():
     ref = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
     assert F.image_mse(a, b) == pytest.approx(ref, rel=1e-12)
     assert F.image_mse(a, a) == 0.0
+
+
+def test_streamed_decoder_pipeline_matches_resident_decode():
+    """StreamedDecoder: several scenes in flight over two buffer slots; every result equals the resident decode."""
+    from synth_scene import make_scene
+    params = _trained_params()
+    scenes = [O.split_msb_lsb(make_scene(4, 150, 176, 12, seed=40 + i), 5)[0] for i in range(5)]
+    dec = F.StreamedDecoder(4, 150, 176, torch.uint8, 5, 2, 64, 2, params, flags=F.Flags(), stripe_rows=64)
+    hosts = [torch.from_numpy(m).pin_memory() for m in scenes]
+    outs = [torch.empty((4, 150, 176), dtype=torch.uint16).pin_memory() for _ in scenes]
+    tickets = [dec.submit(h, o) for h, o in zip(hosts, outs)]
+    for t in tickets:
+        dec.wait(t)
+    for m, o in zip(scenes, outs):
+        assert np.array_equal(o.numpy(), F.decode_image(m, params, 5, 2, 64, 2, flags=F.Flags()))
