@@ -128,46 +128,55 @@ __device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowo
   for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? __fdiv_rn((float)raw[dx], maxv) - ctr : 0.f;
 }
 
-// out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin (dst = natural [BC][Kin] gradient block); THREADS/8 row
-// lanes x 8 column lanes, 64 rows x 64 columns per pass.
+// out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin (dst = natural [BC][Kin] gradient block).
+// Thread (trow = tid%16, tcol = tid/16) owns rows trow + 16x (x<4) and columns tcol + CT*y (y<4, CT = THREADS/16):
+// a 4x4 register tile with 16 independent FFMA chains; per 4-pixel step 4 + (#valid y) LDS.128 feed 16*(#valid y)*4/4 FFMAs.
+// Row loads of a quarter-warp hit 8 consecutive rows (stride 68 floats = 4 banks apart: conflict-free), column loads are
+// broadcasts.  64 rows x 4*CT columns per pass.
 template <int BC, int THREADS>
 __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, const float* __restrict__ A, int Kin,
                                                  int kpad8, float* __restrict__ dst, bool first) {
-  constexpr int LDP = kTrainLDP, NR = THREADS / 8, RA = 64 / NR;
-  const int tid = threadIdx.x, tc = tid & 7, tr = tid >> 3;
+  constexpr int LDP = kTrainLDP, CT = THREADS / 16;
+  const int tid = threadIdx.x, trow = tid & 15, tcol = tid >> 4;
   for (int r0 = 0; r0 < BC; r0 += 64) {
-    for (int q0 = 0; q0 < Kin; q0 += 64) {
-      float acc[RA][8];
+    for (int q0 = 0; q0 < Kin; q0 += 4 * CT) {
+      float acc[4][4];
 #pragma unroll
-      for (int x = 0; x < RA; ++x)
+      for (int x = 0; x < 4; ++x)
 #pragma unroll
-        for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
-      for (int p = 0; p < kTrainNPIX; p += 4) {
-        float4 gv[RA];
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+      bool qok[4];
 #pragma unroll
-        for (int x = 0; x < RA; ++x) {
-          const int r = r0 + tr + NR * x;
-          gv[x] = r < BC ? *reinterpret_cast<const float4*>(G + (size_t)r * LDP + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int y = 0; y < 4; ++y) qok[y] = q0 + tcol + CT * y < kpad8;
+      if (qok[0]) {
+#pragma unroll 2
+        for (int p = 0; p < kTrainNPIX; p += 4) {
+          float4 gv[4], av[4];
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          if (q0 + 8 * y < kpad8) {
-            float4 av = *reinterpret_cast<const float4*>(A + (size_t)(q0 + tc + 8 * y) * LDP + p);
-#pragma unroll
-            for (int x = 0; x < RA; ++x) {
-              acc[x][y] = fmaf(gv[x].x, av.x, acc[x][y]);
-              acc[x][y] = fmaf(gv[x].y, av.y, acc[x][y]);
-              acc[x][y] = fmaf(gv[x].z, av.z, acc[x][y]);
-              acc[x][y] = fmaf(gv[x].w, av.w, acc[x][y]);
-            }
+          for (int x = 0; x < 4; ++x) {
+            const int r = r0 + trow + 16 * x;
+            gv[x] = r < BC ? *reinterpret_cast<const float4*>(G + (size_t)r * LDP + p) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+            av[y] = qok[y] ? *reinterpret_cast<const float4*>(A + (size_t)(q0 + tcol + CT * y) * LDP + p)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+              acc[x][y] = fmaf(gv[x].x, av[y].x, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].y, av[y].y, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].z, av[y].z, acc[x][y]);
+              acc[x][y] = fmaf(gv[x].w, av[y].w, acc[x][y]);
+            }
         }
       }
 #pragma unroll
-      for (int x = 0; x < RA; ++x)
+      for (int x = 0; x < 4; ++x)
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          const int q = q0 + tc + 8 * y, r = r0 + tr + NR * x;
+        for (int y = 0; y < 4; ++y) {
+          const int q = q0 + tcol + CT * y, r = r0 + trow + 16 * x;
           if (q < Kin && r < BC) {
             float* d = dst + (size_t)r * Kin + q;
             *d = first ? acc[x][y] : *d + acc[x][y];
@@ -429,6 +438,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           *d = first ? g : *d + g;
         }
       }
+      LBDRN_PHASE(8)    // bwd: output-layer grads
       for (int l = L - 1; l >= 0; --l) {
         float* Gl = Gbuf + (size_t)l * BC * LDP;
         float acc[TM][TN];
@@ -465,6 +475,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           *gp = g;
         }
         __syncthreads();
+        LBDRN_PHASE(9 + 2 * (l > 0 ? 1 : 0))     // bwd: dh + dz (9: layer 0, 11: layer >= 1)
         // dW_l = dz_l . in_l^T ; db_l = row sums
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
@@ -474,9 +485,10 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           float* d = mypart + net.boff[l] + u;
           *d = first ? g : *d + g;
         }
+        LBDRN_PHASE(10 + 2 * (l > 0 ? 1 : 0))    // bwd: dW + db (10: layer 0, 12: layer >= 1)
       }
       first = false;
-      LBDRN_PHASE(4)   // backward
+      LBDRN_PHASE(4)   // backward (remainder)
     }
     __syncthreads();
     if (tid == 0 && !first) mypart[P] = s_sse;
