@@ -167,6 +167,41 @@ def test_cli_encode_decode_roundtrip(tmp_path):
     meta = load_case("k5d2_small")[0]
     assert abs(psnr - meta["psnr"]) < 0.05                        # 45 steps only: far from converged, looser bound
     assert "bpsp=" in log and "MSE: " in log
-    # the reference decoder's header reader parses our stream
-    hdr = O.unpack_header(open(f"{d}/s.bin", "rb").read())
+    # the reference decoder's header reader parses our stream, and the ORACLE decoder (the reference's arithmetic)
+    # reconstructs the same image from it as our decoder did
+    blob = open(f"{d}/s.bin", "rb").read()
+    hdr = O.unpack_header(blob)
     assert hdr[1:8] == (1, 80, 96, 5, 64, 2, 2)
+    _, tiles = split_stream(blob)
+    base = read_base(tiles[0][1])
+    params = O.unflatten_params(fpzip.decompress(tiles[0][0])[0][0][0], 100, 64, 4, 2)
+    ref = O.decode_image(base, params, 5, 2)
+    mse_ref, psnr_ref, _ = O.quality(img, ref, len(blob))
+    assert abs(psnr_ref - psnr) < 1e-3
+
+
+def test_cli_split_ratio_roundtrip(tmp_path):
+    """-sr 2: four independently trained tiles, header with 4+4 sizes, merge on decode (encode.py:231-262, decode.py:187-197)."""
+    from osgeo import gdal
+    from synth_scene import make_scene
+    img = make_scene(4, 97, 90, 12, seed=9)
+    tif = str(tmp_path / "t.tif")
+    gdal._store(tif, img)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([PKG, SHIMS]))
+    out = str(tmp_path / "out")
+    r = subprocess.run([sys.executable, os.path.join(PKG, "encode.py"), "-K", "5", "-i", tif, "-D", "2", "-bc", "64",
+                        "-nl", "2", "-lr", "0.001", "-bs", "512", "-e", "2", "-sr", "2", "-prec", "16", "-o", out],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    d = f"{out}/t_r2_K5_bc64_nl2_D2_prec16_lr0.001_bs512_e2"
+    blob = open(f"{d}/t.bin", "rb").read()
+    hdr = O.unpack_header(blob)
+    assert hdr[1] == 2 and len(hdr[8]) == 4 and len(hdr[9]) == 4 and hdr[0] == 8 + 7 * 4
+    assert len(blob) == hdr[0] + sum(hdr[8]) + sum(hdr[9])
+    r = subprocess.run([sys.executable, os.path.join(PKG, "decode.py"), "-i", f"{d}/t.bin", "-org", tif],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    log = open(f"{d}/decode.txt").read()
+    psnr = float(log.split("PSNR: ")[1].split()[0])
+    meta = load_case("sr2_tiles")[0]
+    assert abs(psnr - meta["psnr"]) < 0.05
