@@ -125,6 +125,11 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
  * shared-memory operand layout and TMEM read-back as the tensor decode kernel (K multiple of 16, <= 256). */
 int32_t lbdrn_selftest_tc_gemm(const void* a_dev, const void* b_dev, float* d_dev, int32_t K, void* stream);
 
+/* Diagnostic: D[128][N] = A[128][K] * B[N][K]^T (fp16 row-major inputs) with operand A and/or B staged in the MN-major
+ * "[group of 8][k][8]" shared-memory layout and consumed through MN-major UMMA descriptors (a_mn / b_mn != 0). */
+int32_t lbdrn_selftest_tc_gemm2(const void* a_dev, const void* b_dev, float* d_dev, int32_t N, int32_t K, int32_t a_mn,
+                                int32_t b_mn, void* stream);
+
 /* network output y [n_rows*W, C] float32 (pixel-major, like model(x) in decode.py:130) for rows [row0,row1) */
 int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev,
                       const float* coord_tab_dev, float* y_dev, void* stream);

@@ -272,6 +272,12 @@ int32_t lbdrn_selftest_tc_gemm(const void* a_dev, const void* b_dev, float* d_de
   return tc_selftest(a_dev, b_dev, d_dev, K, (cudaStream_t)stream);
 }
 
+int32_t lbdrn_selftest_tc_gemm2(const void* a_dev, const void* b_dev, float* d_dev, int32_t N, int32_t K, int32_t a_mn,
+                                int32_t b_mn, void* stream) {
+  if (!a_dev || !b_dev || !d_dev) return fail(LBDRN_E_INVALID, "null device pointer");
+  return tc_selftest2(a_dev, b_dev, d_dev, N, K, a_mn, b_mn, (cudaStream_t)stream);
+}
+
 int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev, const float* coord_tab_dev,
                       float* y_dev, void* stream) {
   return run_infer<MODE_PREDICT>(d, msb_dev, nullptr, params_dev, coord_tab_dev, y_dev, nullptr, stream);

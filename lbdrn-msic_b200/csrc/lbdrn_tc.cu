@@ -675,6 +675,66 @@ __global__ void __launch_bounds__(TC_THREADS) tc_selftest_kernel(const __half* _
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
 }
 
+// ---- self-test 2: D[128][N] = A[128][K] * B[N][K]^T with either operand in the MN-major "[group of 8][k][8]" layout
+// (the layout the kernels write activations in, read here with the roles of the two dimensions swapped) -----------------
+__device__ __forceinline__ uint32_t umma_idesc_f16_major(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// MN-major, no swizzle: element (mn, k) at ((mn/8)*K + k)*16 + (mn%8)*2 : 8 contiguous MN elements per 16 B, the 8 k-rows
+// of a core matrix are 16 B apart, next k-group +128 B (LBO), next MN-group +K*16 B (SBO).
+__host__ __device__ inline int umma_off_mn(int K, int mn, int k) { return ((mn >> 3) * K + k) * 16 + (mn & 7) * 2; }
+
+__global__ void __launch_bounds__(TC_THREADS) tc_selftest2_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
+                                                                 float* __restrict__ Dout, int N, int K, int a_mn, int b_mn) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * K; i += TC_THREADS) {
+    const int r = i / K, k = i - r * K;
+    *reinterpret_cast<__half*>(sA + (a_mn ? umma_off_mn(K, r, k) : umma_off(128, r, k))) = A[i];
+  }
+  for (int i = tid; i < N * K; i += TC_THREADS) {
+    const int r = i / K, k = i - r * K;
+    *reinterpret_cast<__half*>(sB + (b_mn ? umma_off_mn(K, r, k) : umma_off(N, r, k))) = B[i];
+  }
+  const int cols = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_f16_major(128, N, a_mn, b_mn);
+    for (int i = 0; i < K / 16; ++i) {
+      // K-major: k-chunk stride rows*16 (LBO), 8-row group stride 128 (SBO).  MN-major: k-group stride 128 (LBO),
+      // MN-group stride K*16 (SBO); one instruction consumes 16 k = 2 k-groups -> advance 256 B per step.
+      const uint64_t da = a_mn ? umma_desc(smem_u32(sA) + i * 256, 128, K * 16) : umma_desc(smem_u32(sA) + i * 2 * 2048, 2048, 128);
+      const uint64_t db = b_mn ? umma_desc(smem_u32(sB) + i * 256, 128, K * 16) : umma_desc(smem_u32(sB) + i * 2 * N * 16, N * 16, 128);
+      umma_f16(tmem, da, db, idesc, i > 0);
+    }
+    umma_commit(smem_u32(&s_mbar));
+  }
+  mbar_wait(smem_u32(&s_mbar), 0);
+  tc_fence_after();
+  for (int cb = 0; cb < N; cb += 16) {
+    float acc[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cb, acc);
+    for (int j = 0; j < 16; ++j) Dout[tid * N + cb + j] = acc[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+}
+
 std::mutex& tc_mu() {
   static std::mutex m;
   return m;
@@ -860,6 +920,16 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
   rc = tc_setup_tma(a, dev, st);
   if (rc) return rc;
   return tc_launch(pick_kernel<true, true, TC_SSE, 1>(n), a, h, true, 1, dev, st);
+}
+
+int tc_selftest2(const void* a_dev, const void* b_dev, float* d_dev, int N, int K, int a_mn, int b_mn, cudaStream_t st) {
+  if (K % 16 || K < 16 || K > 256 || N % 16 || N < 16 || N > 128) return fail(LBDRN_E_INVALID, "selftest2 N=%d K=%d", N, K);
+  const size_t smem = (size_t)(128 + N) * K * 2;
+  CUDA_TRY(cudaFuncSetAttribute(tc_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest2_kernel<<<1, TC_THREADS, smem, st>>>((const __half*)a_dev, (const __half*)b_dev, d_dev, N, K, a_mn, b_mn);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
 }
 
 int tc_selftest(const void* a_dev, const void* b_dev, float* d_dev, int K, cudaStream_t st) {

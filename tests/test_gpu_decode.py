@@ -294,3 +294,21 @@ def test_degenerate_and_invalid_inputs_are_rejected():
     # wrong parameter count is caught by the Python layer before the call
     with pytest.raises(ValueError):
         F.decode_image(np.ones((4, 8, 8), np.uint8), np.zeros(100, np.float32), 5, 2, 64, 2, flags=F.Flags())
+
+
+def test_tcgen05_selftest_mn_major_operands():
+    """MN-major UMMA descriptors over the "[group of 8][k][8]" layout (what a tensor-core backward pass would use to
+    re-read forward activations with the roles of the two dimensions swapped)."""
+    lib = cabi.load()
+    rng = np.random.default_rng(1)
+    for (N, K, a_mn, b_mn) in [(64, 64, 0, 0), (128, 64, 0, 0), (16, 128, 0, 0), (64, 64, 1, 0), (64, 64, 0, 1),
+                               (128, 128, 1, 1), (16, 128, 1, 1), (64, 32, 1, 1)]:
+        A = rng.integers(-9, 10, size=(128, K)).astype(np.float16)
+        B = rng.integers(-9, 10, size=(N, K)).astype(np.float16)
+        a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        d = torch.full((128, N), float("nan"), device="cuda")
+        cabi.check(lib.lbdrn_selftest_tc_gemm2(cabi.ptr(a), cabi.ptr(b), cabi.ptr(d), N, K, a_mn, b_mn, cabi.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        got = d.cpu().numpy().astype(np.float64)
+        assert np.array_equal(got, ref), (N, K, a_mn, b_mn, float(np.abs(got - ref).max()))
