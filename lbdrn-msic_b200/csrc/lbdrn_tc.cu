@@ -23,35 +23,11 @@
 
 #include "lbdrn_infer_fp32.cuh"
 #include "lbdrn_internal.h"
+#include "lbdrn_umma.cuh"
 
 namespace lbdrn {
 
 namespace {
-
-constexpr int TC_THREADS = 128;       // one warpgroup: thread t <-> TMEM lane t <-> pixel t of the tile
-constexpr int TC_BC = 64;             // hidden width this kernel is instantiated for
-constexpr int TC_TH = 8, TC_TW = 16;  // 128-pixel tile
-constexpr int TC_TMEM_COLS = 64;      // fp32 accumulator: bc columns (power of two >= 32)
-constexpr int TC_MAX_K1 = 400;        // C*(2D+1)^2 <= 400 (8 bands, D=3 -> 392)
-
-// ---- packed weight block (global scratch and, copied verbatim, shared memory) ------------------------------------
-struct TcHeader {
-  int exact;            // 1: every hidden weight is exactly representable as fp16 after its power-of-two scale
-  int k1, k1pad;        // layer-1 K (= dim_in) and K rounded up to 16
-  int nl;
-  float scale[kMaxLayers];   // per hidden layer: multiply the fp32 accumulator by this (2^-s, and /max for layer 0)
-  int off_bias, off_w3, off_b[kMaxLayers], total;   // byte offsets inside the block
-  int off_blo[kMaxLayers];   // low-order fp16 term of the weights (W*2^s = hi + lo); all zero when `exact`
-  int hi_bytes;              // block size without the lo operands (what the exact-weights kernel copies)
-  int pad[7];
-};
-
-__host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
-
-// byte offset of element (row, k) of a K-major, no-swizzle UMMA operand with `rows` rows:
-// 8x8 core matrices of 128 contiguous bytes; consecutive 8-row groups are contiguous (SBO = 128 B), consecutive
-// 8-element K chunks are rows*16 B apart (LBO).
-__host__ __device__ inline int umma_off(int rows, int row, int k) { return ((k >> 3) * rows + row) * 16 + (k & 7) * 2; }
 
 void plan_block(const Net& n, TcHeader& h) {
   memset(&h, 0, sizeof h);
@@ -129,89 +105,6 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
     H->off_bias = hdr.off_bias; H->off_w3 = hdr.off_w3; H->total = hdr.total; H->hi_bytes = hdr.hi_bytes;
     for (int l = 0; l < net.nl; ++l) { H->off_b[l] = hdr.off_b[l]; H->off_blo[l] = hdr.off_blo[l]; }
   }
-}
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout NONE [61,64)
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-
-// cute::UMMA::InstrDescriptor, kind::f16: D=f32 (bit 4), A=B=f16 (0), both K-major (0), N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ int g_tc_timeout[4];   // diagnostics: {which barrier, tile, block, count}
-
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity, int what = 0, int tile = -1, int no_trap = 0) {
-  // bounded: a lost arrival traps (surfacing as a CUDA error) instead of hanging the GPU
-  for (int it = 0; it < (1 << 22); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(mbar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware instead of re-polling
-        : "memory");
-    if (ok) return;
-  }
-  if (threadIdx.x == 0) {
-    g_tc_timeout[0] = what; g_tc_timeout[1] = tile; g_tc_timeout[2] = blockIdx.x;
-    atomicAdd(&g_tc_timeout[3], 1);
-    __threadfence_system();
-  }
-  if (no_trap) return;      // LBDRN_DEBUG: let the kernel finish (garbage output) so the host can read the diagnostics
-  __nanosleep(1000000);
-  __trap();
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-
-// TMA: one 3-D box (x, y, band) of the MSB planes -> shared memory; out-of-range elements are zero-filled
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t mbar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-      "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar)
-      : "memory");
-}
-
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 struct TcArgs {
@@ -677,14 +570,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_selftest_kernel(const __half* _
 
 // ---- self-test 2: D[128][N] = A[128][K] * B[N][K]^T with either operand in the MN-major "[group of 8][k][8]" layout
 // (the layout the kernels write activations in, read here with the roles of the two dimensions swapped) -----------------
-__device__ __forceinline__ uint32_t umma_idesc_f16_major(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-// MN-major, no swizzle: element (mn, k) at ((mn/8)*K + k)*16 + (mn%8)*2 : 8 contiguous MN elements per 16 B, the 8 k-rows
-// of a core matrix are 16 B apart, next k-group +128 B (LBO), next MN-group +K*16 B (SBO).
-__host__ __device__ inline int umma_off_mn(int K, int mn, int k) { return ((mn >> 3) * K + k) * 16 + (mn & 7) * 2; }
-
 __global__ void __launch_bounds__(TC_THREADS) tc_selftest2_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
                                                                  float* __restrict__ Dout, int N, int K, int a_mn, int b_mn) {
   extern __shared__ __align__(1024) uint8_t smem[];
