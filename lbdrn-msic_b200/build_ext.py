@@ -26,6 +26,7 @@ UNITS = [
     ("infer_sse", "lbdrn_infer_fp32.cu", ["-DLBDRN_INFER_MODE=2"]),
     ("train", "lbdrn_train_fp32.cu", []),
     ("tc", "lbdrn_tc.cu", []),
+    ("tcw", "lbdrn_tcw.cu", []),
 ]
 
 

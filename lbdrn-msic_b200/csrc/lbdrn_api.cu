@@ -117,7 +117,7 @@ namespace {
 
 template <int MODE>
 int run_infer(const LbdrnDesc* d, const void* msb, const void* lsb, const float* params, const float* tab, void* out,
-              double* sse_out, void* stream) {
+              double* sse_out, void* stream, const int* skip_flag = nullptr) {
   Net n;
   int rc = resolve(d, n);
   if (rc) return rc;
@@ -134,6 +134,7 @@ int run_infer(const LbdrnDesc* d, const void* msb, const void* lsb, const float*
   memset(&a, 0, sizeof a);
   a.net = n; a.msb = msb; a.lsb = lsb; a.wpack = sc->wpack; a.tab = tab; a.out = out;
   a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
+  a.skip_flag = skip_flag;
   if (MODE == MODE_DECODE) return infer_fp32_decode(a, *sc, st);
   if (MODE == MODE_PREDICT) return infer_fp32_predict(a, *sc, st);
   return infer_fp32_sse(a, *sc, st);
@@ -213,7 +214,7 @@ int64_t lbdrn_param_count(const LbdrnDesc* d) {
 int32_t lbdrn_has_tensor_path(const LbdrnDesc* d) {
   Net n;
   if (resolve(d, n, false)) return 0;
-  return tc_supported(n) ? 1 : 0;
+  return (tc_supported(n) || tcw_supported(n)) ? 1 : 0;
 }
 
 int32_t lbdrn_split(const uint16_t* img_dev, int64_t n, int32_t K, int32_t msb_dtype, void* msb_dev, void* lsb_dev,
@@ -252,7 +253,8 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
   Net n;
   int rc = resolve(d, n);
   if (rc) return rc;
-  const bool tc_ok = tc_supported(n);
+  const bool tcw_ok = tcw_supported(n);
+  const bool tc_ok = tc_supported(n) || tcw_ok;
   if (d->path == LBDRN_PATH_TENSOR && !tc_ok)
     return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
   if (d->path == LBDRN_PATH_TENSOR_FASTSIN && !tc_ok)
@@ -262,6 +264,14 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
     // AUTO: MUFU sine while the K-bit quantiser leaves >= 10x margin on the 99.99 % identity bar (K <= 8: 99.9996 %
     // identical at K=8 on the parity suite), the 1.3e-7 polynomial above that
     const int fast = d->path == LBDRN_PATH_TENSOR_FASTSIN || (d->path == LBDRN_PATH_AUTO && n.K <= 8);
+    if (tcw_ok) {
+      // bc 128/256: the wide kernel decodes iff the weights are fp16-exact after scaling; the fp32 kernel queued behind
+      // it reads the same device flag and exits at once in that case (and does the work otherwise)
+      const int* exact_flag = nullptr;
+      rc = tcw_decode(n, msb_dev, params_dev, out_dev, fast, &exact_flag, (cudaStream_t)stream);
+      if (rc) return rc;
+      return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream, exact_flag);
+    }
     return tc_decode(n, msb_dev, params_dev, coord_tab_dev, out_dev, fast, (cudaStream_t)stream);
   }
   return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream);

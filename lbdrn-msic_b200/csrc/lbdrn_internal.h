@@ -54,6 +54,10 @@ bool tc_supported(const Net& n);
 int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
               cudaStream_t st);
 int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st);
+// wide (bc 128/256) tcgen05 decode (lbdrn_tcw.cu)
+bool tcw_supported(const Net& n);
+int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out, int fast_sine, const int** exact_flag_out,
+               cudaStream_t st);
 int tc_selftest2(const void* a_dev, const void* b_dev, float* d_dev, int N, int K, int a_mn, int b_mn, cudaStream_t st);
 int tc_selftest(const void* a_dev, const void* b_dev, float* d_dev, int K, cudaStream_t st);
 

@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_selftest2_kernel(const __half* 
     const int r = i / K, k = i - r * K;
     *reinterpret_cast<__half*>(sB + (b_mn ? umma_off_mn(K, r, k) : umma_off(N, r, k))) = B[i];
   }
-  const int cols = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  const int cols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -808,7 +808,7 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
 }
 
 int tc_selftest2(const void* a_dev, const void* b_dev, float* d_dev, int N, int K, int a_mn, int b_mn, cudaStream_t st) {
-  if (K % 16 || K < 16 || K > 256 || N % 16 || N < 16 || N > 128) return fail(LBDRN_E_INVALID, "selftest2 N=%d K=%d", N, K);
+  if (K % 16 || K < 16 || K > 256 || N % 16 || N < 16 || N > 256) return fail(LBDRN_E_INVALID, "selftest2 N=%d K=%d", N, K);
   const size_t smem = (size_t)(128 + N) * K * 2;
   CUDA_TRY(cudaFuncSetAttribute(tc_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest2_kernel<<<1, TC_THREADS, smem, st>>>((const __half*)a_dev, (const __half*)b_dev, d_dev, N, K, a_mn, b_mn);

@@ -1,0 +1,566 @@
+// lbdrn_tcw.cu -- "wide" tcgen05 decode kernel (sm_100a) for hidden widths 128 / 256 (BASELINE config 3: D=3 bc256 nl2,
+// 233 472 flop and 512 sines per pixel).  Same arithmetic as lbdrn_tc.cu (integer-difference features exact in fp16,
+// fp16 hi+lo split activations, fp32 TMEM accumulators, weights exact after a power-of-two scale), different machine
+// mapping, because at bc = 256 neither the weights (B1 106 KB + B2 131 KB as fp16) nor the split activations of a tile
+// (131 KB) fit in shared memory next to each other:
+//
+//   * one CTA per SM, 18 warps, warp-specialised:
+//       warps 0-15  four "epilogue" warpgroups; thread = (warpgroup, pixel = TMEM lane); they stage the patch, build A1,
+//                   and turn accumulator columns into the next layer's operand, 16 columns (one MMA K step) at a time;
+//                   warpgroup w owns the chunks j = w (mod 4)
+//       warp 16     MMA issue (one elected lane): tcgen05.mma M=128 N=bc K=16, kind::f16, cta_group::1
+//       warp 17     weight streamer (one elected lane): cp.async.bulk of the 16-row K chunk of B_l from L2
+//   * B1 (layer 0) is resident in shared memory; B_l (l >= 1) stream through a 3-stage ring, one stage = {A chunk hi,
+//     A chunk lo, B chunk}: the epilogue of layer l-1 produces chunk j while the tensor core consumes chunk j-1, so MMA l
+//     overlaps the sines of layer l-1 and a whole A operand never exists.  L2 -> smem traffic: bc*bc*2 B per 128 pixels
+//     (1 KB / pixel at bc 256), ~2 TB/s at 2 Gpix/s against ~12 TB/s of L2 bandwidth.
+//   * the output layer (bc x C) is one more streamed layer with N padded to 16, so every epilogue is the same code
+//     (sine -> hi/lo split -> operand chunk); the last one reads C accumulator columns: sigmoid -> round -> (m<<K)+r.
+//   * TMEM: two accumulators of bc columns, ping-pong by layer parity (512 columns at bc 256).
+// Weights that are not fp16-exact after scaling (-prec 32 streams): the kernel exits at once and the fp32 kernel
+// launched behind it (skip_flag = !exact) does the work -- decided on the device, no host sync.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "lbdrn_infer_fp32.cuh"
+#include "lbdrn_internal.h"
+#include "lbdrn_umma.cuh"
+
+namespace lbdrn {
+
+namespace {
+
+constexpr int TCW_NWG = 4;                          // epilogue warpgroups
+constexpr int TCW_CTHREADS = 128 * TCW_NWG;         // 512 epilogue threads
+constexpr int TCW_THREADS = TCW_CTHREADS + 64;      // + MMA-issue warp + weight-streamer warp
+constexpr int TCW_STAGES = 3;
+constexpr int TCW_NOUT = 16;                        // output layer: N padded to the smallest legal N at M=128
+constexpr int TCW_PF = 6;                           // patch elements prefetched per thread (512 threads -> 3072 elements)
+constexpr int TCW_HDR = 512;                        // bytes reserved for the header
+
+struct TcwHeader {
+  int exact;                       // 1: every weight is exactly representable as fp16 after its power-of-two scale
+  int k1, k1pad, nl, bc;
+  int off_bias;                    // float [nl*bc + 16]: w0-folded hidden biases, then the output bias
+  int off_b[kMaxLayers + 1];       // operand of layer l (l == nl: output layer, TCW_NOUT rows); B0 is inside res_bytes
+  int res_bytes;                   // prefix of the block copied into shared memory (header, biases, B0)
+  int total;
+  float scale[kMaxLayers + 1];     // accumulator scale per layer (2^-s; /max and *w0 folded as in lbdrn_tc.cu)
+};
+static_assert(sizeof(TcwHeader) <= TCW_HDR, "header does not fit its slot");
+
+__host__ __device__ inline int stage_bytes(int bc) { return 8192 + bc * 32; }   // A hi 4 KB | A lo 4 KB | B chunk
+
+void tcw_plan(const Net& n, TcwHeader& h) {
+  memset(&h, 0, sizeof h);
+  h.k1 = n.dim_in;
+  h.k1pad = align_up(n.dim_in, 16);
+  h.nl = n.nl;
+  h.bc = n.bc;
+  int off = TCW_HDR;
+  h.off_bias = off; off += (n.nl * n.bc + 16) * 4;
+  off = align_up(off, 128);
+  h.off_b[0] = off; off += h.k1pad * n.bc * 2;
+  h.res_bytes = align_up(off, 128);
+  off = h.res_bytes;
+  for (int l = 1; l < n.nl; ++l) { h.off_b[l] = off; off += n.bc * n.bc * 2; }
+  h.off_b[n.nl] = off; off += n.bc * TCW_NOUT * 2;
+  h.total = align_up(off, 128);
+}
+
+// One block: per-layer max -> power-of-two scale -> fp16 operands in the UMMA K-major layout, exactness flag, biases.
+__global__ void tcw_prep_kernel(Net net, TcwHeader hdr, const float* __restrict__ params, uint8_t* __restrict__ blk) {
+  __shared__ float s_max[32];
+  __shared__ int s_exact;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_exact = 1;
+  for (int i = tid; i < hdr.total / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(blk)[i] = 0u;
+  __syncthreads();
+  TcwHeader* H = reinterpret_cast<TcwHeader*>(blk);
+  for (int l = 0; l <= net.nl; ++l) {
+    const int K = l == 0 ? net.dim_in : net.bc;
+    const int rows_real = l < net.nl ? net.bc : net.C, rows = l < net.nl ? net.bc : TCW_NOUT;
+    const float* W = params + net.woff[l];
+    float m = 0.f;
+    for (int i = tid; i < K * rows_real; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((tid & 31) == 0) s_max[tid >> 5] = m;
+    __syncthreads();
+    m = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_max[i]);
+    __syncthreads();
+    const int s = (m > 0.f && isfinite(m)) ? 13 - ilogbf(m) : 0;       // max|W| * 2^s in [2^13, 2^14)
+    const float up = ldexpf(1.0f, s);
+    __half* B = reinterpret_cast<__half*>(blk + hdr.off_b[l]);
+    int bad = 0;
+    for (int i = tid; i < K * rows_real; i += blockDim.x) {
+      const int nrow = i / K, k = i - nrow * K;
+      const float v = W[i] * up;                                          // exact (power of two)
+      const __half hv = __float2half_rn(v);
+      if (v - __half2float(hv) != 0.f) bad = 1;
+      B[umma_off(rows, nrow, k) / 2] = hv;
+    }
+    if (bad) atomicAnd(&s_exact, 0);
+    float* bias = reinterpret_cast<float*>(blk + hdr.off_bias) + l * net.bc;
+    if (l < net.nl) {
+      // sine path: a = w0*(acc*scale + b) is evaluated as one FFMA, acc*(w0*scale) + w0*b (w0 folded here)
+      const float fold = net.relu ? 1.0f : net.w0;
+      if (tid == 0) H->scale[l] = fold * (l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net_maxv(net)) : ldexpf(1.0f, -s));
+      for (int i = tid; i < net.bc; i += blockDim.x) bias[i] = fold * params[net.boff[l] + i];
+    } else {
+      if (tid == 0) H->scale[l] = ldexpf(1.0f, -s);
+      for (int i = tid; i < net.C; i += blockDim.x) bias[i] = params[net.boff[l] + i];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    H->exact = s_exact;
+    H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl; H->bc = hdr.bc;
+    H->off_bias = hdr.off_bias; H->res_bytes = hdr.res_bytes; H->total = hdr.total;
+    for (int l = 0; l <= net.nl; ++l) H->off_b[l] = hdr.off_b[l];
+  }
+}
+
+struct TcwArgs {
+  Net net;
+  const void* msb;
+  const uint8_t* blk;     // packed weight block in global memory
+  uint16_t* out;
+  int tiles_x, n_tiles;
+  int a1_bytes, res_bytes;
+  int no_trap;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(TCW_CTHREADS) : "memory"); }
+
+template <bool FAST>
+__device__ __forceinline__ float tcw_sine(float a) {
+  if (!FAST) return sin_pi9_core(a);
+  const float t = fmaf(a, 0.15915494309189535f, 12582912.0f);
+  const float k = t - 12582912.0f;
+  float r = fmaf(k, -6.28318548202514648f, a);
+  r = fmaf(k, 1.74845553146e-7f, r);       // 2*pi = 6.28318548202514648 - 1.74845553146e-7 (fp32 hi + lo)
+  return __sinf(r);
+}
+
+// A1 chunks kc = WGI, WGI+4, ... of this thread's pixel with every patch offset folded into an immediate.
+template <int CC, int DD, int WGI>
+__device__ __forceinline__ void build_a1_static(const __half* __restrict__ pme, bool rel, uint8_t* __restrict__ sA, int pix) {
+  constexpr int N_ = 2 * DD + 1, NN_ = N_ * N_, K1_ = CC * NN_, TWP_ = TC_TW + 2 * DD, TRW_ = TC_TH + 2 * DD;
+  constexpr int NKC = (K1_ + 15) / 16 * 2;
+  __half2 ctr2[CC];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    const __half cv = rel ? pme[(c * TRW_ + DD) * TWP_ + DD] : __half(0);
+    ctr2[c] = __halves2half2(cv, cv);
+  }
+#pragma unroll
+  for (int kc = WGI; kc < NKC; kc += TCW_NWG) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k0 = kc * 8 + 2 * e, k1_ = k0 + 1;
+      const int c0 = k0 / NN_, c1 = k1_ / NN_;
+      const int o0 = (c0 * TRW_ + (k0 % NN_) / N_) * TWP_ + (k0 % NN_) % N_;
+      const int o1 = (c1 * TRW_ + (k1_ % NN_) / N_) * TWP_ + (k1_ % NN_) % N_;
+      __half2 v = __halves2half2(k0 < K1_ ? pme[o0] : __half(0), k1_ < K1_ ? pme[o1] : __half(0));
+      if (k0 < K1_) {
+        const __half2 cpair = (c0 == c1 || k1_ >= K1_) ? ctr2[c0 < CC ? c0 : 0]
+                                                       : __halves2half2(__low2half(ctr2[c0 < CC ? c0 : 0]),
+                                                                        __low2half(ctr2[c1 < CC ? c1 : 0]));
+        v = __hsub2(v, (k1_ < K1_) ? cpair : __halves2half2(__low2half(cpair), __half(0)));
+      }
+      w[e] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + pix) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// CC/DD > 0: bands / radius known at compile time; CC == 0: table-driven.
+template <bool FAST, int BC, int CC, int DD>
+__global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArgs a) {
+  constexpr int NCH = BC / 16;                       // operand chunks (MMA K steps) per streamed layer
+  constexpr int STAGE = 8192 + BC * 32;
+  const Net& net = a.net;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int C = CC ? CC : net.C, D = CC ? DD : net.D, n = 2 * D + 1;
+  const int trows = TC_TH + 2 * D, twp = TC_TW + 2 * D;
+  const int n_patch = C * trows * twp;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA1 = smem;
+  uint8_t* sStage = smem + a.a1_bytes;
+  uint8_t* sW = sStage + TCW_STAGES * STAGE;
+  __half* patch = reinterpret_cast<__half*>(sW + a.res_bytes);
+  uint16_t* koff = reinterpret_cast<uint16_t*>(patch + align_up(n_patch, 64));   // [k1pad] patch offset of feature k
+  uint16_t* kctr = koff + TC_MAX_K1 + 16;                                        // [k1pad] patch offset of its centre
+  __shared__ __align__(8) uint64_t s_a1_full, s_acc_full[2], s_a2_full[TCW_STAGES], s_b_full[TCW_STAGES],
+      s_free[TCW_STAGES];
+  __shared__ uint32_t s_tmem;
+
+  // ---- one-time setup: resident part of the weight block -> smem, TMEM, mbarriers ----------------------------------
+  {
+    const int4* src = reinterpret_cast<const int4*>(a.blk);
+    int4* dst = reinterpret_cast<int4*>(sW);
+    for (int i = tid; i < a.res_bytes / 16; i += TCW_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const TcwHeader* H = reinterpret_cast<const TcwHeader*>(sW);
+  if (!H->exact) return;                                   // the fp32 kernel queued behind this launch decodes the scene
+  const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
+  if (CC == 0) {
+    for (int k = tid; k < k1pad; k += TCW_THREADS) {
+      int off = 0, ctr = 0;
+      if (k < k1) {
+        const int c = k / (n * n), rem = k - c * n * n, dy = rem / n, dx = rem - dy * n;
+        off = (c * trows + dy) * twp + dx;
+        ctr = (c * trows + D) * twp + D;
+      }
+      koff[k] = (uint16_t)off;
+      kctr[k] = (uint16_t)ctr;
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(2 * BC)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_a1_full), TCW_CTHREADS);
+    mbar_init(smem_u32(&s_acc_full[0]), 1);
+    mbar_init(smem_u32(&s_acc_full[1]), 1);
+    for (int s = 0; s < TCW_STAGES; ++s) {
+      mbar_init(smem_u32(&s_a2_full[s]), 128);
+      mbar_init(smem_u32(&s_b_full[s]), 1);
+      mbar_init(smem_u32(&s_free[s]), 1);
+    }
+  }
+  fence_async_smem();                                      // resident weights (generic-proxy writes) -> tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t stage_u = smem_u32(sStage);
+  const int my_tiles = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == TCW_CTHREADS / 32) {
+    // =============================== MMA issue warp ================================================================
+    if ((tid & 31) == 0) {
+      const uint32_t idesc_h = umma_idesc_f16(128, BC), idesc_o = umma_idesc_f16(128, TCW_NOUT);
+      const uint32_t sA1_u = smem_u32(sA1), sB0_u = smem_u32(sW + H->off_b[0]);
+      uint32_t ph_a1 = 0;
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(smem_u32(&s_a1_full), ph_a1, 3, it, a.no_trap);
+        ph_a1 ^= 1;
+        tc_fence_after();
+        for (int i = 0; i < k1pad / 16; ++i)
+          umma_f16(tmem, umma_desc(sA1_u + i * 4096, 2048, 128), umma_desc(sB0_u + i * (BC * 32), BC * 16, 128), idesc_h, i > 0);
+        umma_commit(smem_u32(&s_acc_full[0]));
+        for (int l = 1; l <= NL; ++l) {
+          const bool outl = l == NL;
+          const uint32_t idesc = outl ? idesc_o : idesc_h, lbo = (outl ? TCW_NOUT : BC) * 16;
+          const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * BC);
+          for (int j = 0; j < NCH; ++j, ++g) {
+            const int s = g % TCW_STAGES;
+            const uint32_t par = (uint32_t)(g / TCW_STAGES) & 1u;
+            mbar_wait(smem_u32(&s_b_full[s]), par, 4, it, a.no_trap);
+            mbar_wait(smem_u32(&s_a2_full[s]), par, 5, it, a.no_trap);
+            tc_fence_after();
+            const uint32_t st = stage_u + s * STAGE;
+            umma_f16(d_tmem, umma_desc(st, 2048, 128), umma_desc(st + 8192, lbo, 128), idesc, j > 0);          // hi
+            umma_f16(d_tmem, umma_desc(st + 4096, 2048, 128), umma_desc(st + 8192, lbo, 128), idesc, 1);       // lo
+            umma_commit(smem_u32(&s_free[s]));
+          }
+          umma_commit(smem_u32(&s_acc_full[l & 1]));
+        }
+      }
+    }
+    __syncwarp();          // lanes 1-31 wait here for the elected lane (no divergent arrival at the final barrier)
+  } else if (warp == TCW_CTHREADS / 32 + 1) {
+    // =============================== weight streamer ===============================================================
+    if ((tid & 31) == 0) {
+      const int total = my_tiles * NL * NCH;
+      for (int g = 0; g < total; ++g) {
+        const int s = g % TCW_STAGES, u = g / TCW_STAGES;
+        if (u > 0) mbar_wait(smem_u32(&s_free[s]), (uint32_t)(u - 1) & 1u, 6, g, a.no_trap);
+        const int l = 1 + (g / NCH) % NL, j = g % NCH;
+        const uint32_t bytes = (uint32_t)((l == NL ? TCW_NOUT : BC) * 32);
+        mbar_expect_tx(smem_u32(&s_b_full[s]), bytes);
+        bulk_g2s(stage_u + s * STAGE + 8192, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue warpgroups ===========================================================
+    const int wg = tid >> 7, pix = tid & 127;
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);      // this warp's 32 TMEM lanes
+    const float* bias = reinterpret_cast<const float*>(sW + H->off_bias);
+    const bool rel = net.relative != 0;
+    const bool pf_ok = n_patch <= TCW_PF * TCW_CTHREADS;
+    uint32_t pf[TCW_PF];
+    auto issue_patch_loads = [&](int tile) {
+      if (tile >= a.n_tiles || !pf_ok) return;
+      const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
+#pragma unroll
+      for (int i = 0; i < TCW_PF; ++i) {
+        const int e = tid + i * TCW_CTHREADS;
+        if (e < n_patch) {
+          const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
+          const int gy = reflect_clamp(y0 + r, net.H), gx = reflect_clamp(x0 + x, net.W);
+          pf[i] = load_msb_int(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx);
+        }
+      }
+    };
+    uint32_t ph_acc = 0u;        // bit p: phase parity of s_acc_full[p]
+    int gbase = 0;
+    issue_patch_loads(blockIdx.x);
+
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
+      // ---- patch: (tile + halo) MSB integers as fp16 -----------------------------------------------------------------
+      if (pf_ok) {
+#pragma unroll
+        for (int i = 0; i < TCW_PF; ++i)
+          if (tid + i * TCW_CTHREADS < n_patch) patch[tid + i * TCW_CTHREADS] = __uint2half_rn(pf[i]);
+      } else {
+        for (int e = tid; e < n_patch; e += TCW_CTHREADS) {
+          const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
+          const int gy = reflect_clamp(ty0 - D + r, net.H), gx = reflect_clamp(tx0 - D + x, net.W);
+          patch[e] = __uint2half_rn(load_msb_int(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx));
+        }
+      }
+      bar_compute();
+      issue_patch_loads(t + gridDim.x);                              // lands while this tile computes
+
+      // ---- A1: integer differences (exact in fp16); warpgroup w writes the K chunks kc = w (mod 4) of its pixel ----------
+      const int pr = pix >> 4, px = pix & 15;
+      const __half* pme = patch + pr * twp + px;
+      if (CC) {
+        switch (wg) {
+          case 0: build_a1_static<CC ? CC : 1, DD, 0>(pme, rel, sA1, pix); break;
+          case 1: build_a1_static<CC ? CC : 1, DD, 1>(pme, rel, sA1, pix); break;
+          case 2: build_a1_static<CC ? CC : 1, DD, 2>(pme, rel, sA1, pix); break;
+          default: build_a1_static<CC ? CC : 1, DD, 3>(pme, rel, sA1, pix); break;
+        }
+      } else {
+        for (int kc = wg; kc < k1pad / 8; kc += TCW_NWG) {
+          __half2 v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = kc * 8 + 2 * e;
+            __half x0 = pme[koff[k]], x1 = pme[koff[k + 1]];
+            if (rel) {
+              x0 = __hsub(x0, pme[kctr[k]]);
+              x1 = __hsub(x1, pme[kctr[k + 1]]);
+            }
+            v[e] = __halves2half2(k < k1 ? x0 : __half(0), k + 1 < k1 ? x1 : __half(0));
+          }
+          *reinterpret_cast<uint4*>(sA1 + (size_t)(kc * 128 + pix) * 16) =
+              make_uint4(*reinterpret_cast<uint32_t*>(&v[0]), *reinterpret_cast<uint32_t*>(&v[1]),
+                         *reinterpret_cast<uint32_t*>(&v[2]), *reinterpret_cast<uint32_t*>(&v[3]));
+        }
+      }
+      // centre MSB of the bands this thread finalises (band = wg, wg + 4)
+      uint32_t mctr[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = wg + 4 * q;
+        mctr[q] = c < C ? (uint32_t)__half2int_rn(patch[(c * trows + pr + D) * twp + px + D]) : 0u;
+      }
+      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&s_a1_full));
+
+      // ---- hidden-layer epilogues: accumulator columns -> operand chunks of the next layer ---------------------------
+      for (int l = 0; l < NL; ++l) {
+        mbar_wait(smem_u32(&s_acc_full[l & 1]), (ph_acc >> (l & 1)) & 1u, 1, t, a.no_trap);
+        ph_acc ^= 1u << (l & 1);
+        tc_fence_after();
+        const float scale = H->scale[l];
+        const float* bl = bias + l * BC;
+        const uint32_t acc_col = tmem_row + (uint32_t)((l & 1) * BC);
+#pragma unroll 1
+        for (int j = wg; j < NCH; j += TCW_NWG) {
+          float acc[16];
+          tmem_ld16(acc_col + j * 16, acc);
+          float h[16];
+          if (net.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h[i] = fmaxf(fmaf(acc[i], scale, bl[j * 16 + i]), 0.f);
+          } else {
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              acc[i] = fmaf(acc[i], scale, bl[j * 16 + i]);          // = w0 * z (w0 folded into scale and bias)
+              amax = fmaxf(amax, fabsf(acc[i]));
+              h[i] = tcw_sine<FAST>(acc[i]);
+            }
+            if (__builtin_expect(!(amax <= 20000.0f), 0)) {         // huge or NaN argument: library slow path, out of line
+#pragma unroll
+              for (int i = 0; i < 16; ++i) h[i] = sin_slow(acc[i]);
+            }
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const __half2 hh = __floats2half2_rn(h[i], h[i + 1]);
+            const float2 back = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(h[i] - back.x, h[i + 1] - back.y);
+            hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const int g = gbase + j, s = g % TCW_STAGES, u = g / TCW_STAGES;
+          if (u > 0) mbar_wait(smem_u32(&s_free[s]), (uint32_t)(u - 1) & 1u, 2, t, a.no_trap);
+          uint8_t* st = sStage + (size_t)s * STAGE;
+          *reinterpret_cast<uint4*>(st + (size_t)pix * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(st + 4096 + (size_t)pix * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(st + 4096 + (size_t)(128 + pix) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(smem_u32(&s_a2_full[s]));
+        }
+        gbase += NCH;
+      }
+
+      // ---- output layer accumulator: sigmoid, inverse quantisation, integer write (decode.py:131-134) -----------------
+      mbar_wait(smem_u32(&s_acc_full[NL & 1]), (ph_acc >> (NL & 1)) & 1u, 1, t, a.no_trap);
+      ph_acc ^= 1u << (NL & 1);
+      tc_fence_after();
+      {
+        const float scale = H->scale[NL];
+        const float* bo = bias + NL * BC;
+        const int gy = ty0 + pr, gx = tx0 + px;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = wg + 4 * q;
+          if (c < C) {                                               // warp-uniform (wg is)
+            const float z = fmaf(tmem_ld1(tmem_row + (uint32_t)((NL & 1) * BC + c)), scale, bo[c]);
+            if (gy < net.row1 && gx < net.W) {
+              const float y = sigmoidf_rn(z);
+              const int res = (int)rintf(y * net.qmax);
+              a.out[((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx] = (uint16_t)((mctr[q] << net.K) + (uint32_t)res);
+            }
+          }
+        }
+      }
+      tc_fence_before();      // our tcgen05.ld's are ordered before the next tile's MMAs (issued after a1_full completes)
+    }
+  }
+
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BC) : "memory");
+}
+
+std::mutex& tcw_mu() {
+  static std::mutex m;
+  return m;
+}
+uint8_t* g_wblk[64] = {nullptr};
+size_t g_wblk_bytes[64] = {0};
+
+using KernW = void (*)(const TcwArgs);
+
+template <bool FAST, int BC>
+KernW pick_wide(const Net& n) {
+  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3>;
+  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2>;
+  return tcw_decode_kernel<FAST, BC, 0, 0>;
+}
+
+size_t tcw_smem_bytes(const Net& n, const TcwHeader& h) {
+  const int n_patch = n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D);
+  return (size_t)align_up(h.k1pad * 256, 1024) + (size_t)TCW_STAGES * stage_bytes(n.bc) + h.res_bytes +
+         (size_t)align_up(n_patch, 64) * 2 + 2 * (TC_MAX_K1 + 16) * 2 + 64;
+}
+
+}  // namespace
+
+bool tcw_supported(const Net& n) {
+  // colours only (integer differences exact in fp16 up to 2048); bc 128 / 256; the resident first-layer operand, the
+  // A1 tile and the 3-stage ring must fit the 227 KB of shared memory
+  if (!((n.bc == 128 || n.bc == 256) && n.nco == 0 && n.ncol > 0 && n.dim_in <= TC_MAX_K1 && n.maxv <= 2048.0f &&
+        n.C <= kMaxC && n.nl >= 1 && n.nl <= kMaxLayers - 1))
+    return false;
+  TcwHeader h;
+  tcw_plan(n, h);
+  return tcw_smem_bytes(n, h) + 1024 <= 232448;
+}
+
+// exact_flag_out: device pointer to the block's exactness word (1 = this kernel decoded the scene), for the skip_flag of
+// the fp32 kernel the caller queues behind this launch.
+int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out, int fast_sine, const int** exact_flag_out,
+               cudaStream_t st) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
+  TcwHeader h;
+  tcw_plan(n, h);
+  {
+    std::lock_guard<std::mutex> lk(tcw_mu());
+    if (g_wblk_bytes[dev] < (size_t)h.total) {
+      if (g_wblk[dev]) CUDA_TRY(cudaFree(g_wblk[dev]));
+      g_wblk[dev] = nullptr; g_wblk_bytes[dev] = 0;
+      CUDA_TRY(cudaMalloc(&g_wblk[dev], (size_t)h.total));
+      g_wblk_bytes[dev] = (size_t)h.total;
+    }
+  }
+  uint8_t* blk = g_wblk[dev];
+  tcw_prep_kernel<<<1, 1024, 0, st>>>(n, h, params, blk);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  TcwArgs a;
+  memset(&a, 0, sizeof a);
+  a.net = n; a.msb = msb; a.blk = blk; a.out = out;
+  a.a1_bytes = align_up(h.k1pad * 256, 1024);
+  a.res_bytes = h.res_bytes;
+  a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
+  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
+  a.no_trap = getenv("LBDRN_DEBUG") != nullptr;
+  const size_t smem = tcw_smem_bytes(n, h);
+  KernW kern = n.bc == 256 ? (fast_sine ? pick_wide<true, 256>(n) : pick_wide<false, 256>(n))
+                           : (fast_sine ? pick_wide<true, 128>(n) : pick_wide<false, 128>(n));
+  int sms = 0, max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem > (size_t)max_smem) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core decode needs %zu B of shared memory", smem);
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = sms < a.n_tiles ? sms : a.n_tiles;             // persistent: one CTA per SM (shared memory + 2*bc TMEM columns)
+  if (const char* e = getenv("LBDRN_TCW_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
+  if (getenv("LBDRN_DEBUG"))
+    fprintf(stderr, "[lbdrn] wide tc kernel: bc %d smem %zu grid %d x %d thr tiles %d k1pad %d nl %d\n", n.bc, smem, grid,
+            TCW_THREADS, a.n_tiles, h.k1pad, h.nl);
+  kern<<<grid, TCW_THREADS, smem, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (a.no_trap) {
+    int h4[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpyFromSymbol(h4, g_tc_timeout, sizeof h4));
+    if (h4[3]) fprintf(stderr, "[lbdrn] wide tc kernel: %d barrier timeouts; last: barrier %d tile %d block %d\n", h4[3], h4[0], h4[1], h4[2]);
+  }
+  if (exact_flag_out) *exact_flag_out = reinterpret_cast<const int*>(blk);   // TcwHeader::exact is the first word
+  return LBDRN_OK;
+}
+
+}  // namespace lbdrn

@@ -13,15 +13,16 @@ namespace {
 #endif
 constexpr int kTT = LBDRN_TRAIN_THREADS;     // threads per CTA = 4*US warps working on one 64-pixel chunk
 
-template <int BC, int CP>
+template <int BC, int CP, int TM>
 int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
+  constexpr int kTrainLDP = train_ldp(TM), kTrainNPIX = train_npix(TM);
   const size_t acts = ((size_t)t.dimpad + 2 * (size_t)n.nl * BC + (2 + kTT / 128) * CP) * kTrainLDP;
   const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
   const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
   if (with_w <= (size_t)max_smem) {
-    t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT>;
+    t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
   } else if (without <= (size_t)max_smem) {
-    t.wsmem = false; t.smem = without; t.kernel = (void*)train_fp32_kernel<BC, CP, false, kTT>;
+    t.wsmem = false; t.smem = without; t.kernel = (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
   } else {
     return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
                 without, BC, n.nl, n.dim_in);
@@ -44,10 +45,13 @@ int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPl
   t.pstride = (round4(n.P + 1) + 28 + 31) & ~31;   // keep CTAs' partials on distinct 128 B lines
   const bool c4 = n.C <= 4;
   switch (n.bc) {
-    case 32: return c4 ? plan_t<32, 4>(n, batch_size, sms, max_smem, t) : plan_t<32, 8>(n, batch_size, sms, max_smem, t);
-    case 64: return c4 ? plan_t<64, 4>(n, batch_size, sms, max_smem, t) : plan_t<64, 8>(n, batch_size, sms, max_smem, t);
-    case 128: return c4 ? plan_t<128, 4>(n, batch_size, sms, max_smem, t) : plan_t<128, 8>(n, batch_size, sms, max_smem, t);
-    default: return fail(LBDRN_E_UNSUPPORTED, "fused training is built for bc=32/64/128 (got %d)", n.bc);
+    case 32: return c4 ? plan_t<32, 4, 4>(n, batch_size, sms, max_smem, t) : plan_t<32, 8, 4>(n, batch_size, sms, max_smem, t);
+    case 64: return c4 ? plan_t<64, 4, 4>(n, batch_size, sms, max_smem, t) : plan_t<64, 8, 4>(n, batch_size, sms, max_smem, t);
+    case 128: return c4 ? plan_t<128, 4, 4>(n, batch_size, sms, max_smem, t) : plan_t<128, 8, 4>(n, batch_size, sms, max_smem, t);
+    // bc = 256 (BASELINE config 3): activations of a 64-pixel chunk (339 KB at D=3, nl=2) exceed shared memory, so the
+    // chunk is 32 pixels (TM = 2) and the weights stay in L2
+    case 256: return c4 ? plan_t<256, 4, 2>(n, batch_size, sms, max_smem, t) : plan_t<256, 8, 2>(n, batch_size, sms, max_smem, t);
+    default: return fail(LBDRN_E_UNSUPPORTED, "fused training is built for bc=32/64/128/256 (got %d)", n.bc);
   }
 }
 

@@ -17,9 +17,11 @@
 namespace lbdrn {
 namespace cg = cooperative_groups;
 
-constexpr int kTrainTM = 4;                 // pixels per thread group
-constexpr int kTrainNPIX = 16 * kTrainTM;   // 64 pixels per chunk
-constexpr int kTrainLDP = kTrainNPIX + 4;   // padded row stride: conflict-free LDS.128 down a column of rows
+// Chunk geometry: TM pixels per thread group, 16 groups -> NPIX = 16*TM pixels per chunk; rows of the activation
+// buffers are padded to LDP = NPIX + 4 floats (conflict-free LDS.128 down a column of rows).  TM = 4 (64-pixel chunks)
+// wherever the working set fits in shared memory; TM = 2 (32-pixel chunks) for bc = 256.
+constexpr int train_npix(int tm) { return 16 * tm; }
+constexpr int train_ldp(int tm) { return 16 * tm + 4; }
 
 enum { TRAIN_FUSED = 0, TRAIN_GRAD_ONLY = 1 };
 
@@ -47,20 +49,22 @@ struct TrainArgs {
   long long* prof;         // optional (LBDRN_TRAIN_PROF=1): clock64 cycles per phase accumulated by CTA 0 / thread 0
 };
 
-__device__ __forceinline__ float row_sum64(const float* __restrict__ row) {
+template <int NPIX>
+__device__ __forceinline__ float row_sum(const float* __restrict__ row) {
   float s = 0.f;
 #pragma unroll
-  for (int p = 0; p < kTrainNPIX; p += 4) {
+  for (int p = 0; p < NPIX; p += 4) {
     float4 v = *reinterpret_cast<const float4*>(row + p);
     s += (v.x + v.y) + (v.z + v.w);
   }
   return s;
 }
 
-__device__ __forceinline__ float row_dot64(const float* __restrict__ a, const float* __restrict__ b) {
+template <int NPIX>
+__device__ __forceinline__ float row_dot(const float* __restrict__ a, const float* __restrict__ b) {
   float s = 0.f;
 #pragma unroll
-  for (int p = 0; p < kTrainNPIX; p += 4) {
+  for (int p = 0; p < NPIX; p += 4) {
     float4 x = *reinterpret_cast<const float4*>(a + p), y = *reinterpret_cast<const float4*>(b + p);
     s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
   }
@@ -96,28 +100,35 @@ __device__ __forceinline__ void load_vec(const float* p, float* out) {
   else if (VEC == 2) { float2 v = *reinterpret_cast<const float2*>(p); out[0] = v.x; out[1] = v.y; }
   else out[0] = *p;
 }
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float* v) {
+  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else if (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  else *p = v[0];
+}
 
 // acc[i][j] += sum_k act[k*LDP + pg*4 + i] * wt[k*BC + ubase + (j/VEC)*8*VEC + j%VEC]   (both operands k-major)
-template <int TN, int VEC, int BC>
-__device__ __forceinline__ void gemm_kmajor_v(float (&acc)[kTrainTM][TN], const float* __restrict__ act, const float* wt,
+template <int TM, int TN, int VEC, int BC>
+__device__ __forceinline__ void gemm_kmajor_v(float (&acc)[TM][TN], const float* __restrict__ act, const float* wt,
                                               int K, int pg, int ubase) {
-  const float* a = act + pg * kTrainTM;
+  constexpr int kTrainLDP = train_ldp(TM);
+  const float* a = act + pg * TM;
   const float* b = wt + ubase;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    float av[4], bv[TN];
-    load_vec<4>(a + (size_t)k * kTrainLDP, av);
+    float av[TM], bv[TN];
+    load_vec<TM>(a + (size_t)k * kTrainLDP, av);
 #pragma unroll
     for (int j = 0; j < TN; j += VEC) load_vec<VEC>(b + (size_t)k * BC + (j / VEC) * 8 * VEC, bv + j);
 #pragma unroll
-    for (int i = 0; i < kTrainTM; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
   }
 }
 
 // One row (fixed dy) of one band's neighbourhood of one pixel; loads issued before first use.
-template <int N_>
+template <int N_, int kTrainLDP>
 __device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowoff, int gx, const Net& net, float maxv,
                                            float ctr, bool ok, float* d) {
   constexpr int D_ = N_ / 2;
@@ -133,10 +144,10 @@ __device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowo
 // a 4x4 register tile with 16 independent FFMA chains; per 4-pixel step 4 + (#valid y) LDS.128 feed 16*(#valid y)*4/4 FFMAs.
 // Row loads of a quarter-warp hit 8 consecutive rows (stride 68 floats = 4 banks apart: conflict-free), column loads are
 // broadcasts.  64 rows x 4*CT columns per pass.
-template <int BC, int THREADS>
+template <int BC, int THREADS, int TM>
 __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, const float* __restrict__ A, int Kin,
                                                  int kpad8, float* __restrict__ dst, bool first) {
-  constexpr int LDP = kTrainLDP, CT = THREADS / 16;
+  constexpr int LDP = train_ldp(TM), kTrainNPIX = train_npix(TM), CT = THREADS / 16;
   const int tid = threadIdx.x, trow = tid & 15, tcol = tid >> 4;
   for (int r0 = 0; r0 < BC; r0 += 64) {
     for (int q0 = 0; q0 < Kin; q0 += 4 * CT) {
@@ -189,9 +200,9 @@ __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, co
 // THREADS = 128 * US: the chunk's 64 pixels x BC units are tiled as 16 pixel groups (4 px) x 8 lanes x US unit splits,
 // so one 64-pixel chunk is worked on by 4*US warps.  The step time is the latency of ONE chunk on ONE SM (every CTA
 // has at most one chunk per step at bs <= 64*grid), so more warps per chunk is what shortens the step.
-template <int BC, int CP, bool WSMEM, int THREADS>
+template <int BC, int CP, bool WSMEM, int THREADS, int TM>
 __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) {
-  constexpr int TM = kTrainTM, NPIX = kTrainNPIX, LDP = kTrainLDP, US = THREADS / 128, TN = BC / 8 / US;
+  constexpr int NPIX = train_npix(TM), LDP = train_ldp(TM), US = THREADS / 128, TN = BC / 8 / US;
   constexpr int VEC = TN >= 4 ? 4 : TN;
   static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
   cg::grid_group grid = cg::this_grid();
@@ -305,10 +316,10 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             float* d = dst + (size_t)(net.nco + (c * n + dy) * n) * LDP;
             const size_t rowoff = (plane + (reflect_clamp(gy + dy - D, net.H) - net.buf_row0)) * net.W;
             switch (n) {
-              case 1: gather_row<1>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
-              case 3: gather_row<3>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
-              case 5: gather_row<5>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
-              case 7: gather_row<7>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 1: gather_row<1, LDP>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 3: gather_row<3, LDP>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 5: gather_row<5, LDP>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
+              case 7: gather_row<7, LDP>(a.msb, net.msb_u16, rowoff, gx, net, maxv, ctr, ok, d); break;
               default:
                 for (int dx = 0; dx < n; ++dx, d += LDP) {
                   float v = load_msb_norm(a.msb, net.msb_u16, rowoff + reflect_clamp(gx + dx - D, net.W), maxv) - ctr;
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 #pragma unroll
           for (int i = 0; i < TM; ++i) acc[i][j] = b;
         }
-        gemm_kmajor_v<TN, VEC, BC>(acc, in, w + net.woff[l], K, pg, ubase);
+        gemm_kmajor_v<TM, TN, VEC, BC>(acc, in, w + net.woff[l], K, pg, ubase);
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
           float g4[TM];
@@ -352,8 +363,11 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             }
           }
           size_t o = (size_t)unit(j) * LDP + pg * TM;
-          *reinterpret_cast<float4*>(Hl + o) = make_float4(h[0][j], h[1][j], h[2][j], h[3][j]);
-          *reinterpret_cast<float4*>(Gl + o) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+          float hv[TM];
+#pragma unroll
+          for (int i = 0; i < TM; ++i) hv[i] = h[i][j];
+          store_vec<TM>(Hl + o, hv);
+          store_vec<TM>(Gl + o, g4);
         }
         layer_sync();
       }
@@ -428,12 +442,12 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         const float* HL = Hbuf + (size_t)(L - 1) * BC * LDP;
         for (int o = tid; o < C * BC; o += THREADS) {
           int c = o / BC, u = o - c * BC;
-          float g = row_dot64(dZo + c * LDP, HL + (size_t)u * LDP);
+          float g = row_dot<NPIX>(dZo + c * LDP, HL + (size_t)u * LDP);
           float* d = mypart + net.woff[L] + o;
           *d = first ? g : *d + g;
         }
         if (tid < C) {
-          float g = row_sum64(dZo + tid * LDP);
+          float g = row_sum<NPIX>(dZo + tid * LDP);
           float* d = mypart + net.boff[L] + tid;
           *d = first ? g : *d + g;
         }
@@ -451,37 +465,38 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
             if (c < C) {
-              float4 dv = *reinterpret_cast<const float4*>(dZo + c * LDP + pg * TM);
+              float dv[TM];
+              load_vec<TM>(dZo + c * LDP + pg * TM, dv);
 #pragma unroll
               for (int j = 0; j < TN; ++j) {
                 float wv = wo[c * BC + unit(j)];
-                acc[0][j] = fmaf(wv, dv.x, acc[0][j]);
-                acc[1][j] = fmaf(wv, dv.y, acc[1][j]);
-                acc[2][j] = fmaf(wv, dv.z, acc[2][j]);
-                acc[3][j] = fmaf(wv, dv.w, acc[3][j]);
+#pragma unroll
+                for (int i = 0; i < TM; ++i) acc[i][j] = fmaf(wv, dv[i], acc[i][j]);
               }
             }
           }
         } else {
           // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p]   (k-major in m on both operands)
-          gemm_kmajor_v<TN, VEC, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, pg, ubase);
+          gemm_kmajor_v<TM, TN, VEC, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, pg, ubase);
         }
         // dz_l = dh_l * act'(z_l): thread-private read-modify-write of its own (unit, pixel) entries
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          float4* gp = reinterpret_cast<float4*>(Gl + (size_t)unit(j) * LDP + pg * TM);
-          float4 g = *gp;
-          g.x *= acc[0][j]; g.y *= acc[1][j]; g.z *= acc[2][j]; g.w *= acc[3][j];
-          *gp = g;
+          float* gp = Gl + (size_t)unit(j) * LDP + pg * TM;
+          float g[TM];
+          load_vec<TM>(gp, g);
+#pragma unroll
+          for (int i = 0; i < TM; ++i) g[i] *= acc[i][j];
+          store_vec<TM>(gp, g);
         }
         __syncthreads();
         LBDRN_PHASE(9 + 2 * (l > 0 ? 1 : 0))     // bwd: dh + dz (9: layer 0, 11: layer >= 1)
         // dW_l = dz_l . in_l^T ; db_l = row sums
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
-        grad_weight_nt_t<BC, THREADS>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
+        grad_weight_nt_t<BC, THREADS, TM>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
         for (int u = tid; u < BC; u += THREADS) {
-          float g = row_sum64(Gl + (size_t)u * LDP);
+          float g = row_sum<NPIX>(Gl + (size_t)u * LDP);
           float* d = mypart + net.boff[l] + u;
           *d = first ? g : *d + g;
         }

@@ -27,9 +27,11 @@ def _setup(case="k5d2_small", seed=19920517):
     return meta, img, blob, recon, model, scene, fl
 
 
-def test_gradients_match_autograd():
-    """lbdrn_train_grad (one batch, unreduced) against torch autograd on the oracle's explicit features."""
-    meta, img, _, _, model, scene, fl = _setup()
+@pytest.mark.parametrize("case", ["k5d2_small", "d3_bc256", "k9_bc128"])
+def test_gradients_match_autograd(case):
+    """lbdrn_train_grad (one batch, unreduced) against torch autograd on the oracle's explicit features.
+    d3_bc256 runs the 32-pixel-chunk instantiation (BASELINE config 3), k9_bc128 the 64-pixel one with nl=1."""
+    meta, img, _, _, model, scene, fl = _setup(case)
     lib = cabi.load()
     tr = F.FusedTrainer(model, scene, meta["D"], 1e-3, 512, 1, flags=fl)
     tr.begin()
@@ -52,9 +54,10 @@ def test_gradients_match_autograd():
     tr.close()
 
 
-def test_first_steps_follow_the_reference_trajectory():
+@pytest.mark.parametrize("case", ["k5d2_small", "d3_bc256", "k9_bc128", "b8_16bit", "k1_nl3", "k3d1_u16"])
+def test_first_steps_follow_the_reference_trajectory(case):
     """Same seed, same init, same batches: per-step losses track the reference's (fp32 rounding differences only)."""
-    meta, img, _, _, model, scene, fl = _setup()
+    meta, img, _, _, model, scene, fl = _setup(case)
     tr = F.FusedTrainer(model, scene, meta["D"], 1e-3, meta["bs"], meta["e"], flags=fl)
     res = tr.run()
     tr.close()
