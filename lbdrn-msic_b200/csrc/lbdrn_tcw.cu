@@ -10,10 +10,13 @@
 //                   warpgroup w owns the chunks j = w (mod 4)
 //       warp 16     MMA issue (one elected lane): tcgen05.mma M=128 N=bc K=16, kind::f16, cta_group::1
 //       warp 17     weight streamer (one elected lane): cp.async.bulk of the 16-row K chunk of B_l from L2
-//   * B1 (layer 0) is resident in shared memory; B_l (l >= 1) stream through a 3-stage ring, one stage = {A chunk hi,
-//     A chunk lo, B chunk}: the epilogue of layer l-1 produces chunk j while the tensor core consumes chunk j-1, so MMA l
-//     overlaps the sines of layer l-1 and a whole A operand never exists.  L2 -> smem traffic: bc*bc*2 B per 128 pixels
-//     (1 KB / pixel at bc 256), ~2 TB/s at 2 Gpix/s against ~12 TB/s of L2 bandwidth.
+//   * B1 (layer 0) is resident in shared memory; for l >= 1 the operands move through two rings, one K step (16 columns)
+//     per slot: the A ring has one slot per warpgroup ({hi, lo} halves of the split activations, 8 KB), the B ring three
+//     slots of bc*32 B filled from L2.  The epilogue of layer l-1 produces chunk j while the tensor core consumes chunk
+//     j-1, so MMA l overlaps the sines of layer l-1 and a whole A operand never exists.  A slot is private to its
+//     warpgroup and the B ring is private to the (in-order) streamer / issuer pair, so every waiter observes every phase
+//     of the barrier it waits on (parity waits are only safe under that condition).  L2 -> smem traffic: bc*bc*2 B per
+//     128 pixels (1 KB / pixel at bc 256), ~2 TB/s at 2 Gpix/s against ~12 TB/s of L2 bandwidth.
 //   * the output layer (bc x C) is one more streamed layer with N padded to 16, so every epilogue is the same code
 //     (sine -> hi/lo split -> operand chunk); the last one reads C accumulator columns: sigmoid -> round -> (m<<K)+r.
 //   * TMEM: two accumulators of bc columns, ping-pong by layer parity (512 columns at bc 256).
@@ -36,7 +39,8 @@ namespace {
 constexpr int TCW_NWG = 4;                          // epilogue warpgroups
 constexpr int TCW_CTHREADS = 128 * TCW_NWG;         // 512 epilogue threads
 constexpr int TCW_THREADS = TCW_CTHREADS + 64;      // + MMA-issue warp + weight-streamer warp
-constexpr int TCW_STAGES = 3;
+constexpr int TCW_BSTAGES = 3;                      // B ring depth (the A ring has TCW_NWG slots)
+constexpr int TCW_ASLOT = 8192;                     // A slot: hi 4 KB | lo 4 KB  (128 rows x 16 K x 2 B each)
 constexpr int TCW_NOUT = 16;                        // output layer: N padded to the smallest legal N at M=128
 constexpr int TCW_PF = 6;                           // patch elements prefetched per thread (512 threads -> 3072 elements)
 constexpr int TCW_HDR = 512;                        // bytes reserved for the header
@@ -52,7 +56,7 @@ struct TcwHeader {
 };
 static_assert(sizeof(TcwHeader) <= TCW_HDR, "header does not fit its slot");
 
-__host__ __device__ inline int stage_bytes(int bc) { return 8192 + bc * 32; }   // A hi 4 KB | A lo 4 KB | B chunk
+__host__ __device__ inline int ring_bytes(int bc) { return TCW_NWG * TCW_ASLOT + TCW_BSTAGES * bc * 32; }
 
 void tcw_plan(const Net& n, TcwHeader& h) {
   memset(&h, 0, sizeof h);
@@ -134,6 +138,42 @@ struct TcwArgs {
   int no_trap;
 };
 
+__device__ int g_tcw_dbg[16];   // diagnostics: [0] first timed-out barrier kind, [1] tile/chunk, [2] block, [3] thread, [8+kind] counts
+
+// Bounded mbarrier wait.  kind: 1 acc_full / 2 stage free (epilogue), 3 a1_full / 4 b_full / 5 a2_full (MMA issue),
+// 6 stage free (streamer).  A lost arrival traps (a CUDA error instead of a hung GPU); with LBDRN_DEBUG the wait gives up
+// early, records who waited on what, and lets the kernel finish with garbage so the host can print the record.
+__device__ __noinline__ void tcw_wait_slow(uint32_t mbar, uint32_t parity, int kind, int where, int no_trap) {
+  const int limit = no_trap ? (1 << 12) : (1 << 22);
+  for (int it = 0; it < limit; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+  }
+  if (atomicCAS(&g_tcw_dbg[0], 0, kind) == 0) {
+    g_tcw_dbg[1] = where; g_tcw_dbg[2] = blockIdx.x; g_tcw_dbg[3] = threadIdx.x;
+  }
+  atomicAdd(&g_tcw_dbg[8 + (kind & 7)], 1);
+  __threadfence_system();
+  if (no_trap) return;
+  __nanosleep(1000000);
+  __trap();
+}
+
+__device__ __forceinline__ void tcw_wait(uint32_t mbar, uint32_t parity, int kind, int where, int no_trap) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(mbar), "r"(parity), "r"(20000u)
+      : "memory");
+  if (!ok) tcw_wait_slow(mbar, parity, kind, where, no_trap);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
@@ -200,7 +240,7 @@ __device__ __forceinline__ void build_a1_static(const __half* __restrict__ pme, 
 template <bool FAST, int BC, int CC, int DD>
 __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArgs a) {
   constexpr int NCH = BC / 16;                       // operand chunks (MMA K steps) per streamed layer
-  constexpr int STAGE = 8192 + BC * 32;
+  constexpr int BSLOT = BC * 32;                     // one K step of a streamed operand (bc rows x 16 K x 2 B)
   const Net& net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = CC ? CC : net.C, D = CC ? DD : net.D, n = 2 * D + 1;
@@ -209,13 +249,14 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA1 = smem;
-  uint8_t* sStage = smem + a.a1_bytes;
-  uint8_t* sW = sStage + TCW_STAGES * STAGE;
+  uint8_t* sAring = smem + a.a1_bytes;
+  uint8_t* sBring = sAring + TCW_NWG * TCW_ASLOT;
+  uint8_t* sW = sBring + TCW_BSTAGES * BSLOT;
   __half* patch = reinterpret_cast<__half*>(sW + a.res_bytes);
   uint16_t* koff = reinterpret_cast<uint16_t*>(patch + align_up(n_patch, 64));   // [k1pad] patch offset of feature k
   uint16_t* kctr = koff + TC_MAX_K1 + 16;                                        // [k1pad] patch offset of its centre
-  __shared__ __align__(8) uint64_t s_a1_full, s_acc_full[2], s_a2_full[TCW_STAGES], s_b_full[TCW_STAGES],
-      s_free[TCW_STAGES];
+  __shared__ __align__(8) uint64_t s_a1_full, s_acc_full[2], s_a_full[TCW_NWG], s_a_free[TCW_NWG], s_b_full[TCW_BSTAGES],
+      s_b_free[TCW_BSTAGES];
   __shared__ uint32_t s_tmem;
 
   // ---- one-time setup: resident part of the weight block -> smem, TMEM, mbarriers ----------------------------------
@@ -249,10 +290,13 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
     mbar_init(smem_u32(&s_a1_full), TCW_CTHREADS);
     mbar_init(smem_u32(&s_acc_full[0]), 1);
     mbar_init(smem_u32(&s_acc_full[1]), 1);
-    for (int s = 0; s < TCW_STAGES; ++s) {
-      mbar_init(smem_u32(&s_a2_full[s]), 128);
+    for (int s = 0; s < TCW_NWG; ++s) {
+      mbar_init(smem_u32(&s_a_full[s]), 128);
+      mbar_init(smem_u32(&s_a_free[s]), 1);
+    }
+    for (int s = 0; s < TCW_BSTAGES; ++s) {
       mbar_init(smem_u32(&s_b_full[s]), 1);
-      mbar_init(smem_u32(&s_free[s]), 1);
+      mbar_init(smem_u32(&s_b_free[s]), 1);
     }
   }
   fence_async_smem();                                      // resident weights (generic-proxy writes) -> tensor core
@@ -260,7 +304,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t stage_u = smem_u32(sStage);
+  const uint32_t aring_u = smem_u32(sAring), bring_u = smem_u32(sBring);
   const int my_tiles = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == TCW_CTHREADS / 32) {
@@ -271,7 +315,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
       uint32_t ph_a1 = 0;
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(smem_u32(&s_a1_full), ph_a1, 3, it, a.no_trap);
+        tcw_wait(smem_u32(&s_a1_full), ph_a1, 3, it, a.no_trap);
         ph_a1 ^= 1;
         tc_fence_after();
         for (int i = 0; i < k1pad / 16; ++i)
@@ -282,15 +326,16 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           const uint32_t idesc = outl ? idesc_o : idesc_h, lbo = (outl ? TCW_NOUT : BC) * 16;
           const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * BC);
           for (int j = 0; j < NCH; ++j, ++g) {
-            const int s = g % TCW_STAGES;
-            const uint32_t par = (uint32_t)(g / TCW_STAGES) & 1u;
-            mbar_wait(smem_u32(&s_b_full[s]), par, 4, it, a.no_trap);
-            mbar_wait(smem_u32(&s_a2_full[s]), par, 5, it, a.no_trap);
+            // chunk g: A slot g % 4 (NCH is a multiple of 4, so this is the producing warpgroup j % 4), B slot g % 3
+            const int sa = g % TCW_NWG, sb = g % TCW_BSTAGES;
+            tcw_wait(smem_u32(&s_b_full[sb]), (uint32_t)(g / TCW_BSTAGES) & 1u, 4, it, a.no_trap);
+            tcw_wait(smem_u32(&s_a_full[sa]), (uint32_t)(g / TCW_NWG) & 1u, 5, it, a.no_trap);
             tc_fence_after();
-            const uint32_t st = stage_u + s * STAGE;
-            umma_f16(d_tmem, umma_desc(st, 2048, 128), umma_desc(st + 8192, lbo, 128), idesc, j > 0);          // hi
-            umma_f16(d_tmem, umma_desc(st + 4096, 2048, 128), umma_desc(st + 8192, lbo, 128), idesc, 1);       // lo
-            umma_commit(smem_u32(&s_free[s]));
+            const uint32_t sta = aring_u + sa * TCW_ASLOT, stb = bring_u + sb * BSLOT;
+            umma_f16(d_tmem, umma_desc(sta, 2048, 128), umma_desc(stb, lbo, 128), idesc, j > 0);          // hi
+            umma_f16(d_tmem, umma_desc(sta + 4096, 2048, 128), umma_desc(stb, lbo, 128), idesc, 1);       // lo
+            umma_commit(smem_u32(&s_a_free[sa]));
+            umma_commit(smem_u32(&s_b_free[sb]));
           }
           umma_commit(smem_u32(&s_acc_full[l & 1]));
         }
@@ -302,12 +347,12 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
     if ((tid & 31) == 0) {
       const int total = my_tiles * NL * NCH;
       for (int g = 0; g < total; ++g) {
-        const int s = g % TCW_STAGES, u = g / TCW_STAGES;
-        if (u > 0) mbar_wait(smem_u32(&s_free[s]), (uint32_t)(u - 1) & 1u, 6, g, a.no_trap);
+        const int s = g % TCW_BSTAGES, u = g / TCW_BSTAGES;
+        if (u > 0) tcw_wait(smem_u32(&s_b_free[s]), (uint32_t)(u - 1) & 1u, 6, g, a.no_trap);
         const int l = 1 + (g / NCH) % NL, j = g % NCH;
         const uint32_t bytes = (uint32_t)((l == NL ? TCW_NOUT : BC) * 32);
         mbar_expect_tx(smem_u32(&s_b_full[s]), bytes);
-        bulk_g2s(stage_u + s * STAGE + 8192, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
+        bulk_g2s(bring_u + s * BSLOT, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
       }
     }
     __syncwarp();
@@ -333,7 +378,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
       }
     };
     uint32_t ph_acc = 0u;        // bit p: phase parity of s_acc_full[p]
-    int gbase = 0;
+    int a_uses = 0;               // chunks this warpgroup has written into its A slot so far
+    uint8_t* const st = sAring + (size_t)wg * TCW_ASLOT;
     issue_patch_loads(blockIdx.x);
 
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
@@ -393,7 +439,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
 
       // ---- hidden-layer epilogues: accumulator columns -> operand chunks of the next layer ---------------------------
       for (int l = 0; l < NL; ++l) {
-        mbar_wait(smem_u32(&s_acc_full[l & 1]), (ph_acc >> (l & 1)) & 1u, 1, t, a.no_trap);
+        tcw_wait(smem_u32(&s_acc_full[l & 1]), (ph_acc >> (l & 1)) & 1u, 1, t, a.no_trap);
         ph_acc ^= 1u << (l & 1);
         tc_fence_after();
         const float scale = H->scale[l];
@@ -429,22 +475,20 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
             lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-          const int g = gbase + j, s = g % TCW_STAGES, u = g / TCW_STAGES;
-          if (u > 0) mbar_wait(smem_u32(&s_free[s]), (uint32_t)(u - 1) & 1u, 2, t, a.no_trap);
-          uint8_t* st = sStage + (size_t)s * STAGE;
+          if (a_uses > 0) tcw_wait(smem_u32(&s_a_free[wg]), (uint32_t)(a_uses - 1) & 1u, 2, t, a.no_trap);
+          ++a_uses;
           *reinterpret_cast<uint4*>(st + (size_t)pix * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           *reinterpret_cast<uint4*>(st + 4096 + (size_t)pix * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(st + 4096 + (size_t)(128 + pix) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           fence_async_smem();
           tc_fence_before();
-          mbar_arrive(smem_u32(&s_a2_full[s]));
+          mbar_arrive(smem_u32(&s_a_full[wg]));
         }
-        gbase += NCH;
       }
 
       // ---- output layer accumulator: sigmoid, inverse quantisation, integer write (decode.py:131-134) -----------------
-      mbar_wait(smem_u32(&s_acc_full[NL & 1]), (ph_acc >> (NL & 1)) & 1u, 1, t, a.no_trap);
+      tcw_wait(smem_u32(&s_acc_full[NL & 1]), (ph_acc >> (NL & 1)) & 1u, 1, t, a.no_trap);
       ph_acc ^= 1u << (NL & 1);
       tc_fence_after();
       {
@@ -490,7 +534,7 @@ KernW pick_wide(const Net& n) {
 
 size_t tcw_smem_bytes(const Net& n, const TcwHeader& h) {
   const int n_patch = n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D);
-  return (size_t)align_up(h.k1pad * 256, 1024) + (size_t)TCW_STAGES * stage_bytes(n.bc) + h.res_bytes +
+  return (size_t)align_up(h.k1pad * 256, 1024) + (size_t)ring_bytes(n.bc) + h.res_bytes +
          (size_t)align_up(n_patch, 64) * 2 + 2 * (TC_MAX_K1 + 16) * 2 + 64;
 }
 
@@ -498,7 +542,7 @@ size_t tcw_smem_bytes(const Net& n, const TcwHeader& h) {
 
 bool tcw_supported(const Net& n) {
   // colours only (integer differences exact in fp16 up to 2048); bc 128 / 256; the resident first-layer operand, the
-  // A1 tile and the 3-stage ring must fit the 227 KB of shared memory
+  // A1 tile and the operand rings must fit the 227 KB of shared memory
   if (!((n.bc == 128 || n.bc == 256) && n.nco == 0 && n.ncol > 0 && n.dim_in <= TC_MAX_K1 && n.maxv <= 2048.0f &&
         n.C <= kMaxC && n.nl >= 1 && n.nl <= kMaxLayers - 1))
     return false;
@@ -554,10 +598,14 @@ int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (a.no_trap) {
-    int h4[4] = {0, 0, 0, 0};
+    int h16[16];
     CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaMemcpyFromSymbol(h4, g_tc_timeout, sizeof h4));
-    if (h4[3]) fprintf(stderr, "[lbdrn] wide tc kernel: %d barrier timeouts; last: barrier %d tile %d block %d\n", h4[3], h4[0], h4[1], h4[2]);
+    CUDA_TRY(cudaMemcpyFromSymbol(h16, g_tcw_dbg, sizeof h16));
+    if (h16[0])
+      fprintf(stderr, "[lbdrn] wide tc kernel: first timeout kind %d where %d block %d thread %d; counts by kind 1..6: %d %d %d %d %d %d\n",
+              h16[0], h16[1], h16[2], h16[3], h16[9], h16[10], h16[11], h16[12], h16[13], h16[14]);
+    memset(h16, 0, sizeof h16);
+    CUDA_TRY(cudaMemcpyToSymbol(g_tcw_dbg, h16, sizeof h16));
   }
   if (exact_flag_out) *exact_flag_out = reinterpret_cast<const int*>(blk);   // TcwHeader::exact is the first word
   return LBDRN_OK;

@@ -19,6 +19,10 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
   const size_t acts = ((size_t)t.dimpad + 2 * (size_t)n.nl * BC + (2 + kTT / 128) * CP) * kTrainLDP;
   const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
   const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
+  // the opt-in limit covers dynamic + static shared memory of the kernel (pixel coordinates, reduction scratch)
+  cudaFuncAttributes fa;
+  CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)train_fp32_kernel<BC, CP, false, kTT, TM>));
+  max_smem -= (int)fa.sharedSizeBytes;
   if (with_w <= (size_t)max_smem) {
     t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
   } else if (without <= (size_t)max_smem) {
