@@ -39,7 +39,6 @@ namespace {
 constexpr int TCW_NWG = 4;                          // epilogue warpgroups
 constexpr int TCW_CTHREADS = 128 * TCW_NWG;         // 512 epilogue threads
 constexpr int TCW_THREADS = TCW_CTHREADS + 64;      // + MMA-issue warp + weight-streamer warp
-constexpr int TCW_BSTAGES = 3;                      // B ring depth (the A ring has TCW_NWG slots)
 constexpr int TCW_ASLOT = 8192;                     // A slot: hi 4 KB | lo 4 KB  (128 rows x 16 K x 2 B each)
 constexpr int TCW_NOUT = 16;                        // output layer: N padded to the smallest legal N at M=128
 constexpr int TCW_PF = 6;                           // patch elements prefetched per thread (512 threads -> 3072 elements)
@@ -56,7 +55,9 @@ struct TcwHeader {
 };
 static_assert(sizeof(TcwHeader) <= TCW_HDR, "header does not fit its slot");
 
-__host__ __device__ inline int ring_bytes(int bc) { return TCW_NWG * TCW_ASLOT + TCW_BSTAGES * bc * 32; }
+// APW: A slots per warpgroup (1 or 2); NB: depth of the B ring.  The bulk copies that fill the B ring have ~1 us of
+// latency (L2 -> smem), the tensor core drains a slot in 256 cycles: the ring has to be deep, the A ring does not.
+__host__ __device__ inline int ring_bytes(int bc, int apw, int nb) { return apw * TCW_NWG * TCW_ASLOT + nb * bc * 32; }
 
 void tcw_plan(const Net& n, TcwHeader& h) {
   memset(&h, 0, sizeof h);
@@ -134,8 +135,10 @@ struct TcwArgs {
   const uint8_t* blk;     // packed weight block in global memory
   uint16_t* out;
   int tiles_x, n_tiles;
-  int a1_bytes, res_bytes;
+  int res_bytes;
   int no_trap;
+  long long* prof;        // optional (LBDRN_TCW_PROF=1): clock64 cycles per role / phase, accumulated by CTA 0
+  int prof_lat;           // LBDRN_TCW_PROF=2: the streamer waits for each copy to land (measures the bulk-copy latency)
 };
 
 __device__ int g_tcw_dbg[16];   // diagnostics: [0] first timed-out barrier kind, [1] tile/chunk, [2] block, [3] thread, [8+kind] counts
@@ -174,6 +177,33 @@ __device__ __forceinline__ void tcw_wait(uint32_t mbar, uint32_t parity, int kin
   if (!ok) tcw_wait_slow(mbar, parity, kind, where, no_trap);
 }
 
+// both barriers at once (the two try_waits overlap instead of serialising their ~90-cycle latency); kind 5 / 4
+__device__ __forceinline__ void tcw_wait2(uint32_t mbar_a, uint32_t par_a, uint32_t mbar_b, uint32_t par_b, int where, int no_trap) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %5;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4, %5;\n\t"
+      "and.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(mbar_a), "r"(par_a), "r"(mbar_b), "r"(par_b), "r"(20000u)
+      : "memory");
+  if (!ok) {
+    tcw_wait_slow(mbar_a, par_a, 5, where, no_trap);
+    tcw_wait_slow(mbar_b, par_b, 4, where, no_trap);
+  }
+}
+
+// One lane of a converged warp.  The control warps run their loops warp-uniformly (every lane waits on the barriers) and
+// only the tcgen05 / bulk-copy instructions sit under this predicate: operands then live in uniform registers.  Issuing
+// from inside `if (lane == 0)` instead makes the compiler wrap every such instruction in an R2UR.BROADCAST / ELECT
+// loop (~80 dependent instructions per K step: 300 cycles on the one thread the whole CTA's tensor work goes through).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
@@ -203,11 +233,35 @@ __device__ __forceinline__ float tcw_sine(float a) {
   return __sinf(r);
 }
 
-// A1 chunks kc = WGI, WGI+4, ... of this thread's pixel with every patch offset folded into an immediate.
-template <int CC, int DD, int WGI>
-__device__ __forceinline__ void build_a1_static(const __half* __restrict__ pme, bool rel, uint8_t* __restrict__ sA, int pix) {
+// ---- A-slot protocol of the epilogue warpgroups: warpgroup w owns slots 2w and 2w+1 and alternates between them, so it
+// can run one chunk ahead of the tensor core.  `uses` counts the chunks the warpgroup has produced so far.
+// The q-th chunk a warpgroup produces within a layer goes to its slot q & (APW-1) (the MMA-issue lane applies the same rule).
+struct SlotRing {
+  uint8_t* base;            // this warpgroup's first slot
+  uint32_t full_u, free_u;  // smem addresses of s_a_full[2w], s_a_free[2w]
+  uint32_t fpar;            // bit sl: parity of the next wait on s_a_free[2w + sl]; starts at 1 = "the phase before the
+                            // first one", which a fresh mbarrier reports as complete, so the first use does not block
+};
+
+__device__ __forceinline__ uint8_t* slot_acquire(SlotRing& r, int sl, int where, int no_trap) {
+  tcw_wait(r.free_u + sl * 8, (r.fpar >> sl) & 1u, 2, where, no_trap);   // MMAs of the slot's previous use are done
+  r.fpar ^= 1u << sl;
+  return r.base + sl * TCW_ASLOT;
+}
+
+__device__ __forceinline__ void slot_release(const SlotRing& r, int sl) {
+  fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();           // our tcgen05.ld's are ordered before MMAs issued after this arrival is observed
+  mbar_arrive(r.full_u + sl * 8);
+}
+
+// Layer-0 operand chunks (16 features = one MMA K step) kc16 = WGI, WGI+4, ... of this thread's pixel, every patch offset
+// folded into an immediate.  Integer differences m_nbr - m_ctr are exact in fp16, so layer 0 has no lo half.
+template <int CC, int DD, int WGI, int APW>
+__device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme, bool rel, SlotRing& ring, int pix, int where,
+                                                  int no_trap) {
   constexpr int N_ = 2 * DD + 1, NN_ = N_ * N_, K1_ = CC * NN_, TWP_ = TC_TW + 2 * DD, TRW_ = TC_TH + 2 * DD;
-  constexpr int NKC = (K1_ + 15) / 16 * 2;
+  constexpr int NK16 = (K1_ + 15) / 16;
   __half2 ctr2[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
@@ -215,11 +269,12 @@ __device__ __forceinline__ void build_a1_static(const __half* __restrict__ pme, 
     ctr2[c] = __halves2half2(cv, cv);
   }
 #pragma unroll
-  for (int kc = WGI; kc < NKC; kc += TCW_NWG) {
-    uint32_t w[4];
+  for (int q = 0; q < (NK16 - WGI + TCW_NWG - 1) / TCW_NWG; ++q) {
+    const int kc16 = WGI + q * TCW_NWG;
+    uint32_t w[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int k0 = kc * 8 + 2 * e, k1_ = k0 + 1;
+    for (int e = 0; e < 8; ++e) {
+      const int k0 = kc16 * 16 + 2 * e, k1_ = k0 + 1;
       const int c0 = k0 / NN_, c1 = k1_ / NN_;
       const int o0 = (c0 * TRW_ + (k0 % NN_) / N_) * TWP_ + (k0 % NN_) % N_;
       const int o1 = (c1 * TRW_ + (k1_ % NN_) / N_) * TWP_ + (k1_ % NN_) % N_;
@@ -232,15 +287,27 @@ __device__ __forceinline__ void build_a1_static(const __half* __restrict__ pme, 
       }
       w[e] = *reinterpret_cast<const uint32_t*>(&v);
     }
-    *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + pix) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    const int sl = q & (APW - 1);
+    uint8_t* st = slot_acquire(ring, sl, where, no_trap);
+    *reinterpret_cast<uint4*>(st + (size_t)pix * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+    slot_release(ring, sl);
   }
 }
 
 // CC/DD > 0: bands / radius known at compile time; CC == 0: table-driven.
-template <bool FAST, int BC, int CC, int DD>
+//
+// Chunk order (the MMA-issue lane, the weight streamer and every epilogue warpgroup walk the same sequence):
+//   L0(first tile);  then per tile t:  L1(t) .. L_{NL-1}(t),  [L0(next tile) if NL is even],  Lout(t),  [L0(next) if NL is odd]
+// where L_l(t) are the K steps of layer l's MMA; chunk j of a layer is produced by warpgroup j mod 4.  With NL even the
+// next tile's first layer runs on the tensor core while this tile's last hidden epilogue computes its sines (accumulator
+// 0 is free by then); the output layer accumulates into columns [0,16) of the last hidden layer's own accumulator, which
+// its epilogue has already consumed when the first output chunk is issued.
+template <bool FAST, int BC, int CC, int DD, int APW, int NB>
 __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArgs a) {
   constexpr int NCH = BC / 16;                       // operand chunks (MMA K steps) per streamed layer
   constexpr int BSLOT = BC * 32;                     // one K step of a streamed operand (bc rows x 16 K x 2 B)
+  constexpr int NSLOT = APW * TCW_NWG;
   const Net& net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = CC ? CC : net.C, D = CC ? DD : net.D, n = 2 * D + 1;
@@ -248,15 +315,13 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   const int n_patch = C * trows * twp;
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA1 = smem;
-  uint8_t* sAring = smem + a.a1_bytes;
-  uint8_t* sBring = sAring + TCW_NWG * TCW_ASLOT;
-  uint8_t* sW = sBring + TCW_BSTAGES * BSLOT;
+  uint8_t* sAring = smem;
+  uint8_t* sBring = sAring + NSLOT * TCW_ASLOT;
+  uint8_t* sW = sBring + NB * BSLOT;
   __half* patch = reinterpret_cast<__half*>(sW + a.res_bytes);
   uint16_t* koff = reinterpret_cast<uint16_t*>(patch + align_up(n_patch, 64));   // [k1pad] patch offset of feature k
   uint16_t* kctr = koff + TC_MAX_K1 + 16;                                        // [k1pad] patch offset of its centre
-  __shared__ __align__(8) uint64_t s_a1_full, s_acc_full[2], s_a_full[TCW_NWG], s_a_free[TCW_NWG], s_b_full[TCW_BSTAGES],
-      s_b_free[TCW_BSTAGES];
+  __shared__ __align__(8) uint64_t s_acc_full[2], s_out_full, s_a_full[NSLOT], s_a_free[NSLOT], s_b_full[NB], s_b_free[NB];
   __shared__ uint32_t s_tmem;
 
   // ---- one-time setup: resident part of the weight block -> smem, TMEM, mbarriers ----------------------------------
@@ -269,6 +334,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   const TcwHeader* H = reinterpret_cast<const TcwHeader*>(sW);
   if (!H->exact) return;                                   // the fp32 kernel queued behind this launch decodes the scene
   const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
+  const int nk16 = k1pad / 16;
+  const bool overlap = (NL & 1) == 0;
   if (CC == 0) {
     for (int k = tid; k < k1pad; k += TCW_THREADS) {
       int off = 0, ctr = 0;
@@ -287,14 +354,14 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&s_a1_full), TCW_CTHREADS);
     mbar_init(smem_u32(&s_acc_full[0]), 1);
     mbar_init(smem_u32(&s_acc_full[1]), 1);
-    for (int s = 0; s < TCW_NWG; ++s) {
+    mbar_init(smem_u32(&s_out_full), 1);
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(smem_u32(&s_a_full[s]), 128);
       mbar_init(smem_u32(&s_a_free[s]), 1);
     }
-    for (int s = 0; s < TCW_BSTAGES; ++s) {
+    for (int s = 0; s < NB; ++s) {
       mbar_init(smem_u32(&s_b_full[s]), 1);
       mbar_init(smem_u32(&s_b_free[s]), 1);
     }
@@ -309,60 +376,118 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
 
   if (warp == TCW_CTHREADS / 32) {
     // =============================== MMA issue warp ================================================================
-    if ((tid & 31) == 0) {
+    {
       const uint32_t idesc_h = umma_idesc_f16(128, BC), idesc_o = umma_idesc_f16(128, TCW_NOUT);
-      const uint32_t sA1_u = smem_u32(sA1), sB0_u = smem_u32(sW + H->off_b[0]);
-      uint32_t ph_a1 = 0;
-      int g = 0;
+      const bool prof = a.prof != nullptr && blockIdx.x == 0;
+      long long pc[2] = {0, 0};             // prof: cycles waiting for operand chunks
+      const long long c_start = prof ? clock64() : 0;
+      // Shared-memory descriptors differ only in their 14-bit start-address field (low word): build them once and add
+      // slot offsets (in 16 B units) per chunk.  The issue lane is ONE thread with mostly dependent instructions, so every
+      // instruction in this loop costs ~4-6 cycles of the whole CTA's tensor throughput: keep it short.
+      const uint64_t dA = umma_desc(aring_u, 2048, 128);
+      const uint64_t dB0 = umma_desc(smem_u32(sW + H->off_b[0]), BC * 16, 128);
+      const uint64_t dBh = umma_desc(bring_u, BC * 16, 128), dBo = umma_desc(bring_u, TCW_NOUT * 16, 128);
+      const uint32_t a_full_u = smem_u32(&s_a_full[0]), a_free_u = smem_u32(&s_a_free[0]);
+      const uint32_t b_full_u = smem_u32(&s_b_full[0]), b_free_u = smem_u32(&s_b_free[0]);
+      uint32_t apar = 0u;                   // bit s: parity of the next wait on s_a_full[s]
+      uint32_t bpar = 0u;                   // parity of the next wait on s_b_full[sb] (flips when the ring wraps)
+      int sb = 0, g = 0;                    // B ring position; streamed-B chunk counter (layers >= 1)
+      auto layer0 = [&](int it) {
+        for (int i = 0; i < nk16; ++i) {
+          const int slot = APW * (i & 3) + ((i >> 2) & (APW - 1));
+          const long long c0 = prof ? clock64() : 0;
+          tcw_wait(a_full_u + slot * 8, (apar >> slot) & 1u, 5, it, a.no_trap);
+          if (prof) pc[1] += clock64() - c0;
+          apar ^= 1u << slot;
+          tc_fence_after();
+          if (elect_one()) {
+            umma_f16(tmem, dA + (uint64_t)(slot * (TCW_ASLOT >> 4)), dB0 + (uint64_t)(i * (BSLOT >> 4)), idesc_h, i > 0);
+            umma_commit(a_free_u + slot * 8);
+            if (i + 1 == nk16) umma_commit(smem_u32(&s_acc_full[0]));
+          }
+          __syncwarp();
+        }
+      };
+      if (my_tiles > 0) layer0(0);
       for (int it = 0; it < my_tiles; ++it) {
-        tcw_wait(smem_u32(&s_a1_full), ph_a1, 3, it, a.no_trap);
-        ph_a1 ^= 1;
-        tc_fence_after();
-        for (int i = 0; i < k1pad / 16; ++i)
-          umma_f16(tmem, umma_desc(sA1_u + i * 4096, 2048, 128), umma_desc(sB0_u + i * (BC * 32), BC * 16, 128), idesc_h, i > 0);
-        umma_commit(smem_u32(&s_acc_full[0]));
+        const bool has_next = it + 1 < my_tiles;
         for (int l = 1; l <= NL; ++l) {
           const bool outl = l == NL;
-          const uint32_t idesc = outl ? idesc_o : idesc_h, lbo = (outl ? TCW_NOUT : BC) * 16;
-          const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * BC);
+          if (outl && overlap && has_next) layer0(it + 1);
+          const uint32_t idesc = outl ? idesc_o : idesc_h;
+          const uint64_t dB = outl ? dBo : dBh;
+          // the output layer accumulates into columns [0,16) of the last hidden layer's accumulator (already consumed)
+          const uint32_t d_tmem = tmem + (uint32_t)(((outl ? l - 1 : l) & 1) * BC);
+#pragma unroll 4
           for (int j = 0; j < NCH; ++j, ++g) {
-            // chunk g: A slot g % 4 (NCH is a multiple of 4, so this is the producing warpgroup j % 4), B slot g % 3
-            const int sa = g % TCW_NWG, sb = g % TCW_BSTAGES;
-            tcw_wait(smem_u32(&s_b_full[sb]), (uint32_t)(g / TCW_BSTAGES) & 1u, 4, it, a.no_trap);
-            tcw_wait(smem_u32(&s_a_full[sa]), (uint32_t)(g / TCW_NWG) & 1u, 5, it, a.no_trap);
+            const int slot = APW * (j & 3) + ((j >> 2) & (APW - 1));
+            const long long c0 = prof ? clock64() : 0;
+            tcw_wait2(a_full_u + slot * 8, (apar >> slot) & 1u, b_full_u + sb * 8, bpar, it, a.no_trap);
+            if (prof) pc[0] += clock64() - c0;
+            apar ^= 1u << slot;
             tc_fence_after();
-            const uint32_t sta = aring_u + sa * TCW_ASLOT, stb = bring_u + sb * BSLOT;
-            umma_f16(d_tmem, umma_desc(sta, 2048, 128), umma_desc(stb, lbo, 128), idesc, j > 0);          // hi
-            umma_f16(d_tmem, umma_desc(sta + 4096, 2048, 128), umma_desc(stb, lbo, 128), idesc, 1);       // lo
-            umma_commit(smem_u32(&s_a_free[sa]));
-            umma_commit(smem_u32(&s_b_free[sb]));
+            const uint64_t da = dA + (uint64_t)(slot * (TCW_ASLOT >> 4)), db = dB + (uint64_t)(sb * (BSLOT >> 4));
+            if (elect_one()) {
+              umma_f16(d_tmem, da, db, idesc, j > 0);                  // hi half of the split activations
+              umma_f16(d_tmem, da + (4096 >> 4), db, idesc, 1);        // lo half
+              umma_commit(a_free_u + slot * 8);
+              umma_commit(b_free_u + sb * 8);
+              if (j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
+            }
+            __syncwarp();
+            if (++sb == NB) { sb = 0; bpar ^= 1u; }
           }
-          umma_commit(smem_u32(&s_acc_full[l & 1]));
         }
+        if (!overlap && has_next) layer0(it + 1);
+      }
+      if (prof && (tid & 31) == 0) {
+        a.prof[0] = pc[0]; a.prof[1] = pc[1]; a.prof[2] = clock64() - c_start; a.prof[3] = (long long)g + (long long)my_tiles * nk16;
       }
     }
-    __syncwarp();          // lanes 1-31 wait here for the elected lane (no divergent arrival at the final barrier)
+    __syncwarp();
   } else if (warp == TCW_CTHREADS / 32 + 1) {
     // =============================== weight streamer ===============================================================
-    if ((tid & 31) == 0) {
+    {
       const int total = my_tiles * NL * NCH;
+      const bool prof = a.prof != nullptr && blockIdx.x == 0;
+      long long pw = 0, plat = 0;
+      int s = 0;
+      uint32_t fpar = 1u;      // parity 1 on the first pass: "the phase before the first one", complete on a fresh barrier
       for (int g = 0; g < total; ++g) {
-        const int s = g % TCW_BSTAGES, u = g / TCW_BSTAGES;
-        if (u > 0) tcw_wait(smem_u32(&s_b_free[s]), (uint32_t)(u - 1) & 1u, 6, g, a.no_trap);
+        const long long c0 = prof ? clock64() : 0;
+        tcw_wait(smem_u32(&s_b_free[s]), fpar, 6, g, a.no_trap);
+        if (prof) pw += clock64() - c0;
         const int l = 1 + (g / NCH) % NL, j = g % NCH;
         const uint32_t bytes = (uint32_t)((l == NL ? TCW_NOUT : BC) * 32);
-        mbar_expect_tx(smem_u32(&s_b_full[s]), bytes);
-        bulk_g2s(bring_u + s * BSLOT, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(&s_b_full[s]), bytes);
+          bulk_g2s(bring_u + s * BSLOT, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
+        }
+        __syncwarp();
+        if (prof && a.prof_lat) {
+          const long long c1 = clock64();
+          tcw_wait(smem_u32(&s_b_full[s]), fpar ^ 1u, 6, g, a.no_trap);
+          plat += clock64() - c1;
+        }
+        if (++s == NB) { s = 0; fpar ^= 1u; }
       }
+      if (prof && (tid & 31) == 0) { a.prof[4] = pw; a.prof[5] = plat; a.prof[6] = total; }
     }
     __syncwarp();
   } else {
     // =============================== epilogue warpgroups ===========================================================
     const int wg = tid >> 7, pix = tid & 127;
+    const int pr = pix >> 4, px = pix & 15;
     const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);      // this warp's 32 TMEM lanes
     const float* bias = reinterpret_cast<const float*>(sW + H->off_bias);
     const bool rel = net.relative != 0;
     const bool pf_ok = n_patch <= TCW_PF * TCW_CTHREADS;
+    const __half* pme = patch + pr * twp + px;
+    SlotRing ring;
+    ring.base = sAring + (size_t)(APW * wg) * TCW_ASLOT;
+    ring.full_u = smem_u32(&s_a_full[APW * wg]);
+    ring.free_u = smem_u32(&s_a_free[APW * wg]);
+    ring.fpar = 3u;
     uint32_t pf[TCW_PF];
     auto issue_patch_loads = [&](int tile) {
       if (tile >= a.n_tiles || !pf_ok) return;
@@ -377,44 +502,41 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
         }
       }
     };
-    uint32_t ph_acc = 0u;        // bit p: phase parity of s_acc_full[p]
-    int a_uses = 0;               // chunks this warpgroup has written into its A slot so far
-    uint8_t* const st = sAring + (size_t)wg * TCW_ASLOT;
-    issue_patch_loads(blockIdx.x);
-
-    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-      const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
-      // ---- patch: (tile + halo) MSB integers as fp16 -----------------------------------------------------------------
+    uint32_t mctr[2] = {0u, 0u}, mctr_next[2] = {0u, 0u};
+    // patch(tile) -> smem, centre MSBs of the bands this thread finalises (band = wg, wg + 4), then the layer-0 operand chunks
+    auto stage_tile = [&](int tile) {
       if (pf_ok) {
 #pragma unroll
         for (int i = 0; i < TCW_PF; ++i)
           if (tid + i * TCW_CTHREADS < n_patch) patch[tid + i * TCW_CTHREADS] = __uint2half_rn(pf[i]);
       } else {
+        const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
         for (int e = tid; e < n_patch; e += TCW_CTHREADS) {
           const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
-          const int gy = reflect_clamp(ty0 - D + r, net.H), gx = reflect_clamp(tx0 - D + x, net.W);
+          const int gy = reflect_clamp(y0 + r, net.H), gx = reflect_clamp(x0 + x, net.W);
           patch[e] = __uint2half_rn(load_msb_int(a.msb, net.msb_u16, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx));
         }
       }
       bar_compute();
-      issue_patch_loads(t + gridDim.x);                              // lands while this tile computes
-
-      // ---- A1: integer differences (exact in fp16); warpgroup w writes the K chunks kc = w (mod 4) of its pixel ----------
-      const int pr = pix >> 4, px = pix & 15;
-      const __half* pme = patch + pr * twp + px;
+      issue_patch_loads(tile + gridDim.x);                              // lands while this tile computes
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = wg + 4 * q;
+        mctr_next[q] = c < C ? (uint32_t)__half2int_rn(patch[(c * trows + pr + D) * twp + px + D]) : 0u;
+      }
       if (CC) {
         switch (wg) {
-          case 0: build_a1_static<CC ? CC : 1, DD, 0>(pme, rel, sA1, pix); break;
-          case 1: build_a1_static<CC ? CC : 1, DD, 1>(pme, rel, sA1, pix); break;
-          case 2: build_a1_static<CC ? CC : 1, DD, 2>(pme, rel, sA1, pix); break;
-          default: build_a1_static<CC ? CC : 1, DD, 3>(pme, rel, sA1, pix); break;
+          case 0: produce_l0_static<CC ? CC : 1, DD, 0, APW>(pme, rel, ring, pix, tile, a.no_trap); break;
+          case 1: produce_l0_static<CC ? CC : 1, DD, 1, APW>(pme, rel, ring, pix, tile, a.no_trap); break;
+          case 2: produce_l0_static<CC ? CC : 1, DD, 2, APW>(pme, rel, ring, pix, tile, a.no_trap); break;
+          default: produce_l0_static<CC ? CC : 1, DD, 3, APW>(pme, rel, ring, pix, tile, a.no_trap); break;
         }
       } else {
-        for (int kc = wg; kc < k1pad / 8; kc += TCW_NWG) {
-          __half2 v[4];
+        for (int kc16 = wg; kc16 < nk16; kc16 += TCW_NWG) {
+          __half2 v[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int k = kc * 8 + 2 * e;
+          for (int e = 0; e < 8; ++e) {
+            const int k = kc16 * 16 + 2 * e;
             __half x0 = pme[koff[k]], x1 = pme[koff[k + 1]];
             if (rel) {
               x0 = __hsub(x0, pme[kctr[k]]);
@@ -422,24 +544,37 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             }
             v[e] = __halves2half2(k < k1 ? x0 : __half(0), k + 1 < k1 ? x1 : __half(0));
           }
-          *reinterpret_cast<uint4*>(sA1 + (size_t)(kc * 128 + pix) * 16) =
+          const int sl = (kc16 >> 2) & (APW - 1);
+          uint8_t* st = slot_acquire(ring, sl, tile, a.no_trap);
+          *reinterpret_cast<uint4*>(st + (size_t)pix * 16) =
               make_uint4(*reinterpret_cast<uint32_t*>(&v[0]), *reinterpret_cast<uint32_t*>(&v[1]),
                          *reinterpret_cast<uint32_t*>(&v[2]), *reinterpret_cast<uint32_t*>(&v[3]));
+          *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) =
+              make_uint4(*reinterpret_cast<uint32_t*>(&v[4]), *reinterpret_cast<uint32_t*>(&v[5]),
+                         *reinterpret_cast<uint32_t*>(&v[6]), *reinterpret_cast<uint32_t*>(&v[7]));
+          slot_release(ring, sl);
         }
       }
-      // centre MSB of the bands this thread finalises (band = wg, wg + 4)
-      uint32_t mctr[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = wg + 4 * q;
-        mctr[q] = c < C ? (uint32_t)__half2int_rn(patch[(c * trows + pr + D) * twp + px + D]) : 0u;
-      }
-      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(smem_u32(&s_a1_full));
+    };
+    uint32_t ph_acc = 0u;        // bit p: phase parity of s_acc_full[p]; bit 2: s_out_full
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && (tid & 127) == 0;   // one lane per warpgroup
+    long long pacc = 0, pslot = 0, pstage = 0, pout = 0;
+    const long long c_start = prof ? clock64() : 0;
+    issue_patch_loads(blockIdx.x);
+    if (blockIdx.x < a.n_tiles) stage_tile(blockIdx.x);
+
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
+      const bool has_next = t + (int)gridDim.x < a.n_tiles;
+      mctr[0] = mctr_next[0]; mctr[1] = mctr_next[1];
 
       // ---- hidden-layer epilogues: accumulator columns -> operand chunks of the next layer ---------------------------
       for (int l = 0; l < NL; ++l) {
+        long long c0 = prof ? clock64() : 0;
+        if (l == NL - 1 && overlap && has_next) stage_tile(t + gridDim.x);   // next tile's layer 0 overlaps this epilogue
+        if (prof) { const long long c1 = clock64(); pstage += c1 - c0; c0 = c1; }
         tcw_wait(smem_u32(&s_acc_full[l & 1]), (ph_acc >> (l & 1)) & 1u, 1, t, a.no_trap);
+        if (prof) pacc += clock64() - c0;
         ph_acc ^= 1u << (l & 1);
         tc_fence_after();
         const float scale = H->scale[l];
@@ -475,21 +610,23 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
             lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-          if (a_uses > 0) tcw_wait(smem_u32(&s_a_free[wg]), (uint32_t)(a_uses - 1) & 1u, 2, t, a.no_trap);
-          ++a_uses;
+          const long long c2 = prof ? clock64() : 0;
+          const int sl = (j >> 2) & (APW - 1);
+          uint8_t* st = slot_acquire(ring, sl, t, a.no_trap);
+          if (prof) pslot += clock64() - c2;
           *reinterpret_cast<uint4*>(st + (size_t)pix * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           *reinterpret_cast<uint4*>(st + 4096 + (size_t)pix * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(st + 4096 + (size_t)(128 + pix) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          fence_async_smem();
-          tc_fence_before();
-          mbar_arrive(smem_u32(&s_a_full[wg]));
+          slot_release(ring, sl);
         }
       }
 
       // ---- output layer accumulator: sigmoid, inverse quantisation, integer write (decode.py:131-134) -----------------
-      tcw_wait(smem_u32(&s_acc_full[NL & 1]), (ph_acc >> (NL & 1)) & 1u, 1, t, a.no_trap);
-      ph_acc ^= 1u << (NL & 1);
+      const long long c3 = prof ? clock64() : 0;
+      tcw_wait(smem_u32(&s_out_full), (ph_acc >> 2) & 1u, 1, t, a.no_trap);
+      if (prof) pout += clock64() - c3;
+      ph_acc ^= 4u;
       tc_fence_after();
       {
         const float scale = H->scale[NL];
@@ -499,7 +636,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
         for (int q = 0; q < 2; ++q) {
           const int c = wg + 4 * q;
           if (c < C) {                                               // warp-uniform (wg is)
-            const float z = fmaf(tmem_ld1(tmem_row + (uint32_t)((NL & 1) * BC + c)), scale, bo[c]);
+            const float z = fmaf(tmem_ld1(tmem_row + (uint32_t)(((NL - 1) & 1) * BC + c)), scale, bo[c]);
             if (gy < net.row1 && gx < net.W) {
               const float y = sigmoidf_rn(z);
               const int res = (int)rintf(y * net.qmax);
@@ -508,7 +645,13 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           }
         }
       }
-      tc_fence_before();      // our tcgen05.ld's are ordered before the next tile's MMAs (issued after a1_full completes)
+      tc_fence_before();
+      bar_compute();          // every warpgroup has read its output columns before any chunk of the next tile can be issued
+      if (!overlap && has_next) stage_tile(t + gridDim.x);
+    }
+    if (prof) {
+      long long* o = a.prof + 8 + 8 * wg;
+      o[0] = pacc; o[1] = pslot; o[2] = pstage; o[3] = pout; o[4] = clock64() - c_start;
     }
   }
 
@@ -525,17 +668,39 @@ size_t g_wblk_bytes[64] = {0};
 
 using KernW = void (*)(const TcwArgs);
 
-template <bool FAST, int BC>
+template <bool FAST, int BC, int APW, int NB>
 KernW pick_wide(const Net& n) {
-  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3>;
-  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2>;
-  return tcw_decode_kernel<FAST, BC, 0, 0>;
+  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3, APW, NB>;
+  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2, APW, NB>;
+  return tcw_decode_kernel<FAST, BC, 0, 0, APW, NB>;
 }
 
-size_t tcw_smem_bytes(const Net& n, const TcwHeader& h) {
+// ring geometries built: (APW, NB) = (1, 10) deep B ring [default at bc 256], (2, 6), and (2, 12) for bc 128
+template <bool FAST, int BC>
+KernW pick_ring(const Net& n, int apw, int nb) {
+  if (apw == 1 && nb == 10) return pick_wide<FAST, BC, 1, 10>(n);
+  if (apw == 2 && nb == 6) return pick_wide<FAST, BC, 2, 6>(n);
+  if (apw == 2 && nb == 12) return pick_wide<FAST, BC, 2, 12>(n);
+  return nullptr;
+}
+
+size_t tcw_smem_bytes(const Net& n, const TcwHeader& h, int apw, int nb) {
   const int n_patch = n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D);
-  return (size_t)align_up(h.k1pad * 256, 1024) + (size_t)ring_bytes(n.bc) + h.res_bytes +
+  return (size_t)ring_bytes(n.bc, apw, nb) + h.res_bytes +
          (size_t)align_up(n_patch, 64) * 2 + 2 * (TC_MAX_K1 + 16) * 2 + 64;
+}
+
+constexpr size_t kTcwSmemLimit = 232448 - 2048;    // 227 KB minus static shared memory and the per-CTA reservation
+
+// deepest B ring that fits
+bool tcw_pick_ring(const Net& n, const TcwHeader& h, int& apw, int& nb) {
+  static const int opts[3][2] = {{2, 12}, {1, 10}, {2, 6}};
+  if (const char* e = getenv("LBDRN_TCW_RING")) {
+    if (sscanf(e, "%dx%d", &apw, &nb) == 2 && tcw_smem_bytes(n, h, apw, nb) <= kTcwSmemLimit) return true;
+  }
+  for (auto& o : opts)
+    if (tcw_smem_bytes(n, h, o[0], o[1]) <= kTcwSmemLimit) { apw = o[0]; nb = o[1]; return true; }
+  return false;
 }
 
 }  // namespace
@@ -548,7 +713,8 @@ bool tcw_supported(const Net& n) {
     return false;
   TcwHeader h;
   tcw_plan(n, h);
-  return tcw_smem_bytes(n, h) + 1024 <= 232448;
+  int apw = 0, nb = 0;
+  return tcw_pick_ring(n, h, apw, nb);
 }
 
 // exact_flag_out: device pointer to the block's exactness word (1 = this kernel decoded the scene), for the skip_flag of
@@ -576,14 +742,16 @@ int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out
   TcwArgs a;
   memset(&a, 0, sizeof a);
   a.net = n; a.msb = msb; a.blk = blk; a.out = out;
-  a.a1_bytes = align_up(h.k1pad * 256, 1024);
   a.res_bytes = h.res_bytes;
   a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
   a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
   a.no_trap = getenv("LBDRN_DEBUG") != nullptr;
-  const size_t smem = tcw_smem_bytes(n, h);
-  KernW kern = n.bc == 256 ? (fast_sine ? pick_wide<true, 256>(n) : pick_wide<false, 256>(n))
-                           : (fast_sine ? pick_wide<true, 128>(n) : pick_wide<false, 128>(n));
+  int apw = 0, nb = 0;
+  if (!tcw_pick_ring(n, h, apw, nb)) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core decode: operand rings do not fit");
+  const size_t smem = tcw_smem_bytes(n, h, apw, nb);
+  KernW kern = n.bc == 256 ? (fast_sine ? pick_ring<true, 256>(n, apw, nb) : pick_ring<false, 256>(n, apw, nb))
+                           : (fast_sine ? pick_ring<true, 128>(n, apw, nb) : pick_ring<false, 128>(n, apw, nb));
+  if (!kern) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core decode: ring geometry %dx%d is not built", apw, nb);
   int sms = 0, max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -592,11 +760,31 @@ int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out
   int grid = sms < a.n_tiles ? sms : a.n_tiles;             // persistent: one CTA per SM (shared memory + 2*bc TMEM columns)
   if (const char* e = getenv("LBDRN_TCW_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;
   if (getenv("LBDRN_DEBUG"))
-    fprintf(stderr, "[lbdrn] wide tc kernel: bc %d smem %zu grid %d x %d thr tiles %d k1pad %d nl %d\n", n.bc, smem, grid,
-            TCW_THREADS, a.n_tiles, h.k1pad, h.nl);
+    fprintf(stderr, "[lbdrn] wide tc kernel: bc %d smem %zu grid %d x %d thr tiles %d k1pad %d nl %d rings A %dx4 B %d\n", n.bc,
+            smem, grid, TCW_THREADS, a.n_tiles, h.k1pad, h.nl, apw, nb);
+  static long long* prof_dev = nullptr;
+  const bool prof = getenv("LBDRN_TCW_PROF") != nullptr;
+  if (prof) {
+    if (!prof_dev) CUDA_TRY(cudaMalloc(&prof_dev, 64 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(prof_dev, 0, 64 * sizeof(long long), st));
+    a.prof = prof_dev;
+    a.prof_lat = atoi(getenv("LBDRN_TCW_PROF")) == 2;
+  }
   kern<<<grid, TCW_THREADS, smem, st>>>(a);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
+  if (prof) {
+    long long h[64];
+    CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const long long tiles = (a.n_tiles + grid - 1) / grid;
+    fprintf(stderr, "[lbdrn] wide prof (CTA 0, %lld tiles, cycles/tile): issuer total %lld wait_B %lld wait_A %lld (chunks/tile %lld); "
+            "streamer wait_free %lld, copy latency %lld cycles/copy; rings A %dx4 B %d\n", tiles, h[2] / tiles, h[0] / tiles,
+            h[1] / tiles, h[3] / tiles, h[4] / tiles, h[6] ? h[5] / h[6] : 0, apw, nb);
+    for (int w = 0; w < TCW_NWG; ++w)
+      fprintf(stderr, "[lbdrn]   warpgroup %d: total %lld acc_wait %lld slot_wait %lld stage_tile %lld out_wait %lld\n", w,
+              h[8 + 8 * w + 4] / tiles, h[8 + 8 * w] / tiles, h[8 + 8 * w + 1] / tiles, h[8 + 8 * w + 2] / tiles, h[8 + 8 * w + 3] / tiles);
+  }
   if (a.no_trap) {
     int h16[16];
     CUDA_TRY(cudaStreamSynchronize(st));
