@@ -275,10 +275,13 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)
   auto stage_next = [&](int tile) {            // called by all threads; exactly one of the two mechanisms is used
     if (tile >= a.n_tiles) return;
     if (tile_uses_tma(tile)) {
-      if (tid == 0) {
+      if (warp == 0) {             // warp-uniform; one elected lane issues (operands stay in uniform registers)
         const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
-        mbar_expect_tx(mbar_tma, box_bytes);
-        tma_load_3d(raw_u, a.tmap_dev, x0 + D - a.box_lead, y0 - net.buf_row0, 0, mbar_tma);
+        if (elect_one()) {
+          mbar_expect_tx(mbar_tma, box_bytes);
+          tma_load_3d(raw_u, a.tmap_dev, x0 + D - a.box_lead, y0 - net.buf_row0, 0, mbar_tma);
+        }
+        __syncwarp();
       }
     } else if (REGPF && pf_ok) {
       issue_patch_loads(tile);
@@ -392,8 +395,11 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)
       fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       wg_sync();
-      if (tid == 0) {
-        tc_fence_after();
+      if (warp == 0) {
+       // warp 0 of the warpgroup, warp-uniform control flow, ONE elected lane issues: issuing from inside `if (tid == 0)`
+       // makes the compiler wrap every tcgen05 instruction in an R2UR.BROADCAST / ELECT loop
+       tc_fence_after();
+       if (elect_one()) {
         const uint32_t sB_u = smem_u32(sW + H->off_b[l]);
         const uint32_t sBlo_u = smem_u32(sW + H->off_blo[l]);
         if (l == 0) {
@@ -411,6 +417,8 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)
               umma_f16(tmem, umma_desc(sA_u + i * 2 * 2048, 2048, 128), umma_desc(sBlo_u + i * 2 * 1024, 1024, 128), idesc, 1);
         }
         umma_commit(mbar);
+       }
+       __syncwarp();
       }
       mbar_wait(mbar, phase, 1, t, a.no_trap);
       phase ^= 1;

@@ -194,16 +194,6 @@ __device__ __forceinline__ void tcw_wait2(uint32_t mbar_a, uint32_t par_a, uint3
   }
 }
 
-// One lane of a converged warp.  The control warps run their loops warp-uniformly (every lane waits on the barriers) and
-// only the tcgen05 / bulk-copy instructions sit under this predicate: operands then live in uniform registers.  Issuing
-// from inside `if (lane == 0)` instead makes the compiler wrap every such instruction in an R2UR.BROADCAST / ELECT
-// loop (~80 dependent instructions per K step: 300 cycles on the one thread the whole CTA's tensor work goes through).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
-
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
