@@ -300,7 +300,7 @@ int32_t lbdrn_eval_sse(const LbdrnDesc* d, const void* msb_dev, const void* lsb_
   if (rc) return rc;
   if (tc_supported(n) && d->path != LBDRN_PATH_PRECISE) {
     if (!msb_dev || !lsb_dev || !params_dev || !sse_dev) return fail(LBDRN_E_INVALID, "null device pointer");
-    return tc_eval_sse(n, msb_dev, lsb_dev, params_dev, sse_dev, (cudaStream_t)stream);
+    return tc_eval_sse(n, msb_dev, lsb_dev, params_dev, coord_tab_dev, sse_dev, (cudaStream_t)stream);
   }
   return run_infer<MODE_SSE>(d, msb_dev, lsb_dev, params_dev, coord_tab_dev, nullptr, sse_dev, stream);
 }

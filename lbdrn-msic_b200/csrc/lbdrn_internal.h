@@ -53,7 +53,8 @@ void launch_adam_apply(const Net& n, const float* grad, float* params, float* wp
 bool tc_supported(const Net& n);
 int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
               cudaStream_t st);
-int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st);
+int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, const float* tab, double* sse_out,
+                cudaStream_t st);
 // wide (bc 128/256) tcgen05 decode (lbdrn_tcw.cu)
 bool tcw_supported(const Net& n);
 int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out, int fast_sine, const int** exact_flag_out,

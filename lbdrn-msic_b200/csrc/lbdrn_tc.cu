@@ -31,8 +31,8 @@ namespace {
 
 void plan_block(const Net& n, TcHeader& h) {
   memset(&h, 0, sizeof h);
-  h.k1 = n.dim_in;
-  h.k1pad = align_up(n.dim_in, 16);
+  h.k1 = n.ncol;                                       // the MMA contracts over the colour features only; coordinate /
+  h.k1pad = align_up(n.ncol > 0 ? n.ncol : 1, 16);     // positional features enter through fp32 row / column tables
   h.nl = n.nl;
   int off = align_up((int)sizeof(TcHeader), 16);
   h.off_bias = off; off += n.nl * TC_BC * 4;
@@ -62,9 +62,11 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
   TcHeader* H = reinterpret_cast<TcHeader*>(blk);
   for (int l = 0; l < net.nl; ++l) {
     const int K = l == 0 ? net.dim_in : net.bc;
+    const int k0 = l == 0 ? net.nco : 0;                 // first colour column of W1 (coordinate columns come first)
     const float* W = params + net.woff[l];
     float m = 0.f;
-    for (int i = tid; i < K * net.bc; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int i = tid; i < K * net.bc; i += blockDim.x)
+      if (i % K >= k0) m = fmaxf(m, fabsf(W[i]));
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if ((tid & 31) == 0) s_max[tid >> 5] = m;
     __syncthreads();
@@ -77,7 +79,8 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
     __half* Blo = reinterpret_cast<__half*>(blk + hdr.off_blo[l]);
     int bad = 0;
     for (int i = tid; i < K * net.bc; i += blockDim.x) {
-      const int nrow = i / K, k = i - nrow * K;
+      const int nrow = i / K, k = i - nrow * K - k0;
+      if (k < 0) continue;
       const float v = W[i] * up;                                          // exact (power of two)
       const __half hv = __float2half_rn(v);
       const float rem = v - __half2float(hv);                             // exact in fp32
@@ -107,7 +110,28 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
   }
 }
 
+// USE_COORDINATES (LBDRNdataset.py:108-118): the coordinate / positional-encoding columns of a pixel are [row block of y |
+// column block of x], so their contribution to the first layer separates: W1[:, :tabw] . rowtab[y] + W1[:, tabw:2 tabw] .
+// coltab[x].  One thread per (row or column, unit) forms that dot product in fp32; the decode epilogue adds
+// rtab[y][u] + ctab[x][u] to the scaled tensor-core accumulator.  rtab also carries the bias; both carry the w0 fold.
+__global__ void tc_coord_tables_kernel(Net net, const float* __restrict__ params, const float* __restrict__ tab,
+                                       float* __restrict__ rtab, float* __restrict__ ctab) {
+  const int total = (net.H + net.W) * TC_BC;
+  const float fold = net.relu ? 1.0f : net.w0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int pos = i / TC_BC, u = i - pos * TC_BC;
+    const bool is_col = pos >= net.H;
+    const float* t = tab + (size_t)pos * net.tabw;                                   // row table then column table
+    const float* w = params + net.woff[0] + (size_t)u * net.dim_in + (is_col ? net.tabw : 0);
+    float acc = is_col ? 0.f : params[net.boff[0] + u];
+    for (int k = 0; k < net.tabw; ++k) acc = fmaf(w[k], t[k], acc);
+    (is_col ? ctab + (size_t)(pos - net.H) * TC_BC : rtab + (size_t)pos * TC_BC)[u] = fold * acc;
+  }
+}
+
 struct TcArgs {
+  const float* rtab;      // USE_COORDINATES: [H][bc] row-table contribution to layer 0 (+ bias), w0-folded; else nullptr
+  const float* ctab;      // [W][bc] column-table contribution
   const CUtensorMap* tmap_dev;  // 3-D tiled map of the MSB buffer (W, buf_rows, C) in global memory; valid when use_tma
   int no_trap;            // debug: do not trap on a barrier timeout
   int use_tma, box_w, box_lead;  // TMA patch staging for interior tiles: the box starts `box_lead` elements left of the
@@ -149,7 +173,8 @@ constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+
 // NWG=2 (TMA-addressable inputs, exact weights): two independent warpgroups share ONE copy of the weights, 2 CTAs/SM
 // = 16 resident warps per SM instead of 12; each warpgroup has its own A region, staging buffers, mbarriers and TMEM
 // columns and synchronises on its own named barrier.
-template <bool FAST, int CC, int DD, bool WLO, int MODE, int NWG>
+// COORDS: USE_COORDINATES feature sets (table-driven colour offsets; fp32 row / column tables added in the first epilogue).
+template <bool FAST, int CC, int DD, bool WLO, int MODE, int NWG, bool COORDS = false>
 __global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)) tc_decode_kernel(const TcArgs a) {
   constexpr int THREADS = TC_THREADS * NWG;
   const Net& net = a.net;
@@ -428,19 +453,30 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)
       const float scale = H->scale[l];
       const float* bl = bias + l * TC_BC;
       const bool last = l + 1 == NL;
+      const bool coords = COORDS && l == 0;
+      const float4* rrow = reinterpret_cast<const float4*>(a.rtab + (size_t)min(ty0 + pr, net.H - 1) * TC_BC);
+      const float4* crow = reinterpret_cast<const float4*>(a.ctab + (size_t)min(tx0 + px, net.W - 1) * TC_BC);
 #pragma unroll 1
       for (int cb = 0; cb < TC_BC; cb += 16) {
         float acc[16];
+        float bterm[COORDS ? 16 : 1];
+        if (coords) {                 // fp32 coordinate contribution (includes the bias) instead of the bias alone
+#pragma unroll
+          for (int q = 0; q < (COORDS ? 4 : 0); ++q) {
+            const float4 r = __ldg(rrow + (cb >> 2) + q), c = __ldg(crow + (cb >> 2) + q);
+            bterm[4 * q] = r.x + c.x; bterm[4 * q + 1] = r.y + c.y; bterm[4 * q + 2] = r.z + c.z; bterm[4 * q + 3] = r.w + c.w;
+          }
+        }
         tmem_ld16(tmem_row + cb, acc);
         float h[16];
         if (net.relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bl[cb + j]), 0.f);
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, coords ? bterm[COORDS ? j : 0] : bl[cb + j]), 0.f);
         } else {
           float amax = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            acc[j] = fmaf(acc[j], scale, bl[cb + j]);          // = w0 * z (w0 folded into scale and bias)
+            acc[j] = fmaf(acc[j], scale, coords ? bterm[COORDS ? j : 0] : bl[cb + j]);   // = w0 * z (w0 folded in)
             amax = fmaxf(amax, fabsf(acc[j]));
             h[j] = tc_sine<FAST>(acc[j]);
           }
@@ -638,9 +674,10 @@ constexpr int kBlkBytes = 1 << 18;
 }  // namespace
 
 bool tc_supported(const Net& n) {
-  // colours only (integer differences are exact in fp16 up to 2048); bc = 64; up to 8 bands, D <= 3
-  return n.bc == TC_BC && n.nco == 0 && n.ncol > 0 && n.dim_in <= TC_MAX_K1 && n.maxv <= 2048.0f && n.C <= kMaxC &&
-         n.nl >= 1 && n.nl <= 4;
+  // bc = 64; colour features as integer differences (exact in fp16 up to 2048), coordinate / positional features as
+  // fp32 row / column tables added in the first epilogue; up to 8 bands, D <= 3
+  return n.bc == TC_BC && n.ncol <= TC_MAX_K1 && n.maxv <= 2048.0f && n.C <= kMaxC && n.nl >= 1 && n.nl <= 4 &&
+         (n.ncol == 0 || n.D <= 3);
 }
 
 namespace {
@@ -649,6 +686,10 @@ using KernT = void (*)(const TcArgs);
 
 template <bool FAST, bool WLO, int MODE, int NWG>
 KernT pick_kernel(const Net& n) {
+  if (n.nco) {                                       // coordinate features (USE_COLORS off: k1 = 0, table-driven kernel)
+    if (n.ncol && n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE, NWG, true>;
+    return tc_decode_kernel<FAST, 0, 0, WLO, MODE, NWG, true>;
+  }
   if (n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE, NWG>;
   if (n.C == 8 && n.D == 2) return tc_decode_kernel<FAST, 8, 2, WLO, MODE, NWG>;
   if (n.C == 4 && n.D == 1) return tc_decode_kernel<FAST, 4, 1, WLO, MODE, NWG>;
@@ -768,11 +809,37 @@ int tc_prepare(const Net& n, const float* params, TcHeader& h, uint8_t*& blk, in
   return LBDRN_OK;
 }
 
+float* g_ctab[64] = {nullptr};
+size_t g_ctab_n[64] = {0};
+
+// row / column contribution tables of the coordinate features (no-op without USE_COORDINATES)
+int tc_coord_tables(const Net& n, const float* params, const float* tab, int dev, TcArgs& a, cudaStream_t st) {
+  a.rtab = a.ctab = nullptr;
+  if (!n.nco) return LBDRN_OK;
+  if (!tab) return fail(LBDRN_E_INVALID, "USE_COORDINATES set but coord_tab_dev is NULL");
+  const size_t need = (size_t)(n.H + n.W) * TC_BC;
+  {
+    std::lock_guard<std::mutex> lk(tc_mu());
+    if (g_ctab_n[dev] < need) {
+      if (g_ctab[dev]) CUDA_TRY(cudaFree(g_ctab[dev]));     // synchronises: no launch still reads the old tables
+      g_ctab[dev] = nullptr; g_ctab_n[dev] = 0;
+      CUDA_TRY(cudaMalloc(&g_ctab[dev], need * sizeof(float)));
+      g_ctab_n[dev] = need;
+    }
+  }
+  a.rtab = g_ctab[dev];
+  a.ctab = g_ctab[dev] + (size_t)n.H * TC_BC;
+  const int blocks = (int)((need + 255) / 256);
+  tc_coord_tables_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(n, params, tab, g_ctab[dev], g_ctab[dev] + (size_t)n.H * TC_BC);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
 }  // namespace
 
 int tc_decode(const Net& n, const void* msb, const float* params, const float* tab, uint16_t* out, int fast_sine,
               cudaStream_t st) {
-  (void)tab;
   TcHeader h;
   uint8_t* blk = nullptr;
   int dev = 0, rc = tc_prepare(n, params, h, blk, dev, st);
@@ -780,6 +847,8 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
   TcArgs a;
   memset(&a, 0, sizeof a);
   a.net = n; a.msb = msb; a.blk = blk; a.out = out;
+  rc = tc_coord_tables(n, params, tab, dev, a, st);
+  if (rc) return rc;
   rc = tc_setup_tma(a, dev, st);
   if (rc) return rc;
   // two sibling launches; the exactness flag computed by tc_prep_kernel decides ON THE DEVICE which one does the work
@@ -797,7 +866,8 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
                    1, dev, st);
 }
 
-int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st) {
+int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, const float* tab, double* sse_out,
+                cudaStream_t st) {
   TcHeader h;
   uint8_t* blk = nullptr;
   int dev = 0, rc = tc_prepare(n, params, h, blk, dev, st);
@@ -810,6 +880,8 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
   a.net = n; a.msb = msb; a.blk = blk; a.lsb = lsb;
   a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
   a.run_if_exact = -1;
+  rc = tc_coord_tables(n, params, tab, dev, a, st);
+  if (rc) return rc;
   rc = tc_setup_tma(a, dev, st);
   if (rc) return rc;
   return tc_launch(pick_kernel<true, true, TC_SSE, 1>(n), a, h, true, 1, dev, st);

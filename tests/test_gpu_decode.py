@@ -276,6 +276,37 @@ def test_edge_shapes_against_oracle(C, H, W, D, bc, nl, K, bits):
         assert (diff != 0).sum() <= max(1, int((3e-3 if K >= 10 else 1e-4) * diff.size)), (path, int((diff != 0).sum()), diff.size)
 
 
+@pytest.mark.parametrize("case", ["coords_pe", "coords_pe_col", "coords_only"])
+def test_coordinate_features_on_the_tensor_path(case):
+    """BASELINE config 4 (USE_COORDINATES / EMBEDDING): the coordinate columns enter the tensor-core kernel as fp32 row /
+    column tables added in the first epilogue.  Trained weights of the reference's own streams, ragged scene, every path,
+    and a two-stripe decode (global row coordinates must index the tables)."""
+    from synth_scene import make_scene
+    meta, _, blob, _ = load_case(case)
+    _, tiles = split_stream(blob)
+    params = np.asarray(fpzip.decompress(tiles[0][0])[0][0][0], dtype=np.float32)
+    fl, ofl = case_flags(meta, F.Flags), case_flags(meta, O.Flags)
+    C, H, W, K, D, bc, nl = 4, 150, 203, meta["K"], meta["D"], meta["bc"], meta["nl"]
+    img = make_scene(C, H, W, 12, seed=31)
+    msb, _ = O.split_msb_lsb(img, K)
+    ref = O.decode_image(msb, O.unflatten_params(params, ofl.dim_in(C, D), bc, C, nl), K, D, ofl)
+    paths = _paths(K, D, bc, nl, C, fl, msb.max())
+    assert "tensor" in paths
+    for path in paths:
+        _check(F.decode_image(msb, params, K, D, bc, nl, flags=fl, path=path), ref, f"{case}/{path}")
+    lib = cabi.load()
+    dev = torch.device("cuda")
+    m = torch.from_numpy(msb).to(dev)
+    out = torch.zeros((C, H, W), dtype=torch.uint16, device=dev)
+    tab = F._tab_tensor(H, W, fl, dev)
+    p = torch.from_numpy(params).to(dev)
+    for (r0, r1) in ((0, 77), (77, H)):
+        d = cabi.make_desc(C, H, W, K, D, bc, nl, fl.bits(), int(msb.max()), msb.max() > 255, n_freq=fl.n_freq,
+                           row0=r0, row1=r1, path=cabi.PATH_TENSOR)
+        cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(m), cabi.ptr(p), cabi.ptr(tab), cabi.ptr(out), cabi.stream_ptr()))
+    _check(out.cpu().numpy(), ref, f"{case}/stripes")
+
+
 def test_degenerate_and_invalid_inputs_are_rejected():
     lib = cabi.load()
     p = torch.zeros(10884, device="cuda")
