@@ -110,6 +110,18 @@ def bench_params(device):
     return flat.to(device)
 
 
+def traffic_from_profile(has_tc):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the bench workload, from the
+    committed `ncu --set full` capture (profiles/r1_traffic.json, written by tools/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not has_tc or not os.path.exists(p):
+        return None
+    j = json.load(open(p))
+    return {"bytes_per_launch": j["dram_bytes_read"] + j["dram_bytes_write"], "dram_bytes_read": j["dram_bytes_read"],
+            "dram_bytes_write": j["dram_bytes_write"], "algorithmic_bytes": SIDE * SIDE * HBM_BYTES_PER_PX,
+            "scene_side": j.get("side"), "source": j["source"]}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU path (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------------------------
@@ -249,7 +261,9 @@ def run_ours(args):
     kern_avg_ms = (sum(step_ms) / len(step_ms)) if world == 1 else kern_ms
     tflops = SIDE * SIDE * FLOP_PER_PX / (kern_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-                "frac": tflops / pk["bf16_burst"], "traffic": None,
+                "frac": tflops / pk["bf16_burst"],
+                "traffic": (traffic_from_profile(has_tc) or {}).get("bytes_per_launch"),
+                "traffic_detail": traffic_from_profile(has_tc),
                 "kernel": "tc_decode_kernel<fast,4,2> (tcgen05 kind::f16, fp16 hi+lo split activations, fp32 TMEM accumulators)"
                 if has_tc else "infer_fp32_kernel<64,8,4,true,DECODE> (fp32 FFMA)",
                 "peak_source": pk["source"] + " bf16 dense burst",
@@ -333,6 +347,37 @@ def run_ours(args):
                   "tensor_roofline_frac": flop / enc_s / 1e12 / pk["bf16_sustained"], "clocks": enc_clk.summary(),
                   "excludes": "GDAL read/write, JPEG-2000 base layer, fpzip (host, unchanged)"}
 
+    # ---- the other BASELINE.json configs on this GPU (N=1 only; not the headline: explanatory lines) -----------------
+    other = None
+    if world == 1 and not args.no_extra:
+        from LBDRNmodel import LBDRNModel
+
+        def timed_decode(D, bc, flags, label, reps=3):
+            torch.manual_seed(19920517)
+            dim_in = flags.dim_in(C_, D)
+            p = (LBDRNModel(dim_in, bc, C_, NL).flat_params().view(torch.int32) & -65536).view(torch.float32).to(dev)
+            F.decode_image(scene.msb, p, K_, D, bc, NL, flags=flags, return_tensor=True, base_max=scene.msb_max)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                F.decode_image(scene.msb, p, K_, D, bc, NL, flags=flags, return_tensor=True, base_max=scene.msb_max)
+            a1.record()
+            torch.cuda.synchronize()
+            ms = a0.elapsed_time(a1) / reps
+            flop_px = 2 * (dim_in * bc + (NL - 1) * bc * bc + bc * C_)
+            tf = SIDE * SIDE * flop_px / (ms * 1e-3) / 1e12
+            return {"config": label, "Mpix_s": SIDE * SIDE / ms / 1e3, "ms_per_scene": ms, "flop_per_pixel": flop_px,
+                    "tflops": tf, "tensor_roofline_frac": tf / pk["bf16_burst"]}
+
+        other = [
+            timed_decode(3, 256, F.Flags(), "configs[2]: D=3 bc256 nl2 (wide tcgen05 kernel, streamed operands)"),
+            timed_decode(2, 64, F.Flags(use_coordinates=True, embedding=True, use_colors=False),
+                         "configs[3]: USE_COORDINATES+EMBEDDING, USE_COLORS off (dim_in 50)"),
+            timed_decode(2, 64, F.Flags(use_coordinates=True, embedding=True, use_colors=True),
+                         "configs[3]: USE_COORDINATES+EMBEDDING with colours (dim_in 150)"),
+        ]
+
     # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample ----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -353,7 +398,7 @@ def run_ours(args):
                            "l2": "inputs+outputs per step = 805 MB > 126 MB L2 (no flush needed)",
                            "parallelism": f"stripe-sharded decode x{world}"},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "encode": encode}
+                "roofline": roofline, "cpu_baseline": cpu, "encode": encode, "other_configs": other}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -368,6 +413,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-encode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the explanatory lines for the other BASELINE configs")
     ap.add_argument("--encode-epochs", type=int, default=10)
     ap.add_argument("--sampler", choices=["reference", "device"], default="device")
     args = ap.parse_args()

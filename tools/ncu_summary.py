@@ -6,6 +6,20 @@ import sys
 pre = sys.argv[1]
 rows = list(csv.reader(open(f"{pre}_raw.csv")))
 r = {h: (v, u) for h, u, v in zip(rows[0], rows[1], rows[2])}
+
+
+def _bytes(key):
+    v, u = r[key]
+    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+
+if "--traffic-json" in sys.argv:      # usage: ncu_summary.py <prefix> --traffic-json <out.json> <side> <source text>
+    import json
+    i = sys.argv.index("--traffic-json")
+    json.dump({"kernel": r.get("Kernel Name", ("?",))[0], "side": int(sys.argv[i + 2]),
+               "dram_bytes_read": _bytes("dram__bytes_read.sum"), "dram_bytes_write": _bytes("dram__bytes_write.sum"),
+               "gpu_time": r["gpu__time_duration.sum"][0] + " " + r["gpu__time_duration.sum"][1],
+               "source": sys.argv[i + 3]}, open(sys.argv[i + 1], "w"), indent=1)
 print("kernel:", r.get("Kernel Name", ("?",))[0])
 keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__occupancy_limit_warps",
