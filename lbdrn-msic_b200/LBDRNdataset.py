@@ -109,6 +109,20 @@ def process(path, K, D, output_path):
     return host_features(msb, D), np.ascontiguousarray(lsb.transpose(1, 2, 0).reshape(-1, lsb.shape[0]))
 
 
+# Scenes already uploaded by the batch scheduler (lbdrn_sched.py): absolute path -> CHW uint16 CUDA tensor.  A K sweep over
+# one scene then reads and uploads the raster once; the MSB/LSB split for each K runs on the device.
+PRELOADED = {}
+
+
+def preload(path, device=None):
+    import lbdrn_fused
+    img = gdal.Open(path).ReadAsArray()
+    img = img.reshape((-1,) + img.shape[-2:])
+    t = torch.from_numpy(np.ascontiguousarray(img.astype(np.uint16, copy=False))).to(lbdrn_fused._device(device))
+    PRELOADED[os.path.abspath(path)] = t
+    return t
+
+
 class LBDRNDataset(Dataset):
     """Scene resident on the GPU as MSB/LSB planes; same attributes as the reference's dataset
     (`n_pixels, n_feature, channels, n_subpixels`) and the same side effect of writing `<out>/<name>_base.tif`."""
@@ -118,7 +132,9 @@ class LBDRNDataset(Dataset):
         name = os.path.splitext(os.path.basename(args.path))[0]
         self.K, self.D = args.K, args.D
         self.flags = lbdrn_fused.Flags.from_constants()
-        img = gdal.Open(args.path).ReadAsArray()
+        img = PRELOADED.get(os.path.abspath(args.path))
+        if img is None:
+            img = gdal.Open(args.path).ReadAsArray()
         self.scene = lbdrn_fused.DeviceScene.from_image(img, args.K)
         self._msb_host = self.scene.msb.cpu().numpy()
         write_tiff_with_gdal(f'{args.output_dir}/{name}_base.tif', self._msb_host)

@@ -64,15 +64,17 @@ def split_msb_lsb(img, K):
 # ----------------------------------------------------------------------------------------------------------
 # a2/a3: per-pixel features (LBDRNdataset.py:104-130, duplicated at decode.py:77-102)
 # ----------------------------------------------------------------------------------------------------------
-def coordinate_block(H, W, flags):
-    """(H, W, num_coords) float32 coordinate / positional-encoding block (LBDRNdataset.py:108-118)."""
-    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+def coordinate_block(H, W, flags, row0=0, row1=None):
+    """(rows, W, num_coords) float32 coordinate / positional-encoding block (LBDRNdataset.py:108-118) for image rows
+    [row0,row1) of an H x W image (every entry depends on its own (y, x) only, so a row range is a slice of the block)."""
+    row1 = H if row1 is None else row1
+    yy, xx = np.meshgrid(np.arange(row0, row1), np.arange(W), indexing="ij")
     c = np.stack([2 * yy / (H - 1) - 1, 2 * xx / (W - 1) - 1], axis=-1).astype(np.float32)
     if flags.embedding:
         freq = flags.sigma ** np.arange(flags.n_freq) * np.pi          # float64
         arg = freq * c[..., None]                                      # float32 coord promoted to float64
         c = np.concatenate([c[..., None], np.sin(arg), np.cos(arg)], axis=-1)
-    return c.reshape(H, W, -1).astype(np.float32)
+    return c.reshape(row1 - row0, W, -1).astype(np.float32)
 
 
 def features(msb, D, flags=DEFAULT_FLAGS, row0=0, row1=None):
@@ -87,7 +89,7 @@ def features(msb, D, flags=DEFAULT_FLAGS, row0=0, row1=None):
     nco, ncl = flags.num_coords(), flags.num_colors(C, D)
     out = np.zeros((row1 - row0, W, nco + ncl), dtype=np.float32)
     if flags.use_coordinates:
-        out[:, :, :nco] = coordinate_block(H, W, flags)[row0:row1]
+        out[:, :, :nco] = coordinate_block(H, W, flags, row0, row1)
     if flags.use_colors:
         s = msb.astype(np.float32) / msb.max()                                   # LBDRNdataset.py:120
         lo, hi = row0 - D, row1 + D                                              # padded-row window

@@ -90,3 +90,19 @@ def test_batch_slices_and_gradient_allreduce_world2():
     slices = sorted(v[0] for v in out.values())
     assert slices[0][0] == 0 and slices[-1][1] == 1000 and slices[0][1] == slices[1][0]
     assert all(v[1] for v in out.values())
+
+
+def _sched_case(rank, world):
+    import lbdrn_sched as S
+    sizes = {f"s{i}.tif": (4, 1000 + 37 * i, 900) for i in range(5)}
+    jobs = S.expand_jobs(sizes, [2, 5, 8])
+    mine = S.plan(jobs, world)[rank]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [tuple(j) for j in mine])
+    return sorted(tuple(j) for j in jobs) == sorted(j for g in gathered for j in g), len(mine)
+
+
+def test_scheduler_ranks_partition_the_job_list_world2():
+    out = _run("_sched_case")
+    assert all(v[0] for v in out.values())
+    assert sum(v[1] for v in out.values()) == 15 and min(v[1] for v in out.values()) >= 6

@@ -105,13 +105,59 @@ def test_config5_shape_8band_16bit_stripe_decode():
     assert torch.equal(out.view(torch.int16), whole.view(torch.int16))
 
 
-def test_config3_d3_bc256_fullsize_band():
-    """Wide variant (D=3, bc=256): fp32 kernel on a 256-row band of an 8192-wide scene vs oracle windows."""
+def test_config3_d3_bc256_fullsize():
+    """BASELINE config 3 (D=3, bc=256) at 8192^2 on the wide tcgen05 kernel: oracle windows, stripe decode bit-identical,
+    and the fp32 kernel within the bar on a band."""
     from synth_scene import make_scene_torch
     K, D = 5, 3
-    img = make_scene_torch(4, 256, 8192, 12, seed=11, device="cuda")
+    img = make_scene_torch(4, 8192, 8192, 12, seed=11, device="cuda")
     scene = F.DeviceScene.from_image(img, K)
+    del img
     params = _params("d3_bc256")
-    whole = F.decode_image(scene.msb, torch.from_numpy(params).cuda(), K, D, 256, 2, flags=F.Flags(), return_tensor=True,
-                           base_max=scene.msb_max)
-    _window_check(scene.msb, whole, params, K, D, 196, 256, 4, 2, n_windows=3, win=48)
+    pd = torch.from_numpy(params).cuda()
+    lib = cabi.load()
+    d = cabi.make_desc(4, 8192, 8192, K, D, 256, 2, F.Flags().bits(), scene.msb_max, False)
+    assert lib.lbdrn_has_tensor_path(ctypes.byref(d)) == 1
+    whole = F.decode_image(scene.msb, pd, K, D, 256, 2, flags=F.Flags(), return_tensor=True, base_max=scene.msb_max)
+    _window_check(scene.msb, whole, params, K, D, 196, 256, 4, 2, n_windows=4, win=48)
+    out = torch.empty_like(whole)
+    for r0, r1 in ((0, 5003), (5003, 8192)):
+        d = cabi.make_desc(4, 8192, 8192, K, D, 256, 2, F.Flags().bits(), scene.msb_max, False, row0=r0, row1=r1)
+        cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(scene.msb), cabi.ptr(pd), None, cabi.ptr(out), cabi.stream_ptr()))
+    assert torch.equal(out.view(torch.int16), whole.view(torch.int16))
+    d = cabi.make_desc(4, 8192, 8192, K, D, 256, 2, F.Flags().bits(), scene.msb_max, False, row0=2048, row1=2304,
+                       path=cabi.PATH_PRECISE)
+    cabi.check(lib.lbdrn_decode(ctypes.byref(d), cabi.ptr(scene.msb), cabi.ptr(pd), None, cabi.ptr(out), cabi.stream_ptr()))
+    diff = (out[:, 2048:2304].view(torch.int16).to(torch.int32) - whole[:, 2048:2304].view(torch.int16).to(torch.int32)).abs()
+    assert int(diff.max()) <= 1 and float((diff != 0).float().mean()) <= 1e-4
+
+
+@pytest.mark.parametrize("case", ["coords_pe", "coords_pe_col"])
+def test_config4_coordinates_fullsize(case):
+    """BASELINE config 4 (USE_COORDINATES + EMBEDDING, without / with colours) at 8192^2 on the tensor path.  Coordinates
+    are absolute, so the oracle is evaluated on full-width row bands of the real scene (not on crops)."""
+    from synth_scene import make_scene_torch
+    from conftest import case_flags
+    meta, _, _, _ = load_case(case)
+    fl, ofl = case_flags(meta, F.Flags), case_flags(meta, O.Flags)
+    K, D, H, W = 5, 2, 8192, 8192
+    img = make_scene_torch(4, H, W, 12, seed=13, device="cuda")
+    scene = F.DeviceScene.from_image(img, K)
+    del img
+    params = _params(case)
+    whole = F.decode_image(scene.msb, torch.from_numpy(params).cuda(), K, D, 64, 2, flags=fl, return_tensor=True,
+                           base_max=scene.msb_max, path="tensor")
+    msb = scene.msb.cpu().numpy()
+    p = O.unflatten_params(params, ofl.dim_in(4, D), 64, 4, 2)
+    bad = tot = 0
+    for r0 in (0, 5000, H - 8):
+        with torch.no_grad():
+            y = O.forward(p, torch.from_numpy(O.features(msb, D, ofl, r0, r0 + 8)))
+        res = torch.round(y * (2 ** K - 1)).numpy().reshape(8, W, 4).transpose(2, 0, 1)
+        ref = np.round((msb[:, r0:r0 + 8].astype(np.uint16) << K).astype(np.float32) + res).astype(np.uint16)
+        got = whole[:, r0:r0 + 8].view(torch.int16).cpu().numpy().view(np.uint16)
+        diff = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+        assert diff.max() <= 1
+        bad += int((diff != 0).sum())
+        tot += diff.size
+    assert bad <= max(1, int(1e-4 * tot)), (bad, tot)

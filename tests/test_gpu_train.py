@@ -208,3 +208,30 @@ def test_cli_split_ratio_roundtrip(tmp_path):
     psnr = float(log.split("PSNR: ")[1].split()[0])
     meta = load_case("sr2_tiles")[0]
     assert abs(psnr - meta["psnr"]) < 0.05
+
+
+def test_scheduler_k_sweep_matches_the_plain_cli(tmp_path):
+    """lbdrn_sched.py (N3): a K sweep over two scenes through the scheduler (one upload per scene, MSB/LSB split per K on
+    the device) writes byte-identical bitstreams to the plain encode.py CLI run job by job."""
+    from osgeo import gdal
+    from synth_scene import make_scene
+    tifs = []
+    for i, (h, w) in enumerate(((64, 72), (80, 56))):
+        tif = str(tmp_path / f"s{i}.tif")
+        gdal._store(tif, make_scene(4, h, w, 12, seed=20 + i))
+        tifs.append(tif)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([PKG, SHIMS]))
+    common = ["-D", "2", "-bc", "64", "-nl", "2", "-lr", "0.001", "-bs", "512", "-prec", "16"]
+    out_s, out_c = str(tmp_path / "sched"), str(tmp_path / "cli")
+    r = subprocess.run([sys.executable, os.path.join(PKG, "lbdrn_sched.py"), "-i"] + tifs + ["-K", "3", "5", "-e", "2"] +
+                       common + ["-o", out_s], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "4 of 4 jobs" in r.stdout
+    for tif in tifs:
+        for K in (3, 5):
+            r = subprocess.run([sys.executable, os.path.join(PKG, "encode.py"), "-i", tif, "-K", str(K), "-e", "2"] + common +
+                               ["-o", out_c], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            name = os.path.splitext(os.path.basename(tif))[0]
+            d = f"{name}_r1_K{K}_bc64_nl2_D2_prec16_lr0.001_bs512_e2/{name}.bin"
+            assert open(f"{out_s}/{d}", "rb").read() == open(f"{out_c}/{d}", "rb").read(), d

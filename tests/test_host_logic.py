@@ -159,3 +159,43 @@ def test_product_path_fails_loudly_without_gpu():
     d = cabi.make_desc(4, 8, 8, 5, 2, 64, 2, cabi.flag_bits(False, False, True, True), 100, False)
     rc = lib.lbdrn_decode(ctypes.byref(d), ctypes.c_void_p(16), ctypes.c_void_p(16), None, ctypes.c_void_p(16), None)
     assert rc == cabi.E_CUDA
+
+
+def test_scheduler_plan_covers_every_job_once_and_balances():
+    """N3: scenes x K -> ranks.  Every job exactly once; K sweeps stay on one rank unless that unbalances
+    the plan; the plan is a pure function of its inputs (every rank computes the same one)."""
+    import lbdrn_sched as S
+    sizes = {f"scene{i}.tif": (4, 7000 + 100 * i, 7300) for i in range(13)}      # run.sh: 13 GF scenes
+    jobs = S.expand_jobs(sizes, [1, 3, 5, 7], epochs=10)
+    assert len(jobs) == 52
+    for world in (1, 2, 3, 8):
+        p = S.plan(jobs, world)
+        assert p == S.plan(list(reversed(jobs)), world)                          # order-independent, deterministic
+        flat = [j for r in p for j in r]
+        assert sorted(flat) == sorted(jobs)
+        loads = [sum(j.cost for j in r) for r in p]
+        assert max(loads) <= 1.35 * (sum(loads) / world)
+        for r in p:                                                              # whole sweeps: one upload per scene
+            for path in {j.path for j in r}:
+                assert len([j for j in r if j.path == path]) == 4
+    one = S.expand_jobs({"big.tif": (8, 16384, 16384)}, [1, 2, 3, 4, 5, 6, 7, 8])  # one scene, 8 GPUs: split K by K
+    p = S.plan(one, 8)
+    assert all(len(r) == 1 for r in p)
+
+
+def test_scheduler_run_rank_groups_by_scene_and_reports_existing(monkeypatch):
+    import LBDRNdataset
+    import lbdrn_sched as S
+    uploads, calls = [], []
+    monkeypatch.setattr(LBDRNdataset, "preload", lambda path, device=None: uploads.append(path))
+
+    def fake_encode(argv):
+        calls.append(tuple(argv))
+        if argv[3] == "3":
+            raise SystemExit                                                     # "Bitstream already created!"
+
+    jobs = [S.Job("a.tif", 1, 1.0), S.Job("a.tif", 3, 1.0), S.Job("b.tif", 1, 1.0)]
+    res = S.run_rank(jobs, ["-D", "2"], encode_main=fake_encode, log=lambda *_: None)
+    assert uploads == ["a.tif", "b.tif"]
+    assert [c[:4] for c in calls] == [("-i", "a.tif", "-K", "1"), ("-i", "a.tif", "-K", "3"), ("-i", "b.tif", "-K", "1")]
+    assert [r[2] for r in res] == ["done", "exists", "done"]
