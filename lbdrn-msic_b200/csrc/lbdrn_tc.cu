@@ -459,24 +459,30 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)
 #pragma unroll 1
       for (int cb = 0; cb < TC_BC; cb += 16) {
         float acc[16];
-        float bterm[COORDS ? 16 : 1];
+        float bterm[16];
         if (coords) {                 // fp32 coordinate contribution (includes the bias) instead of the bias alone
 #pragma unroll
           for (int q = 0; q < (COORDS ? 4 : 0); ++q) {
             const float4 r = __ldg(rrow + (cb >> 2) + q), c = __ldg(crow + (cb >> 2) + q);
             bterm[4 * q] = r.x + c.x; bterm[4 * q + 1] = r.y + c.y; bterm[4 * q + 2] = r.z + c.z; bterm[4 * q + 3] = r.w + c.w;
           }
+        } else {                      // 4 x LDS.128 (broadcast) instead of 16 scalar loads
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bl + cb + 4 * q);
+            bterm[4 * q] = b4.x; bterm[4 * q + 1] = b4.y; bterm[4 * q + 2] = b4.z; bterm[4 * q + 3] = b4.w;
+          }
         }
         tmem_ld16(tmem_row + cb, acc);
         float h[16];
         if (net.relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, coords ? bterm[COORDS ? j : 0] : bl[cb + j]), 0.f);
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bterm[j]), 0.f);
         } else {
           float amax = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            acc[j] = fmaf(acc[j], scale, coords ? bterm[COORDS ? j : 0] : bl[cb + j]);   // = w0 * z (w0 folded in)
+            acc[j] = fmaf(acc[j], scale, bterm[j]);            // = w0 * z (w0 folded into scale and bias)
             amax = fmaxf(amax, fabsf(acc[j]));
             h[j] = tc_sine<FAST>(acc[j]);
           }

@@ -39,7 +39,11 @@ namespace {
 constexpr int TCW_NWG = 4;                          // epilogue warpgroups
 constexpr int TCW_CTHREADS = 128 * TCW_NWG;         // 512 epilogue threads
 constexpr int TCW_THREADS = TCW_CTHREADS + 64;      // + MMA-issue warp + weight-streamer warp
-constexpr int TCW_ASLOT = 8192;                     // A slot: hi 4 KB | lo 4 KB  (128 rows x 16 K x 2 B each)
+constexpr int TCW_KS = 2;                           // MMA K steps (16 columns each) per operand chunk: every hand-off between
+                                                    // an epilogue warpgroup, the issue lane and the tensor core costs
+                                                    // ~250 cycles on top of the MMAs, so chunks carry 32 columns
+constexpr int TCW_AHALF = 4096 * TCW_KS;            // hi (or lo) half of an A slot: KS x (128 rows x 16 K x 2 B)
+constexpr int TCW_ASLOT = 2 * TCW_AHALF;            // A slot: hi | lo
 constexpr int TCW_NOUT = 16;                        // output layer: N padded to the smallest legal N at M=128
 constexpr int TCW_PF = 6;                           // patch elements prefetched per thread (512 threads -> 3072 elements)
 constexpr int TCW_HDR = 512;                        // bytes reserved for the header
@@ -57,7 +61,7 @@ static_assert(sizeof(TcwHeader) <= TCW_HDR, "header does not fit its slot");
 
 // APW: A slots per warpgroup (1 or 2); NB: depth of the B ring.  The bulk copies that fill the B ring have ~1 us of
 // latency (L2 -> smem), the tensor core drains a slot in 256 cycles: the ring has to be deep, the A ring does not.
-__host__ __device__ inline int ring_bytes(int bc, int apw, int nb) { return apw * TCW_NWG * TCW_ASLOT + nb * bc * 32; }
+__host__ __device__ inline int ring_bytes(int bc, int apw, int nb) { return apw * TCW_NWG * TCW_ASLOT + nb * bc * 32 * TCW_KS; }
 
 void tcw_plan(const Net& n, TcwHeader& h) {
   memset(&h, 0, sizeof h);
@@ -245,8 +249,8 @@ __device__ __forceinline__ void slot_release(const SlotRing& r, int sl) {
   mbar_arrive(r.full_u + sl * 8);
 }
 
-// Layer-0 operand chunks (16 features = one MMA K step) kc16 = WGI, WGI+4, ... of this thread's pixel, every patch offset
-// folded into an immediate.  Integer differences m_nbr - m_ctr are exact in fp16, so layer 0 has no lo half.
+// Layer-0 operand chunks (KS x 16 features) c = WGI, WGI+4, ... of this thread's pixel, every patch offset folded into
+// an immediate.  Integer differences m_nbr - m_ctr are exact in fp16, so layer 0 has no lo half.
 template <int CC, int DD, int WGI, int APW>
 __device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme, bool rel, SlotRing& ring, int pix, int where,
                                                   int no_trap) {
@@ -258,9 +262,15 @@ __device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme
     const __half cv = rel ? pme[(c * TRW_ + DD) * TWP_ + DD] : __half(0);
     ctr2[c] = __halves2half2(cv, cv);
   }
+  constexpr int NCH0 = (NK16 + TCW_KS - 1) / TCW_KS;
 #pragma unroll
-  for (int q = 0; q < (NK16 - WGI + TCW_NWG - 1) / TCW_NWG; ++q) {
-    const int kc16 = WGI + q * TCW_NWG;
+  for (int q = 0; q < (NCH0 - WGI + TCW_NWG - 1) / TCW_NWG; ++q) {
+   const int sl = q & (APW - 1);
+   uint8_t* st = nullptr;
+#pragma unroll
+   for (int ks = 0; ks < TCW_KS; ++ks) {
+    const int kc16 = (WGI + q * TCW_NWG) * TCW_KS + ks;
+    if (kc16 >= NK16) break;
     uint32_t w[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -277,11 +287,11 @@ __device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme
       }
       w[e] = *reinterpret_cast<const uint32_t*>(&v);
     }
-    const int sl = q & (APW - 1);
-    uint8_t* st = slot_acquire(ring, sl, where, no_trap);
-    *reinterpret_cast<uint4*>(st + (size_t)pix * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-    slot_release(ring, sl);
+    if (ks == 0) st = slot_acquire(ring, sl, where, no_trap);
+    *reinterpret_cast<uint4*>(st + ks * 4096 + (size_t)pix * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(st + ks * 4096 + (size_t)(128 + pix) * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+   }
+   slot_release(ring, sl);
   }
 }
 
@@ -295,8 +305,11 @@ __device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme
 // its epilogue has already consumed when the first output chunk is issued.
 template <bool FAST, int BC, int CC, int DD, int APW, int NB>
 __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArgs a) {
-  constexpr int NCH = BC / 16;                       // operand chunks (MMA K steps) per streamed layer
-  constexpr int BSLOT = BC * 32;                     // one K step of a streamed operand (bc rows x 16 K x 2 B)
+  constexpr int KS = TCW_KS;
+  constexpr int NCH = BC / (16 * KS);                // operand chunks per streamed layer
+  constexpr int BSTEP = BC * 32;                     // one K step of a hidden-layer operand (bc rows x 16 K x 2 B)
+  constexpr int BSLOT = BSTEP * KS;                  // one chunk of a streamed operand
+  static_assert(NCH % TCW_NWG == 0, "chunks per layer must divide evenly among the warpgroups");
   constexpr int NSLOT = APW * TCW_NWG;
   const Net& net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   const TcwHeader* H = reinterpret_cast<const TcwHeader*>(sW);
   if (!H->exact) return;                                   // the fp32 kernel queued behind this launch decodes the scene
   const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
-  const int nk16 = k1pad / 16;
+  const int nk16 = k1pad / 16, nch0 = (nk16 + KS - 1) / KS;     // layer 0: K steps, chunks
   const bool overlap = (NL & 1) == 0;
   if (CC == 0) {
     for (int k = tid; k < k1pad; k += TCW_THREADS) {
@@ -383,7 +396,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
       uint32_t bpar = 0u;                   // parity of the next wait on s_b_full[sb] (flips when the ring wraps)
       int sb = 0, g = 0;                    // B ring position; streamed-B chunk counter (layers >= 1)
       auto layer0 = [&](int it) {
-        for (int i = 0; i < nk16; ++i) {
+        for (int i = 0; i < nch0; ++i) {
           const int slot = APW * (i & 3) + ((i >> 2) & (APW - 1));
           const long long c0 = prof ? clock64() : 0;
           tcw_wait(a_full_u + slot * 8, (apar >> slot) & 1u, 5, it, a.no_trap);
@@ -391,9 +404,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           apar ^= 1u << slot;
           tc_fence_after();
           if (elect_one()) {
-            umma_f16(tmem, dA + (uint64_t)(slot * (TCW_ASLOT >> 4)), dB0 + (uint64_t)(i * (BSLOT >> 4)), idesc_h, i > 0);
+            for (int ks = 0; ks < KS && i * KS + ks < nk16; ++ks)
+              umma_f16(tmem, dA + (uint64_t)(slot * (TCW_ASLOT >> 4) + ks * 256),
+                       dB0 + (uint64_t)((i * KS + ks) * (BSTEP >> 4)), idesc_h, (i | ks) > 0);
             umma_commit(a_free_u + slot * 8);
-            if (i + 1 == nk16) umma_commit(smem_u32(&s_acc_full[0]));
+            if (i + 1 == nch0) umma_commit(smem_u32(&s_acc_full[0]));
           }
           __syncwarp();
         }
@@ -406,6 +421,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           if (outl && overlap && has_next) layer0(it + 1);
           const uint32_t idesc = outl ? idesc_o : idesc_h;
           const uint64_t dB = outl ? dBo : dBh;
+          const uint32_t bstep16 = (outl ? TCW_NOUT * 32 : BSTEP) >> 4;          // K step of this layer's operand
           // the output layer accumulates into columns [0,16) of the last hidden layer's accumulator (already consumed)
           const uint32_t d_tmem = tmem + (uint32_t)(((outl ? l - 1 : l) & 1) * BC);
 #pragma unroll 4
@@ -418,8 +434,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             tc_fence_after();
             const uint64_t da = dA + (uint64_t)(slot * (TCW_ASLOT >> 4)), db = dB + (uint64_t)(sb * (BSLOT >> 4));
             if (elect_one()) {
-              umma_f16(d_tmem, da, db, idesc, j > 0);                  // hi half of the split activations
-              umma_f16(d_tmem, da + (4096 >> 4), db, idesc, 1);        // lo half
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                umma_f16(d_tmem, da + (uint64_t)(ks * 256), db + (uint64_t)(ks * bstep16), idesc, (j | ks) > 0);    // hi half
+                umma_f16(d_tmem, da + (uint64_t)((TCW_AHALF >> 4) + ks * 256), db + (uint64_t)(ks * bstep16), idesc, 1);  // lo
+              }
               umma_commit(a_free_u + slot * 8);
               umma_commit(b_free_u + sb * 8);
               if (j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
@@ -431,7 +450,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
         if (!overlap && has_next) layer0(it + 1);
       }
       if (prof && (tid & 31) == 0) {
-        a.prof[0] = pc[0]; a.prof[1] = pc[1]; a.prof[2] = clock64() - c_start; a.prof[3] = (long long)g + (long long)my_tiles * nk16;
+        a.prof[0] = pc[0]; a.prof[1] = pc[1]; a.prof[2] = clock64() - c_start; a.prof[3] = (long long)g + (long long)my_tiles * nch0;
       }
     }
     __syncwarp();
@@ -448,7 +467,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
         tcw_wait(smem_u32(&s_b_free[s]), fpar, 6, g, a.no_trap);
         if (prof) pw += clock64() - c0;
         const int l = 1 + (g / NCH) % NL, j = g % NCH;
-        const uint32_t bytes = (uint32_t)((l == NL ? TCW_NOUT : BC) * 32);
+        const uint32_t bytes = (uint32_t)((l == NL ? TCW_NOUT : BC) * 32 * KS);
         if (elect_one()) {
           mbar_expect_tx(smem_u32(&s_b_full[s]), bytes);
           bulk_g2s(bring_u + s * BSLOT, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
@@ -522,7 +541,11 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           default: produce_l0_static<CC ? CC : 1, DD, 3, APW>(pme, rel, ring, pix, tile, a.no_trap); break;
         }
       } else {
-        for (int kc16 = wg; kc16 < nk16; kc16 += TCW_NWG) {
+        for (int c0 = wg; c0 < nch0; c0 += TCW_NWG) {
+         const int sl = (c0 >> 2) & (APW - 1);
+         uint8_t* st = nullptr;
+         for (int ks = 0; ks < KS && c0 * KS + ks < nk16; ++ks) {
+          const int kc16 = c0 * KS + ks;
           __half2 v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -534,15 +557,15 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             }
             v[e] = __halves2half2(k < k1 ? x0 : __half(0), k + 1 < k1 ? x1 : __half(0));
           }
-          const int sl = (kc16 >> 2) & (APW - 1);
-          uint8_t* st = slot_acquire(ring, sl, tile, a.no_trap);
-          *reinterpret_cast<uint4*>(st + (size_t)pix * 16) =
+          if (ks == 0) st = slot_acquire(ring, sl, tile, a.no_trap);
+          *reinterpret_cast<uint4*>(st + ks * 4096 + (size_t)pix * 16) =
               make_uint4(*reinterpret_cast<uint32_t*>(&v[0]), *reinterpret_cast<uint32_t*>(&v[1]),
                          *reinterpret_cast<uint32_t*>(&v[2]), *reinterpret_cast<uint32_t*>(&v[3]));
-          *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) =
+          *reinterpret_cast<uint4*>(st + ks * 4096 + (size_t)(128 + pix) * 16) =
               make_uint4(*reinterpret_cast<uint32_t*>(&v[4]), *reinterpret_cast<uint32_t*>(&v[5]),
                          *reinterpret_cast<uint32_t*>(&v[6]), *reinterpret_cast<uint32_t*>(&v[7]));
-          slot_release(ring, sl);
+         }
+         slot_release(ring, sl);
         }
       }
     };
@@ -572,17 +595,27 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
         const uint32_t acc_col = tmem_row + (uint32_t)((l & 1) * BC);
 #pragma unroll 1
         for (int j = wg; j < NCH; j += TCW_NWG) {
+         const int sl = (j >> 2) & (APW - 1);
+         uint8_t* st = nullptr;
+#pragma unroll 1
+         for (int ks = 0; ks < KS; ++ks) {
+          const int col = (j * KS + ks) * 16;
           float acc[16];
-          tmem_ld16(acc_col + j * 16, acc);
-          float h[16];
+          tmem_ld16(acc_col + col, acc);
+          float h[16], bterm[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {          // 4 x LDS.128 (broadcast) instead of 16 scalar loads
+            const float4 b4 = *reinterpret_cast<const float4*>(bl + col + 4 * q);
+            bterm[4 * q] = b4.x; bterm[4 * q + 1] = b4.y; bterm[4 * q + 2] = b4.z; bterm[4 * q + 3] = b4.w;
+          }
           if (net.relu) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) h[i] = fmaxf(fmaf(acc[i], scale, bl[j * 16 + i]), 0.f);
+            for (int i = 0; i < 16; ++i) h[i] = fmaxf(fmaf(acc[i], scale, bterm[i]), 0.f);
           } else {
             float amax = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              acc[i] = fmaf(acc[i], scale, bl[j * 16 + i]);          // = w0 * z (w0 folded into scale and bias)
+              acc[i] = fmaf(acc[i], scale, bterm[i]);                // = w0 * z (w0 folded into scale and bias)
               amax = fmaxf(amax, fabsf(acc[i]));
               h[i] = tcw_sine<FAST>(acc[i]);
             }
@@ -600,15 +633,18 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
             lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-          const long long c2 = prof ? clock64() : 0;
-          const int sl = (j >> 2) & (APW - 1);
-          uint8_t* st = slot_acquire(ring, sl, t, a.no_trap);
-          if (prof) pslot += clock64() - c2;
-          *reinterpret_cast<uint4*>(st + (size_t)pix * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(st + (size_t)(128 + pix) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<uint4*>(st + 4096 + (size_t)pix * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(st + 4096 + (size_t)(128 + pix) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          slot_release(ring, sl);
+          if (ks == 0) {
+            const long long c2 = prof ? clock64() : 0;
+            st = slot_acquire(ring, sl, t, a.no_trap);
+            if (prof) pslot += clock64() - c2;
+          }
+          uint8_t* sk = st + ks * 4096;
+          *reinterpret_cast<uint4*>(sk + (size_t)pix * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sk + (size_t)(128 + pix) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(sk + TCW_AHALF + (size_t)pix * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(sk + TCW_AHALF + (size_t)(128 + pix) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+         }
+         slot_release(ring, sl);
         }
       }
 
@@ -665,12 +701,12 @@ KernW pick_wide(const Net& n) {
   return tcw_decode_kernel<FAST, BC, 0, 0, APW, NB>;
 }
 
-// ring geometries built: (APW, NB) = (1, 10) deep B ring [default at bc 256], (2, 6), and (2, 12) for bc 128
+// ring geometries built: (APW, NB) = (1, 3) [what fits at bc 256 / D 3], (1, 4), (2, 6) [bc 128]
 template <bool FAST, int BC>
 KernW pick_ring(const Net& n, int apw, int nb) {
-  if (apw == 1 && nb == 10) return pick_wide<FAST, BC, 1, 10>(n);
+  if (apw == 1 && nb == 3) return pick_wide<FAST, BC, 1, 3>(n);
+  if (apw == 1 && nb == 4) return pick_wide<FAST, BC, 1, 4>(n);
   if (apw == 2 && nb == 6) return pick_wide<FAST, BC, 2, 6>(n);
-  if (apw == 2 && nb == 12) return pick_wide<FAST, BC, 2, 12>(n);
   return nullptr;
 }
 
@@ -684,7 +720,7 @@ constexpr size_t kTcwSmemLimit = 232448 - 2048;    // 227 KB minus static shared
 
 // deepest B ring that fits
 bool tcw_pick_ring(const Net& n, const TcwHeader& h, int& apw, int& nb) {
-  static const int opts[3][2] = {{2, 12}, {1, 10}, {2, 6}};
+  static const int opts[3][2] = {{2, 6}, {1, 4}, {1, 3}};
   if (const char* e = getenv("LBDRN_TCW_RING")) {
     if (sscanf(e, "%dx%d", &apw, &nb) == 2 && tcw_smem_bytes(n, h, apw, nb) <= kTcwSmemLimit) return true;
   }
