@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "lbdrn_infer_fp32.cuh"
 #include "lbdrn_internal.h"
@@ -178,6 +179,9 @@ struct LbdrnTrain {
   TrainPlan plan;
   int dev = 0, sms = 0;
   float *params = nullptr, *wpack = nullptr, *m = nullptr, *v = nullptr, *partial = nullptr;
+  float2* adam_tab = nullptr;      // per-step Adam scalars of the launch in flight (ring of two: launches may be queued)
+  size_t adam_tab_n = 0;
+  unsigned adam_tab_slot = 0;
 };
 
 namespace {
@@ -346,7 +350,7 @@ int32_t lbdrn_train_create(const LbdrnDesc* d, const LbdrnTrainCfg* cfg, LbdrnTr
 int32_t lbdrn_train_destroy(LbdrnTrain* t) {
   if (!t) return LBDRN_OK;
   cudaDeviceSynchronize();
-  cudaFree(t->params); cudaFree(t->wpack); cudaFree(t->m); cudaFree(t->v); cudaFree(t->partial);
+  cudaFree(t->params); cudaFree(t->wpack); cudaFree(t->m); cudaFree(t->v); cudaFree(t->partial); cudaFree(t->adam_tab);
   delete t;
   return LBDRN_OK;
 }
@@ -380,6 +384,25 @@ int32_t lbdrn_train_steps(LbdrnTrain* t, const void* msb_dev, const void* lsb_de
   a.msb = msb_dev; a.lsb = lsb_dev; a.tab = coord_tab_dev; a.perm = perm_dev; a.n_perm = n_perm;
   a.bs = t->cfg.batch_size; a.n_steps = n_steps; a.mode = TRAIN_FUSED; a.adam_t0 = adam_t0; a.lr = lr;
   a.losses = losses_dev;
+  {
+    // Adam's bias corrections per step, exactly as torch/optim/adam.py forms them (python floats = C doubles):
+    // step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t)
+    if (t->adam_tab_n < (size_t)n_steps) {
+      if (t->adam_tab) CUDA_TRY(cudaFree(t->adam_tab));
+      t->adam_tab = nullptr; t->adam_tab_n = 0;
+      CUDA_TRY(cudaMalloc(&t->adam_tab, 2 * (size_t)n_steps * sizeof(float2)));
+      t->adam_tab_n = (size_t)n_steps;
+    }
+    std::vector<float2> tab((size_t)n_steps);
+    for (int s = 0; s < n_steps; ++s) {
+      const double tt = (double)(adam_t0 + s + 1);
+      tab[s].x = (float)(lr / (1.0 - std::pow(t->cfg.beta1, tt)));
+      tab[s].y = (float)std::sqrt(1.0 - std::pow(t->cfg.beta2, tt));
+    }
+    float2* dst = t->adam_tab + (size_t)(t->adam_tab_slot++ & 1u) * t->adam_tab_n;
+    CUDA_TRY(cudaMemcpyAsync(dst, tab.data(), (size_t)n_steps * sizeof(float2), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    a.adam_tab = dst;
+  }
   return launch_train(t, a, (cudaStream_t)stream);
 }
 

@@ -74,10 +74,10 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
     long long h[16];
     CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    static const char* names[13] = {"reload", "gather", "fwd", "out+loss", "bwd_rest", "sync1", "reduce+adam", "sync2",
-                                    "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1"};
+    static const char* names[15] = {"reload", "gather", "fwd", "out+loss", "bwd_rest", "sync1", "reduce+adam", "sync2",
+                                    "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1", "pf_commit", "pf_issue"};
     fprintf(stderr, "[lbdrn] train phases (cycles/step on CTA 0, %d steps, grid %d x %d thr):", a.n_steps, plan.grid, kTT);
-    for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
+    for (int i = 0; i < 15; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
     fprintf(stderr, "\n");
   }
   return LBDRN_OK;

@@ -47,6 +47,8 @@ struct TrainArgs {
   float* grad_out;         // GRAD_ONLY: [P+1]
   int dimpad;              // dim_in rounded up to 8 (rows of the X buffer, padding rows are zero)
   long long* prof;         // optional (LBDRN_TRAIN_PROF=1): clock64 cycles per phase accumulated by CTA 0 / thread 0
+  const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
+                           // torch's python floats (two pow() per step in fp64 cost ~3k cycles of every step on the device)
 };
 
 template <int NPIX>
@@ -249,6 +251,149 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     t_prev = t_now;                                        \
   }
 
+  // ---- neighbourhood prefetch (uint8 planes, colours only, window <= 5, <= 4 bands, 8 threads per pixel) ----------------
+  // The gather is bound by LSU sector throughput, not latency: 64 pixels x 100 scattered byte loads, 32 different sectors per
+  // warp instruction = ~10k cycles per step.  Two things fix it:
+  //  * a window row (n <= 5 contiguous bytes, interior pixels) is fetched as the TWO aligned 32-bit words that cover it
+  //    (2 requests instead of 5) and the bytes are extracted with funnel shifts; the pair of threads that owns a band
+  //    (even: rows 0-2, label; odd: rows 3-4, centre) needs 7 / 5 loads per pixel instead of 19;
+  //  * the pixels of step s+1 are known before step s ends (the permutation is an input) and do not depend on the weights:
+  //    the index is read at the start of step s, the words are requested right after the first grid sync, so they arrive
+  //    under the reduction / Adam phase, and are normalised into X at the head of step s+1 (table of the 256 quotients
+  //    float32(m)/MSB.max(): same correctly-rounded values as the reference's division, LBDRNdataset.py:120).
+  // Border pixels (reflected columns) and windows at the very ends of the buffer are fetched byte by byte into the same
+  // registers; every other configuration takes the plain gather.
+  constexpr int NSH_ = THREADS / NPIX;
+  constexpr int PN = 5, PD = 2;              // the window the prefetch path is specialised for (D = 2: the paper's setting)
+  const bool pf_enabled = a.mode == TRAIN_FUSED && NSH_ == 8 && net.nco == 0 && net.ncol != 0 && n == PN && C <= 4 &&
+                          !net.msb_u16 && !net.lsb_u16;
+  uint32_t pf_w[3][2], pf_aux = 0u;          // [row][word]; aux: label code (even thread) or centre byte (odd thread)
+  bool pf_have = false;
+  int pf_state = 0;                          // 1: aligned words in registers, 2: window bytes already extracted (border
+                                             // pixel: reflected per-byte loads), 3: padding lane (beyond the batch)
+  int pf_gy = 0, pf_gx = 0;                  // pixel the registers belong to
+  bool pf_none = true;                       // this CTA has no chunk in the next step (uniform)
+  __shared__ int s_ny[NPIX], s_nx[NPIX];     // next step's pixel coordinates (one division per pixel, not per thread)
+  __shared__ float s_quot[256];
+  if (pf_enabled)
+    for (int i = tid; i < 256; i += THREADS) s_quot[i] = __fdiv_rn((float)i, maxv);
+  const size_t pf_total = (size_t)C * net.buf_rows * net.W;     // bytes in the MSB buffer
+  const bool idx32 = (long long)net.H * net.W < (1ll << 31);
+  // stage A (start of step s): coordinates of the pixels of step s+1
+  auto prefetch_index = [&](int s_next) {
+    pf_none = true;
+    if (!pf_enabled || s_next >= a.n_steps) return;
+    const long long b0n = (long long)s_next * a.bs;
+    const long long remn = a.n_perm - b0n;
+    const int Bn = (int)(remn < a.bs ? remn : a.bs);
+    const int ch = blockIdx.x;
+    if (Bn <= 0 || ch * NPIX >= Bn) return;                       // this CTA has no chunk in the next step
+    pf_none = false;
+    if (tid < NPIX) {
+      int y = -1, x = 0;                                           // y = -1: padding lane
+      if (ch * NPIX + tid < Bn) {
+        const long long idx = a.perm[b0n + (long long)ch * NPIX + tid];
+        if (idx32) { y = (int)((unsigned)idx / (unsigned)net.W); x = (int)((unsigned)idx - (unsigned)y * (unsigned)net.W); }
+        else { y = (int)(idx / net.W); x = (int)(idx - (long long)y * net.W); }
+      }
+      s_ny[tid] = y; s_nx[tid] = x;
+    }
+  };
+  // stage B (after the first grid sync of step s): request the words.  Rows of the window this thread owns: band = share / 2;
+  // even thread rows [0, min(3, n)), odd thread rows [3, n)
+  auto prefetch_issue = [&]() {
+    pf_have = !pf_none;
+    if (pf_none) return;
+    const int pp = tid & (NPIX - 1), share = tid / NPIX, c = share >> 1, odd = share & 1;
+    pf_gy = s_ny[pp]; pf_gx = s_nx[pp];
+    pf_state = 3;
+    if (pf_gy < 0 || c >= C) return;
+    const int gy = pf_gy, gx = pf_gx;
+    const size_t plane = (size_t)c * net.buf_rows;
+    const size_t off = (plane + (gy - net.buf_row0)) * net.W + gx;
+    const uint8_t* base = (const uint8_t*)a.msb;
+    const int r0 = odd ? 3 : 0, r1 = odd ? PN : 3;
+    pf_aux = odd ? (uint32_t)base[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+    // the two aligned words of a row may extend 3 bytes before / 6 bytes after the window: stay inside the buffer, and the
+    // window must not need reflected columns
+    bool fast = gx >= PD && gx + PD < net.W;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int dy = r0 + q;
+      if (dy < r1) {
+        const size_t first = (plane + (reflect_clamp(gy + dy - PD, net.H) - net.buf_row0)) * net.W + gx - PD;
+        fast = fast && first >= 4 && first + 12 <= pf_total;
+      }
+    }
+    pf_state = fast ? 1 : 2;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int dy = r0 + q;
+      if (dy < r1) {
+        const size_t rowoff = (plane + (reflect_clamp(gy + dy - PD, net.H) - net.buf_row0)) * net.W;
+        if (fast) {
+          const uint8_t* p = base + rowoff + gx - PD;
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+          pf_w[q][0] = w[0];
+          pf_w[q][1] = w[1];
+        } else {                                                     // rare: reflected columns, byte by byte
+          uint32_t lo4 = 0u, hi4 = 0u;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            {
+              const uint32_t b = base[rowoff + reflect_clamp(gx + dx - PD, net.W)];
+              if (dx < 4) lo4 |= b << (8 * dx); else hi4 = b;
+            }
+          }
+          pf_w[q][0] = lo4; pf_w[q][1] = hi4;
+        }
+      }
+    }
+  };
+  // head of step s+1: registers -> X / Tl / s_valid (the values the plain gather would write)
+  auto prefetch_commit = [&]() {
+    const int pp = tid & (NPIX - 1), share = tid / NPIX, c = share >> 1, odd = share & 1;
+    const bool ok = pf_state == 1 || pf_state == 2;
+    if (tid < NPIX) s_valid[tid] = pf_gy >= 0;
+    if (c < C) {
+      const int gy = ok ? pf_gy : 0, gx = ok ? pf_gx : 0;
+      const size_t plane = (size_t)c * net.buf_rows;
+      const int r0 = odd ? 3 : 0, r1 = odd ? PN : 3;
+      uint32_t ctr_raw = odd ? pf_aux : 0u;      // the odd thread loaded the centre itself; row D <= 2 belongs to the even one
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int dy = r0 + q;
+        if (dy < r1) {
+          if (pf_state == 1) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>((const uint8_t*)a.msb) +
+                                   (plane + (reflect_clamp(gy + dy - PD, net.H) - net.buf_row0)) * net.W + gx - PD;
+            const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+            const uint32_t lo4 = __funnelshift_r(pf_w[q][0], pf_w[q][1], sh);      // window bytes 0..3
+            const uint32_t hi4 = pf_w[q][1] >> sh;                                 // window byte 4 (n = 5)
+            pf_w[q][0] = lo4; pf_w[q][1] = hi4;
+          }
+          if (!odd && dy == PD) ctr_raw = (pf_w[q][0] >> (8 * PD)) & 255u;
+        }
+      }
+      const float ctr = net.relative ? s_quot[ctr_raw & 255u] : 0.f;
+      if (!odd) Tl[c * LDP + pp] = ok ? __fdiv_rn((float)pf_aux, net.qmax) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int dy = r0 + q;
+        if (dy < r1) {
+          float* d = X + pp + (size_t)((c * PN + dy) * PN) * LDP;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            {
+              const uint32_t b = dx < 4 ? (pf_w[q][0] >> (8 * dx)) & 255u : pf_w[q][1] & 255u;
+              d[(size_t)dx * LDP] = ok ? s_quot[b] - ctr : 0.f;
+            }
+          }
+        }
+      }
+    }
+  };
+
   for (int s = 0; s < a.n_steps; ++s) {
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (WSMEM) {
@@ -263,6 +408,18 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       }
     }
     if (tid == 0) s_sse = 0.f;
+    prefetch_index(s + 1);
+    if (tid == 32 && a.mode == TRAIN_FUSED) {
+      if (a.adam_tab) {
+        const float2 t2 = a.adam_tab[s];
+        s_adam[0] = t2.x; s_adam[1] = t2.y;
+      } else {
+        double t = (double)(a.adam_t0 + s + 1);
+        double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
+        s_adam[0] = (float)(a.lr / bc1);              // step_size
+        s_adam[1] = (float)sqrt(bc2);                 // bias_correction2_sqrt
+      }
+    }
     __syncthreads();
     LBDRN_PHASE(0)   // weight reload
 
@@ -279,6 +436,15 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       __syncthreads();
       // ---- gather: pixel coordinates, centres, labels, features (LBDRNdataset.py:104-131,151-155) --------
       const int nvalid = min(NPIX, B - ch * NPIX);
+      const bool staged = pf_have && ch == (int)blockIdx.x;          // uniform: a function of (step, CTA) only
+      if (staged) {
+        LBDRN_PHASE(1)    // loop-top barrier
+        prefetch_commit();
+        pf_have = false;
+        __syncthreads();
+        LBDRN_PHASE(13)   // commit of the prefetched neighbourhoods
+      }
+      if (!staged) {
       if (tid < NPIX) {
         long long idx = tid < nvalid ? a.perm[b0 + (long long)ch * NPIX + tid] : 0;
         int y = (int)(idx / net.W);
@@ -330,6 +496,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         }
       }
       __syncthreads();
+      }
       LBDRN_PHASE(1)   // gather
 
       // ---- forward (LBDRNmodel.py:79-82), keeping h_l and act'(z_l) per layer ------------------------------
@@ -510,16 +677,13 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     __threadfence();
     grid.sync();
     LBDRN_PHASE(5)   // fence + grid sync 1
+    // next step's neighbourhood loads: in flight during the reduction / Adam phase (itself L2-latency-bound).  Not before
+    // the fence above: a membar waits for the thread's outstanding loads, which would put their latency into the sync.
+    prefetch_issue();
+    LBDRN_PHASE(14)   // issue of the next step's neighbourhood loads
 
     // ---- fixed-order reduction over the CTAs that produced partials, then Adam ----------------------------
     const int n_act = min((int)gridDim.x, n_chunks);
-    if (tid == 0 && a.mode == TRAIN_FUSED) {
-      double t = (double)(a.adam_t0 + s + 1);
-      double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
-      s_adam[0] = (float)(a.lr / bc1);              // step_size
-      s_adam[1] = (float)sqrt(bc2);                 // bias_correction2_sqrt
-    }
-    __syncthreads();
     {
       // 4 lanes per parameter: lane `sub` sums partials sub, sub+4, ... (8 loads in flight), then a fixed-order shuffle
       // tree combines them -- deterministic, and every thread of the grid takes part.
