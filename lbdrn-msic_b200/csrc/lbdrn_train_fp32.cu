@@ -23,10 +23,15 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
   cudaFuncAttributes fa;
   CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)train_fp32_kernel<BC, CP, false, kTT, TM>));
   max_smem -= (int)fa.sharedSizeBytes;
+  // 64-pixel chunks with bc a multiple of 32: the chunk's GEMMs run as warp-level 3xTF32 tensor-core MMAs
+  constexpr bool kMma = TM == 4 && kTT == 512 && BC % 32 == 0 && BC <= 128;
+  const bool mma = kMma && getenv("LBDRN_TRAIN_FFMA") == nullptr;
   if (with_w <= (size_t)max_smem) {
-    t.wsmem = true; t.smem = with_w; t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
+    t.wsmem = true; t.smem = with_w;
+    t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, true, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
   } else if (without <= (size_t)max_smem) {
-    t.wsmem = false; t.smem = without; t.kernel = (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
+    t.wsmem = false; t.smem = without;
+    t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, false, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
   } else {
     return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
                 without, BC, n.nl, n.dim_in);

@@ -129,6 +129,115 @@ __device__ __forceinline__ void gemm_kmajor_v(float (&acc)[TM][TN], const float*
   }
 }
 
+// ---- warp-level tensor-core pieces for the 64-pixel chunk: mma.sync m16n8k8 TF32 with the 3xTF32 split ------------------
+// A training step is the latency of ONE 64-pixel chunk on one SM, with operands (weights, activations, gradients) that
+// change every step and contraction sizes of 64-104: smaller than one tcgen05 tile (M = 128, operands staged in shared
+// memory through descriptors, accumulators in TMEM), so the register-fragment MMA is the right-sized instruction here.
+// fp32 accuracy is kept by splitting both operands, x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and accumulating
+// lo*hi + hi*lo + hi*hi in fp32 (relative error ~2^-21 per product): one MMA instruction replaces 32 FFMA instructions.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(d, al, bh);      // small terms first
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// Fragment coordinates of mma.m16n8k8 (g = lane / 4, t = lane % 4):
+//   A (16x8, row): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+//   B (8x8,  col): b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   C (16x8)     : c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+//
+// acc[j][.] += sum_k act[k][p] * wt[k*BC + u] for the warp's 16-pixel tile (m) and its NT unit tiles (n): warp w owns
+// pixels 16*(w & 3) .. +15 and unit tiles u0 = 8*((w >> 2) + 4*j).  act rows are pixel-contiguous with stride LDP
+// (A loads conflict-free: bank = g + 4t); act has K rounded up to 8 rows (rows >= K are zero); wt rows >= K are not read.
+template <int BC, int LDP, int NT>
+__device__ __forceinline__ void gemm_px_unit_mma(float (&acc)[NT][4], const float* __restrict__ act, const float* wt, int K,
+                                                 int warp, int lane) {
+  const int K8 = (K + 7) & ~7;
+  const int g = lane >> 2, t = lane & 3, p0 = 16 * (warp & 3), ng = warp >> 2;
+  const float* a_ptr = act + (size_t)t * LDP + p0 + g;
+  const float* b_ptr = wt + (size_t)t * BC + 8 * ng + g;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    uint32_t ah[4], al[4];
+    split_tf32(a_ptr[(size_t)k0 * LDP], ah[0], al[0]);
+    split_tf32(a_ptr[(size_t)k0 * LDP + 8], ah[1], al[1]);
+    split_tf32(a_ptr[(size_t)(k0 + 4) * LDP], ah[2], al[2]);
+    split_tf32(a_ptr[(size_t)(k0 + 4) * LDP + 8], ah[3], al[3]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      uint32_t bh[2], bl[2];
+      split_tf32(k0 + t < K ? b_ptr[(size_t)k0 * BC + 32 * j] : 0.f, bh[0], bl[0]);
+      split_tf32(k0 + t + 4 < K ? b_ptr[(size_t)(k0 + 4) * BC + 32 * j] : 0.f, bh[1], bl[1]);
+      mma_3xtf32(acc[j], ah, al, bh, bl);
+    }
+  }
+}
+
+// dst[r*Kin + q] (+)= sum_p G[r][p] * A[q][p] (weight gradient block, natural [BC][Kin] layout) over the chunk's 64 pixels.
+// m = rows r of G (BC/16 tiles), n = rows q of A (ceil(Kin/8) tiles), k = pixels.  Warp w owns m-tile w % MT and the n-tiles
+// (w / MT) + (16 / MT) * j.  Both operands are pixel-contiguous with stride LDP: conflict-free fragment loads.
+template <int BC, int LDP, int NPIX>
+__device__ __forceinline__ void grad_weight_mma(const float* __restrict__ G, const float* __restrict__ A, int Kin, int kpad8,
+                                                float* __restrict__ dst, bool first, int warp, int lane) {
+  constexpr int MT = BC / 16, NW = 16 / MT, MAXN = 4;          // at most 4 n-tiles per warp per pass
+  const int g = lane >> 2, t = lane & 3, r0 = 16 * (warp % MT), nq = kpad8 >> 3;
+  const float* a_ptr = G + (size_t)(r0 + g) * LDP + t;
+  for (int nbase = warp / MT; nbase < nq; nbase += NW * MAXN) {
+    float acc[MAXN][4];
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll 2
+    for (int p0 = 0; p0 < NPIX; p0 += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(a_ptr[p0], ah[0], al[0]);
+      split_tf32(a_ptr[(size_t)8 * LDP + p0], ah[1], al[1]);
+      split_tf32(a_ptr[p0 + 4], ah[2], al[2]);
+      split_tf32(a_ptr[(size_t)8 * LDP + p0 + 4], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < MAXN; ++j) {
+        const int nt = nbase + NW * j;
+        if (nt < nq) {                                           // warp-uniform
+          const float* b_ptr = A + (size_t)(8 * nt + g) * LDP + p0 + t;
+          uint32_t bh[2], bl[2];
+          split_tf32(b_ptr[0], bh[0], bl[0]);
+          split_tf32(b_ptr[4], bh[1], bl[1]);
+          mma_3xtf32(acc[j], ah, al, bh, bl);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j) {
+      const int nt = nbase + NW * j;
+      if (nt < nq) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = r0 + g + (e >> 1) * 8, q = 8 * nt + 2 * t + (e & 1);
+          if (q < Kin) {
+            float* d = dst + (size_t)r * Kin + q;
+            *d = first ? acc[j][e] : *d + acc[j][e];
+          }
+        }
+      }
+    }
+  }
+}
+
 // One row (fixed dy) of one band's neighbourhood of one pixel; loads issued before first use.
 template <int N_, int kTrainLDP>
 __device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowoff, int gx, const Net& net, float maxv,
@@ -202,8 +311,10 @@ __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, co
 // THREADS = 128 * US: the chunk's 64 pixels x BC units are tiled as 16 pixel groups (4 px) x 8 lanes x US unit splits,
 // so one 64-pixel chunk is worked on by 4*US warps.  The step time is the latency of ONE chunk on ONE SM (every CTA
 // has at most one chunk per step at bs <= 64*grid), so more warps per chunk is what shortens the step.
-template <int BC, int CP, bool WSMEM, int THREADS, int TM>
+// MMA: the chunk's GEMMs on warp-level 3xTF32 tensor-core MMAs (64-pixel chunks, bc a multiple of 32); otherwise FFMA.
+template <int BC, int CP, bool WSMEM, int THREADS, int TM, bool MMA = false>
 __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) {
+  static_assert(!MMA || (TM == 4 && THREADS == 512 && BC % 32 == 0 && BC <= 128), "MMA path: 64-pixel chunks, 16 warps");
   constexpr int NPIX = train_npix(TM), LDP = train_ldp(TM), US = THREADS / 128, TN = BC / 8 / US;
   constexpr int VEC = TN >= 4 ? 4 : TN;
   static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
@@ -501,11 +612,44 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 
       // ---- forward (LBDRNmodel.py:79-82), keeping h_l and act'(z_l) per layer ------------------------------
       float h[TM][TN];
+      const int warp = tid >> 5, lane = tid & 31;
       for (int l = 0; l < L; ++l) {
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
         float* Hl = Hbuf + (size_t)l * BC * LDP;
         float* Gl = Gbuf + (size_t)l * BC * LDP;
+        if (MMA) {
+          constexpr int NT = BC / 32;
+          float acc[NT][4];
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+          gemm_px_unit_mma<BC, LDP, NT>(acc, in, w + net.woff[l], K, warp, lane);
+          const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int pixel = 16 * (warp & 3) + g + (e >> 1) * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+              const float z = acc[j][e] + w[net.boff[l] + u];
+              float hv, gv;
+              if (net.relu) {
+                hv = fmaxf(z, 0.f);
+                gv = z > 0.f ? 1.f : 0.f;
+              } else {
+                float sn, cs;
+                sincos_cw(net.w0 * z, sn, cs);
+                hv = sn;
+                gv = cs * net.w0;
+              }
+              Hl[(size_t)u * LDP + pixel] = hv;          // bank = g + 8t: conflict-free
+              Gl[(size_t)u * LDP + pixel] = gv;
+            }
+          }
+          __syncthreads();
+          continue;
+        }
         float acc[TM][TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
@@ -541,8 +685,30 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 
       LBDRN_PHASE(2)   // hidden layers forward
       // ---- output layer + loss (LBDRNloss.py:9) ---------------------------------------------------------
-      float part[TM * CP];
       const float* wo = w + net.woff[L];
+      float sse = 0.f;
+      if (MMA) {
+        // z[c][p] = b[c] + sum_u W_o[c][u] h_L[u][p] from shared memory: one thread per (band, pixel)
+        const float* HL = Hbuf + (size_t)(L - 1) * BC * LDP;
+        if (tid < C * NPIX) {
+          const int c = tid / NPIX, pp = tid - c * NPIX;
+          float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll 4
+          for (int u = 0; u < BC; u += 4) {
+            z0 = fmaf(wo[c * BC + u], HL[(size_t)u * LDP + pp], z0);
+            z1 = fmaf(wo[c * BC + u + 1], HL[(size_t)(u + 1) * LDP + pp], z1);
+            z2 = fmaf(wo[c * BC + u + 2], HL[(size_t)(u + 2) * LDP + pp], z2);
+            z3 = fmaf(wo[c * BC + u + 3], HL[(size_t)(u + 3) * LDP + pp], z3);
+          }
+          const bool ok = s_valid[pp] != 0;
+          const float y = sigmoidf_rn(((z0 + z1) + (z2 + z3)) + w[net.boff[L] + c]);
+          const float d = y - Tl[c * LDP + pp];
+          dZo[c * LDP + pp] = ok ? (gscale * d) * ((1.0f - y) * y) : 0.f;   // mse backward then sigmoid backward
+          if (ok) sse = d * d;
+        }
+      }
+      float part[TM * CP];
+      if (!MMA) {
 #pragma unroll
       for (int c = 0; c < CP; ++c) {
 #pragma unroll
@@ -566,8 +732,8 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             for (int c = 0; c < CP; ++c) Pp[(us * CP + c) * LDP + pg * TM + i] = part[i * CP + c];
         __syncthreads();
       }
-      float sse = 0.f;
-      if (us == 0) {
+      }
+      if (!MMA && us == 0) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
           if (i == tn) {
@@ -642,11 +808,29 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
               }
             }
           }
+        } else if (MMA) {
+          // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p] on the tensor cores; dz_l = dh_l * act'(z_l) at the fragment positions
+          constexpr int NT = BC / 32;
+          float dacc[NT][4];
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dacc[j][e] = 0.f;
+          gemm_px_unit_mma<BC, LDP, NT>(dacc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, warp, lane);
+          const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int pixel = 16 * (warp & 3) + g + (e >> 1) * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+              Gl[(size_t)u * LDP + pixel] *= dacc[j][e];
+            }
         } else {
           // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p]   (k-major in m on both operands)
           gemm_kmajor_v<TM, TN, VEC, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, pg, ubase);
         }
         // dz_l = dh_l * act'(z_l): thread-private read-modify-write of its own (unit, pixel) entries
+        if (!(MMA && l < L - 1))
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
           float* gp = Gl + (size_t)unit(j) * LDP + pg * TM;
@@ -661,7 +845,8 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         // dW_l = dz_l . in_l^T ; db_l = row sums
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
-        grad_weight_nt_t<BC, THREADS, TM>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
+        if (MMA) grad_weight_mma<BC, LDP, NPIX>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first, warp, lane);
+        else grad_weight_nt_t<BC, THREADS, TM>(Gl, in, K, l == 0 ? a.dimpad : BC, mypart + net.woff[l], first);
         for (int u = tid; u < BC; u += THREADS) {
           float g = row_sum<NPIX>(Gl + (size_t)u * LDP);
           float* d = mypart + net.boff[l] + u;
