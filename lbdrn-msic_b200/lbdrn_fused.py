@@ -479,9 +479,20 @@ class FusedTrainer:
         return eval_mse(self.scene, params_dev, self.D, self.bc, self.nl, self.flags, self.relu, self.w0, self.tab)
 
     def run(self):
-        """Train; returns dict(params=best flat params (CPU tensor), losses, val_mse, best_epoch)."""
+        """Train; returns dict(params=best flat params (CPU tensor), losses, val_mse, best_epoch).
+
+        Stream plan: the training launches of consecutive epochs run back to back on a high-priority stream (one
+        cooperative launch per epoch: 128 of the 148 SMs at bs 8192).  The full-scene evaluation of epoch e and the device
+        permutation of epoch e+2 run on a low-priority side stream, i.e. on the idle SMs and in the gaps, while epoch e+1
+        trains; the host reads epoch e's MSE only after epoch e+1 has been queued, so no launch waits for a read-back.
+        Results are identical to the serial order (same permutations, same snapshots)."""
         N = self.scene.H * self.scene.W
-        self.begin()
+        cur_stream = torch.cuda.current_stream(self.dev)
+        main = torch.cuda.Stream(self.dev, priority=-1)
+        side = torch.cuda.Stream(self.dev, priority=0)
+        main.wait_stream(cur_stream)
+        with torch.cuda.stream(main):
+            self.begin()
         seeds = self._plan_seeds()
         host_perm, pinned, uploaded = {}, [None, None], [None, None]
 
@@ -492,41 +503,86 @@ class FusedTrainer:
                 pinned[e % 2] = torch.empty(N, dtype=torch.int64).pin_memory()
             host_perm[e] = torch.randperm(N, generator=g, out=pinned[e % 2])
 
-        if self.sampler == "reference":
-            make_host_perm(1)
-        for e in range(1, self.epochs + 1):
-            th = None
-            if self.sampler == "reference":
-                perm = host_perm.pop(e).to(self.dev, non_blocking=True)
-                uploaded[e % 2] = torch.cuda.Event()
-                uploaded[e % 2].record()
-                if e < self.epochs:
-                    if uploaded[(e + 1) % 2] is not None:
-                        uploaded[(e + 1) % 2].synchronize()      # that pinned buffer is free again
-                    th = threading.Thread(target=make_host_perm, args=(e + 1,))
-                    th.start()
-            else:
+        def device_perm(e):
+            """(perm, event): drawn on the side stream"""
+            with torch.cuda.stream(side):
                 g = torch.Generator(device=self.dev)
                 g.manual_seed(seeds[e - 1] & 0x7FFFFFFFFFFFFFFF)
                 perm = torch.randperm(N, generator=g, device=self.dev)
-            self.losses.append(self.train_epoch(perm, lr_for_epoch(self.lr, e, self.epochs)))
-            if self.epochs == 1:                                        # encode.py:100-103
-                self.best_epoch, self.best_params = e, self.current_params()
-            elif e % min(self.val_duration, self.epochs) == 0:          # encode.py:104-117
-                cur = self.current_params()
-                mse = self.scene_mse(cur)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return perm, ev
+
+        pending = []                                                    # evaluations queued on the side stream
+
+        def collect(upto=None):
+            """Read back finished evaluations in epoch order: best-epoch selection of encode.py:104-117."""
+            while pending and (upto is None or pending[0][0] <= upto):
+                e, sse, cur, done = pending.pop(0)
+                done.synchronize()                                      # .item() only orders against the CURRENT stream
+                mse = float(sse.item()) / (self.scene.C * N)
                 self.val_mse.append(mse)
                 improved = mse < self.best_mse
                 if improved:
                     self.best_mse, self.best_epoch, self.best_params = mse, e, cur
                 if self.on_epoch:
                     self.on_epoch(e, mse, improved)
+
+        if self.sampler == "reference":
+            make_host_perm(1)
+            next_dev = None
+        else:
+            next_dev = device_perm(1)
+        for e in range(1, self.epochs + 1):
+            th = None
+            with torch.cuda.stream(main):
+                if self.sampler == "reference":
+                    perm = host_perm.pop(e).to(self.dev, non_blocking=True)
+                    uploaded[e % 2] = torch.cuda.Event()
+                    uploaded[e % 2].record()
+                    if e < self.epochs:
+                        if uploaded[(e + 1) % 2] is not None:
+                            uploaded[(e + 1) % 2].synchronize()      # that pinned buffer is free again
+                        th = threading.Thread(target=make_host_perm, args=(e + 1,))
+                        th.start()
+                else:
+                    perm, ev = next_dev
+                    main.wait_event(ev)
+                    perm.record_stream(main)
+                self.losses.append(self.train_epoch(perm, lr_for_epoch(self.lr, e, self.epochs)))
+                evaluate = self.epochs != 1 and e % min(self.val_duration, self.epochs) == 0
+                cur = self.current_params() if (evaluate or self.epochs == 1) else None
+                snap = torch.cuda.Event()
+                snap.record(main)
+            if self.sampler != "reference" and e < self.epochs:
+                next_dev = device_perm(e + 1)                           # overlaps this epoch's training
+            if self.epochs == 1:                                        # encode.py:100-103
+                self.best_epoch, self.best_params = e, cur
+            elif evaluate:
+                with torch.cuda.stream(side):
+                    side.wait_event(snap)
+                    cur.record_stream(side)
+                    sse = self._eval_sse_async(cur)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    pending.append((e, sse, cur, done))
+            collect(upto=e - 1)                                         # epoch e-1's result: epoch e is already queued
             del perm
             if th is not None:
                 th.join()
+        collect()
+        cur_stream.wait_stream(main)
+        cur_stream.wait_stream(side)
         if self.best_params is None:                                    # never evaluated (val_duration > epochs)
             raise RuntimeError("no epoch was evaluated; choose val_duration <= epochs")
         losses = torch.cat(self.losses).cpu()
         best = self.best_params.cpu()
         self.model.load_flat_params(best)
         return dict(params=best, losses=losses.tolist(), val_mse=self.val_mse, best_epoch=self.best_epoch)
+
+    def _eval_sse_async(self, params_dev):
+        """Queue the full-scene squared error on the current stream; returns the device double (no host sync)."""
+        sse = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        cabi.check(self.lib.lbdrn_eval_sse(ctypes.byref(self.desc), cabi.ptr(self.scene.msb), cabi.ptr(self.scene.lsb),
+                                           cabi.ptr(params_dev), cabi.ptr(self.tab), cabi.ptr(sse), cabi.stream_ptr()))
+        return sse
