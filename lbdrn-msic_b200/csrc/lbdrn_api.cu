@@ -403,6 +403,15 @@ int32_t lbdrn_train_steps(LbdrnTrain* t, const void* msb_dev, const void* lsb_de
     CUDA_TRY(cudaMemcpyAsync(dst, tab.data(), (size_t)n_steps * sizeof(float2), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     a.adam_tab = dst;
   }
+  if (t->plan.pf_stride) {
+    // TMA maps of the planes for the neighbourhood gather (nullptr when the buffers are not TMA-addressable)
+    const Net& n = t->net;
+    const CUtensorMap *tm = nullptr, *tl = nullptr;
+    int rc = make_tensor_map_3d(msb_dev, 1, n.W, n.buf_rows, n.C, 32, 5, n.C, t->dev, (cudaStream_t)stream, &tm);
+    if (!rc && tm) rc = make_tensor_map_3d(lsb_dev, 1, n.W, n.buf_rows, n.C, 16, 1, n.C, t->dev, (cudaStream_t)stream, &tl);
+    if (rc) return rc;
+    if (tm && tl) { a.tmap_msb = tm; a.tmap_lsb = tl; a.pf_off = t->plan.pf_off; a.pf_stride = t->plan.pf_stride; }
+  }
   return launch_train(t, a, (cudaStream_t)stream);
 }
 

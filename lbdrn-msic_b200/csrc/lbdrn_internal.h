@@ -1,5 +1,7 @@
 // lbdrn_internal.h -- declarations shared by the translation units of liblbdrn_b200 (not part of the ABI).
 #pragma once
+#include <cuda.h>
+
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -42,12 +44,17 @@ struct TrainPlan {
   size_t smem = 0;
   bool wsmem = true;
   int grid = 0, dimpad = 0, pstride = 0;
+  int pf_off = 0, pf_stride = 0;      // TMA neighbourhood boxes: offset inside dynamic smem, bytes per pixel (0: not planned)
 };
 struct TrainArgs;
 int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& plan);
 int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st);
 void launch_adam_apply(const Net& n, const float* grad, float* params, float* wpack, float* m, float* v, float omb1,
                        float omb2, float beta2, float eps, float step_size, float bc2_sqrt, cudaStream_t st);
+
+// TMA descriptor of CHW planes, uploaded into a per-device ring (lbdrn_tc.cu); *out = nullptr if TMA cannot address them
+int make_tensor_map_3d(const void* base, int es, int W, int rows, int C, int box_w, int box_h, int box_c, int dev,
+                       cudaStream_t st, const CUtensorMap** out);
 
 // tcgen05 tensor-core decode (lbdrn_tc.cu)
 bool tc_supported(const Net& n);

@@ -686,6 +686,50 @@ bool tc_supported(const Net& n) {
          (n.ncol == 0 || n.D <= 3);
 }
 
+// 3-D tiled TMA descriptor of CHW planes: dims (W, rows, C) of `es`-byte elements, box (box_w, box_h, box_c).  *out stays
+// nullptr when TMA cannot address the buffer (base / pitches not multiples of 16 B, driver entry point missing).  The
+// descriptor is copied into a per-device ring in global memory (a slot per call, so queued launches do not race).
+int make_tensor_map_3d(const void* base, int es, int W, int rows, int C, int box_w, int box_h, int box_c, int dev,
+                       cudaStream_t st, const CUtensorMap** out) {
+  *out = nullptr;
+  const size_t pitch = (size_t)W * es, plane = pitch * rows;
+  if (getenv("LBDRN_NO_TMA") || ((uintptr_t)base % 16) != 0 || pitch % 16 != 0 || plane % 16 != 0 || box_w > 256 ||
+      box_h > 256 || (box_w * es) % 16 != 0)
+    return LBDRN_OK;
+  // resolved through the runtime so the library has no link-time dependency on libcuda (it must load on CPU-only boxes)
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  if (!encode) return LBDRN_OK;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)C};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
+  cuuint32_t estr[3] = {1, 1, 1};
+  alignas(64) CUtensorMap tm;
+  CUresult r = encode(&tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return LBDRN_OK;
+  static std::mutex mu;
+  static CUtensorMap* ring[64] = {nullptr};
+  static unsigned slot[64] = {0};
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
+  if (!ring[dev]) CUDA_TRY(cudaMalloc(&ring[dev], 64 * sizeof(CUtensorMap)));
+  CUtensorMap* dst = ring[dev] + (slot[dev]++ % 64);
+  CUDA_TRY(cudaMemcpyAsync(dst, &tm, sizeof tm, cudaMemcpyHostToDevice, st));
+  *out = dst;
+  return LBDRN_OK;
+}
+
 namespace {
 
 using KernT = void (*)(const TcArgs);
@@ -712,37 +756,11 @@ int tc_setup_tma(TcArgs& a, int dev, cudaStream_t st) {
   a.use_tma = 0;
   a.box_w = box_w;
   a.box_lead = lead;
-  if (getenv("LBDRN_NO_TMA") || ((uintptr_t)a.msb % 16) != 0 || pitch % 16 != 0 || plane % 16 != 0 || box_w > 256 ||
-      trows > 256 || n.W < box_w)
-    return LBDRN_OK;
-  // resolved through the runtime so the library has no link-time dependency on libcuda (it must load on CPU-only boxes)
-  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  if (!encode) return LBDRN_OK;
-  cuuint64_t dims[3] = {(cuuint64_t)n.W, (cuuint64_t)n.buf_rows, (cuuint64_t)n.C};
-  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
-  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)trows, (cuuint32_t)n.C};
-  cuuint32_t estr[3] = {1, 1, 1};
-  alignas(64) CUtensorMap tm;
-  CUresult r = encode(&tm, n.msb_u16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
-                      const_cast<void*>(a.msb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return LBDRN_OK;
-  // the descriptor lives in global memory (a slot per call in a small ring, so queued launches do not race)
-  static CUtensorMap* ring[64] = {nullptr};
-  static unsigned slot[64] = {0};
-  if (!ring[dev]) CUDA_TRY(cudaMalloc(&ring[dev], 64 * sizeof(CUtensorMap)));
-  CUtensorMap* dst = ring[dev] + (slot[dev]++ % 64);
-  CUDA_TRY(cudaMemcpyAsync(dst, &tm, sizeof tm, cudaMemcpyHostToDevice, st));
+  if (n.W < box_w) return LBDRN_OK;
+  const CUtensorMap* dst = nullptr;
+  int rc = make_tensor_map_3d(a.msb, es, n.W, n.buf_rows, n.C, box_w, trows, n.C, dev, st, &dst);
+  if (rc) return rc;
+  if (!dst) return LBDRN_OK;
   a.tmap_dev = dst;
   a.use_tma = 1;
   return LBDRN_OK;

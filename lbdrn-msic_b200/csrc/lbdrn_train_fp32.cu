@@ -26,11 +26,30 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
   // 64-pixel chunks with bc a multiple of 32: the chunk's GEMMs run as warp-level 3xTF32 tensor-core MMAs
   constexpr bool kMma = TM == 4 && kTT == 512 && BC % 32 == 0 && BC <= 128;
   const bool mma = kMma && getenv("LBDRN_TRAIN_FFMA") == nullptr;
+  // landing boxes of the TMA neighbourhood gather (uint8 planes, 5x5 window, <= 4 bands, colours only, TMA-addressable
+  // rows): 32 x 5 x C bytes of MSB (rounded up to 128) + a 128 B slot for the 16 x 1 x C label box, per pixel.
+  // OPT-IN (LBDRN_TRAIN_TMA=1): measured on B200 it does not beat the register prefetch -- 37.5 vs 36.9 us/step at 8192^2,
+  // 35.7 vs 33.9 at 2048^2: issuing gets cheap (3.2k vs 7.3k cycles at 8192^2) but the copies then contend with the
+  // L2-latency-bound reduction phase (4.7k -> 10.6k cycles), and 128 B-aligned landing slots put the same byte of every
+  // pixel in the same bank (the normalisation pass reads them with ~8-way conflicts).  Kept for the record and for
+  // scenes that do not fit L2 on parts with a slower LSU path.
+  size_t pf_bytes = 0;
+  if (TM == 4 && n.nco == 0 && n.ncol != 0 && n.n == 5 && n.C <= 4 && !n.msb_u16 && !n.lsb_u16 && n.W % 16 == 0 &&
+      ((size_t)n.W * n.buf_rows) % 16 == 0 && n.buf_row0 == 0 && n.buf_rows == n.H && getenv("LBDRN_TRAIN_TMA") != nullptr) {
+    t.pf_stride = ((32 * 5 * n.C + 127) & ~127) + 128;
+    pf_bytes = (size_t)kTrainNPIX * t.pf_stride + 128;      // + slack: the boxes are aligned to 128 B at run time
+  }
+  auto place_boxes = [&](size_t base) {        // boxes go behind the activations / weights if they still fit
+    const size_t off = (base + 127) & ~(size_t)127;
+    if (pf_bytes && off + pf_bytes <= (size_t)max_smem) { t.pf_off = (int)off; return off + pf_bytes; }
+    t.pf_off = 0; t.pf_stride = 0;
+    return base;
+  };
   if (with_w <= (size_t)max_smem) {
-    t.wsmem = true; t.smem = with_w;
+    t.wsmem = true; t.smem = place_boxes(with_w);
     t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, true, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
   } else if (without <= (size_t)max_smem) {
-    t.wsmem = false; t.smem = without;
+    t.wsmem = false; t.smem = place_boxes(without);
     t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, false, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
   } else {
     return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",

@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 
 #include "lbdrn_common.cuh"
+#include "lbdrn_umma.cuh"
 
 namespace lbdrn {
 namespace cg = cooperative_groups;
@@ -47,6 +48,9 @@ struct TrainArgs {
   float* grad_out;         // GRAD_ONLY: [P+1]
   int dimpad;              // dim_in rounded up to 8 (rows of the X buffer, padding rows are zero)
   long long* prof;         // optional (LBDRN_TRAIN_PROF=1): clock64 cycles per phase accumulated by CTA 0 / thread 0
+  const CUtensorMap* tmap_msb;   // TMA neighbourhood gather: 3-D maps of the MSB / LSB planes (boxes 32x5xC / 16x1xC bytes);
+  const CUtensorMap* tmap_lsb;   // nullptr: register prefetch only
+  int pf_off, pf_stride;   // byte offset of the landing boxes inside dynamic shared memory, bytes per pixel
   const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
                            // torch's python floats (two pow() per step in fp64 cost ~3k cycles of every step on the device)
 };
@@ -383,6 +387,19 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   int pf_state = 0;                          // 1: aligned words in registers, 2: window bytes already extracted (border
                                              // pixel: reflected per-byte loads), 3: padding lane (beyond the batch)
   int pf_gy = 0, pf_gx = 0;                  // pixel the registers belong to
+  // TMA variant (state 5): ONE cp.async.bulk.tensor per interior pixel lands the 32 x 5 x C byte box around its window
+  // (16 B-aligned superset) in shared memory, a second one the 16 x 1 x C box holding its labels; 64 + 64 asynchronous
+  // copies per step (four lanes of every warp issue) replace ~3 500 scattered word loads whose outstanding misses stalled every warp
+  // for ~7k cycles at 8192^2 (DRAM-latency x MLP bound).  Border pixels keep the register path.
+  const bool tma_on = pf_enabled && a.tmap_msb != nullptr;
+  // TMA destinations must be 128 B-aligned in the shared window; the dynamic region itself is only 16 B-aligned
+  uint8_t* const pfbox = reinterpret_cast<uint8_t*>(smem4) + a.pf_off +
+                         ((128u - ((smem_u32(smem4) + (uint32_t)a.pf_off) & 127u)) & 127u);
+  const int pf_lsb_off = a.pf_stride - 128;  // the label box sits in the last 128 B of a pixel's slot
+  __shared__ __align__(8) uint64_t s_pf_mbar;
+  uint32_t pf_phase = 0u;
+  bool pf_tma_pending = false;               // uniform: copies of the next chunk are in flight
+  if (tma_on && tid == 0) mbar_init(smem_u32(&s_pf_mbar), NPIX);
   bool pf_none = true;                       // this CTA has no chunk in the next step (uniform)
   __shared__ int s_ny[NPIX], s_nx[NPIX];     // next step's pixel coordinates (one division per pixel, not per thread)
   __shared__ float s_quot[256];
@@ -417,9 +434,26 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     if (pf_none) return;
     const int pp = tid & (NPIX - 1), share = tid / NPIX, c = share >> 1, odd = share & 1;
     pf_gy = s_ny[pp]; pf_gx = s_nx[pp];
+    if (tma_on) {
+      pf_tma_pending = false;
+      if ((tid & 7) == 0) {                                          // 4 lanes of every warp: thread 8p issues for pixel p
+        const int p = tid >> 3, y = s_ny[p], x = s_nx[p];
+        const bool in = y >= PD && y + PD < net.H && x >= PD && x + PD < net.W;
+        // one arrival per pixel (the barrier counts NPIX): with the bytes of its two copies, or with none for a border /
+        // padding pixel -- the commit always waits for exactly one phase per prefetched chunk
+        mbar_expect_tx(smem_u32(&s_pf_mbar), in ? (uint32_t)(32 * PN * C + 16 * C) : 0u);
+        if (in) {
+          const uint32_t dst = smem_u32(pfbox + (size_t)p * a.pf_stride);
+          tma_load_3d(dst, a.tmap_msb, (x - PD) & ~15, y - PD, 0, smem_u32(&s_pf_mbar));
+          tma_load_3d(dst + pf_lsb_off, a.tmap_lsb, x & ~15, y, 0, smem_u32(&s_pf_mbar));
+        }
+      }
+      pf_tma_pending = true;
+    }
     pf_state = 3;
     if (pf_gy < 0 || c >= C) return;
     const int gy = pf_gy, gx = pf_gx;
+    if (tma_on && gy >= PD && gy + PD < net.H && gx >= PD && gx + PD < net.W) { pf_state = 5; return; }
     const size_t plane = (size_t)c * net.buf_rows;
     const size_t off = (plane + (gy - net.buf_row0)) * net.W + gx;
     const uint8_t* base = (const uint8_t*)a.msb;
@@ -464,12 +498,32 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   // head of step s+1: registers -> X / Tl / s_valid (the values the plain gather would write)
   auto prefetch_commit = [&]() {
     const int pp = tid & (NPIX - 1), share = tid / NPIX, c = share >> 1, odd = share & 1;
-    const bool ok = pf_state == 1 || pf_state == 2;
+    const bool ok = pf_state == 1 || pf_state == 2 || pf_state == 5;
+    if (pf_tma_pending) {                                            // uniform
+      mbar_wait(smem_u32(&s_pf_mbar), pf_phase, 7, (int)blockIdx.x);
+      pf_phase ^= 1u;
+      pf_tma_pending = false;
+    }
     if (tid < NPIX) s_valid[tid] = pf_gy >= 0;
     if (c < C) {
       const int gy = ok ? pf_gy : 0, gx = ok ? pf_gx : 0;
       const size_t plane = (size_t)c * net.buf_rows;
       const int r0 = odd ? 3 : 0, r1 = odd ? PN : 3;
+      if (pf_state == 5) {                         // this pixel's boxes are in shared memory
+        const uint8_t* slot = pfbox + (size_t)pp * a.pf_stride;
+        const int o = (gx - PD) & 15;              // window start inside the 16 B-aligned box row
+        pf_aux = odd ? (uint32_t)slot[(c * PN + PD) * 32 + o + PD] : (uint32_t)slot[pf_lsb_off + c * 16 + (gx & 15)];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int dy = r0 + q;
+          if (dy < r1) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(slot + (c * PN + dy) * 32 + (o & ~3));
+            const uint32_t sh = (uint32_t)(o & 3) * 8u;
+            pf_w[q][0] = __funnelshift_r(w[0], w[1], sh);
+            pf_w[q][1] = w[1] >> sh;
+          }
+        }
+      }
       uint32_t ctr_raw = odd ? pf_aux : 0u;      // the odd thread loaded the centre itself; row D <= 2 belongs to the even one
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -503,6 +557,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         }
       }
     }
+    if (tma_on) fence_async_smem();      // our reads of the landing boxes are ordered before the next TMA writes into them
   };
 
   for (int s = 0; s < a.n_steps; ++s) {
