@@ -87,21 +87,22 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
   static long long* prof_dev = nullptr;
   const bool prof = getenv("LBDRN_TRAIN_PROF") != nullptr;
   if (prof) {
-    if (!prof_dev) CUDA_TRY(cudaMalloc(&prof_dev, 16 * sizeof(long long)));
-    CUDA_TRY(cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), st));
+    if (!prof_dev) CUDA_TRY(cudaMalloc(&prof_dev, 24 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(prof_dev, 0, 24 * sizeof(long long), st));
     a.prof = prof_dev;
   }
   void* kargs[] = {(void*)&a};
   CUDA_TRY(cudaLaunchCooperativeKernel(plan.kernel, dim3(plan.grid), dim3(kTT), kargs, plan.smem, st));
   ++g_launches;
   if (prof) {
-    long long h[16];
+    long long h[24];
     CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    static const char* names[15] = {"reload", "gather", "fwd", "out+loss", "bwd_rest", "sync1", "reduce+adam", "sync2",
-                                    "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1", "pf_commit", "pf_issue"};
+    static const char* names[17] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "sync1", "reduce+adam", "sync2",
+                                    "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1", "pf_commit", "pf_issue", "fwd_gemm",
+                                    "fwd_act"};
     fprintf(stderr, "[lbdrn] train phases (cycles/step on CTA 0, %d steps, grid %d x %d thr):", a.n_steps, plan.grid, kTT);
-    for (int i = 0; i < 15; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
+    for (int i = 0; i < 17; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
     fprintf(stderr, "\n");
   }
   return LBDRN_OK;

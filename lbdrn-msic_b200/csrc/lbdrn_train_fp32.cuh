@@ -139,10 +139,19 @@ __device__ __forceinline__ void gemm_kmajor_v(float (&acc)[TM][TN], const float*
 // memory through descriptors, accumulators in TMEM), so the register-fragment MMA is the right-sized instruction here.
 // fp32 accuracy is kept by splitting both operands, x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and accumulating
 // lo*hi + hi*lo + hi*hi in fp32 (relative error ~2^-21 per product): one MMA instruction replaces 32 FFMA instructions.
+// 16-byte asynchronous global -> shared copy through L2 only (.cg: the weights were just rewritten by other SMs).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// cvt.rna.tf32.f32 is not a hardware instruction on sm_100a: ptxas expands it to an Inf/NaN test, an integer add, a select
+// and a mask (~9 instructions per split element, which made the split -- not the MMAs -- the cost of the chunk GEMMs).
+// Same rounding by hand for finite inputs: add half an ulp of the 10-bit mantissa to the magnitude bits (round to nearest,
+// ties away from zero) and clear the 13 low bits; lo = x - hi is exact and is truncated to tf32 (|x - hi - lo| <= 2^-21 |x|).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -563,14 +572,16 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   for (int s = 0; s < a.n_steps; ++s) {
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (WSMEM) {
+      // asynchronous copies: their L2 latency hides under the commit of the prefetched neighbourhoods (or the gather),
+      // neither of which reads weights; cp_async_wait_all() sits in front of the barrier that precedes the forward pass
       const int P4 = P >> 2;
       for (int i = tid; i < P4; i += THREADS)
-        reinterpret_cast<float4*>(wsm)[i] = __ldcg(reinterpret_cast<const float4*>(a.wpack) + i);
+        cp_async16(reinterpret_cast<float4*>(wsm) + i, reinterpret_cast<const float4*>(a.wpack) + i);
       for (int i = (P4 << 2) + tid; i < P; i += THREADS) wsm[i] = __ldcg(a.wpack + i);
       for (int l = 1; l < L; ++l) {
         const float4* src = reinterpret_cast<const float4*>(a.params + net.woff[l]);
         float4* dst = reinterpret_cast<float4*>(wnat_sm + (size_t)(l - 1) * BC * BC);
-        for (int i = tid; i < BC * BC / 4; i += THREADS) dst[i] = __ldcg(src + i);
+        for (int i = tid; i < BC * BC / 4; i += THREADS) cp_async16(dst + i, src + i);
       }
     }
     if (tid == 0) s_sse = 0.f;
@@ -607,6 +618,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         LBDRN_PHASE(1)    // loop-top barrier
         prefetch_commit();
         pf_have = false;
+        if (WSMEM) cp_async_wait_all();
         __syncthreads();
         LBDRN_PHASE(13)   // commit of the prefetched neighbourhoods
       }
@@ -661,6 +673,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           }
         }
       }
+      if (WSMEM) cp_async_wait_all();
       __syncthreads();
       }
       LBDRN_PHASE(1)   // gather
@@ -681,6 +694,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
           gemm_px_unit_mma<BC, LDP, NT>(acc, in, w + net.woff[l], K, warp, lane);
+          LBDRN_PHASE(15)   // fwd: GEMMs
           const int g = lane >> 2, t = lane & 3;
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
@@ -702,6 +716,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
               Gl[(size_t)u * LDP + pixel] = gv;
             }
           }
+          LBDRN_PHASE(16)   // fwd: bias + sine / cosine + stores
           __syncthreads();
           continue;
         }
@@ -912,6 +927,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       first = false;
       LBDRN_PHASE(4)   // backward (remainder)
     }
+    if (WSMEM) cp_async_wait_all();
     __syncthreads();
     if (tid == 0 && !first) mypart[P] = s_sse;
     __threadfence();
@@ -933,9 +949,26 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         const int i = (gt >> 2) + it * stride;
         const bool in = i <= P;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
+        // the parameter's own state does not depend on the partials: requested first, it arrives under their latency
+        const bool upd = in && sub == 0 && a.mode != TRAIN_GRAD_ONLY && i < P;
+        float p_old = 0.f, m_old = 0.f, v_old = 0.f;
+        if (upd) { p_old = __ldcg(a.params + i); m_old = __ldcg(a.m + i); v_old = __ldcg(a.v + i); }
         if (in) {
           const float* pp = a.partial + i;
           int c = sub;
+          if (n_act == 128) {
+            // the common case (bs = 8192: one chunk per CTA, 128 CTAs): all 32 loads of this lane in flight at once -- one L2
+            // round trip instead of four; same summation order as the generic loop below
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __ldcg(pp + (size_t)(sub + 4 * j) * a.pstride);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              g0 += v[j];     g1 += v[j + 1]; g2 += v[j + 2]; g3 += v[j + 3];
+              g4 += v[j + 4]; g5 += v[j + 5]; g6 += v[j + 6]; g7 += v[j + 7];
+            }
+            c = n_act;
+          }
           for (; c + 28 < n_act; c += 32) {
             g0 += __ldcg(pp + (size_t)(c + 0) * a.pstride);  g1 += __ldcg(pp + (size_t)(c + 4) * a.pstride);
             g2 += __ldcg(pp + (size_t)(c + 8) * a.pstride);  g3 += __ldcg(pp + (size_t)(c + 12) * a.pstride);
@@ -953,7 +986,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           } else if (i == P) {
             a.losses[s] = g / ((float)B * (float)C);
           } else {
-            float p = a.params[i], m = a.m[i], v = a.v[i];
+            float p = p_old, m = m_old, v = v_old;
             adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
             a.params[i] = p; a.m[i] = m; a.v[i] = v;
             a.wpack[packed_index(net, i)] = p;
