@@ -45,7 +45,22 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
     t.pf_off = 0; t.pf_stride = 0;
     return base;
   };
-  if (with_w <= (size_t)max_smem) {
+  // fp16 hi+lo split operands + ldmatrix (MMA = 2): bc a multiple of 64, everything resident in shared memory
+  constexpr bool kH2 = kMma && BC % 64 == 0;
+  if constexpr (kH2) {
+    const int KP0 = round16(n.dim_in), L = n.nl;
+    const size_t h2 = ((size_t)t.dimpad * kTrainLDP + (size_t)BC * kTrainLDP + (size_t)L * BC * kLDH +
+                       (size_t)(2 + kTT / 128) * CP * kTrainLDP + (size_t)round4(L * BC + n.C * BC + n.C) +
+                       (size_t)KP0 * kLDH + (size_t)(L - 1) * BC * kLDH + (size_t)BC * (KP0 + 8) +
+                       (size_t)(L - 1) * BC * (BC + 8)) * sizeof(float);
+    if (mma && getenv("LBDRN_TRAIN_TF32") == nullptr && h2 <= (size_t)max_smem) {
+      t.wsmem = true; t.smem = place_boxes(h2);
+      t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT, TM, 2>;
+      t.h2 = true;
+    }
+  }
+  if (t.h2) {
+  } else if (with_w <= (size_t)max_smem) {
     t.wsmem = true; t.smem = place_boxes(with_w);
     t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, true, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
   } else if (without <= (size_t)max_smem) {

@@ -251,6 +251,164 @@ __device__ __forceinline__ void grad_weight_mma(const float* __restrict__ G, con
   }
 }
 
+// ---- fp16 hi+lo split operands fed by ldmatrix (template parameter MMA == 2) -----------------------------------------------
+// Measured on B200 (tools/probe/mma_rate.cu): every warp-level MMA shape issues once per 8 cycles per sub-partition, so
+// m16n8k16 on fp16 does twice the work of m16n8k8 on tf32 per issue slot -- and the 3xTF32 loop above spends ~8 instructions
+// per MMA loading fp32 fragments word by word and splitting them again in each of the 4 warps that share them.  Here every
+// operand is split ONCE by its producer, x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (|x - hi - lo| <= 2^-22 |x| while
+// lo is a normal fp16 number, <= 2^-25 absolute below that), and stored as two 16-bit arrays [feature or unit][pixel] with
+// 144-byte rows; one ldmatrix.x4 (.trans where the contraction runs down the rows) delivers a whole 16x16 fragment, and the
+// product is lo*hi + hi*lo + hi*hi accumulated in fp32: 10 instructions per 6 MMAs of k = 16 in the forward loop.
+// Ranges: features and sine outputs are in [-1, 1] and go in unscaled; weights are scaled by 2^8 (fp16 overflows at
+// |W| >= 256 -- a SIREN weight of that size means sin(7680 x), the loss would be NaN and visible); back-propagated dz is
+// scaled per chunk and layer by the power of two that puts its largest magnitude just under 2^15.
+constexpr int kLDH = 72;                      // halves per row (64 pixels + 8): the 8 row addresses of an 8x8 tile hit 8 different
+                                              // 16-byte bank groups (144 = 9 * 16)
+constexpr float kWScale = 256.f, kWInv = 1.f / 256.f;
+__host__ __device__ constexpr int round16(int x) { return (x + 15) & ~15; }
+
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split_h1(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_h2x3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                         uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_f16(d, al, bh0, bh1);      // small terms first
+  mma_f16(d, ah, bl0, bl1);
+  mma_f16(d, ah, bh0, bh1);
+}
+
+// Fragments of mma.m16n8k16 (g = lane / 4, t = lane % 4), each register a pair of halves:
+//   A (16x16, row): a0 (g, k 2t..2t+1)  a1 (g+8, same k)  a2 (g, k+8)  a3 (g+8, k+8)
+//   B (16x8,  col): b0 (k 2t..2t+1, n g)  b1 (k+8, n g)        C as m16n8k8.
+// acc[j] += sum_k act[k][p] * B[k][u]: warp w owns pixels 16 (w & 3) .. +15 and the unit tiles u0 = 8 ((w >> 2) + 4 j).
+// act_*: shared addresses of the [k][kLDH] arrays (pixel-contiguous, so the A tiles are read with .trans).
+// WT_ROWS_ARE_K false: w_* is W[u][k] (natural weight of the forward pass, rows = output units): B tiles read as stored.
+// WT_ROWS_ARE_K true : w_* is W[k][u] (natural weight of the NEXT layer in dh = W^T dz): B tiles read with .trans.
+template <int NT, bool WT_ROWS_ARE_K>
+__device__ __forceinline__ void gemm_px_unit_h2(float (&acc)[NT][4], uint32_t act_hi, uint32_t act_lo, uint32_t w_hi,
+                                                uint32_t w_lo, int ldw, int ksteps, int warp, int lane) {
+  static_assert(NT % 2 == 0, "unit tiles are loaded in pairs");
+  const int p0 = 16 * (warp & 3), ng = warp >> 2;
+  // A tiles: [k0, p0] [k0, p0+8] [k0+8, p0] [k0+8, p0+8]
+  const uint32_t a_off = (uint32_t)(((lane & 7) + 8 * ((lane >> 4) & 1)) * kLDH + p0 + 8 * ((lane >> 3) & 1)) * 2u;
+  uint32_t b_off[NT / 2];
+#pragma unroll
+  for (int jj = 0; jj < NT / 2; ++jj) {
+    const int u0 = 8 * (ng + 4 * (2 * jj + (lane >> 4)));                 // unit tile of lanes 0-15 / 16-31
+    b_off[jj] = WT_ROWS_ARE_K ? (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * ldw + u0) * 2u      // [k0,u][k0+8,u] x 2 tiles
+                              : (uint32_t)((u0 + (lane & 7)) * ldw + 8 * ((lane >> 3) & 1)) * 2u;    // [u,k0][u,k0+8] x 2 tiles
+  }
+  const uint32_t b_step = WT_ROWS_ARE_K ? (uint32_t)(16 * ldw) * 2u : 32u;
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ++ks) {
+    uint32_t ah[4], al[4];
+    ldsm_x4_t(ah, act_hi + a_off + (uint32_t)ks * (16u * kLDH * 2u));
+    ldsm_x4_t(al, act_lo + a_off + (uint32_t)ks * (16u * kLDH * 2u));
+#pragma unroll
+    for (int jj = 0; jj < NT / 2; ++jj) {
+      uint32_t bh[4], bl[4];
+      if (WT_ROWS_ARE_K) {
+        ldsm_x4_t(bh, w_hi + b_off[jj] + (uint32_t)ks * b_step);
+        ldsm_x4_t(bl, w_lo + b_off[jj] + (uint32_t)ks * b_step);
+      } else {
+        ldsm_x4(bh, w_hi + b_off[jj] + (uint32_t)ks * b_step);
+        ldsm_x4(bl, w_lo + b_off[jj] + (uint32_t)ks * b_step);
+      }
+      mma_h2x3(acc[2 * jj], ah, al, bh[0], bh[1], bl[0], bl[1]);
+      mma_h2x3(acc[2 * jj + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+    }
+  }
+}
+
+// dst[r*Kin + q] (+)= inv * sum_p G[r][p] * IN[q][p] over the chunk's 64 pixels (weight-gradient block, natural [BC][Kin]).
+// g_*: [BC][kLDH] arrays of the scaled dz, in_*: [8 nq][kLDH] arrays of the layer input; both pixel-contiguous = K-contiguous,
+// so every tile is read as stored.  Warp w owns row tile w % MT and the column tiles (w / MT) + (16 / MT) j.
+template <int BC>
+__device__ __forceinline__ void grad_weight_h2(uint32_t g_hi, uint32_t g_lo, uint32_t in_hi, uint32_t in_lo, int Kin, int nq,
+                                               float inv, float* __restrict__ dst, bool first, int warp, int lane) {
+  constexpr int MT = BC / 16, NW = 16 / MT, MAXN = 4;
+  const int g = lane >> 2, t = lane & 3, r0 = 16 * (warp % MT);
+  // A tiles: [r0, p0] [r0+8, p0] [r0, p0+8] [r0+8, p0+8]
+  const uint32_t a_off = (uint32_t)((r0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLDH + 8 * (lane >> 4)) * 2u;
+  for (int nbase = warp / MT; nbase < nq; nbase += NW * MAXN) {
+    float acc[MAXN][4];
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    uint32_t b_off[MAXN / 2];
+#pragma unroll
+    for (int jj = 0; jj < MAXN / 2; ++jj) {
+      int nt = nbase + NW * (2 * jj + (lane >> 4));
+      nt = nt < nq ? nt : nq - 1;                                   // keep the address inside the array; the MMA is skipped
+      b_off[jj] = (uint32_t)((8 * nt + (lane & 7)) * kLDH + 8 * ((lane >> 3) & 1)) * 2u;    // [q, p0] [q, p0+8] x 2 tiles
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {                                // 64 pixels
+      uint32_t ah[4], al[4];
+      ldsm_x4(ah, g_hi + a_off + ks * 32u);
+      ldsm_x4(al, g_lo + a_off + ks * 32u);
+#pragma unroll
+      for (int jj = 0; jj < MAXN / 2; ++jj) {
+        if (nbase + NW * 2 * jj < nq) {                             // warp-uniform
+          uint32_t bh[4], bl[4];
+          ldsm_x4(bh, in_hi + b_off[jj] + ks * 32u);
+          ldsm_x4(bl, in_lo + b_off[jj] + ks * 32u);
+          mma_h2x3(acc[2 * jj], ah, al, bh[0], bh[1], bl[0], bl[1]);
+          if (nbase + NW * (2 * jj + 1) < nq) mma_h2x3(acc[2 * jj + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j) {
+      const int nt = nbase + NW * j;
+      if (nt < nq) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = r0 + g + (e >> 1) * 8, q = 8 * nt + 2 * t + (e & 1);
+          if (q < Kin) {
+            float* d = dst + (size_t)r * Kin + q;
+            const float v = acc[j][e] * inv;
+            *d = first ? v : *d + v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// power of two S with max * S in [2^14, 2^15) (S = 1 for max = 0), and its exact inverse
+__device__ __forceinline__ void dz_scale(uint32_t max_bits, float& S, float& inv) {
+  int f = 268 - (int)(max_bits >> 23);                             // biased exponent field of S
+  f = max_bits == 0u ? 127 : (f > 250 ? 250 : (f < 4 ? 4 : f));
+  S = __uint_as_float((uint32_t)f << 23);
+  inv = __uint_as_float((uint32_t)(254 - f) << 23);
+}
+
 // One row (fixed dy) of one band's neighbourhood of one pixel; loads issued before first use.
 template <int N_, int kTrainLDP>
 __device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowoff, int gx, const Net& net, float maxv,
@@ -324,10 +482,14 @@ __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, co
 // THREADS = 128 * US: the chunk's 64 pixels x BC units are tiled as 16 pixel groups (4 px) x 8 lanes x US unit splits,
 // so one 64-pixel chunk is worked on by 4*US warps.  The step time is the latency of ONE chunk on ONE SM (every CTA
 // has at most one chunk per step at bs <= 64*grid), so more warps per chunk is what shortens the step.
-// MMA: the chunk's GEMMs on warp-level 3xTF32 tensor-core MMAs (64-pixel chunks, bc a multiple of 32); otherwise FFMA.
-template <int BC, int CP, bool WSMEM, int THREADS, int TM, bool MMA = false>
+// MMA = 1: the chunk's GEMMs on warp-level 3xTF32 tensor-core MMAs (64-pixel chunks, bc a multiple of 32); MMA = 2: on fp16
+// hi+lo split operands prepared once by their producers and read with ldmatrix (bc a multiple of 64, weights in shared
+// memory); MMA = 0: FFMA.
+template <int BC, int CP, bool WSMEM, int THREADS, int TM, int MMA = 0>
 __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) {
   static_assert(!MMA || (TM == 4 && THREADS == 512 && BC % 32 == 0 && BC <= 128), "MMA path: 64-pixel chunks, 16 warps");
+  static_assert(MMA != 2 || (WSMEM && BC % 64 == 0), "fp16-split path: weights in shared memory, unit tiles in pairs");
+  constexpr bool H2 = MMA == 2;
   constexpr int NPIX = train_npix(TM), LDP = train_ldp(TM), US = THREADS / 128, TN = BC / 8 / US;
   constexpr int VEC = TN >= 4 ? 4 : TN;
   static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
@@ -342,19 +504,34 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   // ---- shared memory carve-up ----------------------------------------------------------------------------
   extern __shared__ float4 smem4[];
   float* X = reinterpret_cast<float*>(smem4);                   // [dimpad][LDP]   features
+  // H2: Hbuf holds the fp32 output of the LAST hidden layer only (output layer and its gradients read it); a layer's slot
+  // of Gbuf is BC*kLDH floats: act' in fp32 [BC][LDP], overwritten in place by the scaled dz as [hi [BC][kLDH] | lo [BC][kLDH]]
+  constexpr int GSZ = H2 ? BC * kLDH : BC * LDP;
   float* Hbuf = X + (size_t)a.dimpad * LDP;                     // [L][BC][LDP]    hidden outputs
-  float* Gbuf = Hbuf + (size_t)L * BC * LDP;                    // [L][BC][LDP]    act' then dz
-  float* dZo = Gbuf + (size_t)L * BC * LDP;                     // [CP][LDP]       output-layer dz
+  float* Gbuf = Hbuf + (size_t)(H2 ? 1 : L) * BC * LDP;         // [L][GSZ]        act' then dz
+  float* dZo = Gbuf + (size_t)L * GSZ;                          // [CP][LDP]       output-layer dz
   float* Tl = dZo + CP * LDP;                                   // [CP][LDP]       labels
   float* Pp = Tl + CP * LDP;                                    // [US][CP][LDP]   output-layer partial sums per unit split
   float* wsm = Pp + US * CP * LDP;                              // packed weights [P] (+pad) then natural hidden l>=1
   float* wnat_sm = wsm + round4(P);
+  // H2: wsm = [biases of the hidden layers L*BC | W_o C*BC | b_o C] in fp32; behind it the split 16-bit operand arrays
+  const int KP0 = round16(net.dim_in);                          // layer-0 contraction length, zero-padded to k = 16 steps
+  float* h2base = wsm + round4(L * BC + C * BC + C);
+  const uint32_t xh_hi = smem_u32(h2base), xh_lo = xh_hi + (uint32_t)KP0 * kLDH * 2u;      // X split: [KP0][kLDH] halves x 2
+  const uint32_t hh_base = xh_hi + (uint32_t)KP0 * kLDH * 4u;   // outputs of hidden layers l < L-1: [BC][kLDH] halves x 2 each
+  const uint32_t wh_base = hh_base + (uint32_t)(L - 1) * BC * kLDH * 4u;   // W_l natural [BC][ldw_l] halves x 2 (hi | lo)
+  auto ldw_of = [&](int l) { return (l == 0 ? KP0 : BC) + 8; };  // row pitch in halves: an odd multiple of 16 bytes
+  auto wh_of = [&](int l) { return wh_base + (l == 0 ? 0u : (uint32_t)BC * (KP0 + 8) * 4u + (uint32_t)(l - 1) * BC * (BC + 8) * 4u); };
+  __shared__ uint32_t s_dzmax[kMaxLayers];                      // H2: bits of max |dz_l| over the chunk
+  __shared__ float s_db[H2 ? 2 : 1][4][H2 ? BC : 1];            // H2: bias-gradient partials per pixel tile (by layer parity)
   __shared__ int s_py[NPIX], s_px[NPIX], s_valid[NPIX];
   __shared__ float s_red[THREADS / 32];
   __shared__ float s_sse;
   __shared__ float s_adam[2];
 
   const float* w = WSMEM ? wsm : a.wpack;
+  const float* wo_p = H2 ? wsm + L * BC : w + net.woff[L];            // output layer W_o [C][BC] and b_o [C]
+  const float* bo_p = H2 ? wsm + L * BC + C * BC : w + net.boff[L];
   // natural (untransposed) W_l for hidden layers l>=1, used as the k-major B operand of dh = W^T dz
   auto wnat = [&](int l) -> const float* {
     return WSMEM ? (wnat_sm + (size_t)(l - 1) * BC * BC) : (a.params + net.woff[l]);
@@ -571,7 +748,31 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 
   for (int s = 0; s < a.n_steps; ++s) {
     // ---- (re)load weights ----------------------------------------------------------------------------
-    if (WSMEM) {
+    if (H2) {
+      // fp32 part: hidden biases, output layer
+      const int nb = L * BC, nwo = C * BC;
+      for (int i = tid; i < nb + nwo + C; i += THREADS) {
+        const int src = i < nb ? net.boff[i / BC] + i % BC : (i < nb + nwo ? net.woff[L] + (i - nb) : net.boff[L] + (i - nb - nwo));
+        wsm[i] = __ldcg(a.params + src);
+      }
+      // hidden weights, natural [unit][input] layout of the reference -> scaled hi | lo halves, two inputs per thread
+      for (int l = 0; l < L; ++l) {
+        const int K = l == 0 ? net.dim_in : BC, KH = (l == 0 ? KP0 : BC) >> 1, ldw = ldw_of(l);
+        const float* src = a.params + net.woff[l];
+        const uint32_t w_hi = wh_of(l), w_lo = w_hi + (uint32_t)BC * ldw * 2u;
+#pragma unroll 4
+        for (int i = tid; i < BC * KH; i += THREADS) {
+          const int u = i / KH, k = 2 * (i - u * KH);
+          const float x0 = k < K ? __ldcg(src + (size_t)u * K + k) : 0.f;
+          const float x1 = k + 1 < K ? __ldcg(src + (size_t)u * K + k + 1) : 0.f;
+          uint32_t hi, lo;
+          split_h2(x0 * kWScale, x1 * kWScale, hi, lo);
+          const uint32_t o = (uint32_t)(u * ldw + k) * 2u;
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(w_hi + o), "r"(hi) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(w_lo + o), "r"(lo) : "memory");
+        }
+      }
+    } else if (WSMEM) {
       // asynchronous copies: their L2 latency hides under the commit of the prefetched neighbourhoods (or the gather),
       // neither of which reads weights; cp_async_wait_all() sits in front of the barrier that precedes the forward pass
       const int P4 = P >> 2;
@@ -611,6 +812,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 
     for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
       __syncthreads();
+      if (H2 && tid < kMaxLayers) s_dzmax[tid] = 0u;
       // ---- gather: pixel coordinates, centres, labels, features (LBDRNdataset.py:104-131,151-155) --------
       const int nvalid = min(NPIX, B - ch * NPIX);
       const bool staged = pf_have && ch == (int)blockIdx.x;          // uniform: a function of (step, CTA) only
@@ -676,6 +878,20 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       if (WSMEM) cp_async_wait_all();
       __syncthreads();
       }
+      if (H2) {
+        // features -> split 16-bit operand arrays (rows >= dim_in are the zero padding of the last k = 16 step)
+        for (int i = tid; i < KP0 * (NPIX / 2); i += THREADS) {
+          const int k = i / (NPIX / 2), pp = 2 * (i - k * (NPIX / 2));
+          float2 x = make_float2(0.f, 0.f);
+          if (k < net.dim_in) x = *reinterpret_cast<const float2*>(X + (size_t)k * LDP + pp);
+          uint32_t hi, lo;
+          split_h2(x.x, x.y, hi, lo);
+          const uint32_t o = (uint32_t)(k * kLDH + pp) * 2u;
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(xh_hi + o), "r"(hi) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(xh_lo + o), "r"(lo) : "memory");
+        }
+        __syncthreads();
+      }
       LBDRN_PHASE(1)   // gather
 
       // ---- forward (LBDRNmodel.py:79-82), keeping h_l and act'(z_l) per layer ------------------------------
@@ -685,7 +901,75 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
         float* Hl = Hbuf + (size_t)l * BC * LDP;
-        float* Gl = Gbuf + (size_t)l * BC * LDP;
+        float* Gl = Gbuf + (size_t)l * GSZ;
+        if constexpr (H2) {
+          constexpr int NT = BC / 32;
+          float acc[NT][4];
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+          const int Kp = l == 0 ? KP0 : BC, ldw = ldw_of(l);
+          const uint32_t in_hi = l == 0 ? xh_hi : hh_base + (uint32_t)(l - 1) * BC * kLDH * 4u;
+          const uint32_t in_lo = in_hi + (uint32_t)Kp * kLDH * 2u;
+          const uint32_t w_hi = wh_of(l), w_lo = w_hi + (uint32_t)BC * ldw * 2u;
+          gemm_px_unit_h2<NT, false>(acc, in_hi, in_lo, w_hi, w_lo, ldw, Kp >> 4, warp, lane);
+          LBDRN_PHASE(15)   // fwd: GEMMs
+          const int g = lane >> 2, t = lane & 3;
+          const uint32_t out_hi = hh_base + (uint32_t)l * BC * kLDH * 4u, out_lo = out_hi + (uint32_t)BC * kLDH * 2u;
+          float hv[NT][4], gv[NT][4], amax = 0.f;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+              const float z = acc[j][e] * kWInv + wsm[l * BC + u];      // the power-of-two weight scale comes off exactly
+              if (net.relu) {
+                hv[j][e] = fmaxf(z, 0.f);
+                gv[j][e] = z > 0.f ? 1.f : 0.f;
+              } else {
+                const float arg = net.w0 * z;
+                float sn, cs;
+                sincos_cw_core(arg, sn, cs);
+                amax = fmaxf(amax, fabsf(arg));
+                hv[j][e] = sn;
+                gv[j][e] = cs * net.w0;
+              }
+            }
+          if (__builtin_expect(amax > 48000.0f, 0)) {               // one large-argument test per thread, not per value
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+                const float arg = net.w0 * (acc[j][e] * kWInv + wsm[l * BC + u]);
+                if (fabsf(arg) > 48000.0f) { hv[j][e] = sin_slow(arg); gv[j][e] = cos_slow(arg) * net.w0; }
+              }
+          }
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {                          // e = 2 e2, 2 e2 + 1: units u, u+1 of one pixel
+              const int pixel = 16 * (warp & 3) + g + e2 * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t;
+              Gl[(size_t)u * LDP + pixel] = gv[j][2 * e2];              // bank = g + 8t: conflict-free
+              Gl[(size_t)(u + 1) * LDP + pixel] = gv[j][2 * e2 + 1];
+              if (l == L - 1) {
+                Hbuf[(size_t)u * LDP + pixel] = hv[j][2 * e2];
+                Hbuf[(size_t)(u + 1) * LDP + pixel] = hv[j][2 * e2 + 1];
+              } else {
+                uint32_t hi, lo;
+                split_h2(hv[j][2 * e2], hv[j][2 * e2 + 1], hi, lo);
+                const uint32_t o = (uint32_t)(u * kLDH + pixel) * 2u;
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(out_hi + o), "h"((uint16_t)(hi & 0xffffu)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(out_hi + o + kLDH * 2u), "h"((uint16_t)(hi >> 16)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(out_lo + o), "h"((uint16_t)(lo & 0xffffu)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(out_lo + o + kLDH * 2u), "h"((uint16_t)(lo >> 16)) : "memory");
+              }
+            }
+          LBDRN_PHASE(16)   // fwd: bias + sine / cosine + stores
+          __syncthreads();
+          continue;
+        }
         if (MMA) {
           constexpr int NT = BC / 32;
           float acc[NT][4];
@@ -755,11 +1039,11 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 
       LBDRN_PHASE(2)   // hidden layers forward
       // ---- output layer + loss (LBDRNloss.py:9) ---------------------------------------------------------
-      const float* wo = w + net.woff[L];
+      const float* wo = wo_p;
       float sse = 0.f;
       if (MMA) {
         // z[c][p] = b[c] + sum_u W_o[c][u] h_L[u][p] from shared memory: one thread per (band, pixel)
-        const float* HL = Hbuf + (size_t)(L - 1) * BC * LDP;
+        const float* HL = Hbuf + (size_t)(H2 ? 0 : L - 1) * BC * LDP;
         if (tid < C * NPIX) {
           const int c = tid / NPIX, pp = tid - c * NPIX;
           float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
@@ -771,7 +1055,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             z3 = fmaf(wo[c * BC + u + 3], HL[(size_t)(u + 3) * LDP + pp], z3);
           }
           const bool ok = s_valid[pp] != 0;
-          const float y = sigmoidf_rn(((z0 + z1) + (z2 + z3)) + w[net.boff[L] + c]);
+          const float y = sigmoidf_rn(((z0 + z1) + (z2 + z3)) + bo_p[c]);
           const float d = y - Tl[c * LDP + pp];
           dZo[c * LDP + pp] = ok ? (gscale * d) * ((1.0f - y) * y) : 0.f;   // mse backward then sigmoid backward
           if (ok) sse = d * d;
@@ -818,7 +1102,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
 #pragma unroll
                   for (int u2 = 0; u2 < US; ++u2) z += Pp[(u2 * CP + c) * LDP + pp];
                 }
-                float y = sigmoidf_rn(z + w[net.boff[L] + c]);
+                float y = sigmoidf_rn(z + bo_p[c]);
                 float d = y - Tl[c * LDP + pp];
                 float dz = ok ? (gscale * d) * ((1.0f - y) * y) : 0.f;   // mse backward then sigmoid backward
                 dZo[c * LDP + pp] = dz;
@@ -842,7 +1126,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       // ---- backward --------------------------------------------------------------------------------------
       // output layer: dW_o[c][n] = sum_p dz_o[c][p] h_L[n][p];  db_o[c] = sum_p dz_o[c][p]
       {
-        const float* HL = Hbuf + (size_t)(L - 1) * BC * LDP;
+        const float* HL = Hbuf + (size_t)(H2 ? 0 : L - 1) * BC * LDP;
         for (int o = tid; o < C * BC; o += THREADS) {
           int c = o / BC, u = o - c * BC;
           float g = row_dot<NPIX>(dZo + c * LDP, HL + (size_t)u * LDP);
@@ -856,8 +1140,136 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         }
       }
       LBDRN_PHASE(8)    // bwd: output-layer grads
+      float inv_next = 1.f;                                            // H2: 1 / scale of dz_{l+1}
       for (int l = L - 1; l >= 0; --l) {
-        float* Gl = Gbuf + (size_t)l * BC * LDP;
+        float* Gl = Gbuf + (size_t)l * GSZ;
+        if constexpr (H2) {
+          const uint32_t g_hi = smem_u32(Gl), g_lo = g_hi + (uint32_t)BC * kLDH * 2u;
+          constexpr int NT = BC / 32, UPT = BC / 64;
+          const int g = lane >> 2, t = lane & 3, pc = tid & 7;
+          float dzo[UPT][8];          // l == L-1: thread = (unit (tid >> 3) + 64 i, pixels 4 pc .. +3 and 32 + 4 pc .. +3)
+          float dzr[NT][4];           // l <  L-1: the accumulator fragment positions
+          float mx = 0.f;
+          if (l == L - 1) {
+            // dh_L[u][p] = sum_c W_o[c][u] dz_o[c][p];  dz_L = dh_L * act'(z_L);  db_L[u] = sum_p dz_L[u][p]
+#pragma unroll
+            for (int i = 0; i < UPT; ++i) {
+              const int u = (tid >> 3) + 64 * i;
+              const float4 a0 = *reinterpret_cast<const float4*>(Gl + (size_t)u * LDP + 4 * pc);
+              const float4 a1 = *reinterpret_cast<const float4*>(Gl + (size_t)u * LDP + 32 + 4 * pc);
+              float d[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) d[k] = 0.f;
+#pragma unroll
+              for (int c = 0; c < CP; ++c) {
+                if (c < C) {
+                  const float wv = wo[c * BC + u];
+                  const float4 v0 = *reinterpret_cast<const float4*>(dZo + c * LDP + 4 * pc);
+                  const float4 v1 = *reinterpret_cast<const float4*>(dZo + c * LDP + 32 + 4 * pc);
+                  d[0] = fmaf(wv, v0.x, d[0]); d[1] = fmaf(wv, v0.y, d[1]); d[2] = fmaf(wv, v0.z, d[2]); d[3] = fmaf(wv, v0.w, d[3]);
+                  d[4] = fmaf(wv, v1.x, d[4]); d[5] = fmaf(wv, v1.y, d[5]); d[6] = fmaf(wv, v1.z, d[6]); d[7] = fmaf(wv, v1.w, d[7]);
+                }
+              }
+              dzo[i][0] = a0.x * d[0]; dzo[i][1] = a0.y * d[1]; dzo[i][2] = a0.z * d[2]; dzo[i][3] = a0.w * d[3];
+              dzo[i][4] = a1.x * d[4]; dzo[i][5] = a1.y * d[5]; dzo[i][6] = a1.z * d[6]; dzo[i][7] = a1.w * d[7];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) mx = fmaxf(mx, fabsf(dzo[i][k]));
+              float sum = ((dzo[i][0] + dzo[i][1]) + (dzo[i][2] + dzo[i][3])) + ((dzo[i][4] + dzo[i][5]) + (dzo[i][6] + dzo[i][7]));
+              sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+              if (pc == 0) {
+                float* dd = mypart + net.boff[l] + u;
+                *dd = first ? sum : *dd + sum;
+              }
+            }
+          } else {
+            // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p] on the tensor cores; dz_l = dh_l * act'(z_l) at the fragment positions
+            float dacc[NT][4];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) dacc[j][e] = 0.f;
+            const uint32_t gn_hi = smem_u32(Gbuf + (size_t)(l + 1) * GSZ), gn_lo = gn_hi + (uint32_t)BC * kLDH * 2u;
+            const int ldw = ldw_of(l + 1);
+            const uint32_t w_hi = wh_of(l + 1), w_lo = w_hi + (uint32_t)BC * ldw * 2u;
+            gemm_px_unit_h2<NT, true>(dacc, gn_hi, gn_lo, w_hi, w_lo, ldw, BC >> 4, warp, lane);
+            const float sc = kWInv * inv_next;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int pixel = 16 * (warp & 3) + g + (e >> 1) * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+                dzr[j][e] = (dacc[j][e] * sc) * Gl[(size_t)u * LDP + pixel];
+                mx = fmaxf(mx, fabsf(dzr[j][e]));
+              }
+              // bias-gradient partial of this warp's 16 pixels for units 2t, 2t+1 of tile j: fixed-order tree over g
+              float s0 = dzr[j][0] + dzr[j][2], s1 = dzr[j][1] + dzr[j][3];
+#pragma unroll
+              for (int off = 4; off < 32; off <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+              }
+              if (g == 0) {
+                const int u = 8 * ((warp >> 2) + 4 * j) + 2 * t;
+                s_db[l & 1][warp & 3][u] = s0;
+                s_db[l & 1][warp & 3][u + 1] = s1;
+              }
+            }
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+          if (lane == 0) atomicMax(&s_dzmax[l], __float_as_uint(mx));     // non-negative floats order like their bit patterns
+          __syncthreads();                                               // every act' of the layer has been read: overwrite
+          float S, inv;
+          dz_scale(s_dzmax[l], S, inv);
+          if (l == L - 1) {
+#pragma unroll
+            for (int i = 0; i < UPT; ++i) {
+              const int u = (tid >> 3) + 64 * i;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t hi0, lo0, hi1, lo1;
+                split_h2(dzo[i][4 * h] * S, dzo[i][4 * h + 1] * S, hi0, lo0);
+                split_h2(dzo[i][4 * h + 2] * S, dzo[i][4 * h + 3] * S, hi1, lo1);
+                const uint32_t o = (uint32_t)(u * kLDH + 32 * h + 4 * pc) * 2u;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(g_hi + o), "r"(hi0), "r"(hi1) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(g_lo + o), "r"(lo0), "r"(lo1) : "memory");
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const int pixel = 16 * (warp & 3) + g + e2 * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t;
+                uint32_t hi, lo;
+                split_h2(dzr[j][2 * e2] * S, dzr[j][2 * e2 + 1] * S, hi, lo);
+                const uint32_t o = (uint32_t)(u * kLDH + pixel) * 2u;
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(g_hi + o), "h"((uint16_t)(hi & 0xffffu)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(g_hi + o + kLDH * 2u), "h"((uint16_t)(hi >> 16)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(g_lo + o), "h"((uint16_t)(lo & 0xffffu)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(g_lo + o + kLDH * 2u), "h"((uint16_t)(lo >> 16)) : "memory");
+              }
+          }
+          __syncthreads();
+          LBDRN_PHASE(9 + 2 * (l > 0 ? 1 : 0))     // bwd: dh + dz (9: layer 0, 11: layer >= 1)
+          // dW_l = dz_l . in_l^T on the tensor cores
+          const int Kp = l == 0 ? KP0 : BC;
+          const uint32_t in_hi = l == 0 ? xh_hi : hh_base + (uint32_t)(l - 1) * BC * kLDH * 4u;
+          const uint32_t in_lo = in_hi + (uint32_t)Kp * kLDH * 2u;
+          grad_weight_h2<BC>(g_hi, g_lo, in_hi, in_lo, l == 0 ? net.dim_in : BC, Kp >> 3, inv, mypart + net.woff[l], first,
+                             warp, lane);
+          if (l < L - 1)
+            for (int u = tid; u < BC; u += THREADS) {
+              const float sum = (s_db[l & 1][0][u] + s_db[l & 1][1][u]) + (s_db[l & 1][2][u] + s_db[l & 1][3][u]);
+              float* dd = mypart + net.boff[l] + u;
+              *dd = first ? sum : *dd + sum;
+            }
+          inv_next = inv;
+          LBDRN_PHASE(10 + 2 * (l > 0 ? 1 : 0))    // bwd: dW + db (10: layer 0, 12: layer >= 1)
+          continue;
+        }
         float acc[TM][TN];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -886,7 +1298,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) dacc[j][e] = 0.f;
-          gemm_px_unit_mma<BC, LDP, NT>(dacc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, warp, lane);
+          gemm_px_unit_mma<BC, LDP, NT>(dacc, Gbuf + (size_t)(l + 1) * GSZ, wnat(l + 1), BC, warp, lane);
           const int g = lane >> 2, t = lane & 3;
 #pragma unroll
           for (int j = 0; j < NT; ++j)
@@ -897,7 +1309,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             }
         } else {
           // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p]   (k-major in m on both operands)
-          gemm_kmajor_v<TM, TN, VEC, BC>(acc, Gbuf + (size_t)(l + 1) * BC * LDP, wnat(l + 1), BC, pg, ubase);
+          gemm_kmajor_v<TM, TN, VEC, BC>(acc, Gbuf + (size_t)(l + 1) * GSZ, wnat(l + 1), BC, pg, ubase);
         }
         // dz_l = dh_l * act'(z_l): thread-private read-modify-write of its own (unit, pixel) entries
         if (!(MMA && l < L - 1))
