@@ -43,6 +43,7 @@ struct TrainPlan {
   void* kernel = nullptr;
   size_t smem = 0;
   bool wsmem = true;
+  size_t wimg_bytes = 0;              // h2: bytes of the global image of the split weight operands
   bool h2 = false;                    // fp16 hi+lo split operands + ldmatrix variant selected
   int grid = 0, dimpad = 0, pstride = 0;
   int pf_off = 0, pf_stride = 0;      // TMA neighbourhood boxes: offset inside dynamic smem, bytes per pixel (0: not planned)

@@ -57,6 +57,7 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
       t.wsmem = true; t.smem = place_boxes(h2);
       t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT, TM, 2>;
       t.h2 = true;
+      t.wimg_bytes = ((size_t)BC * (KP0 + 8) + (size_t)(L - 1) * BC * (BC + 8)) * sizeof(float);
     }
   }
   if (t.h2) {

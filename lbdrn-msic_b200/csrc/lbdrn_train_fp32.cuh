@@ -51,6 +51,8 @@ struct TrainArgs {
   const CUtensorMap* tmap_msb;   // TMA neighbourhood gather: 3-D maps of the MSB / LSB planes (boxes 32x5xC / 16x1xC bytes);
   const CUtensorMap* tmap_lsb;   // nullptr: register prefetch only
   int pf_off, pf_stride;   // byte offset of the landing boxes inside dynamic shared memory, bytes per pixel
+  uint16_t* wimg;          // fp16-split kernel: global image of the shared-memory weight operands (hi | lo halves per layer,
+                           // padding zero), kept current by the Adam phase so that a reload is one asynchronous copy
   const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
                            // torch's python floats (two pow() per step in fp64 cost ~3k cycles of every step on the device)
 };
@@ -755,8 +757,16 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         const int src = i < nb ? net.boff[i / BC] + i % BC : (i < nb + nwo ? net.woff[L] + (i - nb) : net.boff[L] + (i - nb - nwo));
         wsm[i] = __ldcg(a.params + src);
       }
-      // hidden weights, natural [unit][input] layout of the reference -> scaled hi | lo halves, two inputs per thread
-      for (int l = 0; l < L; ++l) {
+      const bool from_image = s > 0 && a.wimg != nullptr;           // the Adam phase of step s-1 wrote every weight's halves
+      if (from_image) {
+        const int n16 = (int)((wh_of(L) - wh_base) >> 4);           // the image is the shared layout, byte for byte
+        for (int i = tid; i < n16; i += THREADS)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wh_base + 16u * i),
+                       "l"(reinterpret_cast<const uint4*>(a.wimg) + i) : "memory");
+      }
+      // first step of a launch: hidden weights from the master copy, natural [unit][input] layout of the reference ->
+      // scaled hi | lo halves, two inputs per thread
+      for (int l = 0; l < (from_image ? 0 : L); ++l) {
         const int K = l == 0 ? net.dim_in : BC, KH = (l == 0 ? KP0 : BC) >> 1, ldw = ldw_of(l);
         const float* src = a.params + net.woff[l];
         const uint32_t w_hi = wh_of(l), w_lo = w_hi + (uint32_t)BC * ldw * 2u;
@@ -1401,7 +1411,25 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             float p = p_old, m = m_old, v = v_old;
             adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
             a.params[i] = p; a.m[i] = m; a.v[i] = v;
-            a.wpack[packed_index(net, i)] = p;
+            if (H2) {
+              if (a.wimg != nullptr) {
+                uint32_t img = 0u;                                    // halves before layer l's block
+                for (int l = 0; l < L; ++l) {
+                  const int K = l == 0 ? net.dim_in : BC, ldw = ldw_of(l), o = i - net.woff[l];
+                  if (o >= 0 && o < K * BC) {
+                    const int u = o / K, k = o - u * K;
+                    uint16_t hi, lo;
+                    split_h1(p * kWScale, hi, lo);
+                    a.wimg[img + (uint32_t)(u * ldw + k)] = hi;
+                    a.wimg[img + (uint32_t)(BC * ldw + u * ldw + k)] = lo;
+                    break;
+                  }
+                  img += 2u * BC * ldw;
+                }
+              }
+            } else {
+              a.wpack[packed_index(net, i)] = p;
+            }
           }
         }
       }
