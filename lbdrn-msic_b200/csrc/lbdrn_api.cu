@@ -179,6 +179,7 @@ struct LbdrnTrain {
   TrainPlan plan;
   int dev = 0, sms = 0;
   float *params = nullptr, *wpack = nullptr, *m = nullptr, *v = nullptr, *partial = nullptr;
+  unsigned* gbar = nullptr;        // arrival counters of the training kernel's split grid barriers
   uint16_t* wimg = nullptr;        // fp16-split training kernel: image of its shared-memory weight operands (padding stays zero)
   float2* adam_tab = nullptr;      // per-step Adam scalars of the launch in flight (ring of two: launches may be queued)
   size_t adam_tab_n = 0;
@@ -189,7 +190,7 @@ namespace {
 
 int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
   a.net = t->net; a.params = t->params; a.wpack = t->wpack; a.m = t->m; a.v = t->v;
-  a.partial = t->partial; a.pstride = t->plan.pstride; a.dimpad = t->plan.dimpad; a.wimg = t->wimg;
+  a.partial = t->partial; a.pstride = t->plan.pstride; a.dimpad = t->plan.dimpad; a.wimg = t->wimg; a.gbar = t->gbar;
   a.beta1 = t->cfg.beta1; a.beta2 = t->cfg.beta2;
   a.omb1 = (float)(1.0 - t->cfg.beta1); a.omb2 = (float)(1.0 - t->cfg.beta2);
   a.beta2f = (float)t->cfg.beta2; a.eps = (float)t->cfg.eps;
@@ -336,6 +337,7 @@ int32_t lbdrn_train_create(const LbdrnDesc* d, const LbdrnTrainCfg* cfg, LbdrnTr
   if (e == cudaSuccess) e = cudaMalloc(&t->partial, (size_t)t->plan.grid * t->plan.pstride * sizeof(float));
   if (e == cudaSuccess && t->plan.wimg_bytes) e = cudaMalloc(&t->wimg, t->plan.wimg_bytes);
   if (e == cudaSuccess && t->plan.wimg_bytes) e = cudaMemset(t->wimg, 0, t->plan.wimg_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&t->gbar, 64);
   if (e == cudaSuccess) e = cudaMemset(t->params, 0, pb);
   if (e == cudaSuccess) e = cudaMemset(t->wpack, 0, pb);
   if (e == cudaSuccess) e = cudaMemset(t->m, 0, pb);
@@ -354,7 +356,7 @@ int32_t lbdrn_train_destroy(LbdrnTrain* t) {
   if (!t) return LBDRN_OK;
   cudaDeviceSynchronize();
   cudaFree(t->params); cudaFree(t->wpack); cudaFree(t->m); cudaFree(t->v); cudaFree(t->partial); cudaFree(t->adam_tab);
-  cudaFree(t->wimg);
+  cudaFree(t->wimg); cudaFree(t->gbar);
   delete t;
   return LBDRN_OK;
 }

@@ -107,6 +107,7 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(prof_dev, 0, 24 * sizeof(long long), st));
     a.prof = prof_dev;
   }
+  CUDA_TRY(cudaMemsetAsync(a.gbar, 0, 2 * sizeof(unsigned), st));
   void* kargs[] = {(void*)&a};
   CUDA_TRY(cudaLaunchCooperativeKernel(plan.kernel, dim3(plan.grid), dim3(kTT), kargs, plan.smem, st));
   ++g_launches;
@@ -114,7 +115,7 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
     long long h[24];
     CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    static const char* names[17] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "sync1", "reduce+adam", "sync2",
+    static const char* names[17] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "wait1", "reduce+adam", "wait2",
                                     "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1", "pf_commit", "pf_issue", "fwd_gemm",
                                     "fwd_act"};
     fprintf(stderr, "[lbdrn] train phases (cycles/step on CTA 0, %d steps, grid %d x %d thr):", a.n_steps, plan.grid, kTT);

@@ -53,6 +53,7 @@ struct TrainArgs {
   int pf_off, pf_stride;   // byte offset of the landing boxes inside dynamic shared memory, bytes per pixel
   uint16_t* wimg;          // fp16-split kernel: global image of the shared-memory weight operands (hi | lo halves per layer,
                            // padding zero), kept current by the Adam phase so that a reload is one asynchronous copy
+  unsigned* gbar;          // two monotonic arrival counters of the split grid barriers (zeroed before every launch)
   const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
                            // torch's python floats (two pow() per step in fp64 cost ~3k cycles of every step on the device)
 };
@@ -146,6 +147,21 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Split grid barrier on a monotonic counter: arrive (ONE thread, after a __syncthreads() that orders the CTA's writes before
+// its fence -- the same cumulativity cooperative_groups' grid.sync() relies on) ... independent work ... wait (one thread
+// spins, then a __syncthreads() releases the CTA).  Unlike grid.sync() the two halves can bracket work that does not depend
+// on the other CTAs.  Needs all CTAs co-resident: the kernel is still launched cooperatively.
+__device__ __forceinline__ void gbar_arrive(unsigned* bar) {
+  __threadfence();
+  atomicAdd(bar, 1u);
+}
+__device__ __forceinline__ void gbar_wait(const unsigned* bar, unsigned target) {
+  unsigned v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+  } while (v < target);
+}
 
 // cvt.rna.tf32.f32 is not a hardware instruction on sm_100a: ptxas expands it to an Inf/NaN test, an integer add, a select
 // and a mask (~9 instructions per split element, which made the split -- not the MMAs -- the cost of the chunk GEMMs).
@@ -495,7 +511,6 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   constexpr int NPIX = train_npix(TM), LDP = train_ldp(TM), US = THREADS / 128, TN = BC / 8 / US;
   constexpr int VEC = TN >= 4 ? 4 : TN;
   static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
-  cg::grid_group grid = cg::this_grid();
   const Net& net = a.net;
   const int tid = threadIdx.x, us = tid >> 7, t128 = tid & 127, tn = t128 & 7, pg = t128 >> 3;
   const int ubase = us * (BC / US) + tn * VEC;
@@ -749,6 +764,30 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   };
 
   for (int s = 0; s < a.n_steps; ++s) {
+    if (tid == 0) s_sse = 0.f;
+    prefetch_index(s + 1);
+    if (tid == 32 && a.mode == TRAIN_FUSED) {
+      if (a.adam_tab) {
+        const float2 t2 = a.adam_tab[s];
+        s_adam[0] = t2.x; s_adam[1] = t2.y;
+      } else {
+        double t = (double)(a.adam_t0 + s + 1);
+        double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
+        s_adam[0] = (float)(a.lr / bc1);              // step_size
+        s_adam[1] = (float)sqrt(bc2);                 // bias_correction2_sqrt
+      }
+    }
+    // The features of this step's chunk were requested during step s-1 and do not depend on the weights: they are committed
+    // to shared memory BEFORE waiting for the other CTAs' Adam phase (the second half of the split barrier).
+    const bool early = pf_have;                       // uniform: a function of (step, CTA) only
+    if (early) {
+      prefetch_commit();
+      pf_have = false;
+    }
+    LBDRN_PHASE(13)   // commit of the prefetched neighbourhoods
+    if (s > 0 && tid == 0) gbar_wait(a.gbar + 1, (unsigned)s * gridDim.x);
+    __syncthreads();
+    LBDRN_PHASE(7)    // wait for the Adam phase of every CTA (second barrier of the previous step)
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (H2) {
       // fp32 part: hidden biases, output layer
@@ -795,19 +834,20 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         for (int i = tid; i < BC * BC / 4; i += THREADS) cp_async16(dst + i, src + i);
       }
     }
-    if (tid == 0) s_sse = 0.f;
-    prefetch_index(s + 1);
-    if (tid == 32 && a.mode == TRAIN_FUSED) {
-      if (a.adam_tab) {
-        const float2 t2 = a.adam_tab[s];
-        s_adam[0] = t2.x; s_adam[1] = t2.y;
-      } else {
-        double t = (double)(a.adam_t0 + s + 1);
-        double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
-        s_adam[0] = (float)(a.lr / bc1);              // step_size
-        s_adam[1] = (float)sqrt(bc2);                 // bias_correction2_sqrt
+    if (H2 && early) {
+      // features -> split 16-bit operand arrays, under the latency of the weight copies
+      for (int i = tid; i < KP0 * (NPIX / 2); i += THREADS) {
+        const int k = i / (NPIX / 2), pp = 2 * (i - k * (NPIX / 2));
+        float2 x = make_float2(0.f, 0.f);
+        if (k < net.dim_in) x = *reinterpret_cast<const float2*>(X + (size_t)k * LDP + pp);
+        uint32_t hi, lo;
+        split_h2(x.x, x.y, hi, lo);
+        const uint32_t o = (uint32_t)(k * kLDH + pp) * 2u;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(xh_hi + o), "r"(hi) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(xh_lo + o), "r"(lo) : "memory");
       }
     }
+    if (WSMEM) cp_async_wait_all();
     __syncthreads();
     LBDRN_PHASE(0)   // weight reload
 
@@ -825,15 +865,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       if (H2 && tid < kMaxLayers) s_dzmax[tid] = 0u;
       // ---- gather: pixel coordinates, centres, labels, features (LBDRNdataset.py:104-131,151-155) --------
       const int nvalid = min(NPIX, B - ch * NPIX);
-      const bool staged = pf_have && ch == (int)blockIdx.x;          // uniform: a function of (step, CTA) only
-      if (staged) {
-        LBDRN_PHASE(1)    // loop-top barrier
-        prefetch_commit();
-        pf_have = false;
-        if (WSMEM) cp_async_wait_all();
-        __syncthreads();
-        LBDRN_PHASE(13)   // commit of the prefetched neighbourhoods
-      }
+      const bool staged = early && ch == (int)blockIdx.x;            // committed before the barrier wait above
       if (!staged) {
       if (tid < NPIX) {
         long long idx = tid < nvalid ? a.perm[b0 + (long long)ch * NPIX + tid] : 0;
@@ -885,9 +917,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           }
         }
       }
-      if (WSMEM) cp_async_wait_all();
       __syncthreads();
-      }
       if (H2) {
         // features -> split 16-bit operand arrays (rows >= dim_in are the zero padding of the last k = 16 step)
         for (int i = tid; i < KP0 * (NPIX / 2); i += THREADS) {
@@ -901,6 +931,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(xh_lo + o), "r"(lo) : "memory");
         }
         __syncthreads();
+      }
       }
       LBDRN_PHASE(1)   // gather
 
@@ -1349,16 +1380,19 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       first = false;
       LBDRN_PHASE(4)   // backward (remainder)
     }
-    if (WSMEM) cp_async_wait_all();
     __syncthreads();
-    if (tid == 0 && !first) mypart[P] = s_sse;
-    __threadfence();
-    grid.sync();
-    LBDRN_PHASE(5)   // fence + grid sync 1
-    // next step's neighbourhood loads: in flight during the reduction / Adam phase (itself L2-latency-bound).  Not before
-    // the fence above: a membar waits for the thread's outstanding loads, which would put their latency into the sync.
+    if (tid == 0) {
+      if (!first) mypart[P] = s_sse;
+      gbar_arrive(a.gbar);                   // first barrier, arrive: this CTA's gradient partial is complete
+    }
+    // next step's neighbourhood loads, between the two halves of the barrier: in flight while the other CTAs finish and
+    // during the reduction / Adam phase (itself L2-latency-bound).  Only thread 0 fences, before its own loads are issued
+    // (a membar waits for the thread's outstanding loads).
     prefetch_issue();
     LBDRN_PHASE(14)   // issue of the next step's neighbourhood loads
+    if (tid == 0) gbar_wait(a.gbar, (unsigned)(s + 1) * gridDim.x);
+    __syncthreads();
+    LBDRN_PHASE(5)    // first barrier, wait
 
     // ---- fixed-order reduction over the CTAs that produced partials, then Adam ----------------------------
     const int n_act = min((int)gridDim.x, n_chunks);
@@ -1435,9 +1469,8 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       }
     }
     LBDRN_PHASE(6)   // reduce + Adam
-    __threadfence();
-    grid.sync();
-    LBDRN_PHASE(7)   // fence + grid sync 2
+    __syncthreads();
+    if (tid == 0) gbar_arrive(a.gbar + 1);   // second barrier, arrive; the wait is at the head of the next step
   }
 #undef LBDRN_PHASE
 }
