@@ -191,6 +191,13 @@ namespace {
 int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
   a.net = t->net; a.params = t->params; a.wpack = t->wpack; a.m = t->m; a.v = t->v;
   a.partial = t->partial; a.pstride = t->plan.pstride; a.dimpad = t->plan.dimpad; a.wimg = t->wimg; a.gbar = t->gbar;
+  {
+    // both planes of the scene against the device's L2: hints only pay when the window rows are DRAM misses
+    int l2 = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, t->dev);
+    const size_t plane_bytes = (size_t)t->net.C * t->net.buf_rows * t->net.W * ((t->net.msb_u16 ? 2 : 1) + (t->net.lsb_u16 ? 2 : 1));
+    a.l2_hints = plane_bytes > (size_t)l2;
+  }
   a.beta1 = t->cfg.beta1; a.beta2 = t->cfg.beta2;
   a.omb1 = (float)(1.0 - t->cfg.beta1); a.omb2 = (float)(1.0 - t->cfg.beta2);
   a.beta2f = (float)t->cfg.beta2; a.eps = (float)t->cfg.eps;

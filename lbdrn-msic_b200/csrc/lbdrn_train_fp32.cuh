@@ -53,6 +53,7 @@ struct TrainArgs {
   int pf_off, pf_stride;   // byte offset of the landing boxes inside dynamic shared memory, bytes per pixel
   uint16_t* wimg;          // fp16-split kernel: global image of the shared-memory weight operands (hi | lo halves per layer,
                            // padding zero), kept current by the Adam phase so that a reload is one asynchronous copy
+  int l2_hints;            // planes larger than L2: prefetch.global.L2 hints for the next step's neighbourhoods
   unsigned* gbar;          // two monotonic arrival counters of the split grid barriers (zeroed before every launch)
   const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
                            // torch's python floats (two pow() per step in fp64 cost ~3k cycles of every step on the device)
@@ -611,6 +612,14 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   const size_t pf_total = (size_t)C * net.buf_rows * net.W;     // bytes in the MSB buffer
   const bool idx32 = (long long)net.H * net.W < (1ll << 31);
   // stage A (start of step s): coordinates of the pixels of step s+1
+  // the permutation entry itself is read one step earlier still (its global-memory latency was exposed at the head of every step)
+  long long pf_idx = 0;
+  auto prefetch_perm = [&](int s_nn) {
+    if (!pf_enabled || s_nn >= a.n_steps || tid >= NPIX) return;
+    const long long o = (long long)s_nn * a.bs + (long long)blockIdx.x * NPIX + tid;
+    if (o < a.n_perm) pf_idx = __ldg(a.perm + o);
+  };
+  prefetch_perm(1);
   auto prefetch_index = [&](int s_next) {
     pf_none = true;
     if (!pf_enabled || s_next >= a.n_steps) return;
@@ -623,11 +632,39 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     if (tid < NPIX) {
       int y = -1, x = 0;                                           // y = -1: padding lane
       if (ch * NPIX + tid < Bn) {
-        const long long idx = a.perm[b0n + (long long)ch * NPIX + tid];
+        const long long idx = pf_idx;                              // = a.perm[b0n + ch * NPIX + tid], requested a step ago
         if (idx32) { y = (int)((unsigned)idx / (unsigned)net.W); x = (int)((unsigned)idx - (unsigned)y * (unsigned)net.W); }
         else { y = (int)(idx / net.W); x = (int)(idx - (long long)y * net.W); }
       }
       s_ny[tid] = y; s_nx[tid] = x;
+    }
+  };
+  // stage A' (head of step s, once the coordinates are in shared memory): L2 prefetch hints for the same bytes.  At 8192^2
+  // the planes (2 x 268 MB) do not fit in L2, every window row of a random pixel is a DRAM (and TLB) miss, and the register
+  // loads of stage B were bound by the number of misses an SM can keep in flight (issue phase 7k cycles vs 3k at 2048^2).
+  // The hints hold no registers or scoreboard entries and have a whole step to land.
+  auto prefetch_l2 = [&]() {
+    if (pf_none || tma_on || !a.l2_hints) return;
+    const int pp = tid & (NPIX - 1), share = tid / NPIX, c = share >> 1, odd = share & 1;
+    const int gy = s_ny[pp], gx = s_nx[pp];
+    if (gy < 0 || c >= C) return;
+    const size_t plane = (size_t)c * net.buf_rows;
+    const uint8_t* base = (const uint8_t*)a.msb;
+    const int x0 = gx >= PD ? gx - PD : 0, x1 = gx + PD < net.W ? gx + PD : net.W - 1;
+    const int r0 = odd ? 3 : 0, r1 = odd ? PN : 3;
+    if (!odd) {
+      const uint8_t* q = (const uint8_t*)a.lsb + (plane + (gy - net.buf_row0)) * net.W + gx;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int dy = r0 + q;
+      if (dy < r1) {
+        const uint8_t* row = base + (plane + (reflect_clamp(gy + dy - PD, net.H) - net.buf_row0)) * net.W;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + x0));
+        if ((reinterpret_cast<uintptr_t>(row + x0) ^ reinterpret_cast<uintptr_t>(row + x1)) >> 5)     // window spans two sectors
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(row + x1));
+      }
     }
   };
   // stage B (after the first grid sync of step s): request the words.  Rows of the window this thread owns: band = share / 2;
@@ -766,6 +803,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   for (int s = 0; s < a.n_steps; ++s) {
     if (tid == 0) s_sse = 0.f;
     prefetch_index(s + 1);
+    prefetch_perm(s + 2);
     if (tid == 32 && a.mode == TRAIN_FUSED) {
       if (a.adam_tab) {
         const float2 t2 = a.adam_tab[s];
@@ -788,6 +826,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     if (s > 0 && tid == 0) gbar_wait(a.gbar + 1, (unsigned)s * gridDim.x);
     __syncthreads();
     LBDRN_PHASE(7)    // wait for the Adam phase of every CTA (second barrier of the previous step)
+    prefetch_l2();
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (H2) {
       // fp32 part: hidden biases, output layer
