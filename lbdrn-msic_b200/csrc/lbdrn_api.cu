@@ -179,6 +179,9 @@ struct LbdrnTrain {
   TrainPlan plan;
   int dev = 0, sms = 0;
   float *params = nullptr, *wpack = nullptr, *m = nullptr, *v = nullptr, *partial = nullptr;
+  uint32_t *imsb = nullptr, *ilsb = nullptr;   // band-interleaved copies of the uint8 planes for the neighbourhood gather
+  size_t i_npix = 0;
+  bool i_failed = false;           // allocation failed once: gather from the CHW planes
   unsigned* gbar = nullptr;        // arrival counters of the training kernel's split grid barriers
   uint16_t* wimg = nullptr;        // fp16-split training kernel: image of its shared-memory weight operands (padding stays zero)
   float2* adam_tab = nullptr;      // per-step Adam scalars of the launch in flight (ring of two: launches may be queued)
@@ -363,7 +366,7 @@ int32_t lbdrn_train_destroy(LbdrnTrain* t) {
   if (!t) return LBDRN_OK;
   cudaDeviceSynchronize();
   cudaFree(t->params); cudaFree(t->wpack); cudaFree(t->m); cudaFree(t->v); cudaFree(t->partial); cudaFree(t->adam_tab);
-  cudaFree(t->wimg); cudaFree(t->gbar);
+  cudaFree(t->wimg); cudaFree(t->gbar); cudaFree(t->imsb); cudaFree(t->ilsb);
   delete t;
   return LBDRN_OK;
 }
@@ -415,6 +418,36 @@ int32_t lbdrn_train_steps(LbdrnTrain* t, const void* msb_dev, const void* lsb_de
     float2* dst = t->adam_tab + (size_t)(t->adam_tab_slot++ & 1u) * t->adam_tab_n;
     CUDA_TRY(cudaMemcpyAsync(dst, tab.data(), (size_t)n_steps * sizeof(float2), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     a.adam_tab = dst;
+  }
+  {
+    // Band-interleaved copies of the planes (uint8, <= 4 bands, 5x5 colour windows: the configurations the kernel's
+    // neighbourhood prefetch is specialised for), rebuilt before every launch -- the caller owns the planes and may have
+    // changed them; 2 x (C + 4) bytes per pixel of HBM traffic, ~0.3 ms at 8192^2 against ~200 ms per epoch.
+    const Net& n = t->net;
+    const bool eligible = !n.msb_u16 && !n.lsb_u16 && n.C <= 4 && n.n == 5 && n.nco == 0 && n.ncol != 0 &&
+                          getenv("LBDRN_TRAIN_CHW") == nullptr && !t->plan.pf_stride;
+    const size_t npix = (size_t)n.buf_rows * n.W;
+    if (eligible && !t->i_failed && t->i_npix < npix) {
+      cudaFree(t->imsb); cudaFree(t->ilsb);
+      t->imsb = t->ilsb = nullptr; t->i_npix = 0;
+      cudaError_t e = cudaMalloc(&t->imsb, npix * 4 + 64);          // + slack: rows are read as aligned 32-byte pairs
+      if (e == cudaSuccess) e = cudaMalloc(&t->ilsb, npix * 4 + 64);
+      if (e == cudaSuccess) e = cudaMemsetAsync(t->imsb + npix, 0, 64, (cudaStream_t)stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(t->ilsb + npix, 0, 64, (cudaStream_t)stream);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(t->imsb); cudaFree(t->ilsb);
+        t->imsb = t->ilsb = nullptr; t->i_failed = true;            // not an error: the CHW gather needs no extra memory
+      } else {
+        t->i_npix = npix;
+      }
+    }
+    if (eligible && t->imsb) {
+      launch_interleave_u8(msb_dev, n.C, npix, t->imsb, t->sms, (cudaStream_t)stream);
+      launch_interleave_u8(lsb_dev, n.C, npix, t->ilsb, t->sms, (cudaStream_t)stream);
+      CUDA_TRY(cudaGetLastError());
+      a.imsb = t->imsb; a.ilsb = t->ilsb;
+    }
   }
   if (t->plan.pf_stride) {
     // TMA maps of the planes for the neighbourhood gather (nullptr when the buffers are not TMA-addressable)

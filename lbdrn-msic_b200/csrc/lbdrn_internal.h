@@ -51,6 +51,7 @@ struct TrainPlan {
 struct TrainArgs;
 int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& plan);
 int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st);
+void launch_interleave_u8(const void* planes, int C, size_t npix, uint32_t* out, int sms, cudaStream_t st);
 void launch_adam_apply(const Net& n, const float* grad, float* params, float* wpack, float* m, float* v, float omb1,
                        float omb2, float beta2, float eps, float step_size, float bc2_sqrt, cudaStream_t st);
 

@@ -125,6 +125,41 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
   return LBDRN_OK;
 }
 
+// CHW uint8 planes -> one 32-bit word per pixel (band c in byte c, unused bytes zero).  HBM-bound: C + 4 bytes per pixel.
+// VEC: 4 pixels per thread (one 32-bit load per plane, one 16-byte store) when the plane length is a multiple of 4.
+template <bool VEC>
+static __global__ void interleave_u8_kernel(const uint8_t* __restrict__ planes, int C, size_t npix, uint32_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    const size_t n4 = npix >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      for (int c = 0; c < C; ++c) w[c] = reinterpret_cast<const uint32_t*>(planes + (size_t)c * npix)[i];
+      const uint32_t t01 = __byte_perm(w[0], w[1], 0x5140), t23 = __byte_perm(w[2], w[3], 0x5140);   // pixels 0, 1: bands (0,1) / (2,3)
+      const uint32_t u01 = __byte_perm(w[0], w[1], 0x7362), u23 = __byte_perm(w[2], w[3], 0x7362);   // pixels 2, 3
+      uint4 o;
+      o.x = __byte_perm(t01, t23, 0x5410);
+      o.y = __byte_perm(t01, t23, 0x7632);
+      o.z = __byte_perm(u01, u23, 0x5410);
+      o.w = __byte_perm(u01, u23, 0x7632);
+      reinterpret_cast<uint4*>(out)[i] = o;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+      uint32_t w = 0u;
+      for (int c = 0; c < C; ++c) w |= (uint32_t)planes[(size_t)c * npix + i] << (8 * c);
+      out[i] = w;
+    }
+  }
+}
+
+void launch_interleave_u8(const void* planes, int C, size_t npix, uint32_t* out, int sms, cudaStream_t st) {
+  const bool vec = npix % 4 == 0 && reinterpret_cast<uintptr_t>(planes) % 4 == 0;
+  if (vec) interleave_u8_kernel<true><<<sms * 8, 256, 0, st>>>((const uint8_t*)planes, C, npix, out);
+  else interleave_u8_kernel<false><<<sms * 8, 256, 0, st>>>((const uint8_t*)planes, C, npix, out);
+  ++g_launches;
+}
+
 void launch_adam_apply(const Net& n, const float* grad, float* params, float* wpack, float* m, float* v, float omb1,
                        float omb2, float beta2, float eps, float step_size, float bc2_sqrt, cudaStream_t st) {
   adam_apply_kernel<<<(n.P + 255) / 256, 256, 0, st>>>(n, grad, params, wpack, m, v, omb1, omb2, beta2, eps, step_size,

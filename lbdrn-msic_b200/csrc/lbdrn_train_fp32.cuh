@@ -53,6 +53,8 @@ struct TrainArgs {
   int pf_off, pf_stride;   // byte offset of the landing boxes inside dynamic shared memory, bytes per pixel
   uint16_t* wimg;          // fp16-split kernel: global image of the shared-memory weight operands (hi | lo halves per layer,
                            // padding zero), kept current by the Adam phase so that a reload is one asynchronous copy
+  const uint32_t* imsb;    // band-interleaved copies of the uint8 planes (one 32-bit word per pixel, band c in byte c), built
+  const uint32_t* ilsb;    // by the library before each launch; nullptr: gather from the CHW planes
   int l2_hints;            // planes larger than L2: prefetch.global.L2 hints for the next step's neighbourhoods
   unsigned* gbar;          // two monotonic arrival counters of the split grid barriers (zeroed before every launch)
   const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
@@ -735,6 +737,88 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       }
     }
   };
+  // ---- interleaved variant (a.imsb): a window row of ALL bands is 5 consecutive 32-bit words, i.e. inside two aligned 16 B
+  // loads -- 11 requests per pixel (5 rows x 2 + labels) + 4 centre words instead of ~48, and a third of the DRAM sectors.
+  // Thread share = tid / NPIX: shares 0-4 own window row dy = share (8 words + the centre word), share 5 the labels.
+  const bool il = pf_enabled && a.imsb != nullptr && !tma_on;
+  // registers shared with the CHW variant: pf_w[3][2] + il_w6, il_w7 = the aligned 32 bytes holding the row (border pixel: the
+  // 5 words, packed); pf_aux = centre pixel (rows != D) or label word (share 5)
+  uint32_t il_w6 = 0u, il_w7 = 0u;
+  int il_o = 0;                                           // word offset of the window inside the 8 words
+  auto il_row_ptr = [&](int gy, int dy) {
+    return a.imsb + (size_t)(reflect_clamp(gy + dy - PD, net.H) - net.buf_row0) * net.W;
+  };
+  auto prefetch_l2_il = [&]() {
+    if (pf_none || !a.l2_hints) return;
+    const int pp = tid & (NPIX - 1), share = tid / NPIX;
+    const int gy = s_ny[pp], gx = s_nx[pp];
+    if (gy < 0 || share > PN) return;
+    if (share == PN) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ilsb + (size_t)(gy - net.buf_row0) * net.W + gx));
+      return;
+    }
+    const uint32_t* row = il_row_ptr(gy, share);
+    const int x0 = gx >= PD ? gx - PD : 0, x1 = gx + PD < net.W ? gx + PD : net.W - 1;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + x0));
+    if ((reinterpret_cast<uintptr_t>(row + x0) ^ reinterpret_cast<uintptr_t>(row + x1)) >> 5)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + x1));
+  };
+  auto prefetch_issue_il = [&]() {
+    pf_have = !pf_none;
+    if (pf_none) return;
+    const int pp = tid & (NPIX - 1), share = tid / NPIX;
+    pf_gy = s_ny[pp]; pf_gx = s_nx[pp];
+    pf_state = 3;
+    if (pf_gy < 0 || share > PN) return;
+    const int gy = pf_gy, gx = pf_gx;
+    pf_state = 1;
+    if (share == PN) {                                              // labels of all bands: one word
+      pf_aux = a.ilsb[(size_t)(gy - net.buf_row0) * net.W + gx];
+      return;
+    }
+    const uint32_t* row = il_row_ptr(gy, share);
+    if (share != PD) pf_aux = a.imsb[(size_t)(gy - net.buf_row0) * net.W + gx];
+    if (gx >= PD && gx + PD < net.W) {
+      // the aligned 32 bytes around the 20-byte window (the buffers carry 32 bytes of slack behind the last pixel)
+      const uint32_t* p = row + gx - PD;
+      const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
+      il_o = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+      const uint4 qa = q[0], qb = q[1];
+      pf_w[0][0] = qa.x; pf_w[0][1] = qa.y; pf_w[1][0] = qa.z; pf_w[1][1] = qa.w;
+      pf_w[2][0] = qb.x; pf_w[2][1] = qb.y; il_w6 = qb.z; il_w7 = qb.w;
+    } else {                                                        // reflected columns: word by word
+      il_o = 0;
+      pf_w[0][0] = row[reflect_clamp(gx - 2, net.W)]; pf_w[0][1] = row[reflect_clamp(gx - 1, net.W)]; pf_w[1][0] = row[gx];
+      pf_w[1][1] = row[reflect_clamp(gx + 1, net.W)]; pf_w[2][0] = row[reflect_clamp(gx + 2, net.W)];
+    }
+  };
+  auto prefetch_commit_il = [&]() {
+    const int pp = tid & (NPIX - 1), share = tid / NPIX;
+    const bool ok = pf_state == 1;
+    if (tid < NPIX) s_valid[tid] = pf_gy >= 0;
+    if (share == PN) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) Tl[c * LDP + pp] = ok ? __fdiv_rn((float)((pf_aux >> (8 * c)) & 255u), net.qmax) : 0.f;
+    } else if (share < PN) {
+      // window words v[dx] = w[il_o + dx] without indexing registers dynamically
+      const uint32_t w[8] = {pf_w[0][0], pf_w[0][1], pf_w[1][0], pf_w[1][1], pf_w[2][0], pf_w[2][1], il_w6, il_w7};
+      uint32_t v[PN];
+#pragma unroll
+      for (int dx = 0; dx < PN; ++dx)
+        v[dx] = il_o == 0 ? w[dx] : (il_o == 1 ? w[dx + 1] : (il_o == 2 ? w[dx + 2] : w[dx + 3]));
+      const uint32_t cw = share == PD ? v[PD] : pf_aux;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < C) {
+          const float ctr = net.relative ? s_quot[(cw >> (8 * c)) & 255u] : 0.f;
+          float* d = X + pp + (size_t)((c * PN + share) * PN) * LDP;
+#pragma unroll
+          for (int dx = 0; dx < PN; ++dx) d[(size_t)dx * LDP] = ok ? s_quot[(v[dx] >> (8 * c)) & 255u] - ctr : 0.f;
+        }
+      }
+    }
+  };
   // head of step s+1: registers -> X / Tl / s_valid (the values the plain gather would write)
   auto prefetch_commit = [&]() {
     const int pp = tid & (NPIX - 1), share = tid / NPIX, c = share >> 1, odd = share & 1;
@@ -819,14 +903,14 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     // to shared memory BEFORE waiting for the other CTAs' Adam phase (the second half of the split barrier).
     const bool early = pf_have;                       // uniform: a function of (step, CTA) only
     if (early) {
-      prefetch_commit();
+      if (il) prefetch_commit_il(); else prefetch_commit();
       pf_have = false;
     }
     LBDRN_PHASE(13)   // commit of the prefetched neighbourhoods
     if (s > 0 && tid == 0) gbar_wait(a.gbar + 1, (unsigned)s * gridDim.x);
     __syncthreads();
     LBDRN_PHASE(7)    // wait for the Adam phase of every CTA (second barrier of the previous step)
-    prefetch_l2();
+    if (il) prefetch_l2_il(); else prefetch_l2();
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (H2) {
       // fp32 part: hidden biases, output layer
@@ -1427,7 +1511,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     // next step's neighbourhood loads, between the two halves of the barrier: in flight while the other CTAs finish and
     // during the reduction / Adam phase (itself L2-latency-bound).  Only thread 0 fences, before its own loads are issued
     // (a membar waits for the thread's outstanding loads).
-    prefetch_issue();
+    if (il) prefetch_issue_il(); else prefetch_issue();
     LBDRN_PHASE(14)   // issue of the next step's neighbourhood loads
     if (tid == 0) gbar_wait(a.gbar, (unsigned)(s + 1) * gridDim.x);
     __syncthreads();
