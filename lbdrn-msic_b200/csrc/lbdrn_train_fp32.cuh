@@ -74,13 +74,15 @@ __device__ __forceinline__ float row_sum(const float* __restrict__ row) {
 
 template <int NPIX>
 __device__ __forceinline__ float row_dot(const float* __restrict__ a, const float* __restrict__ b) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f;          // two chains: the 64-term dot product was one dependent FFMA chain
 #pragma unroll
-  for (int p = 0; p < NPIX; p += 4) {
+  for (int p = 0; p < NPIX; p += 8) {
     float4 x = *reinterpret_cast<const float4*>(a + p), y = *reinterpret_cast<const float4*>(b + p);
-    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    float4 x2 = *reinterpret_cast<const float4*>(a + p + 4), y2 = *reinterpret_cast<const float4*>(b + p + 4);
+    s0 = fmaf(x.x, y.x, s0); s0 = fmaf(x.y, y.y, s0); s0 = fmaf(x.z, y.z, s0); s0 = fmaf(x.w, y.w, s0);
+    s1 = fmaf(x2.x, y2.x, s1); s1 = fmaf(x2.y, y2.y, s1); s1 = fmaf(x2.z, y2.z, s1); s1 = fmaf(x2.w, y2.w, s1);
   }
-  return s;
+  return s0 + s1;
 }
 
 // index of parameter i inside the packed copy (hidden weights transposed)
@@ -375,6 +377,7 @@ __device__ __forceinline__ void grad_weight_h2(uint32_t g_hi, uint32_t g_lo, uin
   const int g = lane >> 2, t = lane & 3, r0 = 16 * (warp % MT);
   // A tiles: [r0, p0] [r0+8, p0] [r0, p0+8] [r0+8, p0+8]
   const uint32_t a_off = (uint32_t)((r0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLDH + 8 * (lane >> 4)) * 2u;
+  const bool pair_ok = (Kin & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
   for (int nbase = warp / MT; nbase < nq; nbase += NW * MAXN) {
     float acc[MAXN][4];
 #pragma unroll
@@ -408,13 +411,27 @@ __device__ __forceinline__ void grad_weight_h2(uint32_t g_hi, uint32_t g_lo, uin
     for (int j = 0; j < MAXN; ++j) {
       const int nt = nbase + NW * j;
       if (nt < nq) {
+        if (pair_ok) {
+          // c0 | c1 and c2 | c3 are neighbours in a row of the gradient block: 8-byte stores, each warp store fills 8 sectors
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = r0 + g + (e >> 1) * 8, q = 8 * nt + 2 * t + (e & 1);
-          if (q < Kin) {
-            float* d = dst + (size_t)r * Kin + q;
-            const float v = acc[j][e] * inv;
-            *d = first ? v : *d + v;
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int r = r0 + g + e2 * 8, q = 8 * nt + 2 * t;
+            if (q < Kin) {
+              float2* d = reinterpret_cast<float2*>(dst + (size_t)r * Kin + q);
+              float2 v = make_float2(acc[j][2 * e2] * inv, acc[j][2 * e2 + 1] * inv);
+              if (!first) { const float2 o = *d; v.x += o.x; v.y += o.y; }
+              *d = v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = r0 + g + (e >> 1) * 8, q = 8 * nt + 2 * t + (e & 1);
+            if (q < Kin) {
+              float* d = dst + (size_t)r * Kin + q;
+              const float v = acc[j][e] * inv;
+              *d = first ? v : *d + v;
+            }
           }
         }
       }
