@@ -930,19 +930,23 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     if (il) prefetch_l2_il(); else prefetch_l2();
     // ---- (re)load weights ----------------------------------------------------------------------------
     if (H2) {
-      // fp32 part: hidden biases, output layer
-      const int nb = L * BC, nwo = C * BC;
-      for (int i = tid; i < nb + nwo + C; i += THREADS) {
-        const int src = i < nb ? net.boff[i / BC] + i % BC : (i < nb + nwo ? net.woff[L] + (i - nb) : net.boff[L] + (i - nb - nwo));
-        wsm[i] = __ldcg(a.params + src);
-      }
       const bool from_image = s > 0 && a.wimg != nullptr;           // the Adam phase of step s-1 wrote every weight's halves
+      // fp32 part (hidden biases, output layer): requested FIRST (behind 49 KB of copies per SM its round trip tripled),
+      // stored after the copies have been issued
+      const int nb = L * BC, nwo = C * BC;
+      auto lite_src = [&](int i) {
+        return i < nb ? net.boff[i / BC] + i % BC : (i < nb + nwo ? net.woff[L] + (i - nb) : net.boff[L] + (i - nb - nwo));
+      };
+      float lite0 = 0.f;
+      if (tid < nb + nwo + C) lite0 = __ldcg(a.params + lite_src(tid));
       if (from_image) {
         const int n16 = (int)((wh_of(L) - wh_base) >> 4);           // the image is the shared layout, byte for byte
         for (int i = tid; i < n16; i += THREADS)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wh_base + 16u * i),
                        "l"(reinterpret_cast<const uint4*>(a.wimg) + i) : "memory");
       }
+      if (tid < nb + nwo + C) wsm[tid] = lite0;
+      for (int i = tid + THREADS; i < nb + nwo + C; i += THREADS) wsm[i] = __ldcg(a.params + lite_src(i));
       // first step of a launch: hidden weights from the master copy, natural [unit][input] layout of the reference ->
       // scaled hi | lo halves, two inputs per thread
       for (int l = 0; l < (from_image ? 0 : L); ++l) {

@@ -96,6 +96,33 @@ def read_base_like(msb):
     return np.ascontiguousarray(msb)
 
 
+@pytest.mark.parametrize("variant", ["default", "l2hints", "chw", "tf32"])
+def test_odd_scene_multi_chunk_batches_follow_the_oracle(variant, monkeypatch):
+    """A 4x150x131 scene (odd width: scalar re-pack of the planes, every alignment of a window row inside its two 16-byte
+    loads, reflected borders) trained with bs=16384 > 128 chunks x 64 pixels (every CTA takes two chunks of a step and
+    accumulates its gradient partial) against the oracle's loop on the same seed; also with the L2 hints forced, the
+    CHW gather and the 3xTF32 GEMMs selected."""
+    from synth_scene import make_scene
+    if variant != "default":
+        monkeypatch.setenv({"l2hints": "LBDRN_TRAIN_L2HINTS", "chw": "LBDRN_TRAIN_CHW", "tf32": "LBDRN_TRAIN_TF32"}[variant], "1")
+    K, D, bc, nl, bs, epochs = 5, 2, 64, 2, 16384, 3
+    img = make_scene(4, 150, 131, bits=12, seed=7)
+    msb, lsb = O.split_msb_lsb(img, K)
+    torch.manual_seed(2024)
+    ref = O.train(msb, lsb, D, bc, nl, 1e-3, bs, epochs)
+    torch.manual_seed(2024)
+    model = LBDRNModel(4 * (2 * D + 1) ** 2, bc, 4, nl)
+    scene = F.DeviceScene.from_image(img, K)
+    tr = F.FusedTrainer(model, scene, D, 1e-3, bs, epochs, flags=F.Flags())
+    res = tr.run()
+    tr.close()
+    got, want = np.array(res["losses"]), np.array(ref["losses"])
+    assert got.shape == want.shape == (epochs * 2,)
+    assert np.max(np.abs(got - want) / want) < 2e-4, (got, want)
+    assert np.allclose(res["val_mse"], ref["mses"], rtol=2e-4)
+    assert res["best_epoch"] == ref["best_epoch"]
+
+
 def test_partial_last_batch_and_device_sampler():
     meta, img, _, _, model, scene, fl = _setup()
     N = meta["H"] * meta["W"]                                     # 7680 = 15 * 512: use bs=1000 -> ragged last batch
