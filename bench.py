@@ -270,6 +270,17 @@ def run_ours(args):
                 "algorithmic_flop_per_pixel": FLOP_PER_PX,
                 "hbm": {"achieved_gbs": SIDE * SIDE * HBM_BYTES_PER_PX / (kern_avg_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
                         "algorithmic_bytes_per_pixel": HBM_BYTES_PER_PX}}
+    if has_tc:
+        # the resource that actually binds this kernel: instruction issue on the CUDA cores -- the sines of
+        # the reference's activation, their fp16 hi+lo split and the feature build; the tensor and HBM figures above are
+        # the ones SURVEY 8d asks for.  2516 thread-instructions per pixel = smsp__inst_executed.sum * 32 / pixels of the
+        # committed capture (profiles/r1b_ncu_tc_decode_summary.txt); ceiling = 148 SMs x 128 lanes x SM clock / that.
+        instr_px = 2516
+        ceil_gpix = 148 * 128 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6 / instr_px / 1e9
+        roofline["issue"] = {"thread_instr_per_pixel": instr_px, "ceiling_gpix_s": ceil_gpix,
+                             "achieved_gpix_s": SIDE * SIDE / (kern_avg_ms * 1e-3) / 1e9,
+                             "frac": SIDE * SIDE / (kern_avg_ms * 1e-3) / 1e9 / ceil_gpix,
+                             "source": "ncu smsp__inst_executed.sum of the committed capture / pixels"}
 
     # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ------------------------------------
     base_host = scene.msb.cpu().pin_memory()
