@@ -109,6 +109,14 @@ int32_t lbdrn_split(const uint16_t* img_dev, int64_t n, int32_t K, int32_t msb_d
  * result written to *max_dev (device uint32, must be zero-initialised by the caller). */
 int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_t* max_dev, void* stream);
 
+/* ---- a10: batch sampling on the device (encode.py:69-70: one uniform random permutation of the N pixels per epoch) ------
+ * out_dev[i], i < n, is a pseudo-random permutation of 0..n-1 chosen by `seed`: a 6-round Feistel network over the
+ * ceil(log2 n) index bits (murmur3-finalizer round function keyed from the seed by splitmix64) with cycle walking for
+ * indices that land >= n.  A bijection by construction (every pixel exactly once per epoch, like the DataLoader's
+ * RandomSampler); the ORDER is not torch's -- callers that need the reference's exact batches pass the DataLoader's own
+ * permutation to lbdrn_train_steps instead.  8 bytes written per element, no sort, no scratch memory. */
+int32_t lbdrn_randperm(int64_t n, uint64_t seed, int64_t* out_dev, void* stream);
+
 /* ---- a16: quality read-out (decode.py:216): *sse_dev (device uint64, zero-initialised by the caller) += sum over n
  * elements of (a-b)^2 for two uint16 images.  Integer accumulation: exact and order-independent. */
 int32_t lbdrn_sse_u16(const uint16_t* a_dev, const uint16_t* b_dev, int64_t n, uint64_t* sse_dev, void* stream);

@@ -159,6 +159,35 @@ __global__ void max_shifted_kernel(const uint16_t* __restrict__ img, long long n
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
+// a10: pseudo-random permutation of 0..n-1 without a sort: an unbalanced Feistel network over the index bits (each half is
+// XORed with a keyed hash of the other: invertible whatever the hash), cycle-walked into [0, n).  2^bits < 2n, so an index
+// needs fewer than two walks on average.
+constexpr int kRandpermRounds = 6;
+struct RandpermKeys {
+  uint32_t key[kRandpermRounds];
+  int bits_lo, bits_hi;
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {    // murmur3 finalizer
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+static __global__ void randperm_kernel(long long n, RandpermKeys k, int64_t* __restrict__ out) {
+  const uint32_t mlo = (uint32_t)((1ull << k.bits_lo) - 1ull), mhi = (uint32_t)((1ull << k.bits_hi) - 1ull);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long x = (unsigned long long)i;
+    do {
+      uint32_t lo = (uint32_t)x & mlo, hi = (uint32_t)(x >> k.bits_lo) & mhi;
+#pragma unroll
+      for (int r = 0; r < kRandpermRounds; r += 2) {
+        hi ^= mix32(lo ^ k.key[r]) & mhi;
+        lo ^= mix32(hi ^ k.key[r + 1]) & mlo;
+      }
+      x = ((unsigned long long)hi << k.bits_lo) | lo;
+    } while (x >= (unsigned long long)n);
+    out[i] = (int64_t)x;
+  }
+}
+
 __global__ void sse_u16_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, long long n,
                                unsigned long long* out) {
   unsigned long long acc = 0;
@@ -249,6 +278,30 @@ int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_
   long long blocks = (n + 2047) / 2048;
   if (blocks > 148 * 8) blocks = 148 * 8;
   max_shifted_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img_dev, n, K, max_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+int32_t lbdrn_randperm(int64_t n, uint64_t seed, int64_t* out_dev, void* stream) {
+  if (!out_dev || n <= 0 || n > ((int64_t)1 << 62)) return fail(LBDRN_E_INVALID, "lbdrn_randperm: bad argument");
+  RandpermKeys k;
+  int bits = 1;
+  while (((uint64_t)1 << bits) < (uint64_t)n) ++bits;
+  if (bits < 2) bits = 2;                                   // two non-empty halves
+  k.bits_lo = bits / 2;
+  k.bits_hi = bits - k.bits_lo;
+  uint64_t x = seed;
+  for (int r = 0; r < kRandpermRounds; ++r) {               // splitmix64
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    k.key[r] = (uint32_t)((z ^ (z >> 31)) >> 16);
+  }
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  randperm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n, k, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return LBDRN_OK;

@@ -123,6 +123,28 @@ def test_odd_scene_multi_chunk_batches_follow_the_oracle(variant, monkeypatch):
     assert res["best_epoch"] == ref["best_epoch"]
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 64, 1000, (1 << 20) + 7, 4096 * 4096])
+def test_device_permutation_is_a_bijection(n):
+    """lbdrn_randperm (the device sampler of a10): every index exactly once, different seeds give different orders, and the
+    order looks shuffled (no fixed points beyond chance, mean displacement ~ n/3 like a uniform permutation)."""
+    lib = cabi.load()
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    perms = []
+    for seed in (1, 2, 0xDEADBEEFCAFEF00D):
+        cabi.check(lib.lbdrn_randperm(n, seed, cabi.ptr(out), cabi.stream_ptr()))
+        assert torch.equal(torch.sort(out).values, torch.arange(n, device="cuda"))
+        perms.append(out.clone())
+    if n >= 1000:
+        assert not torch.equal(perms[0], perms[1]) and not torch.equal(perms[1], perms[2])
+        idx = torch.arange(n, device="cuda")
+        for p in perms:
+            assert int((p == idx).sum()) < 12                      # a uniform permutation has ~1 fixed point (Poisson(1))
+            disp = (p - idx).abs().double().mean().item() / n
+            assert 0.30 < disp < 0.37                             # E|i - pi(i)| = n/3
+            # neighbouring outputs are unrelated: the lag-1 differences spread like those of independent draws
+            assert ((p[1:] - p[:-1]).abs().double().mean().item() / n) > 0.30
+
+
 def test_training_is_deterministic_run_to_run():
     """Same seed, same permutations: three runs of the fused kernel on a 512x512 scene (all 128 CTAs busy, 64 optimiser
     steps, split grid barriers, prefetch pipeline) give bit-identical losses and parameters -- the gradient reduction is
