@@ -231,6 +231,50 @@ def loader_permutation(n):
     return torch.randperm(n, generator=g)
 
 
+def device_permutation(n, seed, rounds=6):
+    """CPU restatement of the library's own device sampler `lbdrn_randperm` (include/lbdrn.h; NOT a reference function:
+    the reference shuffles with torch's RandomSampler, encode.py:69-70, which `loader_permutation` above restates).
+    A keyed Feistel network over the ceil(log2 n) index bits -- each half XORed with a murmur3-finalizer hash of the
+    other, round keys from splitmix64(seed) -- cycle-walked into [0, n).  Integer arithmetic: the GPU result must be
+    bit-identical (tests/test_gpu_train.py)."""
+    m64 = (1 << 64) - 1
+    keys, x = [], seed & m64
+    for _ in range(rounds):
+        x = (x + 0x9E3779B97F4A7C15) & m64
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m64
+        keys.append(np.uint32(((z ^ (z >> 31)) >> 16) & 0xFFFFFFFF))
+    bits = 1
+    while (1 << bits) < n:
+        bits += 1
+    bits = max(bits, 2)
+    bl = bits // 2
+    mlo, mhi = np.uint32((1 << bl) - 1), np.uint32((1 << (bits - bl)) - 1)
+
+    def mix(h):
+        h = h ^ (h >> np.uint32(16))
+        h = h * np.uint32(0x85EBCA6B)
+        h = h ^ (h >> np.uint32(13))
+        h = h * np.uint32(0xC2B2AE35)
+        return h ^ (h >> np.uint32(16))
+
+    out = np.empty(n, dtype=np.int64)
+    todo, cur = np.arange(n), np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        while len(todo):
+            lo = (cur & np.uint64(mlo)).astype(np.uint32)
+            hi = ((cur >> np.uint64(bl)) & np.uint64(mhi)).astype(np.uint32)
+            for r in range(0, rounds, 2):
+                hi = hi ^ (mix(lo ^ keys[r]) & mhi)
+                lo = lo ^ (mix(hi ^ keys[r + 1]) & mlo)
+            cur = (hi.astype(np.uint64) << np.uint64(bl)) | lo.astype(np.uint64)
+            done = cur < n
+            out[todo[done]] = cur[done].astype(np.int64)
+            todo, cur = todo[~done], cur[~done]
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # a7-a11: the encoder's optimisation loop (encode.py:67-117, modified_ignite_engine.py:18-27,38-43)
 # ----------------------------------------------------------------------------------------------------------

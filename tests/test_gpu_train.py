@@ -134,6 +134,8 @@ def test_device_permutation_is_a_bijection(n):
         cabi.check(lib.lbdrn_randperm(n, seed, cabi.ptr(out), cabi.stream_ptr()))
         assert torch.equal(torch.sort(out).values, torch.arange(n, device="cuda"))
         perms.append(out.clone())
+        if n <= (1 << 20) + 7:                                     # integer work: bit-exact against the restatement
+            assert np.array_equal(out.cpu().numpy(), O.device_permutation(n, seed))
     if n >= 1000:
         assert not torch.equal(perms[0], perms[1]) and not torch.equal(perms[1], perms[2])
         idx = torch.arange(n, device="cuda")

@@ -104,3 +104,19 @@ def test_lr_schedule():
     assert [O.lr_at_epoch(1e-3, e, 10) for e in (1, 3, 4, 6, 7, 9, 10)] == pytest.approx(
         [1e-3, 1e-3, 1e-4, 1e-4, 1e-5, 1e-5, 1e-6], rel=1e-12)
     assert O.lr_at_epoch(1e-3, 2, 1) == pytest.approx(1e-4)     # step_size = max(1, int(1/3)) = 1
+
+
+KAT_PERM_10_SEED1 = [9, 8, 0, 1, 6, 7, 3, 5, 2, 4]
+KAT_PERM_1000_HEAD = [425, 988, 249, 411, 710, 149, 364, 339]
+
+
+def test_device_permutation_restatement_is_a_bijection_with_known_answers():
+    """The restatement of lbdrn_randperm: a permutation for every n, seed-dependent, and pinned by known answers (so that
+    the GPU parity test compares against a fixed target, not against a moving one)."""
+    import lbdrn_oracle as O
+    for n in (1, 2, 3, 5, 64, 1000, 4099):
+        p = O.device_permutation(n, 12345)
+        assert np.array_equal(np.sort(p), np.arange(n))
+    assert not np.array_equal(O.device_permutation(1000, 1), O.device_permutation(1000, 2))
+    assert O.device_permutation(10, 1).tolist() == KAT_PERM_10_SEED1
+    assert O.device_permutation(1000, 0xDEADBEEFCAFEF00D)[:8].tolist() == KAT_PERM_1000_HEAD
