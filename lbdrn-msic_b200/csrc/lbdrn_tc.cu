@@ -173,9 +173,12 @@ constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+
 // NWG=2 (TMA-addressable inputs, exact weights): two independent warpgroups share ONE copy of the weights, 2 CTAs/SM
 // = 16 resident warps per SM instead of 12; each warpgroup has its own A region, staging buffers, mbarriers and TMEM
 // columns and synchronises on its own named barrier.
+// NWG=4 (TMA-addressable inputs, low-order weight operands resident: the per-epoch evaluation of fp32 weights): the weight
+// block is 47 KB with the lo halves, so one CTA per SM with FOUR warpgroups sharing it keeps 16 warps resident where two
+// single-warpgroup CTAs kept 8 (evaluation of an 8192^2 scene 14.9 -> see DESIGN 4.1).
 // COORDS: USE_COORDINATES feature sets (table-driven colour offsets; fp32 row / column tables added in the first epilogue).
 template <bool FAST, int CC, int DD, bool WLO, int MODE, int NWG, bool COORDS = false>
-__global__ void __launch_bounds__(TC_THREADS * NWG, NWG == 2 ? 2 : (WLO ? 2 : 3)) tc_decode_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2 : (WLO ? 2 : 3))) tc_decode_kernel(const TcArgs a) {
   constexpr int THREADS = TC_THREADS * NWG;
   const Net& net = a.net;
   const int gtid = threadIdx.x, wg = gtid >> 7, tid = gtid & 127, warp = tid >> 5;
@@ -766,8 +769,8 @@ int tc_setup_tma(TcArgs& a, int dev, cudaStream_t st) {
   return LBDRN_OK;
 }
 
-// one launch of the tensor kernel family (wlo: smem holds the low-order weight operands too; nwg: warpgroups per CTA)
-int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int dev, cudaStream_t st) {
+// dynamic shared memory of one CTA (fills the region sizes the kernel carves it up with)
+size_t tc_smem_bytes(TcArgs& a, const TcHeader& h, bool wlo, int nwg) {
   const Net& n = a.net;
   const int kmax = h.k1pad > 2 * TC_BC ? h.k1pad : 2 * TC_BC;
   a.a_bytes = align_up(128 * kmax * 2, 1024);
@@ -775,8 +778,14 @@ int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int d
   const int n_patch = n.C * (TC_TH + 2 * n.D) * (TC_TW + 2 * n.D);
   const int raw_bytes = a.box_w * (n.msb_u16 ? 2 : 1) * (TC_TH + 2 * n.D) * n.C;
   a.wg_bytes = align_up(n_patch * 2, 128) + align_up(raw_bytes, 128);
+  return (size_t)nwg * a.a_bytes + a.w_bytes + (size_t)nwg * a.wg_bytes + 2 * (TC_MAX_K1 + 16) * 2 + 64;
+}
+
+// one launch of the tensor kernel family (wlo: smem holds the low-order weight operands too; nwg: warpgroups per CTA)
+int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int dev, cudaStream_t st) {
+  const Net& n = a.net;
   const int threads = TC_THREADS * nwg;
-  const size_t smem = (size_t)nwg * a.a_bytes + a.w_bytes + (size_t)nwg * a.wg_bytes + 2 * (TC_MAX_K1 + 16) * 2 + 64;
+  const size_t smem = tc_smem_bytes(a, h, wlo, nwg);
   int sms = 0, max_smem = 0, smem_sm = 0, regs_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -793,7 +802,7 @@ int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int d
   const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
   if (regs_cta > 0 && regs_sm / regs_cta < occ) occ = regs_sm / regs_cta;
   if (occ * TC_TMEM_COLS * nwg > 512) occ = 512 / (TC_TMEM_COLS * nwg);   // TMEM: 512 columns per SM
-  const int occ_max = nwg == 2 ? 2 : 3;                           // measured optimum for NWG=1 (4 CTAs: 3.0 vs 4.3 Gpix/s)
+  const int occ_max = nwg >= 4 ? 1 : (nwg == 2 ? 2 : 3);          // measured optimum for NWG=1 (4 CTAs: 3.0 vs 4.3 Gpix/s)
   if (occ > occ_max) occ = occ_max;
   if (const char* e = getenv("LBDRN_TC_OCC")) occ = atoi(e);
   if (occ < 1) return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode kernel cannot be made resident");
@@ -908,6 +917,11 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
   if (rc) return rc;
   rc = tc_setup_tma(a, dev, st);
   if (rc) return rc;
+  int max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // four warpgroups sharing one weight block where that fits (C = 4, D = 2: 193 KB); wider inputs keep one warpgroup per CTA
+  if (a.use_tma && !getenv("LBDRN_TC_NWG1") && tc_smem_bytes(a, h, true, 4) + 2048 <= (size_t)max_smem)
+    return tc_launch(pick_kernel<true, true, TC_SSE, 4>(n), a, h, true, 4, dev, st);
   return tc_launch(pick_kernel<true, true, TC_SSE, 1>(n), a, h, true, 1, dev, st);
 }
 

@@ -5,6 +5,8 @@ Small fixtures hold only ~1e4-1e5 sub-pixels, so for them the bar is applied as 
 """
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -138,6 +140,14 @@ def test_tensor_path_with_full_precision_weights():
     mse = F.eval_mse(scene, torch.from_numpy(flat).cuda(), 2, 64, 2, flags=F.Flags())
     assert mse == pytest.approx(O.eval_mse(msb, lsb, p, 2), rel=1e-5)
     assert mse == F.eval_mse(scene, torch.from_numpy(flat).cuda(), 2, 64, 2, flags=F.Flags())   # deterministic
+    # the four-warpgroup evaluation kernel (TMA-addressable scene: W % 16 == 0) against the single-warpgroup one: the same
+    # per-pixel arithmetic, only the order of the double-precision partial sums differs
+    os.environ["LBDRN_TC_NWG1"] = "1"
+    try:
+        mse1 = F.eval_mse(scene, torch.from_numpy(flat).cuda(), 2, 64, 2, flags=F.Flags())
+    finally:
+        del os.environ["LBDRN_TC_NWG1"]
+    assert mse == pytest.approx(mse1, rel=1e-12)
 
 
 def test_stripe_decode_is_bit_identical_to_whole_image():
