@@ -1,14 +1,15 @@
-// lbdrn_train_fp32.cuh -- fused, persistent training kernel (fp32 FFMA): neighbourhood gather by pixel index,
-// forward, LBDRNLoss (MSE), backward, deterministic cross-CTA gradient reduction and Adam, for many consecutive
-// optimiser steps in ONE cooperative launch.  Replaces the per-step ~35-40 library launches + H2D + host sync of
-// the reference (modified_ignite_engine.py:18-27, encode.py:69-70,84-85,95).
+// lbdrn_train_fp32.cuh -- fused, persistent training kernel (fp32 master weights and accumulation): neighbourhood gather
+// by pixel index, forward, LBDRNLoss (MSE), backward, deterministic cross-CTA gradient reduction and Adam, for many
+// consecutive optimiser steps in ONE cooperative launch.  Replaces the per-step ~35-40 library launches + H2D + host
+// sync of the reference (modified_ignite_engine.py:18-27, encode.py:69-70,84-85,95).
 //
-// Per step:   [each CTA]  64-pixel chunks of the batch: gather -> fwd -> bwd -> gradient partial in HBM/L2
-//             grid.sync
-//             [all threads] fixed-order sum of the partials, Adam update of (param, m, v), refresh packed copy
-//             grid.sync ; reload weights into smem
-// Latency-bound by construction (81 920 dependent steps for an 8192^2 scene): the budget is the two grid syncs
-// plus the 43.5 KB weight reload, not flops.
+// Per step:   [each CTA]  64-pixel chunks of the batch: (prefetched) gather -> fwd -> bwd -> gradient partial in L2
+//             arrive 1 ; issue the next step's neighbourhood loads ; wait 1            (split grid barrier)
+//             [all threads] fixed-order sum of the partials, Adam update of (param, m, v), weight image refresh
+//             arrive 2 ; next coordinates, commit of the prefetched neighbourhoods ; wait 2 ; weights -> smem (cp.async)
+// The chunk GEMMs run on the tensor cores through warp-level MMAs (template parameter MMA: 2 = fp16 hi+lo split operands
+// read with ldmatrix, 1 = 3xTF32, 0 = FFMA).  Latency-bound by construction (81 920 dependent steps for an 8192^2
+// scene): the budget is the two grid barriers, the L2 round trips of the reduction and of the weight reload, not flops.
 #pragma once
 #include <cooperative_groups.h>
 
