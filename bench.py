@@ -358,6 +358,39 @@ def run_ours(args):
                   "tensor_roofline_frac": flop / enc_s / 1e12 / pk["bf16_sustained"], "clocks": enc_clk.summary(),
                   "excludes": "GDAL read/write, JPEG-2000 base layer, fpzip (host, unchanged)"}
 
+    # ---- encode, data-parallel mode (N > 1): every rank holds the SAME scene and takes 1/N of each batch; one NCCL
+    # all-reduce of the P+1 gradient floats per step (lbdrn_dist.DataParallelTrainer).  Reported as measured next to the
+    # scene-per-GPU mode above; latency-bound at bs = 8192 (three launches + a collective per step), expected <= 1x.
+    if world > 1 and not args.no_encode and encode is not None:
+        from LBDRNmodel import LBDRNModel
+        shared = F.DeviceScene.from_image(make_scene_torch(C_, SIDE, SIDE, BITS, seed=19920517, device=dev), K_)
+        torch.manual_seed(19920517)
+        tr = F.FusedTrainer(LBDRNModel(DIM_IN, BC, C_, NL), shared, D_, 1e-3, 8192, 1, flags=fl, sampler="device")
+        tr.begin()
+        dp = LD.DataParallelTrainer(tr)
+        dp_steps = 256
+        perm = torch.empty(SIDE * SIDE, dtype=torch.int64, device=dev)
+        cabi.check(lib.lbdrn_randperm(SIDE * SIDE, 19920517, cabi.ptr(perm), cabi.stream_ptr()))   # same order on every rank
+        dp.train_epoch(perm[:16 * 8192], 1e-3)
+        torch.cuda.synchronize()
+        dist.barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        dp_losses = dp.train_epoch(perm[16 * 8192:(16 + dp_steps) * 8192], 1e-3)
+        d1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([d0.elapsed_time(d1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dp_us = float(t.item()) * 1e3 / dp_steps
+        fused_us = encode["us_per_step_incl_eval"]
+        encode["data_parallel"] = {"us_per_step": dp_us, "steps_timed": dp_steps, "n_gpus": world,
+                                   "allreduce_bytes_per_step": 4 * (int(params.numel()) + 1),
+                                   "speedup_vs_one_gpu_fused_step": fused_us / dp_us,
+                                   "last_loss": float(dp_losses[-1].item()),
+                                   "note": "per step: gradient kernel on 1/N of the batch, NCCL all-reduce, Adam kernel"}
+        tr.close()
+        del shared, perm
+
     # ---- the other BASELINE.json configs on this GPU (N=1 only; not the headline: explanatory lines) -----------------
     other = None
     if world == 1 and not args.no_extra:
