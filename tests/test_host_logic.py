@@ -159,6 +159,10 @@ def test_product_path_fails_loudly_without_gpu():
     d = cabi.make_desc(4, 8, 8, 5, 2, 64, 2, cabi.flag_bits(False, False, True, True), 100, False)
     rc = lib.lbdrn_decode(ctypes.byref(d), ctypes.c_void_p(16), ctypes.c_void_p(16), None, ctypes.c_void_p(16), None)
     assert rc == cabi.E_CUDA
+    # the device sampler too: no host-side permutation behind the ABI (the restatement lives in oracle/, for tests only)
+    assert lib.lbdrn_randperm(16, 1, ctypes.c_void_p(16), None) == cabi.E_CUDA
+    assert lib.lbdrn_randperm(0, 1, ctypes.c_void_p(16), None) == cabi.E_INVALID
+    assert lib.lbdrn_randperm(16, 1, None, None) == cabi.E_INVALID
 
 
 def test_scheduler_plan_covers_every_job_once_and_balances():
