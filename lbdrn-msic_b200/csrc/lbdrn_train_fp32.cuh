@@ -40,7 +40,7 @@ struct TrainArgs {
   float omb1, omb2, beta2f, eps;   // (float)(1-beta1), (float)(1-beta2), (float)beta2, (float)eps
   int n_global;            // GRAD_ONLY: global batch size for the 2/(B*C) factor
   float* params;           // master parameters, reference layout
-  float* wpack;            // packed copy (hidden W transposed) kept in sync by the Adam phase
+  float* wpack;            // packed copy (hidden W transposed) kept in sync by the Adam phase (MMA = 0 / 1 kernels)
   float* m;
   float* v;
   float* partial;          // [gridDim.x][pstride]; slot P holds the chunk squared-error sum
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   //    (2 requests instead of 5) and the bytes are extracted with funnel shifts; the pair of threads that owns a band
   //    (even: rows 0-2, label; odd: rows 3-4, centre) needs 7 / 5 loads per pixel instead of 19;
   //  * the pixels of step s+1 are known before step s ends (the permutation is an input) and do not depend on the weights:
-  //    the index is read at the start of step s, the words are requested right after the first grid sync, so they arrive
+  //    the index is read at the start of step s, the words are requested right after this CTA's arrival at the first grid barrier, so they arrive
   //    under the reduction / Adam phase, and are normalised into X at the head of step s+1 (table of the 256 quotients
   //    float32(m)/MSB.max(): same correctly-rounded values as the reference's division, LBDRNdataset.py:120).
   // Border pixels (reflected columns) and windows at the very ends of the buffer are fetched byte by byte into the same
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       }
     }
   };
-  // stage B (after the first grid sync of step s): request the words.  Rows of the window this thread owns: band = share / 2;
+  // stage B (after arriving at the first grid barrier of step s): request the words.  Rows of the window this thread owns: band = share / 2;
   // even thread rows [0, min(3, n)), odd thread rows [3, n)
   auto prefetch_issue = [&]() {
     pf_have = !pf_none;
