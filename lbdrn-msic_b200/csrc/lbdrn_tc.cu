@@ -54,9 +54,9 @@ void plan_block(const Net& n, TcHeader& h) {
 // One block: per-layer max -> power-of-two scale -> fp16 operands in UMMA layout, exactness flag, biases, W3^T.
 __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ params, uint8_t* __restrict__ blk) {
   __shared__ float s_max[32];
-  __shared__ int s_exact;
+  __shared__ int s_exact, s_guard;
   const int tid = threadIdx.x;
-  if (tid == 0) s_exact = 1;
+  if (tid == 0) { s_exact = 1; s_guard = 0; }
   for (int i = tid; i < hdr.total / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(blk)[i] = 0u;
   __syncthreads();
   TcHeader* H = reinterpret_cast<TcHeader*>(blk);
@@ -94,6 +94,18 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
     if (tid == 0) H->scale[l] = fold * (l == 0 ? __fdiv_rn(ldexpf(1.0f, -s), net_maxv(net)) : ldexpf(1.0f, -s));
     float* bias = reinterpret_cast<float*>(blk + hdr.off_bias) + l * TC_BC;
     for (int i = tid; i < net.bc; i += blockDim.x) bias[i] = fold * params[net.boff[l] + i];
+    // Can the sine's argument leave the range its fast reduction is exact for?  |w0 z_u| <= w0 (sum_k |W[u][k]| + |b_u|):
+    // every input is at most 1 in magnitude (features are differences of values divided by the global maximum, hidden
+    // inputs are sines, represented as hi + lo <= 1 + 2^-11; fp16 rounding of the weights adds 2^-11: the 1.001).  The
+    // kernel skips the per-value guard of a layer whose bound is safe; coordinate features and non-finite weights keep it.
+    float bound = 0.f;
+    for (int u = tid; u < net.bc; u += blockDim.x) {
+      float sabs = 0.f;
+      for (int k = k0; k < K; ++k) sabs += fabsf(W[(size_t)u * K + k]);
+      bound = fmaxf(bound, fabsf(fold) * (1.001f * sabs + fabsf(params[net.boff[l] + u])));
+      if (!isfinite(sabs) || !isfinite(params[net.boff[l] + u])) bound = INFINITY;
+    }
+    if (!(bound <= 19000.0f) || (l == 0 && net.nco != 0)) atomicOr(&s_guard, 1 << l);
   }
   float* w3t = reinterpret_cast<float*>(blk + hdr.off_w3);
   for (int i = tid; i < net.bc * net.C; i += blockDim.x) {
@@ -104,6 +116,7 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
   __syncthreads();
   if (tid == 0) {
     H->exact = s_exact;
+    H->guard_mask = s_guard;
     H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl;
     H->off_bias = hdr.off_bias; H->off_w3 = hdr.off_w3; H->total = hdr.total; H->hi_bytes = hdr.hi_bytes;
     for (int l = 0; l < net.nl; ++l) { H->off_b[l] = hdr.off_b[l]; H->off_blo[l] = hdr.off_blo[l]; }
@@ -454,6 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 
       // ---- epilogue of layer l: thread = pixel = TMEM lane ------------------------------------------------------------
       const float scale = H->scale[l];
+      const bool guard = ((H->guard_mask >> l) & 1) != 0;
       const float* bl = bias + l * TC_BC;
       const bool last = l + 1 == NL;
       const bool coords = COORDS && l == 0;
@@ -482,16 +496,19 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 #pragma unroll
           for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bterm[j]), 0.f);
         } else {
-          float amax = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             acc[j] = fmaf(acc[j], scale, bterm[j]);            // = w0 * z (w0 folded into scale and bias)
-            amax = fmaxf(amax, fabsf(acc[j]));
             h[j] = tc_sine<FAST>(acc[j]);
           }
-          if (__builtin_expect(!(amax <= 20000.0f), 0)) {       // huge or NaN argument: library slow path, out of line
+          if (guard) {                                          // uniform: tc_prep_kernel could not bound |w0 z| for this layer
+            float amax = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = sin_slow(acc[j]);
+            for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(acc[j]));
+            if (__builtin_expect(!(amax <= 20000.0f), 0)) {     // huge argument: library slow path, out of line
+#pragma unroll
+              for (int j = 0; j < 16; ++j) h[j] = sin_slow(acc[j]);
+            }
           }
         }
         if (!last) {

@@ -22,7 +22,8 @@ struct TcHeader {
   int off_bias, off_w3, off_b[kMaxLayers], total;   // byte offsets inside the block
   int off_blo[kMaxLayers];   // low-order fp16 term of the weights (W*2^s = hi + lo); all zero when `exact`
   int hi_bytes;              // block size without the lo operands (what the exact-weights kernel copies)
-  int pad[7];
+  int guard_mask;            // bit l set: layer l's sine needs the large-argument guard (|w0 z| may exceed 20000, or unknown)
+  int pad[6];
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
