@@ -274,7 +274,9 @@ def run_ours(args):
         # the resource that actually binds this kernel: instruction issue on the CUDA cores -- the sines of
         # the reference's activation, their fp16 hi+lo split and the feature build; the tensor and HBM figures above are
         # the ones SURVEY 8d asks for.  2516 thread-instructions per pixel = smsp__inst_executed.sum * 32 / pixels of the
-        # committed capture (profiles/r1b_ncu_tc_decode_summary.txt); ceiling = 148 SMs x 128 lanes x SM clock / that.
+        # committed capture (profiles/r1b_ncu_tc_decode_summary.txt, taken before the large-argument guard became
+        # conditional: the current kernel issues ~3 % fewer, so `frac` is on the generous side of the ceiling by that much);
+        # ceiling = 148 SMs x 128 lanes x SM clock / that.
         instr_px = 2516
         ceil_gpix = 148 * 128 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6 / instr_px / 1e9
         roofline["issue"] = {"thread_instr_per_pixel": instr_px, "ceiling_gpix_s": ceil_gpix,
