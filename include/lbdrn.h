@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define LBDRN_ABI_VERSION 2
+/* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added (additive: v2 callers are unaffected) */
+#define LBDRN_ABI_VERSION 3
 
 enum {
   LBDRN_OK = 0,
