@@ -6,7 +6,6 @@ There is no CPU fallback here: every function needs a CUDA device and the native
 """
 import ctypes
 import math
-import threading
 
 import numpy as np
 import torch
@@ -395,6 +394,86 @@ def permutation_from_seed(n, seed):
     return torch.randperm(n, generator=g)
 
 
+class HostPermutations:
+    """The reference's batch orders, produced ahead of the device.
+
+    `torch.randperm` on the CPU is a sequential Fisher-Yates shuffle (about 3 s for the 67 M pixels of an 8192^2 scene --
+    17x the 0.18 s the device needs for the epoch it feeds), but every epoch's seed is known before training starts
+    (`FusedTrainer._plan_seeds`), so the permutations of up to `workers` epochs are drawn concurrently in threads (torch
+    releases the GIL), each into its own (pinned, when CUDA is present) buffer.  `get(e)` blocks until epoch e's order is
+    ready; `release(e, event)` hands its buffer back once `event` (the upload) has completed.  Results are exactly
+    `permutation_from_seed(n, seeds[e-1])`, in epoch order."""
+
+    def __init__(self, seeds, n, workers=None, pin=None, device=None, max_bytes=4 << 30):
+        import concurrent.futures
+        import os
+        self.seeds, self.n, self.device = list(seeds), n, device
+        if workers is None:                          # bounded by the epochs, half the host cores and `max_bytes` of buffers
+            workers = min(len(self.seeds), (os.cpu_count() or 2) // 2, 8, max_bytes // max(1, 8 * n) - 1)
+        self.workers = workers = max(1, workers)
+        self.pin = torch.cuda.is_available() if pin is None else pin
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=workers)
+        self.free, self.n_buffers = [], 0            # idle buffers; buffers allocated so far (at most workers + 1)
+        self.busy = {}                               # epoch -> (buffer, upload event or None)
+        self.fut = {}
+        self.next_epoch = 1
+        self._fill()
+
+    def _draw(self, e, buf):
+        g = torch.Generator()
+        g.manual_seed(self.seeds[e - 1])
+        if buf is None:
+            if self.pin and self.device is not None:
+                torch.cuda.set_device(self.device)   # worker threads start on device 0: pin in this rank's context
+            buf = torch.empty(self.n, dtype=torch.int64, pin_memory=self.pin)
+        return torch.randperm(self.n, generator=g, out=buf)
+
+    def _reclaim(self, block):
+        """Move buffers whose upload has finished back to the free list; with `block`, wait for the oldest one."""
+        for e in sorted(self.busy):
+            buf, ev = self.busy[e]
+            if ev is None:
+                continue                             # handed out, not released yet
+            if block or ev is True or ev.query():
+                if ev is not True:
+                    ev.synchronize()
+                self.free.append(buf)
+                del self.busy[e]
+                block = False
+
+    def _fill(self):
+        while self.next_epoch <= len(self.seeds) and len(self.fut) < self.workers:
+            self._reclaim(block=False)
+            if self.free:
+                buf = self.free.pop()
+            elif self.n_buffers < self.workers + 1:
+                buf, self.n_buffers = None, self.n_buffers + 1       # allocated inside the worker
+            else:
+                return
+            e = self.next_epoch
+            self.next_epoch += 1
+            self.fut[e] = self.pool.submit(self._draw, e, buf)
+
+    def get(self, e):
+        if e not in self.fut:                        # every buffer is out: wait for an upload to finish, then draw
+            self._reclaim(block=True)
+            self._fill()
+        if e not in self.fut:
+            raise RuntimeError(f"permutation of epoch {e} was not scheduled (epochs must be taken in order and released)")
+        perm = self.fut.pop(e).result()
+        self.busy[e] = (perm, None)
+        self._fill()
+        return perm
+
+    def release(self, e, event=None):
+        buf, _ = self.busy[e]
+        self.busy[e] = (buf, True if event is None else event)
+        self._fill()
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
 class FusedTrainer:
     """The encoder's optimisation loop on the device (replaces trainer.run / evaluator.run of encode.py:84-117,157).
 
@@ -494,14 +573,7 @@ class FusedTrainer:
         with torch.cuda.stream(main):
             self.begin()
         seeds = self._plan_seeds()
-        host_perm, pinned, uploaded = {}, [None, None], [None, None]
-
-        def make_host_perm(e):
-            g = torch.Generator()
-            g.manual_seed(seeds[e - 1])
-            if pinned[e % 2] is None:
-                pinned[e % 2] = torch.empty(N, dtype=torch.int64).pin_memory()
-            host_perm[e] = torch.randperm(N, generator=g, out=pinned[e % 2])
+        host = HostPermutations(seeds, N, device=self.dev) if self.sampler == "reference" else None
 
         def device_perm(e):
             """(perm, event): drawn on the side stream"""
@@ -529,23 +601,14 @@ class FusedTrainer:
                 if self.on_epoch:
                     self.on_epoch(e, mse, improved)
 
-        if self.sampler == "reference":
-            make_host_perm(1)
-            next_dev = None
-        else:
-            next_dev = device_perm(1)
+        next_dev = None if self.sampler == "reference" else device_perm(1)
         for e in range(1, self.epochs + 1):
-            th = None
             with torch.cuda.stream(main):
                 if self.sampler == "reference":
-                    perm = host_perm.pop(e).to(self.dev, non_blocking=True)
-                    uploaded[e % 2] = torch.cuda.Event()
-                    uploaded[e % 2].record()
-                    if e < self.epochs:
-                        if uploaded[(e + 1) % 2] is not None:
-                            uploaded[(e + 1) % 2].synchronize()      # that pinned buffer is free again
-                        th = threading.Thread(target=make_host_perm, args=(e + 1,))
-                        th.start()
+                    perm = host.get(e).to(self.dev, non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record()
+                    host.release(e, up)                              # its buffer is reused once the upload has completed
                 else:
                     perm, ev = next_dev
                     main.wait_event(ev)
@@ -569,9 +632,9 @@ class FusedTrainer:
                     pending.append((e, sse, cur, done))
             collect(upto=e - 1)                                         # epoch e-1's result: epoch e is already queued
             del perm
-            if th is not None:
-                th.join()
         collect()
+        if host is not None:
+            host.close()
         cur_stream.wait_stream(main)
         cur_stream.wait_stream(side)
         if self.best_params is None:                                    # never evaluated (val_duration > epochs)

@@ -165,6 +165,29 @@ def test_product_path_fails_loudly_without_gpu():
     assert lib.lbdrn_randperm(16, 1, None, None) == cabi.E_INVALID
 
 
+def test_host_permutation_pipeline_keeps_the_reference_order():
+    """HostPermutations draws the DataLoader-order permutations of several epochs concurrently; whatever the number of
+    workers, epoch e gets exactly permutation_from_seed(n, seed_e), buffers are recycled and bounded."""
+    seeds = [11, 22, 33, 44, 55, 66, 77]
+    for workers in (1, 2, 3, None):
+        h = F.HostPermutations(seeds, 1000, workers=workers, pin=False)
+        for e in range(1, len(seeds) + 1):
+            p = h.get(e)
+            assert torch.equal(p, F.permutation_from_seed(1000, seeds[e - 1])), (workers, e)
+            h.release(e)
+        assert h.n_buffers <= h.workers + 1
+        h.close()
+    h = F.HostPermutations(seeds, 1 << 20, pin=False, max_bytes=3 * 8 * (1 << 20))      # room for two workers + 1 buffers
+    assert h.workers == 2
+    h.close()
+    h = F.HostPermutations(seeds[:3], 10, workers=1, pin=False)                           # one worker: two buffers
+    h.get(1)
+    h.get(2)
+    with pytest.raises(RuntimeError):
+        h.get(3)                                                                          # epochs 1, 2 were never released
+    h.close()
+
+
 def test_scheduler_plan_covers_every_job_once_and_balances():
     """N3: scenes x K -> ranks.  Every job exactly once; K sweeps stay on one rank unless that unbalances
     the plan; the plan is a pure function of its inputs (every rank computes the same one)."""
