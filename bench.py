@@ -428,7 +428,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        side = 1024
+        side = 3072                                # ~10-20 s of host work on a 16-core box: a bounded sample, not the scene
         t = cpu_decode_sample(side, threads)
         cpu = {"value": side * side / t / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"one decode of a {C_}x{side}x{side} synthetic scene ({t:.1f} s) by oracle/lbdrn_oracle.py"}
