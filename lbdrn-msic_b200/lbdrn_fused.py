@@ -478,8 +478,10 @@ class FusedTrainer:
     """The encoder's optimisation loop on the device (replaces trainer.run / evaluator.run of encode.py:84-117,157).
 
     sampler="reference": every epoch's batch order is the permutation the reference's DataLoader would produce from
-    the same torch seed (host randperm, generated one epoch ahead on a worker thread, uploaded as int64 indices).
-    sampler="device": permutation drawn on the GPU (statistically equivalent, no host work).
+    the same torch seed (host randperm -- ~3 s per 67 M pixels -- drawn several epochs ahead by `HostPermutations`,
+    uploaded as int64 indices): bit-for-bit the reference's batches, host-bound for large scenes.
+    sampler="device": permutation written on the GPU by `lbdrn_randperm` (a keyed bijection; every pixel once per epoch,
+    not torch's order; no host work) -- the mode for throughput (`encode.py --sampler device`).
     Adam(lr, betas=(0.9,0.999), eps=1e-8), StepLR, per-epoch full-scene MSE and best-epoch selection follow
     encode.py:84-85,96-117 (including the epochs==1 special case, which skips evaluation)."""
 
