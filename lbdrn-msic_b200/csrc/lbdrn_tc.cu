@@ -57,6 +57,7 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
   __shared__ int s_exact, s_guard;
   const int tid = threadIdx.x;
   if (tid == 0) { s_exact = 1; s_guard = 0; }
+  if (tid == 0) check_maxv_bound(net);
   for (int i = tid; i < hdr.total / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(blk)[i] = 0u;
   __syncthreads();
   TcHeader* H = reinterpret_cast<TcHeader*>(blk);

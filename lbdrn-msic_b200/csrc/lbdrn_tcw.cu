@@ -86,6 +86,7 @@ __global__ void tcw_prep_kernel(Net net, TcwHeader hdr, const float* __restrict_
   __shared__ int s_exact;
   const int tid = threadIdx.x;
   if (tid == 0) s_exact = 1;
+  if (tid == 0) check_maxv_bound(net);
   for (int i = tid; i < hdr.total / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(blk)[i] = 0u;
   __syncthreads();
   TcwHeader* H = reinterpret_cast<TcwHeader*>(blk);

@@ -121,17 +121,18 @@ class StripeBuffer:
         if self.bot:
             w[:, self.top + rows:].copy_(self._recv_dn)
 
-    def _max_args(self, msb_max):
+    def _max_args(self, msb_max, K):
         """msb_max may be an int (host value) or a 1-element int32 CUDA tensor (device value, e.g. fresh from an
-        all-reduce): then the descriptor carries the dtype's upper bound and the device pointer."""
+        all-reduce): then the descriptor carries a TRUE upper bound (255, or 65535 >> K for uint16 planes: the library
+        selects kernels from it) and the device pointer."""
         if torch.is_tensor(msb_max):
-            return (255 if self.buf.dtype == torch.uint8 else 2048), msb_max
+            return (255 if self.buf.dtype == torch.uint8 else (0xFFFF >> K)), msb_max
         return int(msb_max), None
 
     def decode(self, flat_params_dev, K, bc, nl, flags, msb_max, relu=False, w0=30.0, path=cabi.PATH_AUTO, tab=None):
         """Decode the stripe (halos must be current); returns the [C, buf_rows, W] output buffer and the slice of own rows."""
         C, brows, W = self.buf.shape
-        bound, mdev = self._max_args(msb_max)
+        bound, mdev = self._max_args(msb_max, K)
         d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), bound, self.buf.dtype == torch.uint16,
                            row0=self.r0, row1=self.r1, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0,
                            n_freq=flags.n_freq, path=path, msb_max_dev=mdev)
@@ -152,7 +153,7 @@ class StripeBuffer:
         cur = torch.cuda.current_stream(dev)
         lib = cabi.load()
         last = None
-        bound, mdev = self._max_args(msb_max)
+        bound, mdev = self._max_args(msb_max, K)
         for a in range(self.r0, self.r1, sub_rows):
             b = min(self.r1, a + sub_rows)
             d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), bound, self.buf.dtype == torch.uint16,

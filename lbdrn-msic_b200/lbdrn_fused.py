@@ -169,9 +169,12 @@ def decode_image(base, flat_params, K, D, bc, nl, flags=None, relu=False, w0=30.
 _streams = {}
 
 
-def _assume_tensor_range(K):
-    """uint16 base layers: the exact max decides whether the tensor kernel (MSB <= 2048) applies, so it is read back."""
-    return False
+def msb_upper_bound(msb_dtype, K):
+    """A TRUE upper bound of a base layer's maximum, for descriptors that carry the exact value on the device
+    (LbdrnDesc.msb_max_dev): the library selects kernels from the host-side bound (the tcgen05 path needs MSB <= 2048 for
+    its integer differences to be exact in fp16), so it must never under-state the maximum.  MSB = img >> K with img a
+    16-bit word (LBDRNdataset.py:95), hence 65535 >> K for uint16 planes and 255 for uint8 ones."""
+    return 255 if msb_dtype == torch.uint8 else (0xFFFF >> K)
 
 
 def _get_streams(dev):
@@ -228,8 +231,9 @@ def decode_image_streamed(base_host, flat_params, K, D, bc, nl, flags=None, relu
                 max_dev.copy_(msb.max().to(torch.int32).reshape(1))
                 base_max = 255
             else:
+                # uint16 planes: the exact max decides whether the tensor kernel (MSB <= 2048) applies, so it is read back
                 cabi.check(lib.lbdrn_max_shifted(cabi.ptr(msb), msb.numel(), 0, cabi.ptr(max_dev), cabi.stream_ptr()))
-                base_max = int(max_dev.item()) if not _assume_tensor_range(K) else 2048
+                base_max = int(max_dev.item())
         up_all = torch.cuda.Event()
         up_all.record(s_in)
     for i in range(n):
@@ -297,7 +301,7 @@ class StreamedDecoder:
                 sl["mx"].copy_(sl["msb"].max().to(torch.int32).reshape(1))
             up = torch.cuda.Event()
             up.record(self.s_in)
-        bound = 2048 if self.u16 else 255                      # msb_max_dev carries the exact value
+        bound = msb_upper_bound(sl["msb"].dtype, self.K)       # a true bound; msb_max_dev carries the exact value
         last = None
         for i in range(len(self.bounds) - 1):
             r0, r1 = self.bounds[i], self.bounds[i + 1]
@@ -486,7 +490,7 @@ class FusedTrainer:
     encode.py:84-85,96-117 (including the epochs==1 special case, which skips evaluation)."""
 
     def __init__(self, model, scene, D, lr, batch_size, epochs, val_duration=1, flags=None, sampler="reference",
-                 on_epoch=None):
+                 on_epoch=None, betas=(0.9, 0.999), eps=1e-8):
         self.model, self.scene, self.D = model, scene, D
         self.lr, self.bs, self.epochs, self.val_duration = float(lr), int(batch_size), int(epochs), int(val_duration)
         self.flags = _flags(flags)
@@ -501,7 +505,7 @@ class FusedTrainer:
         self.desc = scene.desc(D, self.bc, self.nl, self.flags, self.relu, self.w0)
         cfg = cabi.LbdrnTrainCfg()
         cfg.batch_size, cfg.world_size, cfg.rank = self.bs, 1, 0
-        cfg.beta1, cfg.beta2, cfg.eps = 0.9, 0.999, 1e-8
+        cfg.beta1, cfg.beta2, cfg.eps = float(betas[0]), float(betas[1]), float(eps)   # copied into the handle at create
         self.cfg = cfg
         self.handle = ctypes.c_void_p()
         cabi.check(self.lib.lbdrn_train_create(ctypes.byref(self.desc), ctypes.byref(cfg), ctypes.byref(self.handle)))

@@ -102,9 +102,10 @@ def create_supervised_trainer(model, optimizer, loss_fn, device=None, non_blocki
         tr = ctx.get('trainer')
         if tr is None:
             g = optimizer.param_groups[0]
+            if g.get('weight_decay', 0) or g.get('amsgrad', False):
+                raise NotImplementedError("the fused step implements Adam without weight decay / amsgrad (encode.py:84)")
             tr = lbdrn_fused.FusedTrainer(model, ds.scene, ds.D, g['lr'], loader.batch_size, engine.state.max_epochs,
-                                          flags=ds.flags)
-            tr.cfg.beta1, tr.cfg.beta2, tr.cfg.eps = g['betas'][0], g['betas'][1], g['eps']
+                                          flags=ds.flags, betas=g['betas'], eps=g['eps'])
             tr.begin()
             ctx['trainer'] = tr
         # same default-generator draws as iter(DataLoader(shuffle=True)) in the reference (encode.py:69-70)

@@ -7,8 +7,8 @@ no CPU fallback.
 
 PINNING: the reference has no tests or golden vectors of its own.  This restatement is
 pinned instead against the UNMODIFIED reference executed in the build container (`oracle/run_reference.py`),
-through the fixtures in `tests/golden/` minted by `oracle/make_golden.py`, and live by
-`tests/test_oracle_vs_reference.py` whenever `/root/reference` is present.  One dependency stays unpinned:
+through the fixtures in `tests/golden/` minted by `oracle/make_golden.py` and checked by
+`tests/test_oracle_golden.py` (re-mint with `python oracle/make_golden.py` where `/root/reference` is present).  One dependency stays unpinned:
 `fpzip` (not installed; value map restated in `oracle/shims/fpzip.py`).
 
 Every function cites the reference lines it restates (paths relative to /root/reference).
@@ -145,11 +145,14 @@ def init_params(dim_in, bc, C, nl, w0=30.0, c=6.0):
     return params
 
 
-def forward(params, x, w0=30.0):
-    """y = sigmoid(Wo.sin(w0(...sin(w0(W1 x + b1))...)) + bo)  (LBDRNmodel.py:13,40-41,79-82)."""
+def forward(params, x, w0=30.0, relu=False):
+    """y = sigmoid(Wo.sin(w0(...sin(w0(W1 x + b1))...)) + bo)  (LBDRNmodel.py:13,40-41,79-82).
+    relu=True: the commented alternative of encode.py:75 / decode.py:108 (`activation=torch.nn.ReLU()`): every hidden
+    SirenLayer applies ReLU to its Linear output instead of Sine (LBDRNmodel.py:37,41); init and head are unchanged."""
     h = x
     for i in range(0, len(params) - 2, 2):
-        h = torch.sin(w0 * torch.nn.functional.linear(h, params[i], params[i + 1]))
+        z = torch.nn.functional.linear(h, params[i], params[i + 1])
+        h = torch.relu(z) if relu else torch.sin(w0 * z)
     return torch.sigmoid(torch.nn.functional.linear(h, params[-2], params[-1]))
 
 
@@ -180,32 +183,32 @@ def fpzip_value_map(flat, precision):
 # ----------------------------------------------------------------------------------------------------------
 # a14/a15: decode (decode.py:122-134)
 # ----------------------------------------------------------------------------------------------------------
-def predict(base, params, D, flags=DEFAULT_FLAGS, rows_per_chunk=256):
+def predict(base, params, D, flags=DEFAULT_FLAGS, rows_per_chunk=256, relu=False):
     """Network output y[N, C] float32 for every pixel of the CHW base image (chunked over rows)."""
     C, H, W = base.shape
     outs = []
     with torch.no_grad():
         for r in range(0, H, rows_per_chunk):
             x = torch.from_numpy(features(base, D, flags, r, min(H, r + rows_per_chunk)))
-            outs.append(forward(params, x))
+            outs.append(forward(params, x, relu=relu))
     return torch.cat(outs, 0)
 
 
-def decode_image(base, params, K, D, flags=DEFAULT_FLAGS, rows_per_chunk=256):
+def decode_image(base, params, K, D, flags=DEFAULT_FLAGS, rows_per_chunk=256, relu=False):
     """uint16 CHW reconstruction: round-half-even(y*(2^K-1)) added to base<<K (decode.py:131-134)."""
     base = np.asarray(base).astype(np.uint16)
     C, H, W = base.shape
-    y = predict(base, params, D, flags, rows_per_chunk)
+    y = predict(base, params, D, flags, rows_per_chunk, relu)
     residual = torch.round(y * (2 ** K - 1)).numpy().reshape(H, W, C).transpose(2, 0, 1)
     return np.round((base << K).astype(np.float32) + residual).astype(np.uint16)
 
 
-def eval_mse(msb, lsb, params, D, flags=DEFAULT_FLAGS, rows_per_chunk=256):
+def eval_mse(msb, lsb, params, D, flags=DEFAULT_FLAGS, rows_per_chunk=256, relu=False):
     """Full-scene MSE used for best-epoch selection (encode.py:105-108, LBDRNperformance.py:18-21),
     accumulated in float64 over row chunks (the reference takes one float32 mean over all N*C)."""
     C, H, W = msb.shape
     t = torch.from_numpy(labels(lsb))
-    y = predict(msb, params, D, flags, rows_per_chunk)
+    y = predict(msb, params, D, flags, rows_per_chunk, relu)
     return float(((y.double() - t.double()) ** 2).mean())
 
 
@@ -278,9 +281,21 @@ def device_permutation(n, seed, rounds=6):
 # ----------------------------------------------------------------------------------------------------------
 # a7-a11: the encoder's optimisation loop (encode.py:67-117, modified_ignite_engine.py:18-27,38-43)
 # ----------------------------------------------------------------------------------------------------------
-def train(msb, lsb, D, bc, nl, lr, bs, epochs, flags=DEFAULT_FLAGS, val_duration=1, max_steps=None):
+def device_sampler_permutation(n):
+    """Batch order of the library's `sampler="device"` mode (lbdrn_fused.FusedTrainer): the SAME default-generator draws as
+    `loader_permutation` (so every other draw of a run stays aligned with the reference), but the RandomSampler seed keys
+    `device_permutation` instead of `torch.randperm`."""
+    torch.empty((), dtype=torch.int64).random_()
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return torch.from_numpy(device_permutation(n, seed & ((1 << 64) - 1)))
+
+
+def train(msb, lsb, D, bc, nl, lr, bs, epochs, flags=DEFAULT_FLAGS, val_duration=1, max_steps=None, sampler="loader",
+          relu=False):
     """Overfit the network to one scene.  Call after `torch.manual_seed(seed)` for a fixed-seed run.
-    Returns dict(params=best-epoch tensors, losses=[per-step], mses=[per-epoch], best_epoch)."""
+    Returns dict(params=best-epoch tensors, losses=[per-step], mses=[per-epoch], best_epoch).
+    sampler="loader": the reference's DataLoader order (encode.py:69-70); "device": the library's own device sampler."""
+    draw_perm = loader_permutation if sampler == "loader" else device_sampler_permutation
     C, H, W = msb.shape
     N = H * W
     X = torch.from_numpy(features(msb, D, flags))
@@ -291,11 +306,11 @@ def train(msb, lsb, D, bc, nl, lr, bs, epochs, flags=DEFAULT_FLAGS, val_duration
     for epoch in range(1, epochs + 1):
         for g in opt.param_groups:
             g["lr"] = lr_at_epoch(lr, epoch, epochs)
-        perm = loader_permutation(N)
+        perm = draw_perm(N)
         for s in range(0, N, bs):                                      # last partial batch kept
             idx = perm[s:s + bs]
             opt.zero_grad()
-            loss = torch.nn.functional.mse_loss(forward(params, X[idx]), T[idx])   # LBDRNloss.py:9
+            loss = torch.nn.functional.mse_loss(forward(params, X[idx], relu=relu), T[idx])   # LBDRNloss.py:9
             loss.backward()
             opt.step()
             losses.append(float(loss.detach()))
@@ -310,7 +325,7 @@ def train(msb, lsb, D, bc, nl, lr, bs, epochs, flags=DEFAULT_FLAGS, val_duration
             with torch.no_grad():
                 sse = 0.0
                 for s in range(0, N, 1 << 18):
-                    sse += float(((forward(params, X[s:s + (1 << 18)]).double() - T[s:s + (1 << 18)].double()) ** 2).sum())
+                    sse += float(((forward(params, X[s:s + (1 << 18)], relu=relu).double() - T[s:s + (1 << 18)].double()) ** 2).sum())
             mse = sse / (N * C)
             mses.append(mse)
             if mse < best:

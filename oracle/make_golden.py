@@ -122,6 +122,30 @@ RESULT = dict(ok=True)
 """
 
 
+# the commented alternative of encode.py:75 / decode.py:108: hidden activation ReLU.  Forward outputs, the MSE loss against
+# random targets and its gradient w.r.t. every parameter, from the reference's own module and torch autograd.
+_FORWARD_RELU_SNIPPET = r"""
+import numpy as np, torch
+from LBDRNmodel import LBDRNModel
+from LBDRNloss import LBDRNLoss
+torch.manual_seed(11)
+m = LBDRNModel(dim_in=ARGS['dim_in'], dim_hidden=ARGS['bc'], dim_out=ARGS['C'], num_layers=ARGS['nl'],
+               activation=torch.nn.ReLU())
+with torch.no_grad():
+    for name, p in m.named_parameters():
+        if 'weight' in name: p.mul_(ARGS['gain'])          # spread the pre-activations so that ReLU clips about half
+x = (torch.rand(ARGS['n'], ARGS['dim_in']) - 0.5) * 0.2
+t = torch.rand(ARGS['n'], ARGS['C'])
+y = m(x)
+loss = LBDRNLoss()(y, t)
+loss.backward()
+flat = np.concatenate([v.numpy().reshape(-1) for v in m.state_dict().values()]).astype(np.float32)
+grad = np.concatenate([p.grad.numpy().reshape(-1) for p in m.parameters()]).astype(np.float32)
+np.savez_compressed(ARGS['npz'], x=x.numpy(), t=t.numpy(), y=y.detach().numpy(), params=flat, loss=np.float32(loss.item()), grad=grad)
+RESULT = dict(ok=True)
+"""
+
+
 def main():
     if not rr.available():
         sys.exit("reference not present; fixtures can only be minted in the build container")
@@ -168,6 +192,10 @@ def main():
         rr.call_snippet(_FORWARD_SNIPPET, dict(dim_in=100, bc=64, C=4, nl=2, n=257,
                                                npz=os.path.join(GOLD, "forward_d100_bc64.npz")))
         print("KATs written")
+    if not only or "kat" in only or "kat_relu" in only:
+        rr.call_snippet(_FORWARD_RELU_SNIPPET, dict(dim_in=100, bc=64, C=4, nl=2, n=257, gain=8.0,
+                                                    npz=os.path.join(GOLD, "forward_relu_d100_bc64.npz")))
+        print("ReLU KAT written")
 
     for name, cfg in CASES.items():
         if only and name not in only:

@@ -219,6 +219,73 @@ def test_relu_variant_matches_torch_module():
     assert np.max(np.abs(y - y_ref)) < 2e-6
 
 
+def _relu_net(seed=5, gain=8.0, D=2, bc=64, nl=2, C=4):
+    """A ReLU network with pre-activations spread over both sides of zero (the reference's SIREN init alone leaves every
+    hidden unit near 0), weights as a decoder sees them after fpzip -prec 16."""
+    torch.manual_seed(seed)
+    p = O.init_params(C * (2 * D + 1) ** 2, bc, C, nl)
+    for i in range(0, len(p), 2):
+        p[i] = p[i] * gain
+    flat = O.fpzip_value_map(O.flatten_params(p), 16)
+    return flat, O.unflatten_params(flat, C * (2 * D + 1) ** 2, bc, C, nl)
+
+
+@pytest.mark.parametrize("shape,K", [((4, 64, 80), 5), ((4, 200, 333), 5), ((4, 256, 256), 8), ((4, 96, 2100), 3)])
+def test_relu_variant_on_the_tensor_path_matches_the_oracle(shape, K):
+    """north_star: "ReLU and bias fused".  The ReLU branch of the tcgen05 kernels (hidden activation of encode.py:75 /
+    decode.py:108's commented alternative) against the oracle's ReLU forward, on every decode path; the oracle's ReLU
+    forward itself is pinned against the reference's module (tests/test_oracle_golden.py::test_forward_relu_kat)."""
+    from synth_scene import make_scene
+    C, H, W = shape
+    img = make_scene(C, H, W, 12, seed=H + W + K)
+    msb, _ = O.split_msb_lsb(img, K)
+    flat, p = _relu_net()
+    ref = O.decode_image(msb, p, K, 2, relu=True)
+    assert len(np.unique(ref - (msb.astype(np.uint16) << K))) > (1 << K) // 2        # the residuals use their range
+    for path in _paths(K, 2, 64, 2, 4, F.Flags()):
+        out = F.decode_image(msb, flat, K, 2, 64, 2, flags=F.Flags(), relu=True, path=path)
+        _check(out, ref, f"relu/{shape}/K{K}/{path}")
+    # full-precision (not fp16-exact) weights: the sibling launch with the low-order weight term
+    rng = np.random.default_rng(1)
+    flat32 = (flat.astype(np.float64) * (1.0 + 1e-4 * rng.standard_normal(flat.size))).astype(np.float32)
+    ref32 = O.decode_image(msb, O.unflatten_params(flat32, 100, 64, 4, 2), K, 2, relu=True)
+    _check(F.decode_image(msb, flat32, K, 2, 64, 2, flags=F.Flags(), relu=True, path="tensor"), ref32, "relu/fp32 weights")
+
+
+def test_relu_variant_wide_kernel_matches_the_oracle():
+    """ReLU on the wide (bc 256, D=3) tcgen05 kernel."""
+    from synth_scene import make_scene
+    img = make_scene(4, 96, 144, 12, seed=31)
+    msb, _ = O.split_msb_lsb(img, 5)
+    flat, p = _relu_net(seed=6, gain=6.0, D=3, bc=256)
+    ref = O.decode_image(msb, p, 5, 3, relu=True)
+    for path in ("precise", "tensor"):
+        _check(F.decode_image(msb, flat, 5, 3, 256, 2, flags=F.Flags(), relu=True, path=path), ref, f"relu-wide/{path}")
+
+
+@pytest.mark.parametrize("streamed", ["decode_image_streamed", "StreamedDecoder"])
+def test_uint16_base_layer_above_the_fp16_exact_range_stays_correct(streamed):
+    """A 16-bit scene at K=3: MSB up to 8191 > 2048, so integer differences are no longer exact in fp16 and the tensor
+    kernel must not be selected.  The streaming paths hand the kernels a DEVICE-side maximum plus a host-side upper bound:
+    that bound has to be a true one (65535 >> K), or the result silently diverges from the resident decode."""
+    from synth_scene import make_scene
+    img = make_scene(4, 120, 144, 16, seed=77)
+    msb, _ = O.split_msb_lsb(img, 3)
+    assert msb.dtype == np.uint16 and msb.max() > 2048
+    params = _trained_params()
+    ref = O.decode_image(msb, O.unflatten_params(params, 100, 64, 4, 2), 3, 2)
+    whole = F.decode_image(msb, params, 3, 2, 64, 2, flags=F.Flags())
+    _check(whole, ref, "u16>2048 resident")
+    host = torch.from_numpy(msb).pin_memory()
+    if streamed == "decode_image_streamed":
+        out = F.decode_image_streamed(host, params, 3, 2, 64, 2, flags=F.Flags(), stripe_rows=48)
+    else:
+        dec = F.StreamedDecoder(4, 120, 144, torch.uint16, 3, 2, 64, 2, params, flags=F.Flags(), stripe_rows=48)
+        out = torch.empty((4, 120, 144), dtype=torch.uint16).pin_memory()
+        dec.wait(dec.submit(host, out))
+    assert np.array_equal(out.numpy(), whole)
+
+
 def test_streamed_host_to_host_decode_matches_resident_decode():
     """decode_image_streamed (stripe-pipelined copies, device-side max) is bit-identical to the one-shot decode."""
     from synth_scene import make_scene

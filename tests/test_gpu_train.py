@@ -27,10 +27,13 @@ def _setup(case="k5d2_small", seed=19920517):
     return meta, img, blob, recon, model, scene, fl
 
 
-@pytest.mark.parametrize("case", ["k5d2_small", "d3_bc256", "k9_bc128"])
+@pytest.mark.parametrize("case", ["k5d2_small", "d3_bc256", "k9_bc128", "coords_pe", "coords_pe_col", "coords_only",
+                                  "k5d2_absrel0", "k4d0_abs"])
 def test_gradients_match_autograd(case):
     """lbdrn_train_grad (one batch, unreduced) against torch autograd on the oracle's explicit features.
-    d3_bc256 runs the 32-pixel-chunk instantiation (BASELINE config 3), k9_bc128 the 64-pixel one with nl=1."""
+    d3_bc256 runs the 32-pixel-chunk instantiation (BASELINE config 3), k9_bc128 the 64-pixel one with nl=1; coords_*
+    train on coordinate / positional-encoding columns (LBDRNdataset.py:108-118; BASELINE config 4, with and without the
+    colour columns), k5d2_absrel0 on absolute colours (RELATIVE off, LBDRNdataset.py:126-128), k4d0_abs on D=0."""
     meta, img, _, _, model, scene, fl = _setup(case)
     lib = cabi.load()
     tr = F.FusedTrainer(model, scene, meta["D"], 1e-3, 512, 1, flags=fl)
@@ -39,10 +42,11 @@ def test_gradients_match_autograd(case):
     for nb in (512, 100, 1):                                     # full, partial (not a multiple of 64), single pixel
         idx = torch.randperm(N)[:nb]
         g = torch.zeros(model.flat_params().numel() + 1, device="cuda")
-        cabi.check(lib.lbdrn_train_grad(tr.handle, cabi.ptr(scene.msb), cabi.ptr(scene.lsb), None,
+        cabi.check(lib.lbdrn_train_grad(tr.handle, cabi.ptr(scene.msb), cabi.ptr(scene.lsb), cabi.ptr(tr.tab),
                                         cabi.ptr(idx.cuda()), nb, nb, cabi.ptr(g), cabi.stream_ptr()))
         msb, lsb = O.split_msb_lsb(img, meta["K"])
-        X, T = torch.from_numpy(O.features(msb, meta["D"])), torch.from_numpy(O.labels(lsb))
+        X = torch.from_numpy(O.features(msb, meta["D"], O.Flags(**meta.get("flags", {}))))
+        T = torch.from_numpy(O.labels(lsb))
         params = [p.clone().requires_grad_(True) for p in model.state_dict().values()]
         loss = torch.nn.functional.mse_loss(O.forward(params, X[idx]), T[idx])
         loss.backward()
@@ -54,9 +58,12 @@ def test_gradients_match_autograd(case):
     tr.close()
 
 
-@pytest.mark.parametrize("case", ["k5d2_small", "d3_bc256", "k9_bc128", "b8_16bit", "k1_nl3", "k3d1_u16"])
+@pytest.mark.parametrize("case", ["k5d2_small", "d3_bc256", "k9_bc128", "b8_16bit", "k1_nl3", "k3d1_u16", "coords_pe",
+                                  "coords_pe_col", "coords_only", "k5d2_absrel0", "k4d0_abs"])
 def test_first_steps_follow_the_reference_trajectory(case):
-    """Same seed, same init, same batches: per-step losses track the reference's (fp32 rounding differences only)."""
+    """Same seed, same init, same batches: per-step losses track the reference's (fp32 rounding differences only).
+    Covers every feature set of constants.py:3-14 the fixtures were minted with: colours (relative / absolute / D=0),
+    coordinates + positional encoding with and without colours, plain coordinates."""
     meta, img, _, _, model, scene, fl = _setup(case)
     tr = F.FusedTrainer(model, scene, meta["D"], 1e-3, meta["bs"], meta["e"], flags=fl)
     res = tr.run()
@@ -90,6 +97,56 @@ def test_fixed_seed_encode_psnr_and_rate_within_tolerance(tmp_path):
     again = F.decode_image(read_base_like(msb), np.asarray(fpzip.decompress(nn_stream)[0][0][0], np.float32),
                            meta["K"], meta["D"], meta["bc"], meta["nl"], flags=fl, path="precise")
     assert np.array_equal(again, out)
+
+
+@pytest.mark.parametrize("seed", [19920517, 1, 2, 3, 4])
+def test_device_sampler_encode_quality_is_pinned(seed):
+    """The mode bench.py times (`sampler="device"`: every epoch's order from lbdrn_randperm) has its own quality pin: for
+    five torch seeds the fused encode lands within the north-star tolerance (0.02 dB, 0.5 % bpsp) of the ORACLE's CPU loop
+    trained on the same lbdrn_randperm orders (tests/golden/k5d2_train_samplers.json, oracle/make_sampler_golden.py), and
+    inside the seed-to-seed spread of the reference's own sampler widened by that tolerance."""
+    import json
+    from conftest import GOLD
+    pin = json.load(open(os.path.join(GOLD, "k5d2_train_samplers.json")))
+    meta, img, blob, recon, model, scene, fl = _setup("k5d2_train", seed=seed)
+    tr = F.FusedTrainer(model, scene, meta["D"], 1e-3, meta["bs"], meta["e"], flags=fl, sampler="device")
+    res = tr.run()
+    tr.close()
+    want = pin["device"][str(seed)]
+    assert np.allclose(res["losses"][:8], want["first_losses"], rtol=2e-4)        # same batches as the oracle's loop
+    assert res["best_epoch"] == want["best_epoch"]
+    assert np.allclose(res["val_mse"], want["val_mse"], rtol=5e-3)
+    nn_stream = fpzip.compress(res["params"].numpy(), precision=16, order="C")
+    _, tiles = split_stream(blob)
+    total = len(blob) - len(tiles[0][0]) + len(nn_stream)
+    msb, _ = O.split_msb_lsb(img, meta["K"])
+    out = F.decode_image(msb, O.fpzip_value_map(res["params"].numpy(), 16), meta["K"], meta["D"], meta["bc"], meta["nl"],
+                         flags=fl, path="precise")
+    _, psnr, bpsp = O.quality(img, out, total)
+    assert abs(psnr - want["psnr"]) < 0.02, (psnr, want["psnr"])
+    assert abs(bpsp - want["bpsp"]) / want["bpsp"] < 5e-3
+    lo = min(v["psnr"] for v in pin["loader"].values()) - 0.02
+    hi = max(v["psnr"] for v in pin["loader"].values()) + 0.02
+    assert lo <= psnr <= hi, (psnr, lo, hi)
+
+
+def test_relu_training_follows_the_oracle():
+    """ReLU hidden activation (encode.py:75's commented alternative) through the fused training kernel: per-step losses,
+    per-epoch MSE and best epoch against the oracle's loop on the same seed."""
+    from synth_scene import make_scene
+    img = make_scene(4, 64, 72, 12, seed=15)
+    msb, lsb = O.split_msb_lsb(img, 5)
+    torch.manual_seed(5)
+    ref = O.train(msb, lsb, 2, 64, 2, 1e-3, 512, 3, relu=True)
+    torch.manual_seed(5)
+    model = LBDRNModel(100, 64, 4, 2, activation=torch.nn.ReLU())
+    scene = F.DeviceScene.from_image(img, 5)
+    tr = F.FusedTrainer(model, scene, 2, 1e-3, 512, 3, flags=F.Flags())
+    res = tr.run()
+    tr.close()
+    got, want = np.array(res["losses"]), np.array(ref["losses"])
+    assert got.shape == want.shape and np.max(np.abs(got - want) / want) < 2e-4, (got[:4], want[:4])
+    assert np.allclose(res["val_mse"], ref["mses"], rtol=2e-4) and res["best_epoch"] == ref["best_epoch"]
 
 
 def read_base_like(msb):

@@ -66,6 +66,20 @@ def test_forward_kat():
     assert np.array_equal(y.numpy(), g["y"])
 
 
+def test_forward_relu_kat():
+    """The ReLU variant (encode.py:75 / decode.py:108, commented alternative): the oracle's forward, loss and autograd
+    gradients against the reference's own LBDRNModel(activation=nn.ReLU()) + LBDRNLoss."""
+    g = np.load(os.path.join(GOLD, "forward_relu_d100_bc64.npz"))
+    p = [t.requires_grad_(True) for t in O.unflatten_params(g["params"], 100, 64, 4, 2)]
+    y = O.forward(p, torch.from_numpy(g["x"]), relu=True)
+    assert np.array_equal(y.detach().numpy(), g["y"])
+    assert 0.2 < float((y.detach() > 0.5).float().mean()) < 0.8          # the fixture exercises both sides of the head
+    loss = torch.nn.functional.mse_loss(y, torch.from_numpy(g["t"]))
+    loss.backward()
+    assert np.float32(loss.item()) == g["loss"]
+    assert np.array_equal(np.concatenate([t.grad.numpy().reshape(-1) for t in p]), g["grad"])
+
+
 @pytest.mark.parametrize("name", CODEC_CASES + ["sr2_tiles"])
 def test_decode_matches_reference_bit_exactly(name):
     meta, img, blob, recon = load_case(name)
