@@ -53,7 +53,9 @@ enum { LBDRN_U8 = 0, LBDRN_U16 = 1 };
  * TENSOR = tcgen05 split-precision tensor-core path where the configuration supports it. AUTO picks TENSOR
  * when available, else PRECISE. */
 enum { LBDRN_PATH_AUTO = 0, LBDRN_PATH_PRECISE = 1, LBDRN_PATH_TENSOR = 2,
-       LBDRN_PATH_TENSOR_FASTSIN = 3 /* TENSOR with MUFU.SIN after an exact range reduction (abs err ~4e-7) */ };
+       LBDRN_PATH_TENSOR_FASTSIN = 3,  /* TENSOR with MUFU.SIN after an exact range reduction (abs err ~4e-7) */
+       LBDRN_PATH_TENSOR_FASTSIN2 = 4  /* TENSOR with MUFU.SIN alone: the unit reduces the argument itself after one
+                                          multiplication by 1/(2 pi) rounded toward zero (adds <= |w0 z| * 1.2e-7) */ };
 
 /* One scene (or one row stripe of it) + network shape.  Rows are GLOBAL image rows: a rank that decodes
  * stripe [row0,row1) passes a buffer holding rows [buf_row0, buf_row0+buf_rows) which must cover

@@ -31,6 +31,10 @@ int fail(int code, const char* fmt, ...) {
 
 namespace {
 
+// LBDRN_PATH_AUTO: largest K for which the decode kernels evaluate the sine with MUFU.SIN alone (no explicit range
+// reduction).  0 = never; raised only on the evidence of tests/test_gpu_decode.py::test_decode_k_sweep_identity_fraction.
+constexpr int kAutoMufuMaxK = 0;
+
 // ---- descriptor -> Net ----------------------------------------------------------------------------------
 int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {
   if (!d) return fail(LBDRN_E_INVALID, "null descriptor");
@@ -326,18 +330,21 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
   const bool tc_ok = tc_supported(n) || tcw_ok;
   if (d->path == LBDRN_PATH_TENSOR && !tc_ok)
     return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
-  if (d->path == LBDRN_PATH_TENSOR_FASTSIN && !tc_ok)
+  if ((d->path == LBDRN_PATH_TENSOR_FASTSIN || d->path == LBDRN_PATH_TENSOR_FASTSIN2) && !tc_ok)
     return fail(LBDRN_E_UNSUPPORTED, "tensor-core decode is not built for this configuration");
+  if (d->path < LBDRN_PATH_AUTO || d->path > LBDRN_PATH_TENSOR_FASTSIN2) return fail(LBDRN_E_INVALID, "path=%d", d->path);
   if (tc_ok && d->path != LBDRN_PATH_PRECISE) {
     if (!msb_dev || !params_dev || !out_dev) return fail(LBDRN_E_INVALID, "null device pointer");
     // AUTO: MUFU sine while the K-bit quantiser leaves >= 10x margin on the 99.99 % identity bar (K <= 8: 99.9996 %
     // identical at K=8 on the parity suite), the 1.3e-7 polynomial above that
-    const int fast = d->path == LBDRN_PATH_TENSOR_FASTSIN || (d->path == LBDRN_PATH_AUTO && n.K <= 8);
+    // sine variant of the tensor kernels: 0 polynomial, 1 exact reduction + MUFU.SIN, 2 MUFU.SIN alone (lbdrn_tc.cu)
+    int fast = d->path == LBDRN_PATH_TENSOR_FASTSIN2 ? 2 : (d->path == LBDRN_PATH_TENSOR_FASTSIN ? 1 : 0);
+    if (d->path == LBDRN_PATH_AUTO) fast = n.K <= kAutoMufuMaxK ? 2 : (n.K <= 8 ? 1 : 0);
     if (tcw_ok) {
       // bc 128/256: the wide kernel decodes iff the weights are fp16-exact after scaling; the fp32 kernel queued behind
       // it reads the same device flag and exits at once in that case (and does the work otherwise)
       const int* exact_flag = nullptr;
-      rc = tcw_decode(n, msb_dev, params_dev, out_dev, fast, &exact_flag, (cudaStream_t)stream);
+      rc = tcw_decode(n, msb_dev, params_dev, out_dev, fast != 0, &exact_flag, (cudaStream_t)stream);
       if (rc) return rc;
       return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream, exact_flag);
     }

@@ -29,10 +29,18 @@ namespace lbdrn {
 
 namespace {
 
+// K layout of the first layer's operands (the order of the contraction index is ours to choose: A1 and B1 only have to
+// agree).  0: the reference's column order c*n^2 + dy*n + dx.  1 (`tc_raw8`: uint8 planes, C = 4, D = 2): every window row
+// (c, dy) padded from 5 to 6 entries, k' = (c*5 + dy)*6 + dx, so that a row is three fp16 pairs built from two aligned
+// 32-bit words of the staged bytes; the sixth entry carries a zero weight.
+bool tc_raw8(const Net& n) { return !n.msb_u16 && n.C == 4 && n.D == 2 && n.ncol != 0 && getenv("LBDRN_TC_NO_RAW8") == nullptr; }
+
 void plan_block(const Net& n, TcHeader& h) {
   memset(&h, 0, sizeof h);
   h.k1 = n.ncol;                                       // the MMA contracts over the colour features only; coordinate /
   h.k1pad = align_up(n.ncol > 0 ? n.ncol : 1, 16);     // positional features enter through fp32 row / column tables
+  h.klayout = tc_raw8(n) ? 1 : 0;
+  if (h.klayout == 1) h.k1pad = align_up(n.C * 5 * 6, 16);
   h.nl = n.nl;
   int off = align_up((int)sizeof(TcHeader), 16);
   h.off_bias = off; off += n.nl * TC_BC * 4;
@@ -80,8 +88,10 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
     __half* Blo = reinterpret_cast<__half*>(blk + hdr.off_blo[l]);
     int bad = 0;
     for (int i = tid; i < K * net.bc; i += blockDim.x) {
-      const int nrow = i / K, k = i - nrow * K - k0;
+      const int nrow = i / K;
+      int k = i - nrow * K - k0;
       if (k < 0) continue;
+      if (l == 0 && hdr.klayout == 1) k = (k / 5) * 6 + k % 5;            // window rows padded to 6 entries (plan_block)
       const float v = W[i] * up;                                          // exact (power of two)
       const __half hv = __float2half_rn(v);
       const float rem = v - __half2float(hv);                             // exact in fp32
@@ -118,7 +128,7 @@ __global__ void tc_prep_kernel(Net net, TcHeader hdr, const float* __restrict__ 
   if (tid == 0) {
     H->exact = s_exact;
     H->guard_mask = s_guard;
-    H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl;
+    H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl; H->klayout = hdr.klayout;
     H->off_bias = hdr.off_bias; H->off_w3 = hdr.off_w3; H->total = hdr.total; H->hi_bytes = hdr.hi_bytes;
     for (int l = 0; l < net.nl; ++l) { H->off_b[l] = hdr.off_b[l]; H->off_blo[l] = hdr.off_blo[l]; }
   }
@@ -167,16 +177,25 @@ struct TcArgs {
 
 enum { TC_DECODE = 0, TC_SSE = 1 };
 
-// sin(w0 z): FAST = 3-term Cody-Waite to [-pi, pi] then MUFU.SIN (abs err ~4e-7); else the 7e-8 polynomial version
-template <bool FAST>
+// sin(w0 z).  SINE_POLY: 2-term Cody-Waite(pi) + degree-9 polynomial (1.3e-7 abs).  SINE_CW_MUFU: exact 2-term reduction
+// to [-pi, pi] then MUFU.SIN (abs err ~4e-7).  SINE_MUFU: sin.approx alone -- SASS is FMUL.RZ by 1/(2 pi) + MUFU.SIN, the
+// unit takes the fractional turn itself, so the only error on top of MUFU's own is the one rounding (toward zero) of the
+// argument expressed in turns, <= |a| * 1.2e-7 rad: 3 instructions per hidden unit instead of 7 (with the scale + bias FFMA).
+enum { SINE_POLY = 0, SINE_CW_MUFU = 1, SINE_MUFU = 2 };
+template <int SINE>
 __device__ __forceinline__ float tc_sine(float a) {
-  if (!FAST) return sin_pi9_core(a);
+  if (SINE == SINE_POLY) return sin_pi9_core(a);
+  if (SINE == SINE_MUFU) return __sinf(a);
   const float t = fmaf(a, 0.15915494309189535f, 12582912.0f);
   const float k = t - 12582912.0f;
   float r = fmaf(k, -6.28318548202514648f, a);
   r = fmaf(k, 1.74845553146e-7f, r);       // 2*pi = 6.28318548202514648 - 1.74845553146e-7 (fp32 hi + lo)
   return __sinf(r);
 }
+
+// nn.Sigmoid with the approximate exponential / reciprocal units (SINE_MUFU kernels only): 2^-22 relative on each, i.e.
+// |dy| < 1e-7, an order of magnitude below what the MUFU sine already contributes
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + __expf(-z)); }
 
 constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+2D)*(16+2D) <= 2048)
 
@@ -191,7 +210,11 @@ constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+
 // block is 47 KB with the lo halves, so one CTA per SM with FOUR warpgroups sharing it keeps 16 warps resident where two
 // single-warpgroup CTAs kept 8 (evaluation of an 8192^2 scene 14.9 -> see DESIGN 4.1).
 // COORDS: USE_COORDINATES feature sets (table-driven colour offsets; fp32 row / column tables added in the first epilogue).
-template <bool FAST, int CC, int DD, bool WLO, int MODE, int NWG, bool COORDS = false>
+// RAW8 (uint8 planes, C = 4, D = 2; K layout 1 of plan_block): A1 is built straight from the staged BYTES -- per window row two
+// aligned 32-bit shared-memory loads, byte permutes into fp16 pairs (0x6400 | m is the fp16 number 1024 + m, so the pair
+// minus (1024 + centre) is the exact integer difference) -- no fp16 copy of the patch, 40 loads per pixel instead of 108.
+// PF: the next 16 accumulator columns are requested from tensor memory before the current 16 are consumed.
+template <int SINE, int CC, int DD, bool WLO, int MODE, int NWG, bool COORDS = false, bool RAW8 = false, bool PF = false>
 __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2 : (WLO ? 2 : 3))) tc_decode_kernel(const TcArgs a) {
   constexpr int THREADS = TC_THREADS * NWG;
   const Net& net = a.net;
@@ -268,26 +291,28 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 
   // ---- patch element -> (band, row, col), fixed for the whole kernel; tile loads are prefetched one tile ahead -------
   constexpr int PFN = (CC == 4 && DD <= 2) ? 8 : TC_PF;   // patch elements per thread
-  constexpr bool REGPF = NWG == 1;                        // per-thread register prefetch of non-TMA tiles
+  constexpr bool REGPF = NWG == 1 && !RAW8;               // per-thread register prefetch of non-TMA tiles
   const bool pf_ok = n_patch <= PFN * TC_THREADS;
   const int es = net.msb_u16 ? 2 : 1, box_w = a.box_w;
   int pe[REGPF ? PFN : 1];                         // band << 16 | row << 8 | col, or -1
   uint32_t pf[REGPF ? PFN : 1];
   long long pe_off[REGPF ? PFN : 1];               // element offset relative to the patch origin (interior tiles)
-  int pe_src[PFN];                                 // offset of patch element i inside the TMA box (fixed per kernel), or -1
+  int pe_src[RAW8 ? 1 : PFN];                      // offset of patch element i inside the TMA box (fixed per kernel), or -1
+  if (!RAW8) {
 #pragma unroll
-  for (int i = 0; i < PFN; ++i) {
-    const int e = tid + i * TC_THREADS;
-    const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
-    pe_src[i] = e < n_patch ? (c * trows + r) * box_w + (a.box_lead - D) + x : -1;
-    if (REGPF) {
-      pe[i] = e < n_patch ? ((c << 16) | (r << 8) | x) : -1;
-      pe_off[i] = e < n_patch ? ((long long)c * net.buf_rows + r) * net.W + x : 0;
+    for (int i = 0; i < PFN; ++i) {
+      const int e = tid + i * TC_THREADS;
+      const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
+      pe_src[RAW8 ? 0 : i] = e < n_patch ? (c * trows + r) * box_w + (a.box_lead - D) + x : -1;
+      if (REGPF) {
+        pe[REGPF ? i : 0] = e < n_patch ? ((c << 16) | (r << 8) | x) : -1;
+        pe_off[REGPF ? i : 0] = e < n_patch ? ((long long)c * net.buf_rows + r) * net.W + x : 0;
+      }
     }
   }
-  auto issue_patch_loads = [&](int tile) {
+  // (y0, x0): top-left corner of the halo'd tile
+  auto issue_patch_loads = [&](int y0, int x0) {
     if (!REGPF) return;
-    const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
     if (y0 >= 0 && x0 >= 0 && y0 + trows <= net.H && x0 + twp <= net.W) {      // no reflection needed
       const long long origin = (long long)(y0 - net.buf_row0) * net.W + x0;
 #pragma unroll
@@ -304,38 +329,110 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
     }
   };
   // TMA staging of interior tiles: one elected thread issues the box load for the NEXT tile; it lands in `raw` while
-  // this tile computes and is converted to fp16 at the top of the next iteration.  Border tiles (reflection needed) and
-  // buffers TMA cannot address (row pitch not a multiple of 16 B) use the per-thread prefetch above (NWG=1) or plain
-  // loads (NWG=2: border tiles only, <1 % of a scene).
+  // this tile computes.  Border tiles (reflection needed) and buffers TMA cannot address (row pitch not a multiple of
+  // 16 B) use the per-thread prefetch above (NWG=1, fp16 patch) or plain loads at the top of the tile.
   const uint32_t mbar_tma = smem_u32(&s_mbar_tma[wg]), raw_u = smem_u32(raw);
   const uint32_t box_bytes = (uint32_t)(box_w * trows * C * es);
-  auto tile_uses_tma = [&](int tile) {
-    if (!a.use_tma) return false;
-    const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
-    return y0 >= 0 && x0 >= 0 && y0 + trows <= net.H && x0 + twp <= net.W;
+  // tile index -> image coordinates of its first pixel: one division per tile, for the NEXT tile only
+  auto tile_xy = [&](int tile, int& y0, int& x0) {
+    const int ty = tile / a.tiles_x;
+    y0 = net.row0 + ty * TC_TH;
+    x0 = (tile - ty * a.tiles_x) * TC_TW;
   };
-  auto stage_next = [&](int tile) {            // called by all threads; exactly one of the two mechanisms is used
-    if (tile >= a.n_tiles) return;
-    if (tile_uses_tma(tile)) {
+  auto interior = [&](int y0, int x0) {             // the halo'd tile lies inside the image and TMA can address the buffer
+    return a.use_tma && y0 - D >= 0 && x0 - D >= 0 && y0 - D + trows <= net.H && x0 - D + twp <= net.W;
+  };
+  auto stage_tile = [&](bool valid, int y0, int x0, bool by_tma) {   // called by all threads of the warpgroup
+    if (!valid) return;
+    if (by_tma) {
       if (warp == 0) {             // warp-uniform; one elected lane issues (operands stay in uniform registers)
-        const int y0 = net.row0 + (tile / a.tiles_x) * TC_TH - D, x0 = (tile % a.tiles_x) * TC_TW - D;
         if (elect_one()) {
           mbar_expect_tx(mbar_tma, box_bytes);
-          tma_load_3d(raw_u, a.tmap_dev, x0 + D - a.box_lead, y0 - net.buf_row0, 0, mbar_tma);
+          tma_load_3d(raw_u, a.tmap_dev, x0 - a.box_lead, y0 - D - net.buf_row0, 0, mbar_tma);
         }
         __syncwarp();
       }
     } else if (REGPF && pf_ok) {
-      issue_patch_loads(tile);
+      issue_patch_loads(y0 - D, x0 - D);
     }
   };
   uint32_t phase_tma = 0;
-  bool cur_tma = tile0 < a.n_tiles && tile_uses_tma(tile0);   // staging mechanism of the tile about to be consumed
-  stage_next(tile0);
+  int cy0 = 0, cx0 = 0;
+  bool cur_tma = false;                             // staging mechanism of the tile about to be consumed
+  if (tile0 < a.n_tiles) {
+    tile_xy(tile0, cy0, cx0);
+    cur_tma = interior(cy0, cx0);
+  }
+  stage_tile(tile0 < a.n_tiles, cy0, cx0, cur_tma);
+  const int pr = tid >> 4, px = tid & 15;
 
   for (int t = tile0; t < a.n_tiles; t += tile_step) {
-    const int ty0 = net.row0 + (t / a.tiles_x) * TC_TH, tx0 = (t % a.tiles_x) * TC_TW;
+    const int ty0 = cy0, tx0 = cx0;
+    const bool has_next = t + tile_step < a.n_tiles;
+    int ny0 = 0, nx0 = 0;
+    bool nxt_tma = false;
+    if (has_next) {
+      tile_xy(t + tile_step, ny0, nx0);
+      nxt_tma = interior(ny0, nx0);
+    }
+    uint32_t mctr[RAW8 ? 1 : kMaxC];                // centre MSB integers for the final (m << K) + residual (RAW8: packed bytes)
 
+    if constexpr (RAW8) {
+      // ---- staged bytes of (tile + halo), TMA box layout [band][row][box_w]; A1 straight from them ------------------------
+      if (cur_tma) {
+        mbar_wait(mbar_tma, phase_tma, 2, t, a.no_trap);
+        phase_tma ^= 1;
+      } else {
+        for (int e = tid; e < n_patch; e += TC_THREADS) {
+          const int c = e / (trows * twp), rem = e - c * trows * twp, r = rem / twp, x = rem - r * twp;
+          const int gy = reflect_clamp(ty0 - D + r, net.H), gx = reflect_clamp(tx0 - D + x, net.W);
+          raw[(c * trows + r) * box_w + (a.box_lead - D) + x] =
+              (uint8_t)load_msb_int(a.msb, 0, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx);
+        }
+        wg_sync();
+      }
+      constexpr int TRW_ = TC_TH + 2 * DD;                       // 12 patch rows per band
+      const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw);
+      const int bw4 = box_w >> 2;                                // box_w is a multiple of 16 bytes
+      const int bcol = a.box_lead - DD + px;                     // byte column of the window's first element
+      const uint32_t o = (uint32_t)bcol & 3u;
+      const uint32_t sel_a = 0x3210u + o * 0x1111u;              // bytes o..o+3 of the two words
+      const uint32_t sel_b = (o + 4u) * 0x1111u;                 // byte o+4 (replicated: the sixth entry has a zero weight)
+      const uint32_t* rp = raw32 + pr * bw4 + (bcol >> 2);
+      constexpr uint32_t C64 = 0x64646464u;                      // 0x64mm = fp16(1024 + mm)
+      uint32_t cpk = 0;
+      uint32_t dq[4];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        uint32_t w0[5], w1[5];
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+          const uint32_t lo = rp[(c * TRW_ + dy) * bw4], hi = rp[(c * TRW_ + dy) * bw4 + 1];
+          w0[dy] = __byte_perm(lo, hi, sel_a);
+          w1[dy] = __byte_perm(lo, hi, sel_b);
+        }
+        const uint32_t cpu = rel ? __byte_perm(w0[DD], C64, 0x4242) : 0x64006400u;   // (1024 + centre) twice
+        const __half2 cp = *reinterpret_cast<const __half2*>(&cpu);
+        cpk = __byte_perm(cpk, w0[DD], c == 0 ? 0x3216 : (c == 1 ? 0x3260 : (c == 2 ? 0x3610 : 0x6210)));
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const uint32_t pu = __byte_perm(j < 2 ? w0[dy] : w1[dy], C64, j == 1 ? 0x4342 : 0x4140);
+            const __half2 dv = __hsub2(*reinterpret_cast<const __half2*>(&pu), cp);
+            const int q = (c * 5 + dy) * 3 + j;                  // pair index in K order; four pairs per 16-byte chunk
+            dq[q & 3] = *reinterpret_cast<const uint32_t*>(&dv);
+            if ((q & 3) == 3)
+              *reinterpret_cast<uint4*>(sA + (size_t)((q >> 2) * 128 + tid) * 16) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+          }
+        }
+      }
+      // K is padded from C*30 to a multiple of 16: the pad multiplies zero weights but must be finite
+#pragma unroll
+      for (int kc = CC * 15 / 4; kc < (CC * 30 + 15) / 16 * 2; ++kc)
+        *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      mctr[0] = cpk;
+    } else {
     // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
     if (cur_tma) {
       mbar_wait(mbar_tma, phase_tma, 2, t, a.no_trap);
@@ -343,8 +440,8 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
       if (pf_ok) {                                                   // box offsets precomputed in pe_src[]
 #pragma unroll
         for (int i = 0; i < PFN; ++i) {
-          if (pe_src[i] >= 0) {
-            const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[pe_src[i]] : (uint32_t)raw[pe_src[i]];
+          if (pe_src[RAW8 ? 0 : i] >= 0) {
+            const uint32_t v = net.msb_u16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw)[pe_src[RAW8 ? 0 : i]] : (uint32_t)raw[pe_src[RAW8 ? 0 : i]];
             patch[tid + i * TC_THREADS] = __uint2half_rn(v);
           }
         }
@@ -369,11 +466,9 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
       }
     }
     wg_sync();
-    cur_tma = t + tile_step < a.n_tiles && tile_uses_tma(t + tile_step);
-    stage_next(t + tile_step);                                                       // lands while this tile computes
+    stage_tile(has_next, ny0, nx0, nxt_tma);                                         // lands while this tile computes
 
     // ---- A1 row of this thread's pixel: integer differences (exact in fp16), 16 B per K chunk ---------------------------
-    const int pr = tid >> 4, px = tid & 15;
     const __half* pme = patch + pr * twp + px;
     if (CC) {
       constexpr int N_ = 2 * DD + 1, NN_ = N_ * N_, K1_ = (CC ? CC : 1) * NN_, TWP_ = TC_TW + 2 * DD, TRW_ = TC_TH + 2 * DD;
@@ -423,10 +518,10 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
       }
     }
     // centre MSB integers for the final (m << K) + residual
-    uint32_t mctr[kMaxC];
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c)
-      mctr[c] = c < C ? (uint32_t)__half2int_rn(patch[(c * trows + pr + D) * twp + px + D]) : 0u;
+      mctr[RAW8 ? 0 : c] = c < C ? (uint32_t)__half2int_rn(patch[(c * trows + pr + D) * twp + px + D]) : 0u;
+    }
 
     float yacc[kMaxC];
 #pragma unroll
@@ -434,7 +529,7 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 
     for (int l = 0; l < NL; ++l) {
       // ---- MMA for hidden layer l: one elected thread issues, completion arrives on the mbarrier -----------------------
-      fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      fence_async_smem();          // generic-proxy smem writes (and, RAW8, our reads of `raw`) -> ordered before the async proxy
       tc_fence_before();
       wg_sync();
       if (warp == 0) {
@@ -462,6 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
        }
        __syncwarp();
       }
+      if (RAW8 && l == 0) stage_tile(has_next, ny0, nx0, nxt_tma);    // every thread's reads of `raw` precede the barrier above
       mbar_wait(mbar, phase, 1, t, a.no_trap);
       phase ^= 1;
       tc_fence_after();
@@ -474,9 +570,9 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
       const bool coords = COORDS && l == 0;
       const float4* rrow = reinterpret_cast<const float4*>(a.rtab + (size_t)min(ty0 + pr, net.H - 1) * TC_BC);
       const float4* crow = reinterpret_cast<const float4*>(a.ctab + (size_t)min(tx0 + px, net.W - 1) * TC_BC);
-#pragma unroll 1
-      for (int cb = 0; cb < TC_BC; cb += 16) {
-        float acc[16];
+      // one block of 16 hidden units: scale + bias, activation, then either the hi/lo operand of the next layer or the
+      // output layer's partial sums
+      auto block16 = [&](int cb, float (&acc)[16]) {
         float bterm[16];
         if (coords) {                 // fp32 coordinate contribution (includes the bias) instead of the bias alone
 #pragma unroll
@@ -491,7 +587,6 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
             bterm[4 * q] = b4.x; bterm[4 * q + 1] = b4.y; bterm[4 * q + 2] = b4.z; bterm[4 * q + 3] = b4.w;
           }
         }
-        tmem_ld16(tmem_row + cb, acc);
         float h[16];
         if (net.relu) {
 #pragma unroll
@@ -500,7 +595,7 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             acc[j] = fmaf(acc[j], scale, bterm[j]);            // = w0 * z (w0 folded into scale and bias)
-            h[j] = tc_sine<FAST>(acc[j]);
+            h[j] = tc_sine<SINE>(acc[j]);
           }
           if (guard) {                                          // uniform: tc_prep_kernel could not bound |w0 z| for this layer
             float amax = 0.f;
@@ -542,6 +637,32 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
             }
           }
         }
+      };
+      if constexpr (PF) {
+        // ping-pong: the load of block i+1 is in flight while block i is consumed
+        uint32_t ra[16], rb[16];
+        tmem_ld16_issue(tmem_row, ra);
+#pragma unroll 1
+        for (int cb = 0; cb < TC_BC; cb += 32) {
+          float acc[16];
+          tmem_ld16_wait(ra);
+          tmem_ld16_issue(tmem_row + cb + 16, rb);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(ra[j]);
+          block16(cb, acc);
+          tmem_ld16_wait(rb);
+          if (cb + 32 < TC_BC) tmem_ld16_issue(tmem_row + cb + 32, ra);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rb[j]);
+          block16(cb + 16, acc);
+        }
+      } else {
+#pragma unroll 1
+        for (int cb = 0; cb < TC_BC; cb += 16) {
+          float acc[16];
+          tmem_ld16(tmem_row + cb, acc);
+          block16(cb, acc);
+        }
       }
     }
 
@@ -551,11 +672,13 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 #pragma unroll
       for (int c = 0; c < kMaxC; ++c) {
         if (c < C) {
-          const float y = sigmoidf_rn(yacc[c] + w3t[TC_BC * 8 + c]);
+          const float yz = yacc[c] + w3t[TC_BC * 8 + c];
+          const float y = SINE == SINE_MUFU ? sigmoidf_fast(yz) : sigmoidf_rn(yz);
           const size_t off = ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx;
           if (MODE == TC_DECODE) {
             const int res = (int)rintf(y * net.qmax);
-            a.out[off] = (uint16_t)((mctr[c] << net.K) + (uint32_t)res);
+            const uint32_t m = RAW8 ? ((mctr[0] >> (8 * (c & 3))) & 0xFFu) : mctr[RAW8 ? 0 : c];
+            a.out[off] = (uint16_t)((m << net.K) + (uint32_t)res);
           } else {
             const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
             const float d = y - __fdiv_rn((float)code, net.qmax);
@@ -564,6 +687,7 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
         }
       }
     }
+    cy0 = ny0; cx0 = nx0; cur_tma = nxt_tma;
     tc_fence_before();      // our tcgen05.ld's are ordered before the next tile's MMA (issued after the next barrier)
   }
 
@@ -755,17 +879,37 @@ namespace {
 
 using KernT = void (*)(const TcArgs);
 
-template <bool FAST, bool WLO, int MODE, int NWG>
-KernT pick_kernel(const Net& n) {
+// sine: SINE_POLY / SINE_CW_MUFU / SINE_MUFU (the last one is instantiated for the paper's configuration -- uint8 planes,
+// C = 4, D = 2, colour features -- and falls back to SINE_CW_MUFU elsewhere).  pf: accumulator loads one block ahead
+// (two-warpgroup decode kernel of that configuration only).
+template <int SINE, bool WLO, int MODE, int NWG>
+KernT pick_kernel(const Net& n, bool pf = false) {
+  constexpr int S = SINE == SINE_MUFU ? SINE_CW_MUFU : SINE;      // variant used outside the RAW8 family
+  const bool raw8 = tc_raw8(n);
   if (n.nco) {                                       // coordinate features (USE_COLORS off: k1 = 0, table-driven kernel)
-    if (n.ncol && n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE, NWG, true>;
-    return tc_decode_kernel<FAST, 0, 0, WLO, MODE, NWG, true>;
+    if (n.ncol && n.C == 4 && n.D == 2)
+      return raw8 ? tc_decode_kernel<S, 4, 2, WLO, MODE, NWG, true, true> : tc_decode_kernel<S, 4, 2, WLO, MODE, NWG, true>;
+    return tc_decode_kernel<S, 0, 0, WLO, MODE, NWG, true>;
   }
-  if (n.C == 4 && n.D == 2) return tc_decode_kernel<FAST, 4, 2, WLO, MODE, NWG>;
-  if (n.C == 8 && n.D == 2) return tc_decode_kernel<FAST, 8, 2, WLO, MODE, NWG>;
-  if (n.C == 4 && n.D == 1) return tc_decode_kernel<FAST, 4, 1, WLO, MODE, NWG>;
-  if (n.C == 4 && n.D == 3) return tc_decode_kernel<FAST, 4, 3, WLO, MODE, NWG>;
-  return tc_decode_kernel<FAST, 0, 0, WLO, MODE, NWG>;
+  if (n.C == 4 && n.D == 2) {
+    if (raw8) {
+      if constexpr (!WLO && MODE == TC_DECODE && NWG == 2 && SINE != SINE_POLY)
+        if (pf) return tc_decode_kernel<SINE, 4, 2, WLO, MODE, NWG, false, true, true>;
+      return tc_decode_kernel<SINE, 4, 2, WLO, MODE, NWG, false, true>;
+    }
+    return tc_decode_kernel<S, 4, 2, WLO, MODE, NWG>;
+  }
+  if (n.C == 8 && n.D == 2) return tc_decode_kernel<S, 8, 2, WLO, MODE, NWG>;
+  if (n.C == 4 && n.D == 1) return tc_decode_kernel<S, 4, 1, WLO, MODE, NWG>;
+  if (n.C == 4 && n.D == 3) return tc_decode_kernel<S, 4, 3, WLO, MODE, NWG>;
+  return tc_decode_kernel<S, 0, 0, WLO, MODE, NWG>;
+}
+
+template <bool WLO, int NWG>
+KernT pick_decode(const Net& n, int sine, bool pf) {
+  if (sine == SINE_MUFU) return pick_kernel<SINE_MUFU, WLO, TC_DECODE, NWG>(n, pf);
+  if (sine == SINE_CW_MUFU) return pick_kernel<SINE_CW_MUFU, WLO, TC_DECODE, NWG>(n, pf);
+  return pick_kernel<SINE_POLY, WLO, TC_DECODE, NWG>(n, pf);
 }
 
 // TMA descriptor of the MSB planes: dims (W, buf_rows, C); needs a 16 B-aligned base and row / plane pitches.
@@ -905,16 +1049,13 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
   // two sibling launches; the exactness flag computed by tc_prep_kernel decides ON THE DEVICE which one does the work
   a.run_if_exact = 1;
   const bool two = a.use_tma && !getenv("LBDRN_TC_NWG1");     // TMA-addressable input: two warpgroups per CTA
-  if (two)
-    rc = tc_launch(fast_sine ? pick_kernel<true, false, TC_DECODE, 2>(n) : pick_kernel<false, false, TC_DECODE, 2>(n), a, h,
-                   false, 2, dev, st);
-  else
-    rc = tc_launch(fast_sine ? pick_kernel<true, false, TC_DECODE, 1>(n) : pick_kernel<false, false, TC_DECODE, 1>(n), a, h,
-                   false, 1, dev, st);
+  const char* pfe = getenv("LBDRN_TC_PF");
+  const bool pf = pfe ? atoi(pfe) != 0 : true;
+  rc = two ? tc_launch(pick_decode<false, 2>(n, fast_sine, pf), a, h, false, 2, dev, st)
+           : tc_launch(pick_decode<false, 1>(n, fast_sine, pf), a, h, false, 1, dev, st);
   if (rc) return rc;
   a.run_if_exact = 0;
-  return tc_launch(fast_sine ? pick_kernel<true, true, TC_DECODE, 1>(n) : pick_kernel<false, true, TC_DECODE, 1>(n), a, h, true,
-                   1, dev, st);
+  return tc_launch(pick_decode<true, 1>(n, fast_sine, pf), a, h, true, 1, dev, st);
 }
 
 int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, const float* tab, double* sse_out,
@@ -939,8 +1080,8 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   // four warpgroups sharing one weight block where that fits (C = 4, D = 2: 193 KB); wider inputs keep one warpgroup per CTA
   if (a.use_tma && !getenv("LBDRN_TC_NWG1") && tc_smem_bytes(a, h, true, 4) + 2048 <= (size_t)max_smem)
-    return tc_launch(pick_kernel<true, true, TC_SSE, 4>(n), a, h, true, 4, dev, st);
-  return tc_launch(pick_kernel<true, true, TC_SSE, 1>(n), a, h, true, 1, dev, st);
+    return tc_launch(pick_kernel<SINE_CW_MUFU, true, TC_SSE, 4>(n), a, h, true, 4, dev, st);
+  return tc_launch(pick_kernel<SINE_CW_MUFU, true, TC_SSE, 1>(n), a, h, true, 1, dev, st);
 }
 
 int tc_selftest2(const void* a_dev, const void* b_dev, float* d_dev, int N, int K, int a_mn, int b_mn, cudaStream_t st) {

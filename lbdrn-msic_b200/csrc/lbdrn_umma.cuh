@@ -23,7 +23,8 @@ struct TcHeader {
   int off_blo[kMaxLayers];   // low-order fp16 term of the weights (W*2^s = hi + lo); all zero when `exact`
   int hi_bytes;              // block size without the lo operands (what the exact-weights kernel copies)
   int guard_mask;            // bit l set: layer l's sine needs the large-argument guard (|w0 z| may exceed 20000, or unknown)
-  int pad[6];
+  int klayout;               // order of layer 0's contraction index (lbdrn_tc.cu: plan_block)
+  int pad[5];
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -112,6 +113,25 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tcgen05.ld split into issue and wait so that the next block's load is in flight while this block's values are
+// consumed.  The wait names the destination registers as read-write operands: nothing that uses them can be scheduled
+// above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("LBDRN_LIB", os.path.join(HERE, "liblbdrn_b200.so"))
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4
 USE_COORDINATES, EMBEDDING, USE_COLORS, RELATIVE, ACT_RELU = 1, 2, 4, 8, 16
 U8, U16 = 0, 1
-PATH_AUTO, PATH_PRECISE, PATH_TENSOR, PATH_TENSOR_FASTSIN = 0, 1, 2, 3
+PATH_AUTO, PATH_PRECISE, PATH_TENSOR, PATH_TENSOR_FASTSIN, PATH_TENSOR_FASTSIN2 = 0, 1, 2, 3, 4
 
 # every symbol include/lbdrn.h declares (tests check the library exports exactly these)
 SYMBOLS = ["lbdrn_version", "lbdrn_last_error", "lbdrn_dim_in", "lbdrn_param_count", "lbdrn_has_tensor_path",

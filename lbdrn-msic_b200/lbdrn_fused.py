@@ -131,7 +131,7 @@ def _base_to_device(base, dev, known_max=None):
 
 
 _PATHS = {"auto": cabi.PATH_AUTO, "precise": cabi.PATH_PRECISE, "tensor": cabi.PATH_TENSOR,
-          "tensor_fastsin": cabi.PATH_TENSOR_FASTSIN}
+          "tensor_fastsin": cabi.PATH_TENSOR_FASTSIN, "tensor_fastsin2": cabi.PATH_TENSOR_FASTSIN2}
 
 
 def _tab_tensor(H, W, flags, dev):
