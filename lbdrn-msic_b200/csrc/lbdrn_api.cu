@@ -32,8 +32,11 @@ int fail(int code, const char* fmt, ...) {
 namespace {
 
 // LBDRN_PATH_AUTO: largest K for which the decode kernels evaluate the sine with MUFU.SIN alone (no explicit range
-// reduction).  0 = never; raised only on the evidence of tests/test_gpu_decode.py::test_decode_k_sweep_identity_fraction.
-constexpr int kAutoMufuMaxK = 0;
+// reduction).  Measured on 8.4 M sub-pixels per K with reference-trained weights (tools/sine_parity.py,
+// profiles/r2_sine_parity.txt): its mismatch rate against the reference's fp32 path equals that of the variant with the
+// exact reduction (6.2 vs 6.4 ppm at K = 5, 31 vs 29 ppm at K = 8; bar 100 ppm) -- what separates both from the reference
+// is MUFU.SIN's own 4e-7, not the one extra rounding of the argument.
+constexpr int kAutoMufuMaxK = 8;
 
 // ---- descriptor -> Net ----------------------------------------------------------------------------------
 int resolve(const LbdrnDesc* d, Net& n, bool need_rows = true) {

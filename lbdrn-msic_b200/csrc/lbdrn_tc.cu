@@ -197,6 +197,50 @@ __device__ __forceinline__ float tc_sine(float a) {
 // |dy| < 1e-7, an order of magnitude below what the MUFU sine already contributes
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + __expf(-z)); }
 
+// A1 rows of one pixel straight from the staged bytes (RAW8; K layout 1 of plan_block).  rp: the aligned 32-bit word that
+// holds the first byte of the pixel's top-left window element in band 0; bw4: words per staged row; sel_a / sel_b: byte
+// selectors of window elements 0..3 / 4 inside the two words of a window row (the same for every row of the thread).
+// 0x64mm is the fp16 number 1024 + mm, so (pair) - (1024 + centre) is the exact integer difference.  Returns the four
+// centre bytes packed (band c in byte c) for the final (m << K) + residual.
+template <int CC>
+__device__ __forceinline__ uint32_t build_a1_raw8(const uint32_t* __restrict__ rp, int bw4, uint32_t sel_a, uint32_t sel_b,
+                                                  bool rel, uint8_t* sA, int tid) {
+  constexpr int TRW_ = TC_TH + 4;                              // 12 staged rows per band (D = 2)
+  constexpr uint32_t C64 = 0x64646464u;
+  uint32_t cpk = 0;
+  uint32_t dq[4];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    uint32_t w0[5], w1[5];
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+      const uint32_t lo = rp[(c * TRW_ + dy) * bw4], hi = rp[(c * TRW_ + dy) * bw4 + 1];
+      w0[dy] = __byte_perm(lo, hi, sel_a);
+      w1[dy] = __byte_perm(lo, hi, sel_b);
+    }
+    const uint32_t cpu = rel ? __byte_perm(w0[2], C64, 0x4242) : 0x64006400u;   // (1024 + centre) twice
+    const __half2 cp = *reinterpret_cast<const __half2*>(&cpu);
+    cpk = __byte_perm(cpk, w0[2], c == 0 ? 0x3216 : (c == 1 ? 0x3260 : (c == 2 ? 0x3610 : 0x6210)));
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t pu = __byte_perm(j < 2 ? w0[dy] : w1[dy], C64, j == 1 ? 0x4342 : 0x4140);
+        const __half2 dv = __hsub2(*reinterpret_cast<const __half2*>(&pu), cp);
+        const int q = (c * 5 + dy) * 3 + j;                  // pair index in K order; four pairs per 16-byte chunk
+        dq[q & 3] = *reinterpret_cast<const uint32_t*>(&dv);
+        if ((q & 3) == 3)
+          *reinterpret_cast<uint4*>(sA + (size_t)((q >> 2) * 128 + tid) * 16) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+      }
+    }
+  }
+  // K is padded from C*30 to a multiple of 16: the pad multiplies zero weights but must be finite
+#pragma unroll
+  for (int kc = CC * 15 / 4; kc < (CC * 30 + 15) / 16 * 2; ++kc)
+    *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  return cpk;
+}
+
 constexpr int TC_PF = 16;  // patch elements prefetched per thread (covers C*(8+2D)*(16+2D) <= 2048)
 
 // CC/DD > 0: bands / radius known at compile time (feature offsets fold into immediates); CC == 0: generic tables.
@@ -391,46 +435,11 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
         }
         wg_sync();
       }
-      constexpr int TRW_ = TC_TH + 2 * DD;                       // 12 patch rows per band
-      const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw);
       const int bw4 = box_w >> 2;                                // box_w is a multiple of 16 bytes
       const int bcol = a.box_lead - DD + px;                     // byte column of the window's first element
       const uint32_t o = (uint32_t)bcol & 3u;
-      const uint32_t sel_a = 0x3210u + o * 0x1111u;              // bytes o..o+3 of the two words
-      const uint32_t sel_b = (o + 4u) * 0x1111u;                 // byte o+4 (replicated: the sixth entry has a zero weight)
-      const uint32_t* rp = raw32 + pr * bw4 + (bcol >> 2);
-      constexpr uint32_t C64 = 0x64646464u;                      // 0x64mm = fp16(1024 + mm)
-      uint32_t cpk = 0;
-      uint32_t dq[4];
-#pragma unroll
-      for (int c = 0; c < CC; ++c) {
-        uint32_t w0[5], w1[5];
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy) {
-          const uint32_t lo = rp[(c * TRW_ + dy) * bw4], hi = rp[(c * TRW_ + dy) * bw4 + 1];
-          w0[dy] = __byte_perm(lo, hi, sel_a);
-          w1[dy] = __byte_perm(lo, hi, sel_b);
-        }
-        const uint32_t cpu = rel ? __byte_perm(w0[DD], C64, 0x4242) : 0x64006400u;   // (1024 + centre) twice
-        const __half2 cp = *reinterpret_cast<const __half2*>(&cpu);
-        cpk = __byte_perm(cpk, w0[DD], c == 0 ? 0x3216 : (c == 1 ? 0x3260 : (c == 2 ? 0x3610 : 0x6210)));
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy) {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const uint32_t pu = __byte_perm(j < 2 ? w0[dy] : w1[dy], C64, j == 1 ? 0x4342 : 0x4140);
-            const __half2 dv = __hsub2(*reinterpret_cast<const __half2*>(&pu), cp);
-            const int q = (c * 5 + dy) * 3 + j;                  // pair index in K order; four pairs per 16-byte chunk
-            dq[q & 3] = *reinterpret_cast<const uint32_t*>(&dv);
-            if ((q & 3) == 3)
-              *reinterpret_cast<uint4*>(sA + (size_t)((q >> 2) * 128 + tid) * 16) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
-          }
-        }
-      }
-      // K is padded from C*30 to a multiple of 16: the pad multiplies zero weights but must be finite
-#pragma unroll
-      for (int kc = CC * 15 / 4; kc < (CC * 30 + 15) / 16 * 2; ++kc)
-        *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t cpk = build_a1_raw8<CC ? CC : 1>(reinterpret_cast<const uint32_t*>(raw) + pr * bw4 + (bcol >> 2), bw4,
+                                                      0x3210u + o * 0x1111u, (o + 4u) * 0x1111u, rel, sA, tid);
       mctr[0] = cpk;
     } else {
     // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
@@ -715,6 +724,282 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(TC_TMEM_COLS * NWG) : "memory");
 }
 
+// ---- pipelined decode kernel of the paper's configuration ----------------------------------------------------------------
+// uint8 planes, C = 4, D = 2, colour features, nl = 2, fp16-exact weights, TMA-addressable planes (the headline workload).
+// Same arithmetic as tc_decode_kernel<SINE, 4, 2, false, TC_DECODE, 2, false, true>; what changes is the ORDER of a
+// warpgroup's work, so that it never sleeps on a tensor-core completion.  Each warpgroup owns TWO accumulators (128 TMEM
+// columns; 2 warpgroups x 2 CTAs fill the SM's 512) and keeps one A region.  Per tile i (p = i & 1):
+//   a  wait MMA1(i)               (issued during tile i-1's step e, finished long ago)
+//   b  epilogue 1: acc[p] -> sine -> hi/lo -> A2 in the A region; issue MMA2(i) -> acc[p]
+//   c  while MMA2(i) runs: sigmoid / quantise / store of tile i-1 (its four output sums were kept in registers) and the
+//      coordinates of tile i+2
+//   d  wait MMA2(i)               (the A region is free again)
+//   e  bytes of tile i+1 (TMA issued during tile i) -> A1 in the A region; issue MMA1(i+1) -> acc[p^1]; TMA for tile i+2
+//   f  while MMA1(i+1) runs: epilogue 2 of tile i: acc[p] -> sine -> output layer sums
+template <int SINE>
+__global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs a) {
+  constexpr int NWG = 2, THREADS = TC_THREADS * NWG, CC = 4, DD = 2;
+  constexpr int TROWS = TC_TH + 2 * DD, TWP = TC_TW + 2 * DD, NPATCH = CC * TROWS * TWP;
+  const Net& net = a.net;
+  const int gtid = threadIdx.x, wg = gtid >> 7, tid = gtid & 127, warp = tid >> 5;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + (size_t)wg * a.a_bytes;
+  uint8_t* sW = smem + (size_t)NWG * a.a_bytes;
+  uint8_t* raw = sW + a.w_bytes + (size_t)wg * a.wg_bytes + align_up(NPATCH * 2, 128);   // same carve-up as tc_decode_kernel
+  __shared__ __align__(8) uint64_t s_mbar_tma[NWG];
+  __shared__ __align__(8) uint64_t s_mbar1[NWG];
+  __shared__ __align__(8) uint64_t s_mbar2[NWG];
+  __shared__ uint32_t s_tmem;
+  auto wg_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "r"(TC_THREADS) : "memory"); };
+
+  {
+    const int4* src = reinterpret_cast<const int4*>(a.blk);
+    int4* dst = reinterpret_cast<int4*>(sW);
+    for (int i = gtid; i < a.w_bytes / 16; i += THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const TcHeader* H = reinterpret_cast<const TcHeader*>(sW);
+  if (a.run_if_exact >= 0 && (H->exact != 0) != (a.run_if_exact != 0)) return;   // the sibling launch handles this scene
+  if (gtid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(2 * TC_TMEM_COLS * NWG)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (gtid == 0) {
+    for (int g = 0; g < NWG; ++g) {
+      mbar_init(smem_u32(&s_mbar1[g]), 1);
+      mbar_init(smem_u32(&s_mbar2[g]), 1);
+      mbar_init(smem_u32(&s_mbar_tma[g]), 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem0 = s_tmem + (uint32_t)(wg * 2 * TC_TMEM_COLS);       // this warpgroup's two accumulators
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;                   // this warp's 32 lanes
+  const uint32_t mbar1 = smem_u32(&s_mbar1[wg]), mbar2 = smem_u32(&s_mbar2[wg]), mbar_tma = smem_u32(&s_mbar_tma[wg]);
+  const uint32_t idesc = umma_idesc_f16(128, TC_BC);
+  const uint32_t sA_u = smem_u32(sA), raw_u = smem_u32(raw);
+  const float* bias = reinterpret_cast<const float*>(sW + H->off_bias);
+  const float* w3t = reinterpret_cast<const float*>(sW + H->off_w3);
+  const bool rel = net.relative != 0, relu = net.relu != 0;
+  const int k1pad = H->k1pad;
+  const int box_w = a.box_w, bw4 = box_w >> 2;
+  const uint32_t box_bytes = (uint32_t)(box_w * TROWS * CC);
+  const int pr = tid >> 4, px = tid & 15;
+  const int bcol = a.box_lead - DD + px;
+  const uint32_t o = (uint32_t)bcol & 3u;
+  const uint32_t sel_a = 0x3210u + o * 0x1111u, sel_b = (o + 4u) * 0x1111u;
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw) + pr * bw4 + (bcol >> 2);
+  const int tile0 = blockIdx.x * NWG + wg, tile_step = gridDim.x * NWG;
+
+  auto tile_xy = [&](int tile, int& y0, int& x0) {
+    const int ty = tile / a.tiles_x;
+    y0 = net.row0 + ty * TC_TH;
+    x0 = (tile - ty * a.tiles_x) * TC_TW;
+  };
+  auto interior = [&](int y0, int x0) {
+    return a.use_tma && y0 - DD >= 0 && x0 - DD >= 0 && y0 - DD + TROWS <= net.H && x0 - DD + TWP <= net.W;
+  };
+  auto issue_tma = [&](int y0, int x0) {                 // all threads of the warpgroup; `raw` must be free
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(mbar_tma, box_bytes);
+        tma_load_3d(raw_u, a.tmap_dev, x0 - a.box_lead, y0 - DD - net.buf_row0, 0, mbar_tma);
+      }
+      __syncwarp();
+    }
+  };
+  uint32_t ph_tma = 0, ph1 = 0, ph2 = 0;
+  // staged bytes of (tile + halo) -> A1 in the A region; returns the packed centre bytes
+  auto stage_and_build = [&](int y0, int x0, bool by_tma, int tile) {
+    if (by_tma) {
+      mbar_wait(mbar_tma, ph_tma, 2, tile, a.no_trap);
+      ph_tma ^= 1;
+    } else {                                              // border tile: plain loads with reflection, TMA box layout
+      for (int e = tid; e < NPATCH; e += TC_THREADS) {
+        const int c = e / (TROWS * TWP), rem = e - c * TROWS * TWP, r = rem / TWP, x = rem - r * TWP;
+        const int gy = reflect_clamp(y0 - DD + r, net.H), gx = reflect_clamp(x0 - DD + x, net.W);
+        raw[(c * TROWS + r) * box_w + (a.box_lead - DD) + x] =
+            (uint8_t)load_msb_int(a.msb, 0, ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx);
+      }
+      wg_sync();
+    }
+    return build_a1_raw8<CC>(rp, bw4, sel_a, sel_b, rel, sA, tid);
+  };
+  // all threads of the warpgroup, after the barrier that ordered their operand writes; one elected lane issues
+  auto issue_mma = [&](int layer, uint32_t acc, uint32_t mbar) {
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sB_u = smem_u32(sW + H->off_b[layer]);
+        if (layer == 0) {
+          for (int i = 0; i < k1pad / 16; ++i)
+            umma_f16(acc, umma_desc(sA_u + i * 2 * 2048, 2048, 128), umma_desc(sB_u + i * 2 * 1024, 1024, 128), idesc, i > 0);
+        } else {
+          for (int i = 0; i < 2 * TC_BC / 16; ++i)       // hi half then lo half of A2, both against the same B
+            umma_f16(acc, umma_desc(sA_u + i * 2 * 2048, 2048, 128),
+                     umma_desc(sB_u + (i % (TC_BC / 16)) * 2 * 1024, 1024, 128), idesc, i > 0);
+        }
+        umma_commit(mbar);
+      }
+      __syncwarp();
+    }
+  };
+  // 16 hidden units of one layer: scale + bias, activation (result left in h)
+  auto activate16 = [&](int layer, int cb, uint32_t acc_addr, float (&h)[16]) {
+    const float scale = H->scale[layer];
+    const float* bl = bias + layer * TC_BC;
+    float bterm[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bl + cb + 4 * q);
+      bterm[4 * q] = b4.x; bterm[4 * q + 1] = b4.y; bterm[4 * q + 2] = b4.z; bterm[4 * q + 3] = b4.w;
+    }
+    float acc[16];
+    tmem_ld16(acc_addr + cb, acc);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bterm[j]), 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        acc[j] = fmaf(acc[j], scale, bterm[j]);              // = w0 * z (w0 folded into scale and bias)
+        h[j] = tc_sine<SINE>(acc[j]);
+      }
+      if ((H->guard_mask >> layer) & 1) {                    // uniform: tc_prep_kernel could not bound |w0 z| for this layer
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(acc[j]));
+        if (__builtin_expect(!(amax <= 20000.0f), 0)) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = sin_slow(acc[j]);
+        }
+      }
+    }
+  };
+  auto epilogue_hidden = [&](uint32_t acc_addr) {          // layer 0: h = hi + lo (fp16 pairs) -> A2 chunks
+#pragma unroll 1
+    for (int cb = 0; cb < TC_BC; cb += 16) {
+      float h[16];
+      activate16(0, cb, acc_addr, h);
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const __half2 hh = __floats2half2_rn(h[j], h[j + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(h[j] - back.x, h[j + 1] - back.y);
+        hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      const int kc = cb >> 3;
+      *reinterpret_cast<uint4*>(sA + (size_t)(kc * 128 + tid) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sA + (size_t)((kc + 1) * 128 + tid) * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<uint4*>(sA + (size_t)((TC_BC / 8 + kc) * 128 + tid) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(sA + (size_t)((TC_BC / 8 + kc + 1) * 128 + tid) * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  };
+  auto epilogue_last = [&](uint32_t acc_addr, float (&y)[4]) {   // layer 1 + output layer sums (fp32 FFMA)
+    y[0] = y[1] = y[2] = y[3] = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < TC_BC; cb += 16) {
+      float h[16];
+      activate16(1, cb, acc_addr, h);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 wa = *reinterpret_cast<const float4*>(w3t + (cb + j) * 8);
+        y[0] = fmaf(wa.x, h[j], y[0]); y[1] = fmaf(wa.y, h[j], y[1]);
+        y[2] = fmaf(wa.z, h[j], y[2]); y[3] = fmaf(wa.w, h[j], y[3]);
+      }
+    }
+  };
+  // sigmoid, inverse quantisation, integer write (decode.py:131-134)
+  auto finish = [&](const float (&y)[4], uint32_t cpk, int ty0, int tx0) {
+    const int gy = ty0 + pr, gx = tx0 + px;
+    if (gy < net.row1 && gx < net.W) {
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        const float yz = y[c] + w3t[TC_BC * 8 + c];
+        const float yy = SINE == SINE_MUFU ? sigmoidf_fast(yz) : sigmoidf_rn(yz);
+        const int res = (int)rintf(yy * net.qmax);
+        const uint32_t m = (cpk >> (8 * c)) & 0xFFu;
+        a.out[((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx] = (uint16_t)((m << net.K) + (uint32_t)res);
+      }
+    }
+  };
+
+  if (tile0 < a.n_tiles) {
+    int cy = 0, cx = 0, ny = 0, nx = 0, py = 0, pxx = 0;
+    tile_xy(tile0, cy, cx);
+    bool c_tma = interior(cy, cx);
+    if (c_tma) issue_tma(cy, cx);
+    bool n_valid = tile0 + tile_step < a.n_tiles, n_tma = false;
+    if (n_valid) {
+      tile_xy(tile0 + tile_step, ny, nx);
+      n_tma = interior(ny, nx);
+    }
+    uint32_t cpk = stage_and_build(cy, cx, c_tma, tile0), cpk_prev = 0;
+    fence_async_smem();
+    tc_fence_before();
+    wg_sync();
+    issue_mma(0, tmem0, mbar1);
+    if (n_valid && n_tma) issue_tma(ny, nx);
+    float yprev[4] = {0.f, 0.f, 0.f, 0.f};
+    bool have_prev = false;
+    uint32_t p = 0;
+    for (int t = tile0; t < a.n_tiles; t += tile_step) {
+      const uint32_t acc_p = tmem0 + p * TC_TMEM_COLS + lane_off;
+      // a: first hidden layer's accumulator
+      mbar_wait(mbar1, ph1, 1, t, a.no_trap);
+      ph1 ^= 1;
+      tc_fence_after();
+      // b: epilogue 1 -> A2, second layer's MMAs
+      epilogue_hidden(acc_p);
+      fence_async_smem();
+      tc_fence_before();
+      wg_sync();
+      issue_mma(1, tmem0 + p * TC_TMEM_COLS, mbar2);
+      // c: the previous tile's pixels; where tile i+2 lies
+      if (have_prev) finish(yprev, cpk_prev, py, pxx);
+      int n2y = 0, n2x = 0;
+      const bool n2_valid = t + 2 * tile_step < a.n_tiles;
+      bool n2_tma = false;
+      if (n2_valid) {
+        tile_xy(t + 2 * tile_step, n2y, n2x);
+        n2_tma = interior(n2y, n2x);
+      }
+      // d: second hidden layer's accumulator complete, A region free
+      mbar_wait(mbar2, ph2, 3, t, a.no_trap);
+      ph2 ^= 1;
+      tc_fence_after();
+      // e: next tile's operand and first-layer MMAs
+      uint32_t cpk_next = 0;
+      if (n_valid) {
+        cpk_next = stage_and_build(ny, nx, n_tma, t + tile_step);
+        fence_async_smem();        // operand writes (and our reads of `raw`) are ordered before the async proxy
+        tc_fence_before();
+        wg_sync();
+        issue_mma(0, tmem0 + (p ^ 1u) * TC_TMEM_COLS, mbar1);
+        if (n2_valid && n2_tma) issue_tma(n2y, n2x);
+      }
+      // f: epilogue 2 of this tile
+      epilogue_last(acc_p, yprev);
+      tc_fence_before();           // our tcgen05.ld's are ordered before the MMAs that next write this accumulator
+      cpk_prev = cpk; py = cy; pxx = cx; have_prev = true;
+      cy = ny; cx = nx; cpk = cpk_next;
+      ny = n2y; nx = n2x; n_tma = n2_tma; n_valid = n2_valid;
+      p ^= 1u;
+    }
+    if (have_prev) finish(yprev, cpk_prev, py, pxx);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (gtid < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(2 * TC_TMEM_COLS * NWG) : "memory");
+}
+
 // ---- self-test: D[128][64] = A[128][K] * B[64][K]^T through the same descriptors / layouts / TMEM path ----------------
 __global__ void __launch_bounds__(TC_THREADS) tc_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
                                                                 float* __restrict__ Dout, int K) {
@@ -944,7 +1229,7 @@ size_t tc_smem_bytes(TcArgs& a, const TcHeader& h, bool wlo, int nwg) {
 }
 
 // one launch of the tensor kernel family (wlo: smem holds the low-order weight operands too; nwg: warpgroups per CTA)
-int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int dev, cudaStream_t st) {
+int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int dev, cudaStream_t st, int acc_per_wg = 1) {
   const Net& n = a.net;
   const int threads = TC_THREADS * nwg;
   const size_t smem = tc_smem_bytes(a, h, wlo, nwg);
@@ -963,7 +1248,8 @@ int tc_launch(KernT kern, TcArgs& a, const TcHeader& h, bool wlo, int nwg, int d
   int occ = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));   // +1 KB: per-CTA reservation of the driver
   const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
   if (regs_cta > 0 && regs_sm / regs_cta < occ) occ = regs_sm / regs_cta;
-  if (occ * TC_TMEM_COLS * nwg > 512) occ = 512 / (TC_TMEM_COLS * nwg);   // TMEM: 512 columns per SM
+  const int tmem_cta = TC_TMEM_COLS * nwg * acc_per_wg;
+  if (occ * tmem_cta > 512) occ = 512 / tmem_cta;                 // TMEM: 512 columns per SM
   const int occ_max = nwg >= 4 ? 1 : (nwg == 2 ? 2 : 3);          // measured optimum for NWG=1 (4 CTAs: 3.0 vs 4.3 Gpix/s)
   if (occ > occ_max) occ = occ_max;
   if (const char* e = getenv("LBDRN_TC_OCC")) occ = atoi(e);
@@ -1051,8 +1337,16 @@ int tc_decode(const Net& n, const void* msb, const float* params, const float* t
   const bool two = a.use_tma && !getenv("LBDRN_TC_NWG1");     // TMA-addressable input: two warpgroups per CTA
   const char* pfe = getenv("LBDRN_TC_PF");
   const bool pf = pfe ? atoi(pfe) != 0 : true;
-  rc = two ? tc_launch(pick_decode<false, 2>(n, fast_sine, pf), a, h, false, 2, dev, st)
-           : tc_launch(pick_decode<false, 1>(n, fast_sine, pf), a, h, false, 1, dev, st);
+  // the paper's configuration on TMA-addressable planes: the software-pipelined kernel (two accumulators per warpgroup)
+  const bool pipe = two && tc_raw8(n) && n.nl == 2 && n.nco == 0 && getenv("LBDRN_TC_NOPIPE") == nullptr;
+  if (pipe) {
+    KernT k = fast_sine == SINE_MUFU ? (KernT)tc_pipe_kernel<SINE_MUFU>
+                                     : (fast_sine == SINE_CW_MUFU ? (KernT)tc_pipe_kernel<SINE_CW_MUFU> : (KernT)tc_pipe_kernel<SINE_POLY>);
+    rc = tc_launch(k, a, h, false, 2, dev, st, 2);
+  } else {
+    rc = two ? tc_launch(pick_decode<false, 2>(n, fast_sine, pf), a, h, false, 2, dev, st)
+             : tc_launch(pick_decode<false, 1>(n, fast_sine, pf), a, h, false, 1, dev, st);
+  }
   if (rc) return rc;
   a.run_if_exact = 0;
   return tc_launch(pick_decode<true, 1>(n, fast_sine, pf), a, h, true, 1, dev, st);

@@ -19,10 +19,19 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
   const size_t acts = ((size_t)t.dimpad + 2 * (size_t)n.nl * BC + (2 + kTT / 128) * CP) * kTrainLDP;
   const size_t wts = (size_t)round4(n.P) + (size_t)(n.nl - 1) * BC * BC;
   const size_t with_w = (acts + wts) * sizeof(float), without = acts * sizeof(float);
-  // the opt-in limit covers dynamic + static shared memory of the kernel (pixel coordinates, reduction scratch)
-  cudaFuncAttributes fa;
-  CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)train_fp32_kernel<BC, CP, false, kTT, TM>));
-  max_smem -= (int)fa.sharedSizeBytes;
+  // the opt-in limit covers dynamic + static shared memory of the kernel (pixel coordinates, reduction scratch); the static
+  // part differs between instantiations, so every candidate is checked against its own (fits() below)
+  const int dev_max_smem = max_smem;
+  auto fits = [&](void* kern, size_t dyn) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return false; }
+    return dyn + fa.sharedSizeBytes <= (size_t)dev_max_smem;
+  };
+  {
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)train_fp32_kernel<BC, CP, false, kTT, TM>));
+    max_smem -= (int)fa.sharedSizeBytes;        // placement of the optional TMA boxes (place_boxes) uses this estimate
+  }
   // 64-pixel chunks with bc a multiple of 32: the chunk's GEMMs run as warp-level 3xTF32 tensor-core MMAs
   constexpr bool kMma = TM == 4 && kTT == 512 && BC % 32 == 0 && BC <= 128;
   const bool mma = kMma && getenv("LBDRN_TRAIN_FFMA") == nullptr;
@@ -53,23 +62,30 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
                        (size_t)(2 + kTT / 128) * CP * kTrainLDP + (size_t)round4(L * BC + n.C * BC + n.C) +
                        (size_t)KP0 * kLDH + (size_t)(L - 1) * BC * kLDH + (size_t)BC * (KP0 + 8) +
                        (size_t)(L - 1) * BC * (BC + 8)) * sizeof(float);
-    if (mma && getenv("LBDRN_TRAIN_TF32") == nullptr && h2 <= (size_t)max_smem) {
+    if (mma && getenv("LBDRN_TRAIN_TF32") == nullptr && h2 <= (size_t)max_smem &&
+        fits((void*)train_fp32_kernel<BC, CP, true, kTT, TM, 2>, h2)) {
       t.wsmem = true; t.smem = place_boxes(h2);
       t.kernel = (void*)train_fp32_kernel<BC, CP, true, kTT, TM, 2>;
       t.h2 = true;
       t.wimg_bytes = ((size_t)BC * (KP0 + 8) + (size_t)(L - 1) * BC * (BC + 8)) * sizeof(float);
     }
   }
+  void* k_with = mma ? (void*)train_fp32_kernel<BC, CP, true, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
+  void* k_without = mma ? (void*)train_fp32_kernel<BC, CP, false, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
   if (t.h2) {
-  } else if (with_w <= (size_t)max_smem) {
+  } else if (with_w <= (size_t)max_smem && fits(k_with, with_w)) {
     t.wsmem = true; t.smem = place_boxes(with_w);
-    t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, true, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
-  } else if (without <= (size_t)max_smem) {
+    t.kernel = k_with;
+  } else if (without <= (size_t)max_smem && fits(k_without, without)) {
     t.wsmem = false; t.smem = place_boxes(without);
-    t.kernel = mma ? (void*)train_fp32_kernel<BC, CP, false, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
+    t.kernel = k_without;
   } else {
     return fail(LBDRN_E_UNSUPPORTED, "training working set (%zu B) exceeds shared memory for bc=%d nl=%d dim_in=%d",
                 without, BC, n.nl, n.dim_in);
+  }
+  if (t.pf_off && !fits(t.kernel, t.smem)) {     // the optional TMA boxes pushed it over: drop them
+    t.smem = (size_t)t.pf_off;
+    t.pf_off = 0; t.pf_stride = 0;
   }
   CUDA_TRY(cudaFuncSetAttribute(t.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
   int occ = 0;
