@@ -193,17 +193,35 @@ __device__ __forceinline__ float tc_sine(float a) {
   return __sinf(r);
 }
 
+// two sines at once: the range reduction of SINE_CW_MUFU runs on packed fp32 pairs (same roundings as tc_sine)
+template <int SINE>
+__device__ __forceinline__ void tc_sine2(float a0, float a1, float& s0, float& s1) {
+  if (SINE != SINE_CW_MUFU) {
+    s0 = tc_sine<SINE>(a0);
+    s1 = tc_sine<SINE>(a1);
+    return;
+  }
+  float t0, t1, k0, k1, r0, r1;
+  ffma2(t0, t1, a0, a1, 0.15915494309189535f, 0.15915494309189535f, 12582912.0f, 12582912.0f);
+  fadd2(k0, k1, t0, t1, -12582912.0f, -12582912.0f);
+  ffma2(r0, r1, k0, k1, -6.28318548202514648f, -6.28318548202514648f, a0, a1);
+  ffma2(r0, r1, k0, k1, 1.74845553146e-7f, 1.74845553146e-7f, r0, r1);
+  s0 = __sinf(r0);
+  s1 = __sinf(r1);
+}
+
 // nn.Sigmoid with the approximate exponential / reciprocal units (SINE_MUFU kernels only): 2^-22 relative on each, i.e.
 // |dy| < 1e-7, an order of magnitude below what the MUFU sine already contributes
-__device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 
 // A1 rows of one pixel straight from the staged bytes (RAW8; K layout 1 of plan_block).  rp: the aligned 32-bit word that
-// holds the first byte of the pixel's top-left window element in band 0; bw4: words per staged row; sel_a / sel_b: byte
-// selectors of window elements 0..3 / 4 inside the two words of a window row (the same for every row of the thread).
+// holds the first byte of the pixel's top-left window element in band 0; bw4: words per staged row; sel_a: byte selector
+// of window elements 0..3 inside the two words of a window row, sel_e: selector that expands element 4 (byte o of the
+// second word) into an fp16 pair with itself (the sixth entry of a row has a zero weight); both fixed per thread.
 // 0x64mm is the fp16 number 1024 + mm, so (pair) - (1024 + centre) is the exact integer difference.  Returns the four
 // centre bytes packed (band c in byte c) for the final (m << K) + residual.
 template <int CC>
-__device__ __forceinline__ uint32_t build_a1_raw8(const uint32_t* __restrict__ rp, int bw4, uint32_t sel_a, uint32_t sel_b,
+__device__ __forceinline__ uint32_t build_a1_raw8(const uint32_t* __restrict__ rp, int bw4, uint32_t sel_a, uint32_t sel_e,
                                                   bool rel, uint8_t* sA, int tid) {
   constexpr int TRW_ = TC_TH + 4;                              // 12 staged rows per band (D = 2)
   constexpr uint32_t C64 = 0x64646464u;
@@ -216,7 +234,7 @@ __device__ __forceinline__ uint32_t build_a1_raw8(const uint32_t* __restrict__ r
     for (int dy = 0; dy < 5; ++dy) {
       const uint32_t lo = rp[(c * TRW_ + dy) * bw4], hi = rp[(c * TRW_ + dy) * bw4 + 1];
       w0[dy] = __byte_perm(lo, hi, sel_a);
-      w1[dy] = __byte_perm(lo, hi, sel_b);
+      w1[dy] = hi;                                           // element 4 is byte o of the second word: expanded from there
     }
     const uint32_t cpu = rel ? __byte_perm(w0[2], C64, 0x4242) : 0x64006400u;   // (1024 + centre) twice
     const __half2 cp = *reinterpret_cast<const __half2*>(&cpu);
@@ -225,7 +243,7 @@ __device__ __forceinline__ uint32_t build_a1_raw8(const uint32_t* __restrict__ r
     for (int dy = 0; dy < 5; ++dy) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const uint32_t pu = __byte_perm(j < 2 ? w0[dy] : w1[dy], C64, j == 1 ? 0x4342 : 0x4140);
+        const uint32_t pu = j < 2 ? __byte_perm(w0[dy], C64, j == 1 ? 0x4342 : 0x4140) : __byte_perm(w1[dy], C64, sel_e);
         const __half2 dv = __hsub2(*reinterpret_cast<const __half2*>(&pu), cp);
         const int q = (c * 5 + dy) * 3 + j;                  // pair index in K order; four pairs per 16-byte chunk
         dq[q & 3] = *reinterpret_cast<const uint32_t*>(&dv);
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
       const int bcol = a.box_lead - DD + px;                     // byte column of the window's first element
       const uint32_t o = (uint32_t)bcol & 3u;
       const uint32_t cpk = build_a1_raw8<CC ? CC : 1>(reinterpret_cast<const uint32_t*>(raw) + pr * bw4 + (bcol >> 2), bw4,
-                                                      0x3210u + o * 0x1111u, (o + 4u) * 0x1111u, rel, sA, tid);
+                                                      0x3210u + o * 0x1111u, 0x4040u + o * 0x0101u, rel, sA, tid);
       mctr[0] = cpk;
     } else {
     // ---- patch: (tile + halo) MSB integers as fp16 ---------------------------------------------------------------------
@@ -597,15 +615,15 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
           }
         }
         float h[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2)                        // = w0 * z (w0 folded into scale and bias), two per FFMA2
+          ffma2(acc[j], acc[j + 1], acc[j], acc[j + 1], scale, scale, bterm[j], bterm[j + 1]);
         if (net.relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bterm[j]), 0.f);
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(acc[j], 0.f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            acc[j] = fmaf(acc[j], scale, bterm[j]);            // = w0 * z (w0 folded into scale and bias)
-            h[j] = tc_sine<SINE>(acc[j]);
-          }
+          for (int j = 0; j < 16; j += 2) tc_sine2<SINE>(acc[j], acc[j + 1], h[j], h[j + 1]);
           if (guard) {                                          // uniform: tc_prep_kernel could not bound |w0 z| for this layer
             float amax = 0.f;
 #pragma unroll
@@ -623,7 +641,9 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
           for (int j = 0; j < 16; j += 2) {
             const __half2 hh = __floats2half2_rn(h[j], h[j + 1]);
             const float2 back = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(h[j] - back.x, h[j + 1] - back.y);
+            float l0, l1;
+            ffma2(l0, l1, back.x, back.y, -1.0f, -1.0f, h[j], h[j + 1]);      // h - hi, exact
+            const __half2 ll = __floats2half2_rn(l0, l1);
             hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
             lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
           }
@@ -637,12 +657,12 @@ __global__ void __launch_bounds__(TC_THREADS * NWG, NWG >= 4 ? 1 : (NWG == 2 ? 2
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float4 wa = *reinterpret_cast<const float4*>(w3t + (cb + j) * 8);
-            yacc[0] = fmaf(wa.x, h[j], yacc[0]); yacc[1] = fmaf(wa.y, h[j], yacc[1]);
-            yacc[2] = fmaf(wa.z, h[j], yacc[2]); yacc[3] = fmaf(wa.w, h[j], yacc[3]);
+            ffma2(yacc[0], yacc[1], wa.x, wa.y, h[j], h[j], yacc[0], yacc[1]);
+            ffma2(yacc[2], yacc[3], wa.z, wa.w, h[j], h[j], yacc[2], yacc[3]);
             if (C > 4) {
               const float4 wb = *reinterpret_cast<const float4*>(w3t + (cb + j) * 8 + 4);
-              yacc[4] = fmaf(wb.x, h[j], yacc[4]); yacc[5] = fmaf(wb.y, h[j], yacc[5]);
-              yacc[6] = fmaf(wb.z, h[j], yacc[6]); yacc[7] = fmaf(wb.w, h[j], yacc[7]);
+              ffma2(yacc[4], yacc[5], wb.x, wb.y, h[j], h[j], yacc[4], yacc[5]);
+              ffma2(yacc[6], yacc[7], wb.z, wb.w, h[j], h[j], yacc[6], yacc[7]);
             }
           }
         }
@@ -750,6 +770,7 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
   __shared__ __align__(8) uint64_t s_mbar_tma[NWG];
   __shared__ __align__(8) uint64_t s_mbar1[NWG];
   __shared__ __align__(8) uint64_t s_mbar2[NWG];
+  __shared__ __align__(8) uint64_t s_mbar_rdy[NWG];      // "operands written / accumulator read": 128 arrivals per phase
   __shared__ uint32_t s_tmem;
   auto wg_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "r"(TC_THREADS) : "memory"); };
 
@@ -772,6 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       mbar_init(smem_u32(&s_mbar1[g]), 1);
       mbar_init(smem_u32(&s_mbar2[g]), 1);
       mbar_init(smem_u32(&s_mbar_tma[g]), 1);
+      mbar_init(smem_u32(&s_mbar_rdy[g]), TC_THREADS);
     }
   }
   tc_fence_before();
@@ -780,6 +802,7 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
   const uint32_t tmem0 = s_tmem + (uint32_t)(wg * 2 * TC_TMEM_COLS);       // this warpgroup's two accumulators
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;                   // this warp's 32 lanes
   const uint32_t mbar1 = smem_u32(&s_mbar1[wg]), mbar2 = smem_u32(&s_mbar2[wg]), mbar_tma = smem_u32(&s_mbar_tma[wg]);
+  const uint32_t mbar_rdy = smem_u32(&s_mbar_rdy[wg]);
   const uint32_t idesc = umma_idesc_f16(128, TC_BC);
   const uint32_t sA_u = smem_u32(sA), raw_u = smem_u32(raw);
   const float* bias = reinterpret_cast<const float*>(sW + H->off_bias);
@@ -791,7 +814,7 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
   const int pr = tid >> 4, px = tid & 15;
   const int bcol = a.box_lead - DD + px;
   const uint32_t o = (uint32_t)bcol & 3u;
-  const uint32_t sel_a = 0x3210u + o * 0x1111u, sel_b = (o + 4u) * 0x1111u;
+  const uint32_t sel_a = 0x3210u + o * 0x1111u, sel_e = 0x4040u + o * 0x0101u;
   const uint32_t* rp = reinterpret_cast<const uint32_t*>(raw) + pr * bw4 + (bcol >> 2);
   const int tile0 = blockIdx.x * NWG + wg, tile_step = gridDim.x * NWG;
 
@@ -812,7 +835,7 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       __syncwarp();
     }
   };
-  uint32_t ph_tma = 0, ph1 = 0, ph2 = 0;
+  uint32_t ph_tma = 0, ph1 = 0, ph2 = 0, ph_rdy = 0;
   // staged bytes of (tile + halo) -> A1 in the A region; returns the packed centre bytes
   auto stage_and_build = [&](int y0, int x0, bool by_tma, int tile) {
     if (by_tma) {
@@ -827,11 +850,19 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       }
       wg_sync();
     }
-    return build_a1_raw8<CC>(rp, bw4, sel_a, sel_b, rel, sA, tid);
+    return build_a1_raw8<CC>(rp, bw4, sel_a, sel_e, rel, sA, tid);
   };
-  // all threads of the warpgroup, after the barrier that ordered their operand writes; one elected lane issues
+  // Hand-off to the tensor core WITHOUT a warpgroup barrier.  Every thread announces that its operand rows are written
+  // (and its reads of the accumulator about to be overwritten, and of `raw`, are done) by arriving on `mbar_rdy`; only
+  // warp 0 waits for the 128 arrivals, then one elected lane issues.  The other three warps go straight on to work that
+  // does not depend on this MMA.  A thread can never run two phases ahead: between two of its arrivals it waits for an
+  // MMA completion, which the issuer only produces after the previous phase completed.
   auto issue_mma = [&](int layer, uint32_t acc, uint32_t mbar) {
+    fence_async_smem();          // generic-proxy writes of the operand (and reads of `raw`) -> ordered before the async proxy
+    tc_fence_before();
+    mbar_arrive(mbar_rdy);
     if (warp == 0) {
+      mbar_wait(mbar_rdy, ph_rdy, 4, layer, a.no_trap);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sB_u = smem_u32(sW + H->off_b[layer]);
@@ -847,6 +878,7 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       }
       __syncwarp();
     }
+    ph_rdy ^= 1;
   };
   // 16 hidden units of one layer: scale + bias, activation (result left in h)
   auto activate16 = [&](int layer, int cb, uint32_t acc_addr, float (&h)[16]) {
@@ -860,15 +892,15 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
     }
     float acc[16];
     tmem_ld16(acc_addr + cb, acc);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2)                          // = w0 * z (w0 folded into scale and bias), two per FFMA2
+      ffma2(acc[j], acc[j + 1], acc[j], acc[j + 1], scale, scale, bterm[j], bterm[j + 1]);
     if (relu) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) h[j] = fmaxf(fmaf(acc[j], scale, bterm[j]), 0.f);
+      for (int j = 0; j < 16; ++j) h[j] = fmaxf(acc[j], 0.f);
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        acc[j] = fmaf(acc[j], scale, bterm[j]);              // = w0 * z (w0 folded into scale and bias)
-        h[j] = tc_sine<SINE>(acc[j]);
-      }
+      for (int j = 0; j < 16; j += 2) tc_sine2<SINE>(acc[j], acc[j + 1], h[j], h[j + 1]);
       if ((H->guard_mask >> layer) & 1) {                    // uniform: tc_prep_kernel could not bound |w0 z| for this layer
         float amax = 0.f;
 #pragma unroll
@@ -890,7 +922,9 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       for (int j = 0; j < 16; j += 2) {
         const __half2 hh = __floats2half2_rn(h[j], h[j + 1]);
         const float2 back = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(h[j] - back.x, h[j + 1] - back.y);
+        float l0, l1;
+        ffma2(l0, l1, back.x, back.y, -1.0f, -1.0f, h[j], h[j + 1]);          // h - hi, exact
+        const __half2 ll = __floats2half2_rn(l0, l1);
         hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
         lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
       }
@@ -910,8 +944,8 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float4 wa = *reinterpret_cast<const float4*>(w3t + (cb + j) * 8);
-        y[0] = fmaf(wa.x, h[j], y[0]); y[1] = fmaf(wa.y, h[j], y[1]);
-        y[2] = fmaf(wa.z, h[j], y[2]); y[3] = fmaf(wa.w, h[j], y[3]);
+        ffma2(y[0], y[1], wa.x, wa.y, h[j], h[j], y[0], y[1]);
+        ffma2(y[2], y[3], wa.z, wa.w, h[j], h[j], y[2], y[3]);
       }
     }
   };
@@ -941,9 +975,6 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       n_tma = interior(ny, nx);
     }
     uint32_t cpk = stage_and_build(cy, cx, c_tma, tile0), cpk_prev = 0;
-    fence_async_smem();
-    tc_fence_before();
-    wg_sync();
     issue_mma(0, tmem0, mbar1);
     if (n_valid && n_tma) issue_tma(ny, nx);
     float yprev[4] = {0.f, 0.f, 0.f, 0.f};
@@ -957,9 +988,6 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       tc_fence_after();
       // b: epilogue 1 -> A2, second layer's MMAs
       epilogue_hidden(acc_p);
-      fence_async_smem();
-      tc_fence_before();
-      wg_sync();
       issue_mma(1, tmem0 + p * TC_TMEM_COLS, mbar2);
       // c: the previous tile's pixels; where tile i+2 lies
       if (have_prev) finish(yprev, cpk_prev, py, pxx);
@@ -978,9 +1006,6 @@ __global__ void __launch_bounds__(TC_THREADS * 2, 2) tc_pipe_kernel(const TcArgs
       uint32_t cpk_next = 0;
       if (n_valid) {
         cpk_next = stage_and_build(ny, nx, n_tma, t + tile_step);
-        fence_async_smem();        // operand writes (and our reads of `raw`) are ordered before the async proxy
-        tc_fence_before();
-        wg_sync();
         issue_mma(0, tmem0 + (p ^ 1u) * TC_TMEM_COLS, mbar1);
         if (n2_valid && n2_tma) issue_tma(n2y, n2x);
       }
