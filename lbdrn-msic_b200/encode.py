@@ -31,6 +31,25 @@ def sh(cmd, input=''):
     return r.stdout.decode('utf-8')
 
 
+def write_scalars(log_dir, filename, result, args):
+    """The reference's TensorBoard event file (encode.py:89,95,107): `train/loss/<name>` per iteration and `val/MSE/<name>`
+    per evaluated epoch, same tags and steps.  The reference writes the loss scalar inside the loop, which forces a device
+    synchronisation per step (encode.py:95); here the per-step losses come back as one vector per epoch and are flushed
+    after the run.  Skipped silently when tensorboard is not installed (the reference lists it in requirements.txt)."""
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+    except Exception:                                                  # noqa: BLE001 -- optional dependency
+        return False
+    writer = SummaryWriter(log_dir=log_dir)
+    for it, loss in enumerate(result['losses'], start=1):
+        writer.add_scalar(f'train/loss/{filename}', loss, it)
+    step = min(args.val_duration, args.epochs)
+    for i, mse in enumerate(result['val_mse'], start=1):
+        writer.add_scalar(f'val/MSE/{filename}', mse, i * step)
+    writer.close()
+    return True
+
+
 def train(args):
     """Overfit one network to the raster at args.path; leaves `<name>_nn.bin` and `<name>_base.jp2` in output_dir."""
     import lbdrn_fused
@@ -55,6 +74,7 @@ def train(args):
     result = trainer.run()
     trainer.close()
     logger.log.info('best epoch: {}'.format(result['best_epoch']))
+    write_scalars(args.output_dir, name, result, args)
 
     params = result['params'].numpy().reshape(-1)                      # state_dict order, C order
     nn_path = f'{args.output_dir}/{name}_nn.bin'

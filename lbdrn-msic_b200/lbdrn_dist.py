@@ -129,15 +129,23 @@ class StripeBuffer:
             return (255 if self.buf.dtype == torch.uint8 else (0xFFFF >> K)), msb_max
         return int(msb_max), None
 
-    def decode(self, flat_params_dev, K, bc, nl, flags, msb_max, relu=False, w0=30.0, path=cabi.PATH_AUTO, tab=None):
-        """Decode the stripe (halos must be current); returns the [C, buf_rows, W] output buffer and the slice of own rows."""
+    def decode_rows(self, row_a, row_b, flat_params_dev, K, bc, nl, flags, msb_max, relu=False, w0=30.0,
+                    path=cabi.PATH_AUTO, tab=None):
+        """Decode image rows [row_a, row_b) of this rank's stripe into `self.out` (current stream).  Rows closer than D to
+        a stripe seam need current halo rows; the others only the rank's own rows."""
         C, brows, W = self.buf.shape
+        if not (self.r0 <= row_a < row_b <= self.r1):
+            raise ValueError(f"rows [{row_a},{row_b}) outside this rank's stripe [{self.r0},{self.r1})")
         bound, mdev = self._max_args(msb_max, K)
         d = cabi.make_desc(C, self.H, W, K, self.D, bc, nl, flags.bits(relu), bound, self.buf.dtype == torch.uint16,
-                           row0=self.r0, row1=self.r1, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0,
+                           row0=row_a, row1=row_b, buf_row0=self.r0 - self.top, buf_rows=brows, w0=w0,
                            n_freq=flags.n_freq, path=path, msb_max_dev=mdev)
         cabi.check(cabi.load().lbdrn_decode(ctypes.byref(d), cabi.ptr(self.buf), cabi.ptr(flat_params_dev), cabi.ptr(tab),
                                             cabi.ptr(self.out), cabi.stream_ptr()))
+
+    def decode(self, flat_params_dev, K, bc, nl, flags, msb_max, relu=False, w0=30.0, path=cabi.PATH_AUTO, tab=None):
+        """Decode the stripe (halos must be current); returns the [C, buf_rows, W] output buffer and the slice of own rows."""
+        self.decode_rows(self.r0, self.r1, flat_params_dev, K, bc, nl, flags, msb_max, relu, w0, path, tab)
         return self.out, slice(self.top, self.top + (self.r1 - self.r0))
 
 
@@ -173,6 +181,128 @@ class StripeBuffer:
         if last is not None:
             last.synchronize()
         return out_host
+
+
+def plan_pieces(r0, r1, has_top, has_bot, D, sub_rows):
+    """Row ranges [(a, b, needs_halo)] that cover stripe [r0, r1) exactly once: interior rows first (their (2D+1)^2 windows
+    stay inside the rank's own rows, so they can be decoded before the halo swap has finished), in sub-stripes of at most
+    `sub_rows` rows, then the edge bands next to a neighbouring stripe.  Bands are whole tile rows (8) and at least D high."""
+    edge = max(8, -(-D // 8) * 8)
+    lo, hi = r0 + (edge if has_top else 0), r1 - (edge if has_bot else 0)
+    if hi <= lo:                                               # thinner than its bands: everything after the halos
+        return [(r0, r1, bool(has_top or has_bot))]
+    pieces = [(a, min(hi, a + sub_rows), False) for a in range(lo, hi, sub_rows)]
+    if has_top:
+        pieces.append((r0, lo, True))
+    if has_bot:
+        pieces.append((hi, r1, True))
+    return pieces
+
+
+class StreamedStripeDecoder:
+    """One rank's share of a STREAM of same-shaped scenes decoded as row stripes (SURVEY.md 8e/8f-N1 on N GPUs).
+
+    Per scene the only exchanges are the scalar `MSB.max()` all-reduce and one D-row halo swap with each neighbouring
+    stripe; neither sits in front of the kernels:
+
+      copy stream   : H2D of this rank's stripe (pinned host memory) -> local max (device reduction) -> all-reduce(MAX)
+                      -> halo swap (NCCL send/recv over NVLink), all queued while the PREVIOUS scene still computes
+      compute stream: waits for the max only, decodes the INTERIOR rows (those whose window stays inside the rank's own
+                      rows: no halo needed), then waits for the halos and decodes the two edge bands
+      output stream : D2H of every finished sub-stripe while the next one computes
+
+    Two buffer slots, so scene i+1's upload / collectives overlap scene i's kernels and scene i-1's download; a rank that
+    runs ahead only queues work, ranks meet in the collectives of the NEXT scene while this one computes.  The kernels
+    read the normaliser from the all-reduced device word (LbdrnDesc.msb_max_dev): no host round trip anywhere.
+    Output is bit-identical to the 1-GPU decode of the whole scene (tests/test_gpu_dist.py, bench.py's stripe check)."""
+
+    def __init__(self, H, W, C, D, msb_dtype, K, bc, nl, flat_params, flags, device, group=None, slots=2, sub_rows=1024,
+                 relu=False, w0=30.0, path=cabi.PATH_AUTO, tab=None):
+        import lbdrn_fused
+        self.group, self.K, self.bc, self.nl, self.flags = group, K, bc, nl, flags
+        self.relu, self.w0, self.path, self.tab, self.sub_rows = relu, w0, path, tab, sub_rows
+        self.dev = torch.device(device)
+        self.params = torch.as_tensor(flat_params, dtype=torch.float32).to(self.dev).contiguous()
+        self.s_in, self.s_cmp, self.s_out = lbdrn_fused._get_streams(self.dev)
+        self.slots = [dict(sb=StripeBuffer(H, W, C, D, msb_dtype, self.dev, group),
+                           mx=torch.zeros(1, dtype=torch.int32, device=self.dev), cmp_done=None, out_done=None)
+                      for _ in range(slots)]
+        sb = self.slots[0]["sb"]
+        self.r0, self.r1, self.D = sb.r0, sb.r1, D
+        self.n = 0
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def preload(self, stripe_dev):
+        """Resident mode: put the same stripe into every slot once; `submit()` without a source then reuses it."""
+        for sl in self.slots:
+            sl["sb"].load(stripe_dev)
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def submit(self, stripe_host=None, out_host=None):
+        """Queue one scene and return at once.  stripe_host: [C, rows, W] CPU tensor (pinned) with this rank's OWN rows, or
+        None when the slot already holds them (`preload`).  out_host: [C, rows, W] uint16 CPU tensor (pinned) or None.
+        Returns an event that completes when the scene's reconstruction is in `out_host` (or in the slot's `out`)."""
+        import lbdrn_cabi as cabi_
+        sl = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        sb, lib = sl["sb"], cabi_.load()
+        rows = self.r1 - self.r0
+        with torch.cuda.stream(self.s_in):
+            if sl["cmp_done"] is not None:
+                self.s_in.wait_event(sl["cmp_done"])           # the kernels that read this slot's planes are done
+            if stripe_host is not None:
+                src = sb._wire(stripe_host)
+                for c in range(src.shape[0]):
+                    sb.own[c].copy_(src[c], non_blocking=True)
+            own = sb.buf[:, sb.top:sb.top + rows]
+            if sb.buf.dtype == torch.uint8:
+                sl["mx"].copy_(own.max().to(torch.int32).reshape(1))
+            else:
+                sl["mx"].zero_()
+                for c in range(own.shape[0]):                  # own rows of every plane are contiguous
+                    cabi_.check(lib.lbdrn_max_shifted(cabi_.ptr(own[c]), own[c].numel(), 0, cabi_.ptr(sl["mx"]),
+                                                      cabi_.stream_ptr()))
+            if sb.world > 1:
+                dist.all_reduce(sl["mx"], op=dist.ReduceOp.MAX, group=self.group)
+            ev_max = torch.cuda.Event()
+            ev_max.record(self.s_in)
+            sb.exchange()
+            ev_halo = torch.cuda.Event()
+            ev_halo.record(self.s_in)
+        pieces = plan_pieces(self.r0, self.r1, bool(sb.top), bool(sb.bot), self.D, self.sub_rows)
+        last = None
+        waited_halo = False
+        for i, (a, b, needs_halo) in enumerate(pieces):
+            with torch.cuda.stream(self.s_cmp):
+                if i == 0:
+                    self.s_cmp.wait_event(ev_max)
+                    if sl["out_done"] is not None:
+                        self.s_cmp.wait_event(sl["out_done"])  # the previous download from this slot's output is done
+                if needs_halo and not waited_halo:
+                    self.s_cmp.wait_event(ev_halo)
+                    waited_halo = True
+                sb.decode_rows(a, b, self.params, self.K, self.bc, self.nl, self.flags, sl["mx"], self.relu, self.w0,
+                               self.path, self.tab)
+                ev = torch.cuda.Event()
+                ev.record(self.s_cmp)
+            last = ev
+            if out_host is not None:
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev)
+                    for c in range(out_host.shape[0]):
+                        out_host[c, a - self.r0:b - self.r0].copy_(sb.out[c, sb.top + a - self.r0:sb.top + b - self.r0],
+                                                                   non_blocking=True)
+                    last = torch.cuda.Event()
+                    last.record(self.s_out)
+        sl["cmp_done"] = ev
+        sl["out_done"] = last if out_host is not None else None
+        sl["ticket"] = last
+        return last
+
+    def result(self, slot_index):
+        """[C, rows, W] view of a slot's reconstruction on the device (own rows)."""
+        sb = self.slots[slot_index % len(self.slots)]["sb"]
+        return sb.out[:, sb.top:sb.top + (self.r1 - self.r0)]
 
 
 def decode_stripe(stripe_msb, H, flat_params_dev, K, D, bc, nl, flags, msb_max, group=None, relu=False, w0=30.0,

@@ -106,3 +106,21 @@ def test_scheduler_ranks_partition_the_job_list_world2():
     out = _run("_sched_case")
     assert all(v[0] for v in out.values())
     assert sum(v[1] for v in out.values()) == 15 and min(v[1] for v in out.values()) >= 6
+
+
+def test_stripe_piece_plan_covers_every_row_once_and_orders_interior_first():
+    """lbdrn_dist.plan_pieces (used by StreamedStripeDecoder): exact cover of the stripe, interior rows (no halo needed)
+    before the edge bands, bands at least D high and whole tile rows, thin stripes handled."""
+    import lbdrn_dist as LD
+    for (r0, r1, top, bot, D, sub) in [(0, 8192, False, True, 2, 1024), (8192, 16384, True, True, 2, 1024),
+                                       (100, 117, True, True, 2, 1024), (0, 13, False, False, 2, 4), (7, 4103, True, False, 3, 1000),
+                                       (2048, 4096, True, True, 9, 512)]:
+        pieces = LD.plan_pieces(r0, r1, top, bot, D, sub)
+        rows = sorted(r for a, b, _ in pieces for r in range(a, b))
+        assert rows == list(range(r0, r1)), (r0, r1, pieces)
+        flags = [h for _, _, h in pieces]
+        assert flags == sorted(flags), pieces                               # interior (False) first
+        for a, b, needs in pieces:
+            if not needs:                                                   # windows stay inside the rank's own rows
+                assert (not top or a - D >= r0) and (not bot or b - 1 + D < r1), (a, b, pieces)
+                assert b - a <= sub

@@ -102,6 +102,68 @@ def test_stripe_sharded_decode_equals_single_gpu():
         assert np.array_equal(got, whole), name
 
 
+def _streamed_stripes(rank, world):
+    """StreamedStripeDecoder: a stream of different scenes through two slots (host -> host), uint8 and uint16 planes,
+    plus the resident mode bench.py times; each rank returns its rows of every scene."""
+    import lbdrn_dist as LD
+    import lbdrn_fused as F
+    import lbdrn_oracle as O
+    from synth_scene import make_scene
+    _, _, params = _scene_and_params()
+    out = {}
+    for bits, K, H, W, sub in ((12, 5, 301, 256, 64), (16, 5, 160, 272, 1024)):
+        scenes = [O.split_msb_lsb(make_scene(4, H, W, bits, seed=50 + i), K)[0] for i in range(4)]
+        r0, r1 = LD.stripe_bounds(H, world, rank)
+        dt = torch.uint16 if scenes[0].dtype == np.uint16 else torch.uint8
+        dec = LD.StreamedStripeDecoder(H, W, 4, 2, dt, K, 64, 2, params, F.Flags(), torch.device("cuda", rank), sub_rows=sub)
+        hosts = [torch.from_numpy(np.ascontiguousarray(m[:, r0:r1])).pin_memory() for m in scenes]
+        outs = [torch.empty((4, r1 - r0, W), dtype=torch.uint16).pin_memory() for _ in scenes]
+        tickets = [dec.submit(h, o) for h, o in zip(hosts, outs)]
+        for t in tickets:
+            t.synchronize()
+        out[bits] = (r0, r1, [o.numpy().copy() for o in outs])
+        # resident mode: the slots keep scene 0's stripe; repeated submits give the same rows
+        dec.preload(hosts[0].cuda())
+        for i in range(3):
+            dec.submit().synchronize()
+            assert np.array_equal(dec.result(dec.n - 1).cpu().numpy(), outs[0].numpy()), (bits, i)
+    return out
+
+
+def test_streamed_stripe_decoder_equals_single_gpu():
+    _need2()
+    import lbdrn_fused as F
+    import lbdrn_oracle as O
+    from synth_scene import make_scene
+    res = _run("_streamed_stripes")
+    _, _, params = _scene_and_params()
+    for bits, K, H, W in ((12, 5, 301, 256), (16, 5, 160, 272)):
+        for i in range(4):
+            msb = O.split_msb_lsb(make_scene(4, H, W, bits, seed=50 + i), K)[0]
+            whole = F.decode_image(msb, params, K, 2, 64, 2, flags=F.Flags())
+            got = np.zeros_like(whole)
+            for rank, out in res.items():
+                r0, r1, outs = out[bits]
+                got[:, r0:r1] = outs[i]
+            assert np.array_equal(got, whole), (bits, i)
+
+
+def test_streamed_stripe_decoder_single_rank():
+    """The same decoder with a one-rank group (runs on a 1-GPU box too): stream of scenes through two slots, interior /
+    band split and sub-stripe downloads, against the resident decode."""
+    res = _run("_streamed_stripes", world=1)
+    import lbdrn_fused as F
+    import lbdrn_oracle as O
+    from synth_scene import make_scene
+    _, _, params = _scene_and_params()
+    for bits, K, H, W in ((12, 5, 301, 256), (16, 5, 160, 272)):
+        r0, r1, outs = res[0][bits]
+        assert (r0, r1) == (0, H)
+        for i in range(4):
+            msb = O.split_msb_lsb(make_scene(4, H, W, bits, seed=50 + i), K)[0]
+            assert np.array_equal(outs[i], F.decode_image(msb, params, K, 2, 64, 2, flags=F.Flags())), (bits, i)
+
+
 def _dp_train(rank, world):
     import lbdrn_dist as LD
     import lbdrn_fused as F

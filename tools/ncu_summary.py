@@ -16,9 +16,15 @@ def _bytes(key):
 if "--traffic-json" in sys.argv:      # usage: ncu_summary.py <prefix> --traffic-json <out.json> <side> <source text>
     import json
     i = sys.argv.index("--traffic-json")
-    json.dump({"kernel": r.get("Kernel Name", ("?",))[0], "side": int(sys.argv[i + 2]),
+    side = int(sys.argv[i + 2])
+    json.dump({"kernel": r.get("Kernel Name", ("?",))[0], "side": side,
                "dram_bytes_read": _bytes("dram__bytes_read.sum"), "dram_bytes_write": _bytes("dram__bytes_write.sum"),
                "gpu_time": r["gpu__time_duration.sum"][0] + " " + r["gpu__time_duration.sum"][1],
+               "warp_instructions": float(r["smsp__inst_executed.sum"][0]),
+               "thread_instr_per_pixel": float(r["smsp__inst_executed.sum"][0]) * 32.0 / (side * side),
+               "issue_active_pct": float(r["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+               "tensor_pipe_active_pct": float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
+               "registers_per_thread": float(r["launch__registers_per_thread"][0]),
                "source": sys.argv[i + 3]}, open(sys.argv[i + 1], "w"), indent=1)
 print("kernel:", r.get("Kernel Name", ("?",))[0])
 keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
