@@ -27,8 +27,9 @@
 extern "C" {
 #endif
 
-/* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added (additive: v2 callers are unaffected) */
-#define LBDRN_ABI_VERSION 3
+/* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added; 4: LBDRN_PATH_TENSOR_FASTSIN2 and the
+ * lbdrn_fpz_* nn sub-stream codec added (all additive: older callers are unaffected) */
+#define LBDRN_ABI_VERSION 4
 
 enum {
   LBDRN_OK = 0,
@@ -172,6 +173,18 @@ int32_t lbdrn_train_grad(LbdrnTrain* t, const void* msb_dev, const void* lsb_dev
                          const int64_t* batch_dev, int32_t n_local, int32_t n_global, float* grad_dev,
                          void* stream);
 int32_t lbdrn_train_apply(LbdrnTrain* t, const float* grad_dev, int64_t adam_t, double lr, void* stream);
+
+/* ---- a12/a13: nn sub-stream codec (HOST code: no device needed) ------------------------------------------------------
+ * Replaces `fpzip.compress(params, precision=prec, order='C')` (encode.py:129) and `fpzip.decompress(bytes, order='C')`
+ * (decode.py:113) when the fpzip package is not installed: the published fpzip algorithm for a flat float32 vector (PCmap
+ * value map keeping the top `precision` bits, one-dimensional Lorenzo predictor, adaptive range coder).  Decoded values
+ * are the inputs with their low 32-precision bits cleared, exactly as with fpzip (precision 0 or 32 = lossless); byte
+ * compatibility of the payload with the real library is unverified (the library is not available to this build).
+ * All pointers are HOST memory.  lbdrn_fpz_bound(n) = output capacity that always suffices for n values. */
+int64_t lbdrn_fpz_bound(int64_t n);
+int32_t lbdrn_fpz_compress(const float* data, int64_t n, int32_t precision, uint8_t* out, int64_t out_cap, int64_t* out_bytes);
+int32_t lbdrn_fpz_header(const uint8_t* in, int64_t in_bytes, int64_t* n_out, int32_t* precision_out);
+int32_t lbdrn_fpz_decompress(const uint8_t* in, int64_t in_bytes, float* out, int64_t out_cap);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ UNITS = [
     ("train", "lbdrn_train_fp32.cu", []),
     ("tc", "lbdrn_tc.cu", []),
     ("tcw", "lbdrn_tcw.cu", []),
+    ("fpz", "lbdrn_fpz.cpp", []),          # host-only: the nn sub-stream codec
 ]
 
 

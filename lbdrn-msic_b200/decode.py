@@ -12,7 +12,10 @@ import subprocess
 import sys
 import time
 
-import fpzip
+try:
+    import fpzip                       # the reference's dependency (requirements.txt:2): used whenever it is installed
+except ImportError:                    # same algorithm from liblbdrn_b200 (csrc/lbdrn_fpz.cpp)
+    import lbdrn_fpzip as fpzip
 import numpy as np
 import torch
 from osgeo import gdal

@@ -18,7 +18,8 @@ PATH_AUTO, PATH_PRECISE, PATH_TENSOR, PATH_TENSOR_FASTSIN, PATH_TENSOR_FASTSIN2 
 SYMBOLS = ["lbdrn_version", "lbdrn_last_error", "lbdrn_dim_in", "lbdrn_param_count", "lbdrn_has_tensor_path",
            "lbdrn_launch_count", "lbdrn_selftest_tc_gemm", "lbdrn_selftest_tc_gemm2", "lbdrn_split", "lbdrn_sse_u16", "lbdrn_max_shifted", "lbdrn_randperm", "lbdrn_decode", "lbdrn_predict",
            "lbdrn_eval_sse", "lbdrn_train_create", "lbdrn_train_destroy", "lbdrn_train_set_params",
-           "lbdrn_train_get_params", "lbdrn_train_steps", "lbdrn_train_grad", "lbdrn_train_apply"]
+           "lbdrn_train_get_params", "lbdrn_train_steps", "lbdrn_train_grad", "lbdrn_train_apply",
+           "lbdrn_fpz_bound", "lbdrn_fpz_compress", "lbdrn_fpz_header", "lbdrn_fpz_decompress"]
 
 
 class LbdrnError(RuntimeError):
@@ -81,6 +82,10 @@ def load(build_if_missing=True):
         "lbdrn_train_steps": (i32, [vp, vp, vp, vp, vp, i64, i32, i64, f64, vp, vp]),
         "lbdrn_train_grad": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
         "lbdrn_train_apply": (i32, [vp, vp, i64, f64, vp]),
+        "lbdrn_fpz_bound": (i64, [i64]),
+        "lbdrn_fpz_compress": (i32, [vp, i64, i32, vp, i64, P(i64)]),
+        "lbdrn_fpz_header": (i32, [vp, i64, P(i64), P(i32)]),
+        "lbdrn_fpz_decompress": (i32, [vp, i64, vp, i64]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)

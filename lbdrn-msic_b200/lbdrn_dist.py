@@ -42,6 +42,12 @@ def global_max_dev(local_max_dev, group=None):
     return local_max_dev
 
 
+def _bytes(t):
+    """Byte view of a contiguous halo buffer for the wire: NCCL has no 16-bit integer type ("Short" is rejected), so
+    uint16 planes (held as int16 views, which torch can slice and copy) travel as uint8."""
+    return t if t.dtype == torch.uint8 else t.view(torch.uint8)
+
+
 def exchange_halos(stripe, D, group=None):
     """stripe: [C, rows, W] tensor holding this rank's own rows.  Returns ([C, rows + top + bottom, W], top) where
     `top` halo rows came from rank-1 and the bottom ones from rank+1 (none at the image border).  Works on CUDA
@@ -57,11 +63,11 @@ def exchange_halos(stripe, D, group=None):
     down = torch.empty((C, D, W), dtype=wire.dtype, device=wire.device) if rank + 1 < world else None
     ops = []
     if rank > 0:
-        ops += [dist.P2POp(dist.isend, wire[:, :D].contiguous(), rank - 1, group),
-                dist.P2POp(dist.irecv, up, rank - 1, group)]
+        ops += [dist.P2POp(dist.isend, _bytes(wire[:, :D].contiguous()), rank - 1, group),
+                dist.P2POp(dist.irecv, _bytes(up), rank - 1, group)]
     if rank + 1 < world:
-        ops += [dist.P2POp(dist.isend, wire[:, rows - D:].contiguous(), rank + 1, group),
-                dist.P2POp(dist.irecv, down, rank + 1, group)]
+        ops += [dist.P2POp(dist.isend, _bytes(wire[:, rows - D:].contiguous()), rank + 1, group),
+                dist.P2POp(dist.irecv, _bytes(down), rank + 1, group)]
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     parts = ([up] if up is not None else []) + [wire] + ([down] if down is not None else [])
@@ -108,12 +114,12 @@ class StripeBuffer:
         ops = []
         if self.top:
             self._send_up.copy_(w[:, self.top:self.top + D])
-            ops += [dist.P2POp(dist.isend, self._send_up, self.rank - 1, self.group),
-                    dist.P2POp(dist.irecv, self._recv_up, self.rank - 1, self.group)]
+            ops += [dist.P2POp(dist.isend, _bytes(self._send_up), self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, _bytes(self._recv_up), self.rank - 1, self.group)]
         if self.bot:
             self._send_dn.copy_(w[:, self.top + rows - D:self.top + rows])
-            ops += [dist.P2POp(dist.isend, self._send_dn, self.rank + 1, self.group),
-                    dist.P2POp(dist.irecv, self._recv_dn, self.rank + 1, self.group)]
+            ops += [dist.P2POp(dist.isend, _bytes(self._send_dn), self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, _bytes(self._recv_dn), self.rank + 1, self.group)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         if self.top:

@@ -38,7 +38,7 @@ def _run(fn_name, world=2):
     procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
     for p in procs:
         p.start()
-    out = dict(q.get(timeout=300) for _ in range(world))
+    out = dict(q.get(timeout=150) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

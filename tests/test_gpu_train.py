@@ -313,6 +313,41 @@ def test_cli_encode_decode_roundtrip(tmp_path):
     assert abs(psnr_ref - psnr) < 1e-3
 
 
+def test_cli_roundtrip_with_the_builtin_nn_codec(tmp_path):
+    """No `fpzip` importable (only the GDAL stand-in is on the path): encode.py / decode.py fall back to the library's own
+    nn sub-stream codec (lbdrn_fpzip -> lbdrn_fpz_*), the stream round-trips, and its weights are the prec-16 values."""
+    from osgeo import gdal
+    from synth_scene import make_scene
+    import lbdrn_fpzip
+    img = make_scene(4, 96, 80, 12, seed=1)
+    tif = str(tmp_path / "s.tif")
+    gdal._store(tif, img)
+    only_gdal = tmp_path / "shims_gdal_only"
+    only_gdal.mkdir()
+    os.symlink(os.path.join(SHIMS, "osgeo"), only_gdal / "osgeo")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([PKG, str(only_gdal)]))
+    out = str(tmp_path / "out")
+    args = ["-K", "5", "-i", tif, "-D", "2", "-bc", "64", "-nl", "2", "-lr", "0.001", "-bs", "512", "-e", "3", "-sr", "1",
+            "-prec", "16", "-o", out]
+    r = subprocess.run([sys.executable, "-c", "import fpzip"], env=env, capture_output=True, text=True)
+    assert r.returncode != 0                                         # the stand-in really is out of reach
+    r = subprocess.run([sys.executable, os.path.join(PKG, "encode.py")] + args, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    d = f"{out}/s_r1_K5_bc64_nl2_D2_prec16_lr0.001_bs512_e3"
+    r = subprocess.run([sys.executable, os.path.join(PKG, "decode.py"), "-i", f"{d}/s.bin", "-org", tif],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    psnr = float(open(f"{d}/decode.txt").read().split("PSNR: ")[1].split()[0])
+    assert abs(psnr - load_case("k5d2_small")[0]["psnr"]) < 0.05
+    blob = open(f"{d}/s.bin", "rb").read()
+    _, tiles = split_stream(blob)
+    w = lbdrn_fpzip.decompress(tiles[0][0])[0][0][0]
+    assert w.size == 10884 and np.array_equal(w.view(np.uint32) & 0xFFFF, np.zeros(w.size, np.uint32))
+    # the ORACLE decoder fed with those weights reconstructs what our decoder wrote
+    ref = O.decode_image(read_base(tiles[0][1]), O.unflatten_params(w, 100, 64, 4, 2), 5, 2)
+    assert abs(O.quality(img, ref, len(blob))[1] - psnr) < 1e-3
+
+
 def test_cli_split_ratio_roundtrip(tmp_path):
     """-sr 2: four independently trained tiles, header with 4+4 sizes, merge on decode (encode.py:231-262, decode.py:187-197)."""
     from osgeo import gdal
