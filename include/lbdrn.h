@@ -29,7 +29,7 @@ extern "C" {
 
 /* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added; 4: LBDRN_PATH_TENSOR_FASTSIN2 and the
  * lbdrn_fpz_* nn sub-stream codec added (all additive: older callers are unaffected) */
-#define LBDRN_ABI_VERSION 4
+#define LBDRN_ABI_VERSION 5
 
 enum {
   LBDRN_OK = 0,
@@ -141,6 +141,15 @@ int32_t lbdrn_selftest_tc_gemm(const void* a_dev, const void* b_dev, float* d_de
  * "[group of 8][k][8]" shared-memory layout and consumed through MN-major UMMA descriptors (a_mn / b_mn != 0). */
 int32_t lbdrn_selftest_tc_gemm2(const void* a_dev, const void* b_dev, float* d_dev, int32_t N, int32_t K, int32_t a_mn,
                                 int32_t b_mn, void* stream);
+
+/* Diagnostic: D[64][N] = A . B^T with the M = 64 instruction shape of the fused training step (modified_ignite_engine.py:18-27:
+ * its chunk GEMMs), operands passed as ready-made fp16 "images" (element (r, k) of a [rows][K] array at byte
+ * ((k>>3)*rows + r)*16 + (k&7)*2) and read through the K-major (x_mn = 0) or the MN-major (x_mn = 1: the image's k index is
+ * the M / N index, its row index is contracted) descriptor; ksteps = contraction length / 16.  raw_dev (optional): all 128
+ * TMEM lanes x N columns. */
+int32_t lbdrn_selftest_tc_gemm3(const void* a_img_dev, int32_t a_bytes, const void* b_img_dev, int32_t b_bytes, float* d_dev,
+                                float* raw_dev, int32_t N, int32_t ksteps, int32_t a_mn, int32_t a_rows, int32_t b_mn,
+                                int32_t b_rows, void* stream);
 
 /* network output y [n_rows*W, C] float32 (pixel-major, like model(x) in decode.py:130) for rows [row0,row1) */
 int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev,

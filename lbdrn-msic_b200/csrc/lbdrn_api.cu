@@ -367,6 +367,14 @@ int32_t lbdrn_selftest_tc_gemm2(const void* a_dev, const void* b_dev, float* d_d
   return tc_selftest2(a_dev, b_dev, d_dev, N, K, a_mn, b_mn, (cudaStream_t)stream);
 }
 
+int32_t lbdrn_selftest_tc_gemm3(const void* a_img_dev, int32_t a_bytes, const void* b_img_dev, int32_t b_bytes, float* d_dev,
+                                float* raw_dev, int32_t N, int32_t ksteps, int32_t a_mn, int32_t a_rows, int32_t b_mn,
+                                int32_t b_rows, void* stream) {
+  if (!a_img_dev || !b_img_dev || !d_dev) return fail(LBDRN_E_INVALID, "null device pointer");
+  return tc_selftest3(a_img_dev, a_bytes, b_img_dev, b_bytes, d_dev, raw_dev, N, ksteps, a_mn, a_rows, b_mn, b_rows,
+                      (cudaStream_t)stream);
+}
+
 int32_t lbdrn_predict(const LbdrnDesc* d, const void* msb_dev, const float* params_dev, const float* coord_tab_dev,
                       float* y_dev, void* stream) {
   return run_infer<MODE_PREDICT>(d, msb_dev, nullptr, params_dev, coord_tab_dev, y_dev, nullptr, stream);

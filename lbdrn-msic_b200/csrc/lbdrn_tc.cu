@@ -1125,6 +1125,63 @@ __global__ void __launch_bounds__(TC_THREADS) tc_selftest2_kernel(const __half* 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
 }
 
+
+// ---- self-test 3: D[64][N] = A . B^T with M = 64 (the shape of the training step's chunk GEMMs), operands given as raw
+// "images" (lbdrn_umma.cuh: img_off) and consumed through the K-major or the MN-major view; read back with the 16x256b
+// shape (Dout) and, for diagnosis, with 32x32b over all 128 lanes (Raw[128][N]) -------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS) tc_selftest3_kernel(const uint8_t* __restrict__ A, int a_bytes,
+                                                                 const uint8_t* __restrict__ B, int b_bytes,
+                                                                 float* __restrict__ Dout, float* __restrict__ Raw, int N,
+                                                                 int ksteps, int a_mn, int a_rows, int b_mn, int b_rows) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ((a_bytes + 127) & ~127);
+  __shared__ __align__(8) uint64_t s_mbar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < a_bytes; i += TC_THREADS) sA[i] = A[i];
+  for (int i = tid; i < b_bytes; i += TC_THREADS) sB[i] = B[i];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  // poison the accumulator region so that untouched lanes are visible in Raw
+  if (warp == 0 && elect_one()) {
+    const uint32_t idesc = umma_idesc_f16_major(64, N, a_mn, b_mn);
+    for (int i = 0; i < ksteps; ++i)
+      umma_f16(tmem, img_desc(smem_u32(sA), a_rows, a_mn, i), img_desc(smem_u32(sB), b_rows, b_mn, i), idesc, i > 0);
+    umma_commit(smem_u32(&s_mbar));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&s_mbar), 0);
+  tc_fence_after();
+  const int g = lane >> 2, t = lane & 3;
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t r[4];
+    tmem_ld16x256_x1(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait4(r);
+    Dout[(16 * warp + g) * N + c0 + 2 * t] = __uint_as_float(r[0]);
+    Dout[(16 * warp + g) * N + c0 + 2 * t + 1] = __uint_as_float(r[1]);
+    Dout[(16 * warp + g + 8) * N + c0 + 2 * t] = __uint_as_float(r[2]);
+    Dout[(16 * warp + g + 8) * N + c0 + 2 * t + 1] = __uint_as_float(r[3]);
+  }
+  if (Raw != nullptr)
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float acc[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      for (int j = 0; j < 16 && c0 + j < N; ++j) Raw[tid * N + c0 + j] = acc[j];
+    }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
 std::mutex& tc_mu() {
   static std::mutex m;
   return m;
@@ -1408,6 +1465,19 @@ int tc_selftest2(const void* a_dev, const void* b_dev, float* d_dev, int N, int 
   const size_t smem = (size_t)(128 + N) * K * 2;
   CUDA_TRY(cudaFuncSetAttribute(tc_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest2_kernel<<<1, TC_THREADS, smem, st>>>((const __half*)a_dev, (const __half*)b_dev, d_dev, N, K, a_mn, b_mn);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return LBDRN_OK;
+}
+
+int tc_selftest3(const void* a_img, int a_bytes, const void* b_img, int b_bytes, float* d_dev, float* raw_dev, int N,
+                 int ksteps, int a_mn, int a_rows, int b_mn, int b_rows, cudaStream_t st) {
+  if (N % 8 || N < 8 || N > 256 || ksteps < 1 || a_bytes <= 0 || b_bytes <= 0 || a_bytes + b_bytes > 200 * 1024)
+    return fail(LBDRN_E_INVALID, "selftest3 N=%d ksteps=%d", N, ksteps);
+  const size_t smem = (size_t)((a_bytes + 127) & ~127) + b_bytes + 128;
+  CUDA_TRY(cudaFuncSetAttribute(tc_selftest3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest3_kernel<<<1, TC_THREADS, smem, st>>>((const uint8_t*)a_img, a_bytes, (const uint8_t*)b_img, b_bytes, d_dev,
+                                                  raw_dev, N, ksteps, a_mn, a_rows, b_mn, b_rows);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return LBDRN_OK;

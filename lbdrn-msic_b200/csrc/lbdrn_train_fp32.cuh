@@ -525,10 +525,12 @@ __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, co
 // hi+lo split operands prepared once by their producers and read with ldmatrix (bc a multiple of 64, weights in shared
 // memory); MMA = 0: FFMA.
 template <int BC, int CP, bool WSMEM, int THREADS, int TM, int MMA = 0>
-__global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs a) {
   static_assert(!MMA || (TM == 4 && THREADS == 512 && BC % 32 == 0 && BC <= 128), "MMA path: 64-pixel chunks, 16 warps");
   static_assert(MMA != 2 || (WSMEM && BC % 64 == 0), "fp16-split path: weights in shared memory, unit tiles in pairs");
+  static_assert(MMA != 3 || (WSMEM && BC == 64), "tcgen05 path: M = 64 chunk GEMMs, everything resident in shared memory");
   constexpr bool H2 = MMA == 2;
+  constexpr bool TC5 = MMA == 3;          // chunk GEMMs on tcgen05 (M = 64, accumulators in TMEM), see the TC5 block below
   constexpr int NPIX = train_npix(TM), LDP = train_ldp(TM), US = THREADS / 128, TN = BC / 8 / US;
   constexpr int VEC = TN >= 4 ? 4 : TN;
   static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
@@ -546,11 +548,11 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   // of Gbuf is BC*kLDH floats: act' in fp32 [BC][LDP], overwritten in place by the scaled dz as [hi [BC][kLDH] | lo [BC][kLDH]]
   constexpr int GSZ = H2 ? BC * kLDH : BC * LDP;
   float* Hbuf = X + (size_t)a.dimpad * LDP;                     // [L][BC][LDP]    hidden outputs
-  float* Gbuf = Hbuf + (size_t)(H2 ? 1 : L) * BC * LDP;         // [L][GSZ]        act' then dz
+  float* Gbuf = Hbuf + (size_t)(TC5 ? 0 : (H2 ? 1 : L)) * BC * LDP;   // [L][GSZ]  act' then dz
   float* dZo = Gbuf + (size_t)L * GSZ;                          // [CP][LDP]       output-layer dz
-  float* Tl = dZo + CP * LDP;                                   // [CP][LDP]       labels
+  float* Tl = dZo + (TC5 ? 0 : CP * LDP);                       // [CP][LDP]       labels
   float* Pp = Tl + CP * LDP;                                    // [US][CP][LDP]   output-layer partial sums per unit split
-  float* wsm = Pp + US * CP * LDP;                              // packed weights [P] (+pad) then natural hidden l>=1
+  float* wsm = Pp + (TC5 ? 0 : US * CP * LDP);                  // packed weights [P] (+pad) then natural hidden l>=1
   float* wnat_sm = wsm + round4(P);
   // H2: wsm = [biases of the hidden layers L*BC | W_o C*BC | b_o C] in fp32; behind it the split 16-bit operand arrays
   const int KP0 = round16(net.dim_in);                          // layer-0 contraction length, zero-padded to k = 16 steps
@@ -560,6 +562,29 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   const uint32_t wh_base = hh_base + (uint32_t)(L - 1) * BC * kLDH * 4u;   // W_l natural [BC][ldw_l] halves x 2 (hi | lo)
   auto ldw_of = [&](int l) { return (l == 0 ? KP0 : BC) + 8; };  // row pitch in halves: an odd multiple of 16 bytes
   auto wh_of = [&](int l) { return wh_base + (l == 0 ? 0u : (uint32_t)BC * (KP0 + 8) * 4u + (uint32_t)(l - 1) * BC * (BC + 8) * 4u); };
+  // ---- TC5: operand images (lbdrn_umma.cuh: img_off) behind the fp32 part, 128 B-aligned ---------------------------------
+  //   weights (byte for byte the global image a.wimg): per hidden layer [hi Kp*BC | lo Kp*BC] halves, then W_o with 16 rows
+  //   [hi 16*BC | lo 16*BC]; X split [hi (KP0+8)*NPIX | lo]; hidden outputs h_l [hi (BC+8)*NPIX | lo] (the extra group of 8
+  //   is the constant block 1,0,..,0 per pixel in hi, zero in lo: read as one more input row it makes the bias gradient a
+  //   column of the weight-gradient GEMM); scaled dz_l [hi BC*NPIX | lo]; scaled output dz [hi 16*NPIX | lo].
+  const uint32_t t5_base = (smem_u32(h2base) + 127u) & ~127u;
+  auto t5_wbytes = [&](int l) { return (uint32_t)(l == 0 ? KP0 : BC) * BC * 2u; };      // one half (hi or lo) of layer l
+  auto t5_w = [&](int l) { return t5_base + (l == 0 ? 0u : 2u * t5_wbytes(0) + (uint32_t)(l - 1) * 2u * t5_wbytes(1)); };
+  const uint32_t t5_wo = t5_w(L), t5_wend = t5_wo + 2u * 16u * BC * 2u;
+  const uint32_t t5_xbytes = (uint32_t)(KP0 + 8) * NPIX * 2u, t5_hbytes = (uint32_t)(BC + 8) * NPIX * 2u;
+  const uint32_t t5_x = t5_wend, t5_h0 = t5_x + 2u * t5_xbytes;
+  auto t5_h = [&](int l) { return t5_h0 + (uint32_t)l * 2u * t5_hbytes; };
+  const uint32_t t5_dzbytes = (uint32_t)BC * NPIX * 2u;
+  auto t5_dz = [&](int l) { return t5_h0 + (uint32_t)L * 2u * t5_hbytes + (uint32_t)l * 2u * t5_dzbytes; };
+  const uint32_t t5_dzo = t5_dz(L), t5_dzobytes = 16u * NPIX * 2u;
+  // TMEM columns: two forward / dh accumulators, the output accumulator, then the weight-gradient accumulators
+  constexpr uint32_t T5_ZO = 2 * BC, T5_DWO = 2 * BC + 16, T5_DW0 = 2 * BC + 32;
+  auto t5_dwcol = [&](int l) { return T5_DW0 + (l == 0 ? 0u : (uint32_t)(KP0 + 8) + (uint32_t)(l - 1) * (BC + 8)); };
+  __shared__ __align__(8) uint64_t s_t5_mbar;
+  __shared__ uint32_t s_t5_tmem;
+  __shared__ float s_t5_inv[kMaxLayers];                        // TC5: 1 / scale of dz_l (read-out of the gradient accumulators)
+  __shared__ float s_t5_dbo[4][8];                              // TC5: output-bias gradient partials per sub-partition
+  uint32_t t5_phase = 0u;
   __shared__ uint32_t s_dzmax[kMaxLayers];                      // H2: bits of max |dz_l| over the chunk
   __shared__ float s_db[H2 ? 2 : 1][4][H2 ? BC : 1];            // H2: bias-gradient partials per pixel tile (by layer parity)
   __shared__ int s_py[NPIX], s_px[NPIX], s_valid[NPIX];
@@ -568,8 +593,8 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   __shared__ float s_adam[2];
 
   const float* w = WSMEM ? wsm : a.wpack;
-  const float* wo_p = H2 ? wsm + L * BC : w + net.woff[L];            // output layer W_o [C][BC] and b_o [C]
-  const float* bo_p = H2 ? wsm + L * BC + C * BC : w + net.boff[L];
+  const float* wo_p = (H2 || TC5) ? wsm + L * BC : w + net.woff[L];   // output layer W_o [C][BC] and b_o [C]
+  const float* bo_p = (H2 || TC5) ? wsm + L * BC + C * BC : w + net.boff[L];
   // natural (untransposed) W_l for hidden layers l>=1, used as the k-major B operand of dh = W^T dz
   auto wnat = [&](int l) -> const float* {
     return WSMEM ? (wnat_sm + (size_t)(l - 1) * BC * BC) : (a.params + net.woff[l]);
@@ -580,6 +605,30 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
   };
 
   for (int i = net.dim_in * LDP + tid; i < a.dimpad * LDP; i += THREADS) X[i] = 0.f;   // padding rows stay zero
+  uint32_t t5_tmem = 0u;
+  if constexpr (TC5) {
+    // tensor memory: one CTA per SM (shared memory), all 512 columns; constant operand blocks; completion barrier
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_t5_tmem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) mbar_init(smem_u32(&s_t5_mbar), 1);
+    // everything behind the weights starts as zero (padding features, bands >= C of the output dz, lo halves of the
+    // constant blocks), then the hi halves of the constant blocks: element 0 of each pixel's 16-byte row = 1.0
+    for (uint32_t o = t5_wend + 16u * tid; o < t5_dzo + 2u * t5_dzobytes; o += 16u * THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(o), "r"(0u) : "memory");
+    __syncthreads();
+    for (int i = tid; i < (L + 1) * NPIX; i += THREADS) {
+      const int which = i / NPIX, pp = i - which * NPIX;
+      const uint32_t blk = which == 0 ? t5_x + (uint32_t)KP0 * NPIX * 2u : t5_h(which - 1) + (uint32_t)BC * NPIX * 2u;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(blk + 16u * pp), "h"((uint16_t)0x3c00) : "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    t5_tmem = s_t5_tmem;
+  }
   long long t_prev = 0;
   const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
   if (prof) t_prev = clock64();
@@ -902,6 +951,21 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     if (tma_on) fence_async_smem();      // our reads of the landing boxes are ordered before the next TMA writes into them
   };
 
+  // TC5: features -> split operand image.  A warp covers 8 pixels x 4 feature pairs = 8 x 16 contiguous bytes per store
+  // instruction (conflict-free), reading X at banks 8*pair + pixel (conflict-free).
+  auto t5_split_x = [&]() {
+    for (int i = tid; i < KP0 * (NPIX / 2); i += THREADS) {
+      const int kp = i & 3, pp = ((i >> 2) & 7) + 8 * ((i >> 5) & 7), k = 8 * (i >> 8) + 2 * kp;
+      const float x0 = k < net.dim_in ? X[(size_t)k * LDP + pp] : 0.f;
+      const float x1 = k + 1 < net.dim_in ? X[(size_t)(k + 1) * LDP + pp] : 0.f;
+      uint32_t hi, lo;
+      split_h2(x0, x1, hi, lo);
+      const uint32_t o = (uint32_t)img_off(NPIX, pp, k);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_x + o), "r"(hi) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_x + t5_xbytes + o), "r"(lo) : "memory");
+    }
+  };
+
   for (int s = 0; s < a.n_steps; ++s) {
     if (tid == 0) s_sse = 0.f;
     prefetch_index(s + 1);
@@ -930,7 +994,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     LBDRN_PHASE(7)    // wait for the Adam phase of every CTA (second barrier of the previous step)
     if (il) prefetch_l2_il(); else prefetch_l2();
     // ---- (re)load weights ----------------------------------------------------------------------------
-    if (H2) {
+    if (H2 || TC5) {
       const bool from_image = s > 0 && a.wimg != nullptr;           // the Adam phase of step s-1 wrote every weight's halves
       // fp32 part (hidden biases, output layer): requested FIRST (behind 49 KB of copies per SM its round trip tripled),
       // stored after the copies have been issued
@@ -941,9 +1005,10 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       float lite0 = 0.f;
       if (tid < nb + nwo + C) lite0 = __ldcg(a.params + lite_src(tid));
       if (from_image) {
-        const int n16 = (int)((wh_of(L) - wh_base) >> 4);           // the image is the shared layout, byte for byte
+        const uint32_t img0 = TC5 ? t5_base : wh_base;
+        const int n16 = (int)(((TC5 ? t5_wend : wh_of(L)) - img0) >> 4);   // the image is the shared layout, byte for byte
         for (int i = tid; i < n16; i += THREADS)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wh_base + 16u * i),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(img0 + 16u * i),
                        "l"(reinterpret_cast<const uint4*>(a.wimg) + i) : "memory");
       }
       if (tid < nb + nwo + C) wsm[tid] = lite0;
@@ -953,7 +1018,7 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
       for (int l = 0; l < (from_image ? 0 : L); ++l) {
         const int K = l == 0 ? net.dim_in : BC, KH = (l == 0 ? KP0 : BC) >> 1, ldw = ldw_of(l);
         const float* src = a.params + net.woff[l];
-        const uint32_t w_hi = wh_of(l), w_lo = w_hi + (uint32_t)BC * ldw * 2u;
+        const uint32_t w_hi = TC5 ? t5_w(l) : wh_of(l), w_lo = w_hi + (TC5 ? t5_wbytes(l) : (uint32_t)BC * ldw * 2u);
 #pragma unroll 4
         for (int i = tid; i < BC * KH; i += THREADS) {
           const int u = i / KH, k = 2 * (i - u * KH);
@@ -961,9 +1026,22 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
           const float x1 = k + 1 < K ? __ldcg(src + (size_t)u * K + k + 1) : 0.f;
           uint32_t hi, lo;
           split_h2(x0 * kWScale, x1 * kWScale, hi, lo);
-          const uint32_t o = (uint32_t)(u * ldw + k) * 2u;
+          const uint32_t o = TC5 ? (uint32_t)img_off(BC, u, k) : (uint32_t)(u * ldw + k) * 2u;
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(w_hi + o), "r"(hi) : "memory");
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(w_lo + o), "r"(lo) : "memory");
+        }
+      }
+      if (TC5 && !from_image) {
+        // output layer as a 16-row image (rows >= C zero): W_o[c][u] pairs along u
+        const float* src = a.params + net.woff[L];
+        for (int i = tid; i < 16 * (BC / 2); i += THREADS) {
+          const int c = i / (BC / 2), u = 2 * (i - c * (BC / 2));
+          const float x0 = c < C ? __ldcg(src + c * BC + u) : 0.f, x1 = c < C ? __ldcg(src + c * BC + u + 1) : 0.f;
+          uint32_t hi, lo;
+          split_h2(x0 * kWScale, x1 * kWScale, hi, lo);
+          const uint32_t o = (uint32_t)img_off(16, c, u);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_wo + o), "r"(hi) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_wo + 16u * BC * 2u + o), "r"(lo) : "memory");
         }
       }
     } else if (WSMEM) {
@@ -992,7 +1070,9 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(xh_lo + o), "r"(lo) : "memory");
       }
     }
+    if (TC5 && early) t5_split_x();
     if (WSMEM) cp_async_wait_all();
+    if (TC5) fence_async_smem();      // weights and features were written through the generic proxy; the MMAs read them
     __syncthreads();
     LBDRN_PHASE(0)   // weight reload
 
@@ -1077,12 +1157,293 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
         }
         __syncthreads();
       }
+      if (TC5) {
+        t5_split_x();
+        fence_async_smem();
+        __syncthreads();
+      }
       }
       LBDRN_PHASE(1)   // gather
 
       // ---- forward (LBDRNmodel.py:79-82), keeping h_l and act'(z_l) per layer ------------------------------
       float h[TM][TN];
       const int warp = tid >> 5, lane = tid & 31;
+      if constexpr (TC5) {
+        // ================= chunk forward + backward on tcgen05 (M = 64 pixels, accumulators in tensor memory) ==============
+        // Every product is hi*hi + hi*lo + lo*hi of fp16 split operands accumulated in fp32 (as the MMA = 2 kernel), issued by
+        // one elected lane; completion comes back through one mbarrier.  Thread <-> accumulator element as in a warp-level
+        // m16n8 fragment: sub-partition sp = warp % 4 holds pixels 16 sp .. +15 (rows g, g + 8), column group cg = warp / 4
+        // holds 16 columns (two 8-column tiles j; columns 2t, 2t + 1 of each).
+        const int sp = warp & 3, cg = warp >> 2, g = lane >> 2, t = lane & 3;
+        const uint32_t tm_lane = t5_tmem + ((uint32_t)(32 * sp) << 16);
+        const uint32_t mbar = smem_u32(&s_t5_mbar);
+        auto mma3 = [&](uint32_t d_col, uint32_t a_img, uint32_t a_half, int a_rows, int a_mn, uint32_t b_img, uint32_t b_half,
+                        int b_rows, int b_mn, int N, int ksteps) {
+          const uint32_t idesc = umma_idesc_f16_major(64, N, a_mn, b_mn);
+          for (int i = 0; i < ksteps; ++i) {       // small terms first
+            umma_f16(t5_tmem + d_col, img_desc(a_img + a_half, a_rows, a_mn, i), img_desc(b_img, b_rows, b_mn, i), idesc, i > 0);
+            umma_f16(t5_tmem + d_col, img_desc(a_img, a_rows, a_mn, i), img_desc(b_img + b_half, b_rows, b_mn, i), idesc, 1u);
+            umma_f16(t5_tmem + d_col, img_desc(a_img, a_rows, a_mn, i), img_desc(b_img, b_rows, b_mn, i), idesc, 1u);
+          }
+        };
+        auto t5_wait = [&]() {
+          mbar_wait(mbar, t5_phase, 8, (int)blockIdx.x);
+          t5_phase ^= 1u;
+          tc_fence_after();
+        };
+        // ---- forward (LBDRNmodel.py:79-82) ----------------------------------------------------------------------------------
+        for (int l = 0; l < L; ++l) {
+          const int Kp = l == 0 ? KP0 : BC;
+          if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+              mma3((uint32_t)(l & 1) * BC, l == 0 ? t5_x : t5_h(l - 1), l == 0 ? t5_xbytes : t5_hbytes, NPIX, 0, t5_w(l),
+                   t5_wbytes(l), BC, 0, BC, Kp >> 4);
+              umma_commit(mbar);
+            }
+            __syncwarp();
+          }
+          t5_wait();
+          LBDRN_PHASE(15)   // fwd: GEMMs
+          uint32_t r[8];
+          tmem_ld16x256_x2(tm_lane + (uint32_t)(l & 1) * BC + 16u * cg, r);
+          tmem_ld_wait8(r);
+          float* Gl = Gbuf + (size_t)l * GSZ;
+          float hv[2][4], gv[2][4], amax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int u = 16 * cg + 8 * j + 2 * t + (e & 1);
+              const float z = __uint_as_float(r[4 * j + e]) * kWInv + wsm[l * BC + u];
+              if (net.relu) {
+                hv[j][e] = fmaxf(z, 0.f);
+                gv[j][e] = z > 0.f ? 1.f : 0.f;
+              } else {
+                const float arg = net.w0 * z;
+                float sn, cs;
+                sincos_cw_core(arg, sn, cs);
+                amax = fmaxf(amax, fabsf(arg));
+                hv[j][e] = sn;
+                gv[j][e] = cs * net.w0;
+              }
+            }
+          if (__builtin_expect(amax > 48000.0f, 0)) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int u = 16 * cg + 8 * j + 2 * t + (e & 1);
+                const float arg = net.w0 * (__uint_as_float(r[4 * j + e]) * kWInv + wsm[l * BC + u]);
+                if (fabsf(arg) > 48000.0f) { hv[j][e] = sin_slow(arg); gv[j][e] = cos_slow(arg) * net.w0; }
+              }
+          }
+          const uint32_t o_hi = t5_h(l), o_lo = o_hi + t5_hbytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int pixel = 16 * sp + g + 8 * e2, u = 16 * cg + 8 * j + 2 * t;
+              Gl[(size_t)u * LDP + pixel] = gv[j][2 * e2];              // bank = g + 8t: conflict-free
+              Gl[(size_t)(u + 1) * LDP + pixel] = gv[j][2 * e2 + 1];
+              uint32_t hi, lo;
+              split_h2(hv[j][2 * e2], hv[j][2 * e2 + 1], hi, lo);
+              const uint32_t o = (uint32_t)img_off(NPIX, pixel, u);    // 8 pixels x 16 contiguous bytes per store instruction
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_hi + o), "r"(hi) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_lo + o), "r"(lo) : "memory");
+            }
+          fence_async_smem();
+          tc_fence_before();
+          __syncthreads();
+          LBDRN_PHASE(16)   // fwd: bias + sine / cosine + stores
+        }
+        LBDRN_PHASE(2)
+        // ---- output layer + loss (LBDRNloss.py:9): z_o = h_L . W_o^T with N = 16 (rows >= C of the image are zero) ------------
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            mma3(T5_ZO, t5_h(L - 1), t5_hbytes, NPIX, 0, t5_wo, 16u * BC * 2u, 16, 0, 16, BC >> 4);
+            umma_commit(mbar);
+          }
+          __syncwarp();
+        }
+        t5_wait();
+        // d(mean((y-t)^2))/dz_o = gscale (y-t) y (1-y); stored as (y-t) y (1-y) 2^16 (|.| <= 2^14: fp16 range, no underflow of
+        // small errors), the factor gscale 2^-16 comes off in the fp32 epilogues downstream
+        const float inv_o = gscale * (1.0f / 65536.0f);
+        float sse = 0.f;
+        if (cg == 0) {
+          uint32_t r[4];
+          tmem_ld16x256_x1(tm_lane + T5_ZO, r);
+          tmem_ld_wait4(r);
+          float dsum0 = 0.f, dsum1 = 0.f;
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int pixel = 16 * sp + g + 8 * e2;
+            const bool ok = s_valid[pixel] != 0;
+            float v[2];
+#pragma unroll
+            for (int e1 = 0; e1 < 2; ++e1) {
+              const int c = 2 * t + e1;
+              v[e1] = 0.f;
+              if (c < C) {
+                const float y = sigmoidf_rn(__uint_as_float(r[2 * e2 + e1]) * kWInv + bo_p[c]);
+                const float d = y - Tl[c * LDP + pixel];
+                if (ok) { v[e1] = (d * ((1.0f - y) * y)) * 65536.0f; sse += d * d; }
+              }
+            }
+            dsum0 += v[0]; dsum1 += v[1];
+            uint32_t hi, lo;
+            split_h2(v[0], v[1], hi, lo);
+            const uint32_t o = (uint32_t)img_off(NPIX, pixel, 2 * t);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_dzo + o), "r"(hi) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_dzo + t5_dzobytes + o), "r"(lo) : "memory");
+          }
+          // output-bias gradient: fixed-order tree over the 16 pixels of the sub-partition, then over the 4 sub-partitions
+#pragma unroll
+          for (int off = 4; off < 32; off <<= 1) {
+            dsum0 += __shfl_xor_sync(0xffffffffu, dsum0, off);
+            dsum1 += __shfl_xor_sync(0xffffffffu, dsum1, off);
+          }
+          if (g == 0) { s_t5_dbo[sp][2 * t] = dsum0; s_t5_dbo[sp][2 * t + 1] = dsum1; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
+        if (lane == 0) s_red[warp] = sse;
+        if (tid < kMaxLayers) s_dzmax[tid] = 0u;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          float tsum = 0.f;
+          for (int i = 0; i < THREADS / 32; ++i) tsum += s_red[i];
+          s_sse += tsum;
+        }
+        if (tid < C) {
+          const float gsum = ((s_t5_dbo[0][tid] + s_t5_dbo[1][tid]) + (s_t5_dbo[2][tid] + s_t5_dbo[3][tid])) * inv_o;
+          float* dd = mypart + net.boff[L] + tid;
+          *dd = first ? gsum : *dd + gsum;
+        }
+        LBDRN_PHASE(3)   // output layer + loss
+        // ---- backward -----------------------------------------------------------------------------------------------------------
+        // dh_L = dz_o . W_o (W_o image read MN-major) first: the layers wait for it; dW_o = h_L^T . dz_o (both MN-major) behind it
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            mma3((uint32_t)((L - 1) & 1) * BC, t5_dzo, t5_dzobytes, NPIX, 0, t5_wo, 16u * BC * 2u, 16, 1, BC, 1);
+            umma_commit(mbar);
+            mma3(T5_DWO, t5_h(L - 1), t5_hbytes, NPIX, 1, t5_dzo, t5_dzobytes, NPIX, 1, 16, NPIX >> 4);
+          }
+          __syncwarp();
+        }
+        float inv_next = inv_o;
+        for (int l = L - 1; l >= 0; --l) {
+          t5_wait();
+          uint32_t r[8];
+          tmem_ld16x256_x2(tm_lane + (uint32_t)(l & 1) * BC + 16u * cg, r);
+          tmem_ld_wait8(r);
+          const float* Gl = Gbuf + (size_t)l * GSZ;
+          const float sc = kWInv * inv_next;
+          float dz[2][4], mx = 0.f;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int pixel = 16 * sp + g + (e >> 1) * 8, u = 16 * cg + 8 * j + 2 * t + (e & 1);
+              dz[j][e] = (__uint_as_float(r[4 * j + e]) * sc) * Gl[(size_t)u * LDP + pixel];
+              mx = fmaxf(mx, fabsf(dz[j][e]));
+            }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+          if (lane == 0) atomicMax(&s_dzmax[l], __float_as_uint(mx));     // order-independent: the step stays deterministic
+          tc_fence_before();
+          __syncthreads();
+          float S, inv;
+          dz_scale(s_dzmax[l], S, inv);
+          const uint32_t o_hi = t5_dz(l), o_lo = o_hi + t5_dzbytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int pixel = 16 * sp + g + 8 * e2, u = 16 * cg + 8 * j + 2 * t;
+              uint32_t hi, lo;
+              split_h2(dz[j][2 * e2] * S, dz[j][2 * e2 + 1] * S, hi, lo);
+              const uint32_t o = (uint32_t)img_off(NPIX, pixel, u);
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_hi + o), "r"(hi) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_lo + o), "r"(lo) : "memory");
+            }
+          if (tid == 0) s_t5_inv[l] = inv;
+          fence_async_smem();
+          __syncthreads();
+          LBDRN_PHASE(9 + 2 * (l > 0 ? 1 : 0))     // bwd: dh + dz (9: layer 0, 11: layer >= 1)
+          if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+              const int Kp = l == 0 ? KP0 : BC;
+              if (l > 0) {
+                // dh_{l-1} = dz_l . W_l (W_l image read MN-major)
+                mma3((uint32_t)((l - 1) & 1) * BC, t5_dz(l), t5_dzbytes, NPIX, 0, t5_w(l), t5_wbytes(l), BC, 1, BC, BC >> 4);
+                umma_commit(mbar);
+              }
+              // [dW_l | db_l] = dz_l^T . [in_l | 1] (both images read MN-major; the constant block follows the input's hi half)
+              mma3(t5_dwcol(l), t5_dz(l), t5_dzbytes, NPIX, 1, l == 0 ? t5_x : t5_h(l - 1), l == 0 ? t5_xbytes : t5_hbytes, NPIX,
+                   1, Kp + 8, NPIX >> 4);
+              if (l == 0) umma_commit(mbar);          // covers every gradient GEMM issued before it
+            }
+            __syncwarp();
+          }
+          inv_next = inv;
+        }
+        // ---- gradient accumulators -> this CTA's partial (rows = units: sub-partition sp holds units 16 sp + g, + 8) ---------
+        t5_wait();
+        for (int l = 0; l < L; ++l) {
+          const int Kin = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, ntile = (Kp + 8) >> 3;
+          const float inv = s_t5_inv[l];
+          float* dst = mypart + net.woff[l];
+          const bool pair_ok = (Kin & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+          for (int tt = cg; tt < ntile; tt += 4) {
+            uint32_t r[4];
+            tmem_ld16x256_x1(tm_lane + t5_dwcol(l) + 8u * tt, r);
+            tmem_ld_wait4(r);
+            const int q = 8 * tt + 2 * t;
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int u = 16 * sp + g + 8 * e2;
+              const float v0 = __uint_as_float(r[2 * e2]) * inv, v1 = __uint_as_float(r[2 * e2 + 1]) * inv;
+              if (q == Kp) {                                       // the constant block's column: bias gradient
+                float* dd = mypart + net.boff[l] + u;
+                *dd = first ? v0 : *dd + v0;
+              } else if (pair_ok && q + 1 < Kin) {
+                float2* d2 = reinterpret_cast<float2*>(dst + (size_t)u * Kin + q);
+                float2 v = make_float2(v0, v1);
+                if (!first) { const float2 o = *d2; v.x += o.x; v.y += o.y; }
+                *d2 = v;
+              } else {
+                if (q < Kin) { float* d1 = dst + (size_t)u * Kin + q; *d1 = first ? v0 : *d1 + v0; }
+                if (q + 1 < Kin) { float* d1 = dst + (size_t)u * Kin + q + 1; *d1 = first ? v1 : *d1 + v1; }
+              }
+            }
+          }
+        }
+        if (cg == 0) {
+          uint32_t r[4];
+          tmem_ld16x256_x1(tm_lane + T5_DWO, r);
+          tmem_ld_wait4(r);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int u = 16 * sp + g + (e >> 1) * 8, c = 2 * t + (e & 1);
+            if (c < C) {
+              float* d1 = mypart + net.woff[L] + c * BC + u;
+              const float v = __uint_as_float(r[e]) * inv_o;
+              *d1 = first ? v : *d1 + v;
+            }
+          }
+        }
+        tc_fence_before();       // the accumulators are read: the next chunk / step may overwrite them after its barrier
+        first = false;
+        LBDRN_PHASE(4)   // backward (remainder)
+        continue;
+      }
       for (int l = 0; l < L; ++l) {
         const int K = l == 0 ? net.dim_in : BC;
         const float* in = l == 0 ? X : Hbuf + (size_t)(l - 1) * BC * LDP;
@@ -1590,7 +1951,34 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
             float p = p_old, m = m_old, v = v_old;
             adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
             a.params[i] = p; a.m[i] = m; a.v[i] = v;
-            if (H2) {
+            if (TC5) {
+              if (a.wimg != nullptr) {
+                uint32_t img = 0u;                                    // halves before layer l's block
+                bool done = false;
+                for (int l = 0; l < L && !done; ++l) {
+                  const int K = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, o = i - net.woff[l];
+                  if (o >= 0 && o < K * BC) {
+                    const int u = o / K, k = o - u * K;
+                    uint16_t hi, lo;
+                    split_h1(p * kWScale, hi, lo);
+                    const uint32_t e = img + (uint32_t)(img_off(BC, u, k) >> 1);
+                    a.wimg[e] = hi;
+                    a.wimg[e + (uint32_t)Kp * BC] = lo;
+                    done = true;
+                  }
+                  img += 2u * (uint32_t)Kp * BC;
+                }
+                const int oo = i - net.woff[L];
+                if (!done && oo >= 0 && oo < C * BC) {
+                  const int c = oo / BC, u = oo - c * BC;
+                  uint16_t hi, lo;
+                  split_h1(p * kWScale, hi, lo);
+                  const uint32_t e = img + (uint32_t)(img_off(16, c, u) >> 1);
+                  a.wimg[e] = hi;
+                  a.wimg[e + 16u * BC] = lo;
+                }
+              }
+            } else if (H2) {
               if (a.wimg != nullptr) {
                 uint32_t img = 0u;                                    // halves before layer l's block
                 for (int l = 0; l < L; ++l) {
@@ -1616,6 +2004,11 @@ __global__ void __launch_bounds__(THREADS) train_fp32_kernel(const TrainArgs a) 
     LBDRN_PHASE(6)   // reduce + Adam
     __syncthreads();
     if (tid == 0) gbar_arrive(a.gbar + 1);   // second barrier, arrive; the wait is at the head of the next step
+  }
+  if constexpr (TC5) {
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t5_tmem), "r"(512) : "memory");
   }
 #undef LBDRN_PHASE
 }

@@ -176,4 +176,38 @@ __device__ __forceinline__ uint32_t umma_idesc_f16_major(int M, int N, int a_mn,
 // of a core matrix are 16 B apart, next k-group +128 B (LBO), next MN-group +K*16 B (SBO).
 __host__ __device__ inline int umma_off_mn(int K, int mn, int k) { return ((mn >> 3) * K + k) * 16 + (mn & 7) * 2; }
 
+
+// ---- operand images shared by the forward and the backward GEMMs of the tcgen05 training step ------------------------------
+// An "image" is a [rows][K] fp16 array in the canonical no-swizzle layout: element (r, k) at ((k>>3)*rows + r)*16 + (k&7)*2.
+//  * K-major view  (r indexes M or N, k is contracted):  LBO = rows*16, SBO = 128, one K = 16 step advances rows*32 bytes;
+//  * MN-major view (k indexes M or N, r is contracted; the contraction length is `rows`): LBO = 128, SBO = rows*16, one
+//    step of 16 contracted rows advances 256 bytes.
+// So ONE copy of an activation / weight / gradient block serves x.W^T, dz.W and dz^T.x alike.
+__host__ __device__ inline int img_off(int rows, int r, int k) { return ((k >> 3) * rows + r) * 16 + (k & 7) * 2; }
+__device__ __forceinline__ uint64_t img_desc(uint32_t saddr, int rows, int mn_major, int kstep) {
+  return mn_major ? umma_desc(saddr + (uint32_t)kstep * 256u, 128u, (uint32_t)rows * 16u)
+                  : umma_desc(saddr + (uint32_t)kstep * (uint32_t)rows * 32u, (uint32_t)rows * 16u, 128u);
+}
+
+// tcgen05.ld 16x256b: the warp reads 16 lanes (its sub-partition's lanes 0-15: where an M = 64 accumulator keeps rows
+// 16*(warp%4) .. +15) x 8 columns per repetition; register 4j+0/1 = row lane/4, columns 8j + 2*(lane%4) + {0,1};
+// 4j+2/3 = row lane/4 + 8, same columns -- the accumulator fragment of a warp-level m16n8 MMA.
+__device__ __forceinline__ void tmem_ld16x256_x1(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16x256_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+// the wait names the destination registers as read-write operands so that no use of them is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait4(uint32_t (&r)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) : : "memory");
+}
+
 }  // namespace lbdrn

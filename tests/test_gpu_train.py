@@ -153,15 +153,16 @@ def read_base_like(msb):
     return np.ascontiguousarray(msb)
 
 
-@pytest.mark.parametrize("variant", ["default", "l2hints", "chw", "tf32"])
+@pytest.mark.parametrize("variant", ["default", "l2hints", "chw", "tf32", "h2"])
 def test_odd_scene_multi_chunk_batches_follow_the_oracle(variant, monkeypatch):
     """A 4x150x131 scene (odd width: scalar re-pack of the planes, every alignment of a window row inside its two 16-byte
     loads, reflected borders) trained with bs=16384 > 128 chunks x 64 pixels (every CTA takes two chunks of a step and
     accumulates its gradient partial) against the oracle's loop on the same seed; also with the L2 hints forced, the
-    CHW gather and the 3xTF32 GEMMs selected."""
+    CHW gather, the 3xTF32 GEMMs and the warp-level fp16-split GEMMs (h2; the default is the tcgen05 kernel) selected."""
     from synth_scene import make_scene
     if variant != "default":
-        monkeypatch.setenv({"l2hints": "LBDRN_TRAIN_L2HINTS", "chw": "LBDRN_TRAIN_CHW", "tf32": "LBDRN_TRAIN_TF32"}[variant], "1")
+        monkeypatch.setenv({"l2hints": "LBDRN_TRAIN_L2HINTS", "chw": "LBDRN_TRAIN_CHW", "tf32": "LBDRN_TRAIN_TF32",
+                            "h2": "LBDRN_TRAIN_H2"}[variant], "1")
     K, D, bc, nl, bs, epochs = 5, 2, 64, 2, 16384, 3
     img = make_scene(4, 150, 131, bits=12, seed=7)
     msb, lsb = O.split_msb_lsb(img, K)
@@ -400,3 +401,48 @@ def test_scheduler_k_sweep_matches_the_plain_cli(tmp_path):
             name = os.path.splitext(os.path.basename(tif))[0]
             d = f"{name}_r1_K{K}_bc64_nl2_D2_prec16_lr0.001_bs512_e2/{name}.bin"
             assert open(f"{out_s}/{d}", "rb").read() == open(f"{out_c}/{d}", "rb").read(), d
+
+
+def _img(a):
+    """[rows][K] fp16 array -> the canonical operand image (lbdrn_umma.cuh: img_off)."""
+    rows, K = a.shape
+    out = np.zeros(rows * K, np.float16)
+    r, k = np.meshgrid(np.arange(rows), np.arange(K), indexing="ij")
+    out[(((k >> 3) * rows + r) * 16 + (k & 7) * 2) // 2] = a
+    return out
+
+
+@pytest.mark.gpu
+def test_tcgen05_m64_images_serve_forward_and_backward_views():
+    """The M = 64 instruction shape and the two views of one operand image that the tcgen05 training step relies on:
+    x.W^T (both K-major), dz.W (B read MN-major), dz^T.x (both MN-major), widths 16 / 64 / 72 / 120, 16-row images."""
+    lib = cabi.load()
+    rng = np.random.default_rng(5)
+    # (N, contraction, a_mn, a_rows, b_mn, b_rows)
+    cases = [(64, 112, 0, 64, 0, 64),     # forward layer 0: X[64 px][112] . W0[64][112]^T
+             (64, 64, 0, 64, 0, 64),      # forward layer 1
+             (16, 64, 0, 64, 0, 16),      # output layer: H[64 px][64] . Wo[16][64]^T
+             (64, 16, 0, 64, 1, 16),      # dH_L = dZo[64 px][16] . Wo[16][64]     (Wo image read MN-major)
+             (64, 64, 0, 64, 1, 64),      # dH_l = dZ[64 px][64] . W[64][64]       (W image read MN-major)
+             (72, 64, 1, 64, 1, 64),      # dW_l = dZ^T[64 u][64 px] . H[64 px][72] (both images read MN-major)
+             (120, 64, 1, 64, 1, 64),     # dW_0 (112 features + the ones block)
+             (16, 64, 1, 64, 1, 64)]      # dW_o = H^T . dZo
+    for (N, Kc, a_mn, a_rows, b_mn, b_rows) in cases:
+        # logical operands: A [64][Kc], B [N][Kc]; the image holds the array with `rows` rows
+        A = rng.integers(-9, 10, size=(64, Kc)).astype(np.float16)
+        B = rng.integers(-9, 10, size=(N, Kc)).astype(np.float16)
+        a_img = _img(A.T.copy() if a_mn else A)
+        b_img = _img(B.T.copy() if b_mn else B)
+        assert (A.T if a_mn else A).shape[0] == a_rows and (B.T if b_mn else B).shape[0] == b_rows
+        a, b = torch.from_numpy(a_img).cuda(), torch.from_numpy(b_img).cuda()
+        d = torch.full((64, N), float("nan"), device="cuda")
+        raw = torch.full((128, N), float("nan"), device="cuda")
+        cabi.check(lib.lbdrn_selftest_tc_gemm3(cabi.ptr(a), a_img.nbytes, cabi.ptr(b), b_img.nbytes, cabi.ptr(d), cabi.ptr(raw),
+                                               N, Kc // 16, a_mn, a_rows, b_mn, b_rows, cabi.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        got = d.cpu().numpy().astype(np.float64)
+        if not np.array_equal(got, ref):
+            rw = raw.cpu().numpy()
+            lanes = [int(np.argmin(np.abs(rw - ref[i][None, :]).sum(1))) for i in (0, 1, 8, 15, 16, 17, 32, 48, 63)]
+            raise AssertionError((N, Kc, a_mn, b_mn, float(np.abs(got - ref).max()), "raw lanes of rows 0,1,8,15,16,17,32,48,63:", lanes))

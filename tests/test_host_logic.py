@@ -121,7 +121,7 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == sorted(cabi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lbdrn_version() == int(re.search(r"#define\s+LBDRN_ABI_VERSION\s+(\d+)", hdr).group(1)) == 4
+    assert lib.lbdrn_version() == int(re.search(r"#define\s+LBDRN_ABI_VERSION\s+(\d+)", hdr).group(1)) == 5
 
 
 def test_cabi_struct_layout_matches_header():
