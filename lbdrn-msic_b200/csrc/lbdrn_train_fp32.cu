@@ -77,7 +77,7 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
     const int KP0 = round16(n.dim_in), L = n.nl;
     const size_t fl = (size_t)t.dimpad * kTrainLDP + (size_t)L * BC * kTrainLDP + (size_t)CP * kTrainLDP +
                       (size_t)round4(L * BC + n.C * BC + n.C);
-    const size_t wimg = ((size_t)2 * KP0 * BC + (size_t)(L - 1) * 2 * BC * BC + (size_t)2 * 16 * BC) * 2;
+    const size_t wimg = ((size_t)2 * KP0 * BC + (size_t)(L - 1) * 2 * BC * BC) * 2;
     const size_t imgs = wimg + (size_t)2 * (KP0 + 8) * kTrainNPIX * 2 + (size_t)L * 2 * (BC + 8) * kTrainNPIX * 2 +
                         (size_t)L * 2 * BC * kTrainNPIX * 2 + (size_t)2 * 16 * kTrainNPIX * 2;
     const size_t t5 = fl * sizeof(float) + 128 + imgs;
@@ -152,11 +152,11 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
     long long h[24];
     CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    static const char* names[17] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "wait1", "reduce+adam", "wait2",
+    static const char* names[22] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "wait1", "reduce+adam", "wait2",
                                     "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1", "pf_commit", "pf_issue", "fwd_gemm",
-                                    "fwd_act"};
+                                    "fwd_act", "red_batches", "red_tail", "red_sync", "arrive2", "head"};
     fprintf(stderr, "[lbdrn] train phases (cycles/step on CTA 0, %d steps, grid %d x %d thr):", a.n_steps, plan.grid, kTT);
-    for (int i = 0; i < 17; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
+    for (int i = 0; i < 22; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
     fprintf(stderr, "\n");
   }
   return LBDRN_OK;

@@ -563,27 +563,30 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   auto ldw_of = [&](int l) { return (l == 0 ? KP0 : BC) + 8; };  // row pitch in halves: an odd multiple of 16 bytes
   auto wh_of = [&](int l) { return wh_base + (l == 0 ? 0u : (uint32_t)BC * (KP0 + 8) * 4u + (uint32_t)(l - 1) * BC * (BC + 8) * 4u); };
   // ---- TC5: operand images (lbdrn_umma.cuh: img_off) behind the fp32 part, 128 B-aligned ---------------------------------
-  //   weights (byte for byte the global image a.wimg): per hidden layer [hi Kp*BC | lo Kp*BC] halves, then W_o with 16 rows
-  //   [hi 16*BC | lo 16*BC]; X split [hi (KP0+8)*NPIX | lo]; hidden outputs h_l [hi (BC+8)*NPIX | lo] (the extra group of 8
+  //   weights (byte for byte the global image a.wimg): per hidden layer [hi Kp*BC | lo Kp*BC] halves (the output layer stays in
+  //   fp32: it is applied from registers); X split [hi (KP0+8)*NPIX | lo]; hidden outputs h_l [hi (BC+8)*NPIX | lo] (the extra group of 8
   //   is the constant block 1,0,..,0 per pixel in hi, zero in lo: read as one more input row it makes the bias gradient a
   //   column of the weight-gradient GEMM); scaled dz_l [hi BC*NPIX | lo]; scaled output dz [hi 16*NPIX | lo].
   const uint32_t t5_base = (smem_u32(h2base) + 127u) & ~127u;
   auto t5_wbytes = [&](int l) { return (uint32_t)(l == 0 ? KP0 : BC) * BC * 2u; };      // one half (hi or lo) of layer l
   auto t5_w = [&](int l) { return t5_base + (l == 0 ? 0u : 2u * t5_wbytes(0) + (uint32_t)(l - 1) * 2u * t5_wbytes(1)); };
-  const uint32_t t5_wo = t5_w(L), t5_wend = t5_wo + 2u * 16u * BC * 2u;
+  const uint32_t t5_wend = t5_w(L);
   const uint32_t t5_xbytes = (uint32_t)(KP0 + 8) * NPIX * 2u, t5_hbytes = (uint32_t)(BC + 8) * NPIX * 2u;
   const uint32_t t5_x = t5_wend, t5_h0 = t5_x + 2u * t5_xbytes;
   auto t5_h = [&](int l) { return t5_h0 + (uint32_t)l * 2u * t5_hbytes; };
   const uint32_t t5_dzbytes = (uint32_t)BC * NPIX * 2u;
   auto t5_dz = [&](int l) { return t5_h0 + (uint32_t)L * 2u * t5_hbytes + (uint32_t)l * 2u * t5_dzbytes; };
   const uint32_t t5_dzo = t5_dz(L), t5_dzobytes = 16u * NPIX * 2u;
-  // TMEM columns: two forward / dh accumulators, the output accumulator, then the weight-gradient accumulators
-  constexpr uint32_t T5_ZO = 2 * BC, T5_DWO = 2 * BC + 16, T5_DW0 = 2 * BC + 32;
+  // fp32 scratch of the output layer, over the (not yet written) dz_0 image: partial sums per column group, then dz_o
+  float* const Pp5 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem4) + (t5_dz(0) - smem_u32(smem4)));   // [4][CP][LDP]
+  float* const dZo5 = Pp5 + 4 * CP * LDP;                                                                          // [CP][LDP]
+  static_assert(!TC5 || 5 * CP * LDP * 4 <= 2 * BC * NPIX * 2, "output-layer scratch must fit in one dz image");
+  // TMEM columns: two forward / dh accumulators, then the weight-gradient accumulators
+  constexpr uint32_t T5_DWO = 2 * BC + 16, T5_DW0 = 2 * BC + 32;
   auto t5_dwcol = [&](int l) { return T5_DW0 + (l == 0 ? 0u : (uint32_t)(KP0 + 8) + (uint32_t)(l - 1) * (BC + 8)); };
   __shared__ __align__(8) uint64_t s_t5_mbar;
   __shared__ uint32_t s_t5_tmem;
   __shared__ float s_t5_inv[kMaxLayers];                        // TC5: 1 / scale of dz_l (read-out of the gradient accumulators)
-  __shared__ float s_t5_dbo[4][8];                              // TC5: output-bias gradient partials per sub-partition
   uint32_t t5_phase = 0u;
   __shared__ uint32_t s_dzmax[kMaxLayers];                      // H2: bits of max |dz_l| over the chunk
   __shared__ float s_db[H2 ? 2 : 1][4][H2 ? BC : 1];            // H2: bias-gradient partials per pixel tile (by layer parity)
@@ -984,6 +987,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     // The features of this step's chunk were requested during step s-1 and do not depend on the weights: they are committed
     // to shared memory BEFORE waiting for the other CTAs' Adam phase (the second half of the split barrier).
     const bool early = pf_have;                       // uniform: a function of (step, CTA) only
+    LBDRN_PHASE(21)  // step head: next coordinates, permutation prefetch, Adam table
     if (early) {
       if (il) prefetch_commit_il(); else prefetch_commit();
       pf_have = false;
@@ -1029,19 +1033,6 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           const uint32_t o = TC5 ? (uint32_t)img_off(BC, u, k) : (uint32_t)(u * ldw + k) * 2u;
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(w_hi + o), "r"(hi) : "memory");
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(w_lo + o), "r"(lo) : "memory");
-        }
-      }
-      if (TC5 && !from_image) {
-        // output layer as a 16-row image (rows >= C zero): W_o[c][u] pairs along u
-        const float* src = a.params + net.woff[L];
-        for (int i = tid; i < 16 * (BC / 2); i += THREADS) {
-          const int c = i / (BC / 2), u = 2 * (i - c * (BC / 2));
-          const float x0 = c < C ? __ldcg(src + c * BC + u) : 0.f, x1 = c < C ? __ldcg(src + c * BC + u + 1) : 0.f;
-          uint32_t hi, lo;
-          split_h2(x0 * kWScale, x1 * kWScale, hi, lo);
-          const uint32_t o = (uint32_t)img_off(16, c, u);
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_wo + o), "r"(hi) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_wo + 16u * BC * 2u + o), "r"(lo) : "memory");
         }
       }
     } else if (WSMEM) {
@@ -1252,67 +1243,68 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_hi + o), "r"(hi) : "memory");
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(o_lo + o), "r"(lo) : "memory");
             }
+          if (l == L - 1) {
+            // output layer (LBDRNmodel.py:76-77) from registers: partial sums over this thread's 4 units of each of its 2 pixels,
+            // then over the 4 lanes t of the pixel row (fixed order); lane t publishes band t (and t + 4) of its column group
+            float part[2][CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+              part[0][c] = 0.f; part[1][c] = 0.f;
+              if (c < C) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const float2 w2 = *reinterpret_cast<const float2*>(wo_p + c * BC + 16 * cg + 8 * j + 2 * t);
+                  part[0][c] = fmaf(w2.x, hv[j][0], part[0][c]); part[0][c] = fmaf(w2.y, hv[j][1], part[0][c]);
+                  part[1][c] = fmaf(w2.x, hv[j][2], part[1][c]); part[1][c] = fmaf(w2.y, hv[j][3], part[1][c]);
+                }
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                part[e2][c] += __shfl_xor_sync(0xffffffffu, part[e2][c], 1);
+                part[e2][c] += __shfl_xor_sync(0xffffffffu, part[e2][c], 2);
+              }
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+              if ((c & 3) == t && c < C) {
+                Pp5[(cg * CP + c) * LDP + 16 * sp + g] = part[0][c];
+                Pp5[(cg * CP + c) * LDP + 16 * sp + g + 8] = part[1][c];
+              }
+          }
           fence_async_smem();
           tc_fence_before();
           __syncthreads();
           LBDRN_PHASE(16)   // fwd: bias + sine / cosine + stores
         }
         LBDRN_PHASE(2)
-        // ---- output layer + loss (LBDRNloss.py:9): z_o = h_L . W_o^T with N = 16 (rows >= C of the image are zero) ------------
-        if (warp == 0) {
-          tc_fence_after();
-          if (elect_one()) {
-            mma3(T5_ZO, t5_h(L - 1), t5_hbytes, NPIX, 0, t5_wo, 16u * BC * 2u, 16, 0, 16, BC >> 4);
-            umma_commit(mbar);
-          }
-          __syncwarp();
-        }
-        t5_wait();
-        // d(mean((y-t)^2))/dz_o = gscale (y-t) y (1-y); stored as (y-t) y (1-y) 2^16 (|.| <= 2^14: fp16 range, no underflow of
-        // small errors), the factor gscale 2^-16 comes off in the fp32 epilogues downstream
+        // ---- output layer + loss (LBDRNloss.py:9): one thread per (band, pixel) sums the four column groups --------------------
+        // d(mean((y-t)^2))/dz_o = gscale (y-t) y (1-y): in fp32 for dh_L and db_o; for dW_o = h_L^T . dz_o on the tensor core it is
+        // stored as (y-t) y (1-y) 2^16 (|.| <= 2^14: fp16 range, no underflow of small errors), gscale 2^-16 comes off at read-out
         const float inv_o = gscale * (1.0f / 65536.0f);
         float sse = 0.f;
-        if (cg == 0) {
-          uint32_t r[4];
-          tmem_ld16x256_x1(tm_lane + T5_ZO, r);
-          tmem_ld_wait4(r);
-          float dsum0 = 0.f, dsum1 = 0.f;
-#pragma unroll
-          for (int e2 = 0; e2 < 2; ++e2) {
-            const int pixel = 16 * sp + g + 8 * e2;
-            const bool ok = s_valid[pixel] != 0;
-            float v[2];
-#pragma unroll
-            for (int e1 = 0; e1 < 2; ++e1) {
-              const int c = 2 * t + e1;
-              v[e1] = 0.f;
-              if (c < C) {
-                const float y = sigmoidf_rn(__uint_as_float(r[2 * e2 + e1]) * kWInv + bo_p[c]);
-                const float d = y - Tl[c * LDP + pixel];
-                if (ok) { v[e1] = (d * ((1.0f - y) * y)) * 65536.0f; sse += d * d; }
-              }
-            }
-            dsum0 += v[0]; dsum1 += v[1];
-            uint32_t hi, lo;
-            split_h2(v[0], v[1], hi, lo);
-            const uint32_t o = (uint32_t)img_off(NPIX, pixel, 2 * t);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_dzo + o), "r"(hi) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(t5_dzo + t5_dzobytes + o), "r"(lo) : "memory");
-          }
-          // output-bias gradient: fixed-order tree over the 16 pixels of the sub-partition, then over the 4 sub-partitions
-#pragma unroll
-          for (int off = 4; off < 32; off <<= 1) {
-            dsum0 += __shfl_xor_sync(0xffffffffu, dsum0, off);
-            dsum1 += __shfl_xor_sync(0xffffffffu, dsum1, off);
-          }
-          if (g == 0) { s_t5_dbo[sp][2 * t] = dsum0; s_t5_dbo[sp][2 * t + 1] = dsum1; }
+        if (tid < C * NPIX) {
+          const int c = tid / NPIX, pp = tid - c * NPIX;
+          const float z = (Pp5[(0 * CP + c) * LDP + pp] + Pp5[(1 * CP + c) * LDP + pp]) +
+                          (Pp5[(2 * CP + c) * LDP + pp] + Pp5[(3 * CP + c) * LDP + pp]);
+          const bool ok = s_valid[pp] != 0;
+          const float y = sigmoidf_rn(z + bo_p[c]);
+          const float d = y - Tl[c * LDP + pp];
+          const float q = (1.0f - y) * y;
+          dZo5[c * LDP + pp] = ok ? (gscale * d) * q : 0.f;                 // mse backward then sigmoid backward
+          uint16_t hi, lo;
+          split_h1(ok ? (d * q) * 65536.0f : 0.f, hi, lo);
+          const uint32_t o = (uint32_t)img_off(NPIX, pp, c);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(t5_dzo + o), "h"(hi) : "memory");
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(t5_dzo + t5_dzobytes + o), "h"(lo) : "memory");
+          if (ok) sse = d * d;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
         if (lane == 0) s_red[warp] = sse;
         if (tid < kMaxLayers) s_dzmax[tid] = 0u;
         fence_async_smem();
-        tc_fence_before();
         __syncthreads();
         if (tid == 0) {
           float tsum = 0.f;
@@ -1320,44 +1312,70 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           s_sse += tsum;
         }
         if (tid < C) {
-          const float gsum = ((s_t5_dbo[0][tid] + s_t5_dbo[1][tid]) + (s_t5_dbo[2][tid] + s_t5_dbo[3][tid])) * inv_o;
+          const float gsum = row_sum<NPIX>(dZo5 + tid * LDP);
           float* dd = mypart + net.boff[L] + tid;
           *dd = first ? gsum : *dd + gsum;
         }
         LBDRN_PHASE(3)   // output layer + loss
         // ---- backward -----------------------------------------------------------------------------------------------------------
-        // dh_L = dz_o . W_o (W_o image read MN-major) first: the layers wait for it; dW_o = h_L^T . dz_o (both MN-major) behind it
+        // dW_o = h_L^T . dz_o (both images read MN-major) goes to the tensor core now and is collected with the last commit
         if (warp == 0) {
           tc_fence_after();
-          if (elect_one()) {
-            mma3((uint32_t)((L - 1) & 1) * BC, t5_dzo, t5_dzobytes, NPIX, 0, t5_wo, 16u * BC * 2u, 16, 1, BC, 1);
-            umma_commit(mbar);
-            mma3(T5_DWO, t5_h(L - 1), t5_hbytes, NPIX, 1, t5_dzo, t5_dzobytes, NPIX, 1, 16, NPIX >> 4);
-          }
+          if (elect_one()) mma3(T5_DWO, t5_h(L - 1), t5_hbytes, NPIX, 1, t5_dzo, t5_dzobytes, NPIX, 1, 16, NPIX >> 4);
           __syncwarp();
         }
-        float inv_next = inv_o;
+        float inv_next = 1.f;
         for (int l = L - 1; l >= 0; --l) {
-          t5_wait();
-          uint32_t r[8];
-          tmem_ld16x256_x2(tm_lane + (uint32_t)(l & 1) * BC + 16u * cg, r);
-          tmem_ld_wait8(r);
           const float* Gl = Gbuf + (size_t)l * GSZ;
-          const float sc = kWInv * inv_next;
           float dz[2][4], mx = 0.f;
+          if (l == L - 1) {
+            // dh_L[u][p] = sum_c W_o[c][u] dz_o[c][p] from registers (4 bands: not worth a round trip through the tensor core)
+            float dh[2][4];
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int pixel = 16 * sp + g + (e >> 1) * 8, u = 16 * cg + 8 * j + 2 * t + (e & 1);
-              dz[j][e] = (__uint_as_float(r[4 * j + e]) * sc) * Gl[(size_t)u * LDP + pixel];
-              mx = fmaxf(mx, fabsf(dz[j][e]));
+              for (int e = 0; e < 4; ++e) dh[j][e] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+              if (c < C) {
+                const float d0 = dZo5[c * LDP + 16 * sp + g], d1 = dZo5[c * LDP + 16 * sp + g + 8];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const float2 w2 = *reinterpret_cast<const float2*>(wo_p + c * BC + 16 * cg + 8 * j + 2 * t);
+                  dh[j][0] = fmaf(w2.x, d0, dh[j][0]); dh[j][1] = fmaf(w2.y, d0, dh[j][1]);
+                  dh[j][2] = fmaf(w2.x, d1, dh[j][2]); dh[j][3] = fmaf(w2.y, d1, dh[j][3]);
+                }
+              }
             }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int pixel = 16 * sp + g + (e >> 1) * 8, u = 16 * cg + 8 * j + 2 * t + (e & 1);
+                dz[j][e] = dh[j][e] * Gl[(size_t)u * LDP + pixel];
+                mx = fmaxf(mx, fabsf(dz[j][e]));
+              }
+          } else {
+            t5_wait();
+            uint32_t r[8];
+            tmem_ld16x256_x2(tm_lane + (uint32_t)(l & 1) * BC + 16u * cg, r);
+            tmem_ld_wait8(r);
+            const float sc = kWInv * inv_next;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int pixel = 16 * sp + g + (e >> 1) * 8, u = 16 * cg + 8 * j + 2 * t + (e & 1);
+                dz[j][e] = (__uint_as_float(r[4 * j + e]) * sc) * Gl[(size_t)u * LDP + pixel];
+                mx = fmaxf(mx, fabsf(dz[j][e]));
+              }
+          }
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
           if (lane == 0) atomicMax(&s_dzmax[l], __float_as_uint(mx));     // order-independent: the step stays deterministic
           tc_fence_before();
           __syncthreads();
+          LBDRN_PHASE(8)    // bwd: dh (MMA wait or registers) * act' + chunk maximum
           float S, inv;
           dz_scale(s_dzmax[l], S, inv);
           const uint32_t o_hi = t5_dz(l), o_lo = o_hi + t5_dzbytes;
@@ -1395,12 +1413,86 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           inv_next = inv;
         }
         // ---- gradient accumulators -> this CTA's partial (rows = units: sub-partition sp holds units 16 sp + g, + 8) ---------
+        // every load of the thread is issued before the one wait (the read-out is latency, not bandwidth): layer 0's columns
+        // in four 32-column slices (one per column group; columns >= KP0 + 8 of the last slice belong to the next accumulator
+        // and are ignored), a later layer's 64 weight columns in 16-column slices, its bias column and W_o by column group 0
         t5_wait();
-        for (int l = 0; l < L; ++l) {
-          const int Kin = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, ntile = (Kp + 8) >> 3;
+        LBDRN_PHASE(10)   // bwd: wait for the last weight-gradient GEMM
+        {
+          uint32_t r0[16], r1[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, rb[4] = {0u, 0u, 0u, 0u}, ro[4] = {0u, 0u, 0u, 0u};
+          tmem_ld16x256_x4(tm_lane + t5_dwcol(0) + 32u * cg, r0);
+          if (L > 1) tmem_ld16x256_x2(tm_lane + t5_dwcol(1) + 16u * cg, r1);
+          if (cg == 0) {
+            if (L > 1) tmem_ld16x256_x1(tm_lane + t5_dwcol(1) + (uint32_t)BC, rb);
+            tmem_ld16x256_x1(tm_lane + T5_DWO, ro);
+          }
+          tmem_ld_wait16(r0);
+          tmem_ld_wait8(r1);
+          tmem_ld_wait4(rb);
+          tmem_ld_wait4(ro);
+          auto put_pair = [&](float* dst, int Kin, bool pair_ok, int u, int q, float v0, float v1) {
+            if (pair_ok && q + 1 < Kin) {
+              float2* d2 = reinterpret_cast<float2*>(dst + (size_t)u * Kin + q);
+              float2 v = make_float2(v0, v1);
+              if (!first) { const float2 o = *d2; v.x += o.x; v.y += o.y; }
+              *d2 = v;
+            } else {
+              if (q < Kin) { float* d1 = dst + (size_t)u * Kin + q; *d1 = first ? v0 : *d1 + v0; }
+              if (q + 1 < Kin) { float* d1 = dst + (size_t)u * Kin + q + 1; *d1 = first ? v1 : *d1 + v1; }
+            }
+          };
+          auto put_bias = [&](int l, int u, float v) {
+            float* dd = mypart + net.boff[l] + u;
+            *dd = first ? v : *dd + v;
+          };
+          {
+            const float inv = s_t5_inv[0];
+            float* dst = mypart + net.woff[0];
+            const bool pair_ok = (net.dim_in & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const int u = 16 * sp + g + 8 * e2, q = 32 * cg + 8 * j + 2 * t;
+                const float v0 = __uint_as_float(r0[4 * j + 2 * e2]) * inv, v1 = __uint_as_float(r0[4 * j + 2 * e2 + 1]) * inv;
+                if (q == KP0) put_bias(0, u, v0);                  // the constant block's column: bias gradient
+                else put_pair(dst, net.dim_in, pair_ok, u, q, v0, v1);
+              }
+          }
+          if (L > 1) {
+            const float inv = s_t5_inv[1];
+            float* dst = mypart + net.woff[1];
+            const bool pair_ok = (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const int u = 16 * sp + g + 8 * e2, q = 16 * cg + 8 * j + 2 * t;
+                put_pair(dst, BC, pair_ok, u, q, __uint_as_float(r1[4 * j + 2 * e2]) * inv, __uint_as_float(r1[4 * j + 2 * e2 + 1]) * inv);
+              }
+            if (cg == 0 && t == 0) {
+              put_bias(1, 16 * sp + g, __uint_as_float(rb[0]) * inv);
+              put_bias(1, 16 * sp + g + 8, __uint_as_float(rb[2]) * inv);
+            }
+          }
+          if (cg == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int u = 16 * sp + g + (e >> 1) * 8, c = 2 * t + (e & 1);
+              if (c < C) {
+                float* d1 = mypart + net.woff[L] + c * BC + u;
+                const float v = __uint_as_float(ro[e]) * inv_o;
+                *d1 = first ? v : *d1 + v;
+              }
+            }
+          }
+        }
+        // layers beyond the second (nl >= 3): tile by tile
+        for (int l = 2; l < L; ++l) {
+          const int ntile = (BC + 8) >> 3;
           const float inv = s_t5_inv[l];
           float* dst = mypart + net.woff[l];
-          const bool pair_ok = (Kin & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+          const bool pair_ok = (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
           for (int tt = cg; tt < ntile; tt += 4) {
             uint32_t r[4];
             tmem_ld16x256_x1(tm_lane + t5_dwcol(l) + 8u * tt, r);
@@ -1410,32 +1502,19 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             for (int e2 = 0; e2 < 2; ++e2) {
               const int u = 16 * sp + g + 8 * e2;
               const float v0 = __uint_as_float(r[2 * e2]) * inv, v1 = __uint_as_float(r[2 * e2 + 1]) * inv;
-              if (q == Kp) {                                       // the constant block's column: bias gradient
+              if (q == BC) {
                 float* dd = mypart + net.boff[l] + u;
                 *dd = first ? v0 : *dd + v0;
-              } else if (pair_ok && q + 1 < Kin) {
-                float2* d2 = reinterpret_cast<float2*>(dst + (size_t)u * Kin + q);
+              } else if (pair_ok) {
+                float2* d2 = reinterpret_cast<float2*>(dst + (size_t)u * BC + q);
                 float2 v = make_float2(v0, v1);
                 if (!first) { const float2 o = *d2; v.x += o.x; v.y += o.y; }
                 *d2 = v;
               } else {
-                if (q < Kin) { float* d1 = dst + (size_t)u * Kin + q; *d1 = first ? v0 : *d1 + v0; }
-                if (q + 1 < Kin) { float* d1 = dst + (size_t)u * Kin + q + 1; *d1 = first ? v1 : *d1 + v1; }
+                float* d1 = dst + (size_t)u * BC + q;
+                d1[0] = first ? v0 : d1[0] + v0;
+                d1[1] = first ? v1 : d1[1] + v1;
               }
-            }
-          }
-        }
-        if (cg == 0) {
-          uint32_t r[4];
-          tmem_ld16x256_x1(tm_lane + T5_DWO, r);
-          tmem_ld_wait4(r);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int u = 16 * sp + g + (e >> 1) * 8, c = 2 * t + (e & 1);
-            if (c < C) {
-              float* d1 = mypart + net.woff[L] + c * BC + u;
-              const float v = __uint_as_float(r[e]) * inv_o;
-              *d1 = first ? v : *d1 + v;
             }
           }
         }
@@ -1903,46 +1982,69 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     // ---- fixed-order reduction over the CTAs that produced partials, then Adam ----------------------------
     const int n_act = min((int)gridDim.x, n_chunks);
     {
-      // 4 lanes per parameter: lane `sub` sums partials sub, sub+4, ... (8 loads in flight), then a fixed-order shuffle
-      // tree combines them -- deterministic, and every thread of the grid takes part.
-      const int gt = blockIdx.x * THREADS + tid, sub = gt & 3, stride = (gridDim.x * THREADS) >> 2;
-      const int iters = (P + 1 + stride - 1) / stride;
-      for (int it = 0; it < iters; ++it) {
-        const int i = (gt >> 2) + it * stride;
-        const bool in = i <= P;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
-        // the parameter's own state does not depend on the partials: requested first, it arrives under their latency
-        const bool upd = in && sub == 0 && a.mode != TRAIN_GRAD_ONLY && i < P;
+      // Every partial row is read as whole 128-byte lines (8 lanes x float4 = 32 consecutive parameters of one row) and ALL
+      // loads of the phase are in flight at once: the CTA owns `per_cta` float4 columns; 12 warps = 3 column blocks of 8 x
+      // 16 row groups, a thread sums rows rg, rg + 16, ... (8 loads at 128 rows) of its column, the 16 row-group sums of a
+      // column meet in shared memory (over the feature buffer, dead here) and thread (column, component) adds them in a fixed
+      // order and owns that parameter's Adam update.  History: 4 lanes per parameter with 32-bit loads touched four lines per
+      // warp instruction and used a quarter of each (7.3k cycles, bound by the L1 wavefront queue); 3 warps x 2 batches of 16
+      // float4 loads were bound by latency x bytes in flight (5k).  Deterministic: the order of every sum is fixed by the code.
+      const int n4 = (P + 4) >> 2;                                    // float4 columns of a partial row (P + 1 floats)
+      const int per_cta = (((n4 + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;   // multiple of 8: whole lines
+      const size_t ps4 = (size_t)(a.pstride >> 2);
+      constexpr int RW = THREADS >= 384 ? 12 : 3;                     // loader warps (3 column blocks x RW / 3 groups of 4 row groups)
+      constexpr int NRG = 4 * (RW / 3);                               // row groups
+      static_assert(THREADS / 32 >= RW && THREADS >= 96, "reduction layout needs 12 (or 3) warps");
+      float4* const rbuf = reinterpret_cast<float4*>(smem4);          // [NRG][24]
+      const int r_lane = tid & 31, r_warp = tid >> 5;
+      const int cblk = r_warp % 3, rg = (r_warp / 3) * 4 + (r_lane >> 3);
+      const bool loader = r_warp < RW;
+      for (int cb = 0; cb < per_cta; cb += 24) {
+        // owner of (column cb + tid / 4, component tid % 4): its parameter's state is requested first
+        const int oc = cb + (tid >> 2), i = 4 * (blockIdx.x * per_cta + oc) + (tid & 3);
+        const bool in = tid < 96 && oc < per_cta && i <= P;
+        const bool upd = in && a.mode != TRAIN_GRAD_ONLY && i < P;
         float p_old = 0.f, m_old = 0.f, v_old = 0.f;
         if (upd) { p_old = __ldcg(a.params + i); m_old = __ldcg(a.m + i); v_old = __ldcg(a.v + i); }
-        if (in) {
-          const float* pp = a.partial + i;
-          int c = sub;
-          if (n_act == 128) {
-            // the common case (bs = 8192: one chunk per CTA, 128 CTAs): all 32 loads of this lane in flight at once -- one L2
-            // round trip instead of four; same summation order as the generic loop below
-            float v[32];
+        if (loader) {
+          const int col = cb + 8 * cblk + (r_lane & 7), i4 = blockIdx.x * per_cta + col;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col < per_cta && i4 < n4) {
+            // plain loads: ordered after the other CTAs' stores by the acquire in gbar_wait + the CTA barrier behind it
+            const float4* pp = reinterpret_cast<const float4*>(a.partial) + i4;
+            float4 v[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __ldcg(pp + (size_t)(sub + 4 * j) * a.pstride);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              g0 += v[j];     g1 += v[j + 1]; g2 += v[j + 2]; g3 += v[j + 3];
-              g4 += v[j + 4]; g5 += v[j + 5]; g6 += v[j + 6]; g7 += v[j + 7];
+            for (int j = 0; j < 8; ++j) {
+              const int r = rg + NRG * j;
+              v[j] = r < n_act ? pp[(size_t)r * ps4] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            c = n_act;
+            acc.x = ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+            acc.y = ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
+            acc.z = ((v[0].z + v[1].z) + (v[2].z + v[3].z)) + ((v[4].z + v[5].z) + (v[6].z + v[7].z));
+            acc.w = ((v[0].w + v[1].w) + (v[2].w + v[3].w)) + ((v[4].w + v[5].w) + (v[6].w + v[7].w));
+            for (int r = rg + NRG * 8; r < n_act; r += NRG) {          // more rows than 8 per group
+              const float4 t4 = pp[(size_t)r * ps4];
+              acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+            }
           }
-          for (; c + 28 < n_act; c += 32) {
-            g0 += __ldcg(pp + (size_t)(c + 0) * a.pstride);  g1 += __ldcg(pp + (size_t)(c + 4) * a.pstride);
-            g2 += __ldcg(pp + (size_t)(c + 8) * a.pstride);  g3 += __ldcg(pp + (size_t)(c + 12) * a.pstride);
-            g4 += __ldcg(pp + (size_t)(c + 16) * a.pstride); g5 += __ldcg(pp + (size_t)(c + 20) * a.pstride);
-            g6 += __ldcg(pp + (size_t)(c + 24) * a.pstride); g7 += __ldcg(pp + (size_t)(c + 28) * a.pstride);
-          }
-          for (; c < n_act; c += 4) g0 += __ldcg(pp + (size_t)c * a.pstride);
+          rbuf[rg * 24 + 8 * cblk + (r_lane & 7)] = acc;
         }
-        float g = ((g0 + g1) + (g2 + g3)) + ((g4 + g5) + (g6 + g7));
-        g += __shfl_xor_sync(0xffffffffu, g, 1);
-        g += __shfl_xor_sync(0xffffffffu, g, 2);
-        if (in && sub == 0) {
+        __syncthreads();
+        LBDRN_PHASE(17)   // reduce: row loads + exchange
+        float g = 0.f;
+        if (tid < 96) {
+          const float* rb = reinterpret_cast<const float*>(rbuf) + tid;       // column tid / 4, component tid % 4
+          float t[NRG];
+#pragma unroll
+          for (int q = 0; q < NRG; ++q) t[q] = rb[q * 96];
+#pragma unroll
+          for (int w = 1; w < NRG; w <<= 1)
+#pragma unroll
+            for (int q = 0; q < NRG; q += 2 * w) t[q] += t[q + w];
+          g = t[0];
+        }
+        LBDRN_PHASE(18)   // reduce: row-group sums
+        if (in) {
           if (a.mode == TRAIN_GRAD_ONLY) {
             a.grad_out[i] = g;
           } else if (i == P) {
@@ -1968,15 +2070,6 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
                   }
                   img += 2u * (uint32_t)Kp * BC;
                 }
-                const int oo = i - net.woff[L];
-                if (!done && oo >= 0 && oo < C * BC) {
-                  const int c = oo / BC, u = oo - c * BC;
-                  uint16_t hi, lo;
-                  split_h1(p * kWScale, hi, lo);
-                  const uint32_t e = img + (uint32_t)(img_off(16, c, u) >> 1);
-                  a.wimg[e] = hi;
-                  a.wimg[e + 16u * BC] = lo;
-                }
               }
             } else if (H2) {
               if (a.wimg != nullptr) {
@@ -1999,11 +2092,14 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             }
           }
         }
+        if (cb + 24 < per_cta) __syncthreads();      // the exchange buffer is reused by the next column block
       }
     }
     LBDRN_PHASE(6)   // reduce + Adam
     __syncthreads();
+    LBDRN_PHASE(19)  // slowest warp of the CTA in reduce + Adam
     if (tid == 0) gbar_arrive(a.gbar + 1);   // second barrier, arrive; the wait is at the head of the next step
+    LBDRN_PHASE(20)  // fence + arrive 2
   }
   if constexpr (TC5) {
     tc_fence_before();
