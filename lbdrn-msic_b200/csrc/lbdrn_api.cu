@@ -236,6 +236,7 @@ int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, t->dev);
     const size_t plane_bytes = (size_t)t->net.C * t->net.buf_rows * t->net.W * ((t->net.msb_u16 ? 2 : 1) + (t->net.lsb_u16 ? 2 : 1));
     a.l2_hints = plane_bytes > (size_t)l2 || getenv("LBDRN_TRAIN_L2HINTS") != nullptr;   // the variable forces them (tests)
+    a.fast_sine = getenv("LBDRN_TRAIN_FASTSIN") != nullptr;
   }
   a.beta1 = t->cfg.beta1; a.beta2 = t->cfg.beta2;
   a.omb1 = (float)(1.0 - t->cfg.beta1); a.omb2 = (float)(1.0 - t->cfg.beta2);

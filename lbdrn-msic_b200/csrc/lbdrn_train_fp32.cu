@@ -33,7 +33,8 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
     max_smem -= (int)fa.sharedSizeBytes;        // placement of the optional TMA boxes (place_boxes) uses this estimate
   }
   // 64-pixel chunks with bc a multiple of 32: the chunk's GEMMs run as warp-level 3xTF32 tensor-core MMAs
-  constexpr bool kMma = TM == 4 && kTT == 512 && BC % 32 == 0 && BC <= 128;
+  // (32-pixel chunks: bc 256, where a 64-pixel chunk's activations do not fit -- 3xTF32 only)
+  constexpr bool kMma = kTT == 512 && BC % 32 == 0 && ((TM == 4 && BC <= 128) || (TM == 2 && BC % 64 == 0));
   const bool mma = kMma && getenv("LBDRN_TRAIN_FFMA") == nullptr;
   // landing boxes of the TMA neighbourhood gather (uint8 planes, 5x5 window, <= 4 bands, colours only, TMA-addressable
   // rows): 32 x 5 x C bytes of MSB (rounded up to 128) + a 128 B slot for the 16 x 1 x C label box, per pixel.
@@ -55,7 +56,7 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
     return base;
   };
   // fp16 hi+lo split operands + ldmatrix (MMA = 2): bc a multiple of 64, everything resident in shared memory
-  constexpr bool kH2 = kMma && BC % 64 == 0;
+  constexpr bool kH2 = kMma && TM == 4 && BC % 64 == 0;
   if constexpr (kH2) {
     const int KP0 = round16(n.dim_in), L = n.nl;
     const size_t h2 = ((size_t)t.dimpad * kTrainLDP + (size_t)BC * kTrainLDP + (size_t)L * BC * kLDH +
@@ -73,7 +74,7 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
   // tcgen05 variant (MMA = 3): M = 64 chunk GEMMs with the accumulators in tensor memory; bc = 64, operand images of the
   // whole step resident in shared memory, gradient accumulators within the 512 TMEM columns.  Preferred over MMA = 2 when it
   // fits: it overrides the MMA = 2 selection above (LBDRN_TRAIN_H2=1 keeps the warp-level kernel for A/B).
-  if constexpr (kMma && BC == 64) {
+  if constexpr (kMma && TM == 4 && BC == 64) {
     const int KP0 = round16(n.dim_in), L = n.nl;
     const size_t fl = (size_t)t.dimpad * kTrainLDP + (size_t)L * BC * kTrainLDP + (size_t)CP * kTrainLDP +
                       (size_t)round4(L * BC + n.C * BC + n.C);

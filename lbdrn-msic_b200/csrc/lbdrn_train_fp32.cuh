@@ -58,6 +58,7 @@ struct TrainArgs {
   const uint32_t* ilsb;    // by the library before each launch; nullptr: gather from the CHW planes
   int l2_hints;            // planes larger than L2: prefetch.global.L2 hints for the next step's neighbourhoods
   unsigned* gbar;          // two monotonic arrival counters of the split grid barriers (zeroed before every launch)
+  int fast_sine;           // tcgen05 kernel: hidden sine / cosine through MUFU (A/B switch, off by default)
   const float2* adam_tab;  // FUSED: per step {lr / (1 - beta1^t), sqrt(1 - beta2^t)}, formed on the host in double like
                            // torch's python floats (two pow() per step in fp64 cost ~3k cycles of every step on the device)
 };
@@ -197,14 +198,17 @@ __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4
 //   B (8x8,  col): b0 (k = t, n = g)  b1 (k = t+4, n = g)
 //   C (16x8)     : c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
 //
-// acc[j][.] += sum_k act[k][p] * wt[k*BC + u] for the warp's 16-pixel tile (m) and its NT unit tiles (n): warp w owns
-// pixels 16*(w & 3) .. +15 and unit tiles u0 = 8*((w >> 2) + 4*j).  act rows are pixel-contiguous with stride LDP
-// (A loads conflict-free: bank = g + 4t); act has K rounded up to 8 rows (rows >= K are zero); wt rows >= K are not read.
-template <int BC, int LDP, int NT>
+// acc[j][.] += sum_k act[k][p] * wt[k*BC + u] for the warp's 16-pixel tile (m) and its NT unit tiles (n): with PT pixel
+// tiles per chunk (4: 64 pixels, 2: 32 pixels) and NG = 16 / PT unit groups, warp w owns pixels 16*(w % PT) .. +15 and unit
+// tiles u0 = 8*((w / PT) + NG*j).  act rows are pixel-contiguous with stride LDP (A loads conflict-free: bank = g + 4t for
+// LDP = 4 mod 32); act has K rounded up to 8 rows (rows >= K are zero); wt rows >= K are not read.
+template <int BC, int LDP, int NT, int PT>
 __device__ __forceinline__ void gemm_px_unit_mma(float (&acc)[NT][4], const float* __restrict__ act, const float* wt, int K,
                                                  int warp, int lane) {
+  constexpr int NG = 16 / PT;
+  static_assert(NT * NG * 8 == BC, "unit tiles must cover the layer");
   const int K8 = (K + 7) & ~7;
-  const int g = lane >> 2, t = lane & 3, p0 = 16 * (warp & 3), ng = warp >> 2;
+  const int g = lane >> 2, t = lane & 3, p0 = 16 * (warp % PT), ng = warp / PT;
   const float* a_ptr = act + (size_t)t * LDP + p0 + g;
   const float* b_ptr = wt + (size_t)t * BC + 8 * ng + g;
 #pragma unroll 2
@@ -217,8 +221,8 @@ __device__ __forceinline__ void gemm_px_unit_mma(float (&acc)[NT][4], const floa
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       uint32_t bh[2], bl[2];
-      split_tf32(k0 + t < K ? b_ptr[(size_t)k0 * BC + 32 * j] : 0.f, bh[0], bl[0]);
-      split_tf32(k0 + t + 4 < K ? b_ptr[(size_t)(k0 + 4) * BC + 32 * j] : 0.f, bh[1], bl[1]);
+      split_tf32(k0 + t < K ? b_ptr[(size_t)k0 * BC + 8 * NG * j] : 0.f, bh[0], bl[0]);
+      split_tf32(k0 + t + 4 < K ? b_ptr[(size_t)(k0 + 4) * BC + 8 * NG * j] : 0.f, bh[1], bl[1]);
       mma_3xtf32(acc[j], ah, al, bh, bl);
     }
   }
@@ -231,21 +235,44 @@ template <int BC, int LDP, int NPIX>
 __device__ __forceinline__ void grad_weight_mma(const float* __restrict__ G, const float* __restrict__ A, int Kin, int kpad8,
                                                 float* __restrict__ dst, bool first, int warp, int lane) {
   constexpr int MT = BC / 16, NW = 16 / MT, MAXN = 4;          // at most 4 n-tiles per warp per pass
+  constexpr int KST = NPIX / 8;                                // k steps (8 pixels each)
   const int g = lane >> 2, t = lane & 3, r0 = 16 * (warp % MT), nq = kpad8 >> 3;
   const float* a_ptr = G + (size_t)(r0 + g) * LDP + t;
+  // 32-pixel chunks (bc 256: every warp walks ~57 column groups with the same 16 rows of dz): the split A fragments of all
+  // k steps stay in registers; 64-pixel chunks re-load them per pass (64 registers would not fit)
+  constexpr bool HOIST = KST <= 4;
+  uint32_t ahh[HOIST ? KST : 1][4], all_[HOIST ? KST : 1][4];
+  if (HOIST) {
+#pragma unroll
+    for (int ks = 0; ks < KST; ++ks) {
+      const int p0 = 8 * ks;
+      split_tf32(a_ptr[p0], ahh[ks][0], all_[ks][0]);
+      split_tf32(a_ptr[(size_t)8 * LDP + p0], ahh[ks][1], all_[ks][1]);
+      split_tf32(a_ptr[p0 + 4], ahh[ks][2], all_[ks][2]);
+      split_tf32(a_ptr[(size_t)8 * LDP + p0 + 4], ahh[ks][3], all_[ks][3]);
+    }
+  }
+  // c0 | c1 and c2 | c3 are neighbours in a row of the gradient block: 8-byte stores when the row pitch allows
+  const bool pair_ok = (Kin & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
   for (int nbase = warp / MT; nbase < nq; nbase += NW * MAXN) {
     float acc[MAXN][4];
 #pragma unroll
     for (int j = 0; j < MAXN; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-#pragma unroll 2
-    for (int p0 = 0; p0 < NPIX; p0 += 8) {
+#pragma unroll
+    for (int ks = 0; ks < KST; ++ks) {
+      const int p0 = 8 * ks;
       uint32_t ah[4], al[4];
-      split_tf32(a_ptr[p0], ah[0], al[0]);
-      split_tf32(a_ptr[(size_t)8 * LDP + p0], ah[1], al[1]);
-      split_tf32(a_ptr[p0 + 4], ah[2], al[2]);
-      split_tf32(a_ptr[(size_t)8 * LDP + p0 + 4], ah[3], al[3]);
+      if (HOIST) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ah[i] = ahh[ks][i]; al[i] = all_[ks][i]; }
+      } else {
+        split_tf32(a_ptr[p0], ah[0], al[0]);
+        split_tf32(a_ptr[(size_t)8 * LDP + p0], ah[1], al[1]);
+        split_tf32(a_ptr[p0 + 4], ah[2], al[2]);
+        split_tf32(a_ptr[(size_t)8 * LDP + p0 + 4], ah[3], al[3]);
+      }
 #pragma unroll
       for (int j = 0; j < MAXN; ++j) {
         const int nt = nbase + NW * j;
@@ -262,12 +289,25 @@ __device__ __forceinline__ void grad_weight_mma(const float* __restrict__ G, con
     for (int j = 0; j < MAXN; ++j) {
       const int nt = nbase + NW * j;
       if (nt < nq) {
+        if (pair_ok) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = r0 + g + (e >> 1) * 8, q = 8 * nt + 2 * t + (e & 1);
-          if (q < Kin) {
-            float* d = dst + (size_t)r * Kin + q;
-            *d = first ? acc[j][e] : *d + acc[j][e];
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int r = r0 + g + e2 * 8, q = 8 * nt + 2 * t;
+            if (q < Kin) {
+              float2* d = reinterpret_cast<float2*>(dst + (size_t)r * Kin + q);
+              float2 v = make_float2(acc[j][2 * e2], acc[j][2 * e2 + 1]);
+              if (!first) { const float2 o = *d; v.x += o.x; v.y += o.y; }
+              *d = v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = r0 + g + (e >> 1) * 8, q = 8 * nt + 2 * t + (e & 1);
+            if (q < Kin) {
+              float* d = dst + (size_t)r * Kin + q;
+              *d = first ? acc[j][e] : *d + acc[j][e];
+            }
           }
         }
       }
@@ -526,7 +566,10 @@ __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, co
 // memory); MMA = 0: FFMA.
 template <int BC, int CP, bool WSMEM, int THREADS, int TM, int MMA = 0>
 __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs a) {
-  static_assert(!MMA || (TM == 4 && THREADS == 512 && BC % 32 == 0 && BC <= 128), "MMA path: 64-pixel chunks, 16 warps");
+  static_assert(!MMA || (THREADS == 512 && BC % 32 == 0 && (TM == 4 || (MMA == 1 && TM == 2 && BC % 64 == 0))),
+                "MMA paths: 16 warps, 64-pixel chunks (3xTF32 also 32-pixel chunks: bc 256)");
+  static_assert(MMA < 2 || TM == 4, "fp16-split and tcgen05 paths: 64-pixel chunks");
+  constexpr int PT = train_npix(TM) / 16, NGW = 16 / PT;      // MMA = 1: pixel tiles per chunk, unit groups (warp = (tile, group))
   static_assert(MMA != 2 || (WSMEM && BC % 64 == 0), "fp16-split path: weights in shared memory, unit tiles in pairs");
   static_assert(MMA != 3 || (WSMEM && BC == 64), "tcgen05 path: M = 64 chunk GEMMs, everything resident in shared memory");
   constexpr bool H2 = MMA == 2;
@@ -1210,6 +1253,12 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
               if (net.relu) {
                 hv[j][e] = fmaxf(z, 0.f);
                 gv[j][e] = z > 0.f ? 1.f : 0.f;
+              } else if (a.fast_sine) {
+                // MUFU.SIN / MUFU.COS (opt-in, LBDRN_TRAIN_FASTSIN=1): the unit reduces the argument itself, abs. error
+                // ~ 6e-8 |arg| + 4e-7 instead of 7e-8
+                const float arg = net.w0 * z;
+                hv[j][e] = __sinf(arg);
+                gv[j][e] = __cosf(arg) * net.w0;
               } else {
                 const float arg = net.w0 * z;
                 float sn, cs;
@@ -1597,20 +1646,20 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           continue;
         }
         if (MMA) {
-          constexpr int NT = BC / 32;
+          constexpr int NT = BC / 8 / NGW;
           float acc[NT][4];
 #pragma unroll
           for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-          gemm_px_unit_mma<BC, LDP, NT>(acc, in, w + net.woff[l], K, warp, lane);
+          gemm_px_unit_mma<BC, LDP, NT, PT>(acc, in, w + net.woff[l], K, warp, lane);
           LBDRN_PHASE(15)   // fwd: GEMMs
           const int g = lane >> 2, t = lane & 3;
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int pixel = 16 * (warp & 3) + g + (e >> 1) * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+              const int pixel = 16 * (warp % PT) + g + (e >> 1) * 8, u = 8 * ((warp / PT) + NGW * j) + 2 * t + (e & 1);
               const float z = acc[j][e] + w[net.boff[l] + u];
               float hv, gv;
               if (net.relu) {
@@ -1918,19 +1967,19 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           }
         } else if (MMA) {
           // dh_l[u][p] = sum_m W_{l+1}[m][u] dz_{l+1}[m][p] on the tensor cores; dz_l = dh_l * act'(z_l) at the fragment positions
-          constexpr int NT = BC / 32;
+          constexpr int NT = BC / 8 / NGW;
           float dacc[NT][4];
 #pragma unroll
           for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) dacc[j][e] = 0.f;
-          gemm_px_unit_mma<BC, LDP, NT>(dacc, Gbuf + (size_t)(l + 1) * GSZ, wnat(l + 1), BC, warp, lane);
+          gemm_px_unit_mma<BC, LDP, NT, PT>(dacc, Gbuf + (size_t)(l + 1) * GSZ, wnat(l + 1), BC, warp, lane);
           const int g = lane >> 2, t = lane & 3;
 #pragma unroll
           for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int pixel = 16 * (warp & 3) + g + (e >> 1) * 8, u = 8 * ((warp >> 2) + 4 * j) + 2 * t + (e & 1);
+              const int pixel = 16 * (warp % PT) + g + (e >> 1) * 8, u = 8 * ((warp / PT) + NGW * j) + 2 * t + (e & 1);
               Gl[(size_t)u * LDP + pixel] *= dacc[j][e];
             }
         } else {
