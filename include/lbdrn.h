@@ -28,7 +28,8 @@ extern "C" {
 #endif
 
 /* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added; 4: LBDRN_PATH_TENSOR_FASTSIN2 and the
- * lbdrn_fpz_* nn sub-stream codec added (all additive: older callers are unaffected) */
+ * lbdrn_fpz_* nn sub-stream codec added; 5: lbdrn_selftest_tc_gemm3, lbdrn_host_randperm (all additive: older callers
+ * are unaffected) */
 #define LBDRN_ABI_VERSION 5
 
 enum {
@@ -120,6 +121,12 @@ int32_t lbdrn_max_shifted(const uint16_t* img_dev, int64_t n, int32_t K, uint32_
  * RandomSampler); the ORDER is not torch's -- callers that need the reference's exact batches pass the DataLoader's own
  * permutation to lbdrn_train_steps instead.  8 bytes written per element, no sort, no scratch memory. */
 int32_t lbdrn_randperm(int64_t n, uint64_t seed, int64_t* out_dev, void* stream);
+
+/* The REFERENCE's batch order (encode.py:69-70: DataLoader(shuffle=True) -> RandomSampler -> torch.randperm(n, generator=g)
+ * with g.manual_seed(seed)), written to HOST memory: bit-identical to torch's CPU randperm for n < 2^32/20 (forward
+ * Fisher-Yates on MT19937 outputs; larger n return LBDRN_E_UNSUPPORTED -- use torch), about 3x faster because the draws run
+ * ahead of the swaps and the lines they will touch are prefetched.  Host-only; thread-safe; no device is needed. */
+int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host);
 
 /* ---- a16: quality read-out (decode.py:216): *sse_dev (device uint64, zero-initialised by the caller) += sum over n
  * elements of (a-b)^2 for two uint16 images.  Integer accumulation: exact and order-independent. */

@@ -28,6 +28,7 @@ UNITS = [
     ("tc", "lbdrn_tc.cu", []),
     ("tcw", "lbdrn_tcw.cu", []),
     ("fpz", "lbdrn_fpz.cpp", []),          # host-only: the nn sub-stream codec
+    ("hostperm", "lbdrn_hostperm.cpp", []),   # host-only: the reference sampler's permutation
 ]
 
 

