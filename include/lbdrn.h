@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 /* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added; 4: LBDRN_PATH_TENSOR_FASTSIN2 and the
- * lbdrn_fpz_* nn sub-stream codec added; 5: lbdrn_selftest_tc_gemm3, lbdrn_host_randperm (all additive: older callers
+ * lbdrn_fpz_* nn sub-stream codec added; 5: lbdrn_selftest_tc_gemm3, lbdrn_host_randperm[32] (all additive: older callers
  * are unaffected) */
 #define LBDRN_ABI_VERSION 5
 
@@ -127,6 +127,7 @@ int32_t lbdrn_randperm(int64_t n, uint64_t seed, int64_t* out_dev, void* stream)
  * Fisher-Yates on MT19937 outputs; larger n return LBDRN_E_UNSUPPORTED -- use torch), about 3x faster because the draws run
  * ahead of the swaps and the lines they will touch are prefetched.  Host-only; thread-safe; no device is needed. */
 int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host);
+int32_t lbdrn_host_randperm32(int64_t n, uint64_t seed, int32_t* out_host);   /* same order as 32-bit indices (half the traffic) */
 
 /* ---- a16: quality read-out (decode.py:216): *sse_dev (device uint64, zero-initialised by the caller) += sum over n
  * elements of (a-b)^2 for two uint16 images.  Integer accumulation: exact and order-independent. */

@@ -17,10 +17,13 @@
 
 #include "../../include/lbdrn.h"
 
-extern "C" int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host) {
+namespace {
+
+template <typename T>
+int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host) {
   if (n < 0 || (n > 0 && out_host == nullptr)) return LBDRN_E_INVALID;
   if (n >= (int64_t)(UINT32_MAX / 20)) return LBDRN_E_UNSUPPORTED;     // torch's other branch (random64, inside-out)
-  for (int64_t i = 0; i < n; ++i) out_host[i] = i;
+  for (int64_t i = 0; i < n; ++i) out_host[i] = (T)i;
   if (n < 2) return LBDRN_OK;
   std::mt19937 eng((uint32_t)(seed & 0xffffffffu));
   constexpr int64_t LA = 128;                    // look-ahead (iterations): ~LA independent misses in flight
@@ -39,9 +42,16 @@ extern "C" int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_ho
       ring[i & (LA - 1)] = zj;
       __builtin_prefetch(out_host + j + zj, 1, 0);
     }
-    const int64_t sav = out_host[i];
+    const T sav = out_host[i];
     out_host[i] = out_host[i + z];
     out_host[i + z] = sav;
   }
   return LBDRN_OK;
 }
+
+}  // namespace
+
+extern "C" int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host) { return host_randperm_t(n, seed, out_host); }
+
+// the same permutation as 32-bit indices (every n in range fits): half the memory traffic of the shuffle and of the upload
+extern "C" int32_t lbdrn_host_randperm32(int64_t n, uint64_t seed, int32_t* out_host) { return host_randperm_t(n, seed, out_host); }

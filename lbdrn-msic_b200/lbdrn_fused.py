@@ -399,17 +399,22 @@ def torch_permutation_from_seed(n, seed, out=None):
     return torch.randperm(n, generator=g) if out is None else torch.randperm(n, generator=g, out=out)
 
 
-def permutation_from_seed(n, seed, out=None):
+def permutation_from_seed(n, seed, out=None, dtype=torch.int64):
     """The same permutation, from the library's restatement of torch's CPU randperm (`lbdrn_host_randperm`: forward
-    Fisher-Yates on MT19937 outputs with the draws running ahead of the swaps, ~3x faster at 67 M pixels; bit-exactness
-    against torch is a CPU test).  Sizes outside its range (n >= 2^32 / 20: torch switches algorithm) go to torch."""
+    Fisher-Yates on MT19937 outputs with the draws running ahead of the swaps, ~2x faster at 67 M pixels; bit-exactness
+    against torch is a CPU test).  dtype=torch.int32 gives the same order as 32-bit indices (half the traffic).  Sizes
+    outside the library's range (n >= 2^32 / 20: torch switches algorithm) go to torch."""
     if n < (1 << 32) // 20:
-        buf = torch.empty(n, dtype=torch.int64) if out is None else out
-        assert buf.dtype == torch.int64 and buf.is_contiguous() and buf.numel() == n and buf.device.type == "cpu"
-        rc = cabi.load().lbdrn_host_randperm(n, seed & 0xFFFFFFFFFFFFFFFF, buf.data_ptr())
-        if rc == 0:
+        buf = torch.empty(n, dtype=dtype) if out is None else out
+        assert buf.dtype in (torch.int64, torch.int32) and buf.is_contiguous() and buf.numel() == n and buf.device.type == "cpu"
+        fn = cabi.load().lbdrn_host_randperm if buf.dtype == torch.int64 else cabi.load().lbdrn_host_randperm32
+        if fn(n, seed & 0xFFFFFFFFFFFFFFFF, buf.data_ptr()) == 0:
             return buf
-    return torch_permutation_from_seed(n, seed, out)
+    perm = torch_permutation_from_seed(n, seed, out if (out is not None and out.dtype == torch.int64) else None)
+    if out is not None and out.dtype != torch.int64:
+        out.copy_(perm)
+        return out
+    return perm if dtype == torch.int64 else perm.to(dtype)
 
 
 class HostPermutations:
@@ -418,18 +423,24 @@ class HostPermutations:
     `torch.randperm` on the CPU is a sequential Fisher-Yates shuffle (about 3 s for the 67 M pixels of an 8192^2 scene --
     17x the 0.18 s the device needs for the epoch it feeds), but every epoch's seed is known before training starts
     (`FusedTrainer._plan_seeds`), so the permutations of up to `workers` epochs are drawn concurrently in threads (torch
-    releases the GIL), each into its own (pinned, when CUDA is present) buffer.  `get(e)` blocks until epoch e's order is
+    releases the GIL; the native shuffle `lbdrn_host_randperm32` is called through ctypes, which does too), each into its
+    own buffer (32-bit indices when they suffice; pageable unless `pin`).  `get(e)` blocks until epoch e's order is
     ready; `release(e, event)` hands its buffer back once `event` (the upload) has completed.  Results are exactly
     `permutation_from_seed(n, seeds[e-1])`, in epoch order."""
 
-    def __init__(self, seeds, n, workers=None, pin=None, device=None, max_bytes=4 << 30):
+    def __init__(self, seeds, n, workers=None, pin=False, device=None, max_bytes=4 << 30, dtype=None):
         import concurrent.futures
         import os
         self.seeds, self.n, self.device = list(seeds), n, device
-        if workers is None:                          # bounded by the epochs, half the host cores and `max_bytes` of buffers
-            workers = min(len(self.seeds), (os.cpu_count() or 2) // 2, 8, max_bytes // max(1, 8 * n) - 1)
+        # 32-bit indices whenever they suffice: half the shuffle's memory traffic and half the upload (widened on the device)
+        self.dtype = dtype or (torch.int32 if n < (1 << 31) and n < (1 << 32) // 20 else torch.int64)
+        esz = 4 if self.dtype == torch.int32 else 8
+        if workers is None:                          # bounded by the epochs, the host cores and `max_bytes` of buffers
+            workers = min(len(self.seeds), max(1, (os.cpu_count() or 2) - 2), 10, max_bytes // max(1, esz * n) - 1)
         self.workers = workers = max(1, workers)
-        self.pin = torch.cuda.is_available() if pin is None else pin
+        # pageable buffers by default: pinning 10 x 268 MB costs ~1 s up front (the driver serialises it), more than the staged
+        # uploads lose -- those run on the side stream while the previous epoch trains
+        self.pin = bool(pin) and torch.cuda.is_available()
         self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=workers)
         self.free, self.n_buffers = [], 0            # idle buffers; buffers allocated so far (at most workers + 1)
         self.busy = {}                               # epoch -> (buffer, upload event or None)
@@ -441,7 +452,7 @@ class HostPermutations:
         if buf is None:
             if self.pin and self.device is not None:
                 torch.cuda.set_device(self.device)   # worker threads start on device 0: pin in this rank's context
-            buf = torch.empty(self.n, dtype=torch.int64, pin_memory=self.pin)
+            buf = torch.empty(self.n, dtype=self.dtype, pin_memory=self.pin)
         return permutation_from_seed(self.n, self.seeds[e - 1], out=buf)
 
     def _reclaim(self, block):
@@ -619,25 +630,36 @@ class FusedTrainer:
                 if self.on_epoch:
                     self.on_epoch(e, mse, improved)
 
-        next_dev = None if self.sampler == "reference" else device_perm(1)
+        upl = torch.cuda.Stream(self.dev, priority=0) if host is not None else None
+
+        def host_perm(e):
+            """(perm, event): the reference sampler's order of epoch e, uploaded (and widened to int64) on its own stream
+            while the previous epoch trains; blocks the host until the order has been drawn"""
+            with torch.cuda.stream(upl):
+                perm = host.get(e).to(self.dev, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(upl)
+                host.release(e, up)                                  # its buffer is reused once the upload has completed
+                if perm.dtype != torch.int64:
+                    perm = perm.to(torch.int64)
+                ev = torch.cuda.Event()
+                ev.record(upl)
+            return perm, ev
+
+        next_perm = host_perm if host is not None else device_perm
+        next_dev = next_perm(1)
         for e in range(1, self.epochs + 1):
             with torch.cuda.stream(main):
-                if self.sampler == "reference":
-                    perm = host.get(e).to(self.dev, non_blocking=True)
-                    up = torch.cuda.Event()
-                    up.record()
-                    host.release(e, up)                              # its buffer is reused once the upload has completed
-                else:
-                    perm, ev = next_dev
-                    main.wait_event(ev)
-                    perm.record_stream(main)
+                perm, ev = next_dev
+                main.wait_event(ev)
+                perm.record_stream(main)
                 self.losses.append(self.train_epoch(perm, lr_for_epoch(self.lr, e, self.epochs)))
                 evaluate = self.epochs != 1 and e % min(self.val_duration, self.epochs) == 0
                 cur = self.current_params() if (evaluate or self.epochs == 1) else None
                 snap = torch.cuda.Event()
                 snap.record(main)
-            if self.sampler != "reference" and e < self.epochs:
-                next_dev = device_perm(e + 1)                           # overlaps this epoch's training
+            if e < self.epochs:
+                next_dev = next_perm(e + 1)                             # overlaps this epoch's training
             if self.epochs == 1:                                        # encode.py:100-103
                 self.best_epoch, self.best_params = e, cur
             elif evaluate:
@@ -655,6 +677,8 @@ class FusedTrainer:
             host.close()
         cur_stream.wait_stream(main)
         cur_stream.wait_stream(side)
+        if upl is not None:
+            cur_stream.wait_stream(upl)
         if self.best_params is None:                                    # never evaluated (val_duration > epochs)
             raise RuntimeError("no epoch was evaluated; choose val_duration <= epochs")
         losses = torch.cat(self.losses).cpu()

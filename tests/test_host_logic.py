@@ -173,11 +173,12 @@ def test_host_permutation_pipeline_keeps_the_reference_order():
         h = F.HostPermutations(seeds, 1000, workers=workers, pin=False)
         for e in range(1, len(seeds) + 1):
             p = h.get(e)
-            assert torch.equal(p, F.permutation_from_seed(1000, seeds[e - 1])), (workers, e)
+            assert p.dtype == torch.int32                          # 32-bit indices whenever n allows
+            assert torch.equal(p.to(torch.int64), F.permutation_from_seed(1000, seeds[e - 1])), (workers, e)
             h.release(e)
         assert h.n_buffers <= h.workers + 1
         h.close()
-    h = F.HostPermutations(seeds, 1 << 20, pin=False, max_bytes=3 * 8 * (1 << 20))      # room for two workers + 1 buffers
+    h = F.HostPermutations(seeds, 1 << 20, pin=False, max_bytes=3 * 4 * (1 << 20))      # room for two workers + 1 buffers
     assert h.workers == 2
     h.close()
     h = F.HostPermutations(seeds[:3], 10, workers=1, pin=False)                           # one worker: two buffers
@@ -238,6 +239,8 @@ def test_host_randperm_is_torch_randperm():
             got = F.permutation_from_seed(n, seed)
             want = F.torch_permutation_from_seed(n, seed)
             assert got.dtype == torch.int64 and torch.equal(got, want), (n, seed)
+            got32 = F.permutation_from_seed(n, seed, dtype=torch.int32)
+            assert got32.dtype == torch.int32 and torch.equal(got32.to(torch.int64), want), (n, seed)
             if n > (1 << 20):
                 break                                  # one seed at the large sizes keeps the suite quick
     # into a caller-provided buffer (what HostPermutations does), and the speed-up that motivates it

@@ -12,10 +12,10 @@ img = make_scene_torch(4, side, side, 12, device="cuda")
 scene = F.DeviceScene.from_image(img, 5)
 del img
 
-def once(tag):
+def once(tag, sampler="device"):
     torch.manual_seed(19920517)
     model = LBDRNModel(100, 64, 4, 2)
-    tr = F.FusedTrainer(model, scene, 2, 1e-3, 8192, 10, flags=F.Flags(), sampler="device")
+    tr = F.FusedTrainer(model, scene, 2, 1e-3, 8192, 10, flags=F.Flags(), sampler=sampler)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = tr.run()
@@ -26,3 +26,5 @@ def once(tag):
 
 for _ in range(3):
     once("device sampler (lbdrn_randperm)")
+for _ in range(2):
+    once("reference sampler (lbdrn_host_randperm orders = torch.randperm)", "reference")
