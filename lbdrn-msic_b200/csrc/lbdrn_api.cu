@@ -390,6 +390,12 @@ int32_t lbdrn_eval_sse(const LbdrnDesc* d, const void* msb_dev, const void* lsb_
     if (!msb_dev || !lsb_dev || !params_dev || !sse_dev) return fail(LBDRN_E_INVALID, "null device pointer");
     return tc_eval_sse(n, msb_dev, lsb_dev, params_dev, coord_tab_dev, sse_dev, (cudaStream_t)stream);
   }
+  // bc 128 / 256 with colour features: the wide tensor-core kernel with the low-order weight operands (LBDRN_EVAL_FP32=1
+  // keeps the fp32 kernel for A/B)
+  if (tcw_supported(n) && d->path != LBDRN_PATH_PRECISE && getenv("LBDRN_EVAL_FP32") == nullptr) {
+    if (!msb_dev || !lsb_dev || !params_dev || !sse_dev) return fail(LBDRN_E_INVALID, "null device pointer");
+    return tcw_eval_sse(n, msb_dev, lsb_dev, params_dev, sse_dev, (cudaStream_t)stream);
+  }
   return run_infer<MODE_SSE>(d, msb_dev, lsb_dev, params_dev, coord_tab_dev, nullptr, sse_dev, stream);
 }
 

@@ -69,6 +69,7 @@ int tc_eval_sse(const Net& n, const void* msb, const void* lsb, const float* par
 bool tcw_supported(const Net& n);
 int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out, int fast_sine, const int** exact_flag_out,
                cudaStream_t st);
+int tcw_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st);
 int tc_selftest2(const void* a_dev, const void* b_dev, float* d_dev, int N, int K, int a_mn, int b_mn, cudaStream_t st);
 int tc_selftest3(const void* a_img, int a_bytes, const void* b_img, int b_bytes, float* d_dev, float* raw_dev, int N,
                  int ksteps, int a_mn, int a_rows, int b_mn, int b_rows, cudaStream_t st);

@@ -56,6 +56,11 @@ struct TcwHeader {
   int res_bytes;                   // prefix of the block copied into shared memory (header, biases, B0)
   int total;
   float scale[kMaxLayers + 1];     // accumulator scale per layer (2^-s; /max and *w0 folded as in lbdrn_tc.cu)
+  int wlo;                         // 1: low-order weight operands present (W 2^s = hi + lo, for weights that are not
+                                   // fp16-exact: the fp32 weights evaluated during training).  Layer 0's lo image sits at
+                                   // off_b0lo; the streamed operands of layers >= 1 are then stored chunk-interleaved,
+                                   // [hi chunk 0 | lo chunk 0 | hi chunk 1 | ...], so the streamer walks them linearly
+  int off_b0lo;
 };
 static_assert(sizeof(TcwHeader) <= TCW_HDR, "header does not fit its slot");
 
@@ -63,20 +68,23 @@ static_assert(sizeof(TcwHeader) <= TCW_HDR, "header does not fit its slot");
 // latency (L2 -> smem), the tensor core drains a slot in 256 cycles: the ring has to be deep, the A ring does not.
 __host__ __device__ inline int ring_bytes(int bc, int apw, int nb) { return apw * TCW_NWG * TCW_ASLOT + nb * bc * 32 * TCW_KS; }
 
-void tcw_plan(const Net& n, TcwHeader& h) {
+void tcw_plan(const Net& n, TcwHeader& h, bool wlo = false) {
   memset(&h, 0, sizeof h);
   h.k1 = n.dim_in;
   h.k1pad = align_up(n.dim_in, 16);
   h.nl = n.nl;
   h.bc = n.bc;
+  h.wlo = wlo ? 1 : 0;
+  const int mul = wlo ? 2 : 1;
   int off = TCW_HDR;
   h.off_bias = off; off += (n.nl * n.bc + 16) * 4;
   off = align_up(off, 128);
   h.off_b[0] = off; off += h.k1pad * n.bc * 2;
   h.res_bytes = align_up(off, 128);
   off = h.res_bytes;
-  for (int l = 1; l < n.nl; ++l) { h.off_b[l] = off; off += n.bc * n.bc * 2; }
-  h.off_b[n.nl] = off; off += n.bc * TCW_NOUT * 2;
+  if (wlo) { h.off_b0lo = off; off += align_up(h.k1pad * n.bc * 2, 128); }
+  for (int l = 1; l < n.nl; ++l) { h.off_b[l] = off; off += mul * n.bc * n.bc * 2; }
+  h.off_b[n.nl] = off; off += mul * n.bc * TCW_NOUT * 2;
   h.total = align_up(off, 128);
 }
 
@@ -105,13 +113,27 @@ __global__ void tcw_prep_kernel(Net net, TcwHeader hdr, const float* __restrict_
     const int s = (m > 0.f && isfinite(m)) ? 13 - ilogbf(m) : 0;       // max|W| * 2^s in [2^13, 2^14)
     const float up = ldexpf(1.0f, s);
     __half* B = reinterpret_cast<__half*>(blk + hdr.off_b[l]);
+    __half* B0lo = reinterpret_cast<__half*>(blk + hdr.off_b0lo);
+    const int bstep = rows * 32, bchunk = bstep * TCW_KS;                 // one K step / one chunk of this layer's operand
     int bad = 0;
     for (int i = tid; i < K * rows_real; i += blockDim.x) {
       const int nrow = i / K, k = i - nrow * K;
       const float v = W[i] * up;                                          // exact (power of two)
       const __half hv = __float2half_rn(v);
-      if (v - __half2float(hv) != 0.f) bad = 1;
-      B[umma_off(rows, nrow, k) / 2] = hv;
+      const float rest = v - __half2float(hv);
+      if (rest != 0.f) bad = 1;
+      if (!hdr.wlo) {
+        B[umma_off(rows, nrow, k) / 2] = hv;
+      } else if (l == 0) {
+        B[umma_off(rows, nrow, k) / 2] = hv;
+        B0lo[umma_off(rows, nrow, k) / 2] = __float2half_rn(rest);
+      } else {
+        // chunk-interleaved: K step ks16 = k / 16 belongs to chunk j = ks16 / KS; [hi chunk j | lo chunk j] are neighbours
+        const int ks16 = k >> 4, j = ks16 / TCW_KS;
+        const int o = (2 * j) * bchunk + (ks16 - j * TCW_KS) * bstep + ((((k >> 3) & 1) * rows + nrow) * 16 + (k & 7) * 2);
+        B[o / 2] = hv;
+        B[(o + bchunk) / 2] = __float2half_rn(rest);
+      }
     }
     if (bad) atomicAnd(&s_exact, 0);
     float* bias = reinterpret_cast<float*>(blk + hdr.off_bias) + l * net.bc;
@@ -130,6 +152,7 @@ __global__ void tcw_prep_kernel(Net net, TcwHeader hdr, const float* __restrict_
     H->exact = s_exact;
     H->k1 = hdr.k1; H->k1pad = hdr.k1pad; H->nl = hdr.nl; H->bc = hdr.bc;
     H->off_bias = hdr.off_bias; H->res_bytes = hdr.res_bytes; H->total = hdr.total;
+    H->wlo = hdr.wlo; H->off_b0lo = hdr.off_b0lo;
     for (int l = 0; l <= net.nl; ++l) H->off_b[l] = hdr.off_b[l];
   }
 }
@@ -142,6 +165,10 @@ struct TcwArgs {
   int tiles_x, n_tiles;
   int res_bytes;
   int no_trap;
+  const void* lsb;        // SSE mode: label codes (LSB planes), same geometry as msb
+  double* partials;       // SSE mode: [gridDim.x]
+  unsigned int* counter;  // SSE mode: zero on entry / exit
+  double* sse_out;        // SSE mode: sum over rows [row0,row1), all bands, of (y - code/(2^K-1))^2
   long long* prof;        // optional (LBDRN_TCW_PROF=1): clock64 cycles per role / phase, accumulated by CTA 0
   int prof_lat;           // LBDRN_TCW_PROF=2: the streamer waits for each copy to land (measures the bulk-copy latency)
 };
@@ -304,7 +331,11 @@ __device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme
 // next tile's first layer runs on the tensor core while this tile's last hidden epilogue computes its sines (accumulator
 // 0 is free by then); the output layer accumulates into columns [0,16) of the last hidden layer's own accumulator, which
 // its epilogue has already consumed when the first output chunk is issued.
-template <bool FAST, int BC, int CC, int DD, int APW, int NB>
+// SSE: full-scene squared error against the labels instead of the reconstruction (encode.py:105-108), with weights that are
+// NOT fp16-exact (the fp32 weights of the epoch just trained): every product also takes the low-order weight operand,
+// A.(B_hi + B_lo) -- layer 0: one more MMA per K step against the streamed lo image; layers >= 1: A_hi.B_lo next to
+// A_hi.B_hi + A_lo.B_hi (the lo chunk follows its hi chunk through the same ring).
+template <bool FAST, int BC, int CC, int DD, int APW, int NB, bool SSE = false>
 __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArgs a) {
   constexpr int KS = TCW_KS;
   constexpr int NCH = BC / (16 * KS);                // operand chunks per streamed layer
@@ -327,6 +358,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   uint16_t* kctr = koff + TC_MAX_K1 + 16;                                        // [k1pad] patch offset of its centre
   __shared__ __align__(8) uint64_t s_acc_full[2], s_out_full, s_a_full[NSLOT], s_a_free[NSLOT], s_b_full[NB], s_b_free[NB];
   __shared__ uint32_t s_tmem;
+  __shared__ double s_red[TCW_CTHREADS / 32];
 
   // ---- one-time setup: resident part of the weight block -> smem, TMEM, mbarriers ----------------------------------
   {
@@ -336,7 +368,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   }
   __syncthreads();
   const TcwHeader* H = reinterpret_cast<const TcwHeader*>(sW);
-  if (!H->exact) return;                                   // the fp32 kernel queued behind this launch decodes the scene
+  if (!SSE && !H->exact) return;                           // the fp32 kernel queued behind this launch decodes the scene
   const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
   const int nk16 = k1pad / 16, nch0 = (nk16 + KS - 1) / KS;     // layer 0: K steps, chunks
   const bool overlap = (NL & 1) == 0;
@@ -408,10 +440,27 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             for (int ks = 0; ks < KS && i * KS + ks < nk16; ++ks)
               umma_f16(tmem, dA + (uint64_t)(slot * (TCW_ASLOT >> 4) + ks * 256),
                        dB0 + (uint64_t)((i * KS + ks) * (BSTEP >> 4)), idesc_h, (i | ks) > 0);
-            umma_commit(a_free_u + slot * 8);
-            if (i + 1 == nch0) umma_commit(smem_u32(&s_acc_full[0]));
+            if (!SSE) {
+              umma_commit(a_free_u + slot * 8);
+              if (i + 1 == nch0) umma_commit(smem_u32(&s_acc_full[0]));
+            }
           }
           __syncwarp();
+          if (SSE) {
+            // the same chunk against the low-order weights, streamed through the B ring
+            tcw_wait(b_full_u + sb * 8, bpar, 4, it, a.no_trap);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int ks = 0; ks < KS && i * KS + ks < nk16; ++ks)
+                umma_f16(tmem, dA + (uint64_t)(slot * (TCW_ASLOT >> 4) + ks * 256),
+                         dBh + (uint64_t)(sb * (BSLOT >> 4) + ks * (BSTEP >> 4)), idesc_h, 1);
+              umma_commit(a_free_u + slot * 8);
+              umma_commit(b_free_u + sb * 8);
+              if (i + 1 == nch0) umma_commit(smem_u32(&s_acc_full[0]));
+            }
+            __syncwarp();
+            if (++sb == NB) { sb = 0; bpar ^= 1u; }
+          }
         }
       };
       if (my_tiles > 0) layer0(0);
@@ -440,12 +489,27 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
                 umma_f16(d_tmem, da + (uint64_t)(ks * 256), db + (uint64_t)(ks * bstep16), idesc, (j | ks) > 0);    // hi half
                 umma_f16(d_tmem, da + (uint64_t)((TCW_AHALF >> 4) + ks * 256), db + (uint64_t)(ks * bstep16), idesc, 1);  // lo
               }
-              umma_commit(a_free_u + slot * 8);
+              if (!SSE) umma_commit(a_free_u + slot * 8);
               umma_commit(b_free_u + sb * 8);
-              if (j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
+              if (!SSE && j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
             }
             __syncwarp();
             if (++sb == NB) { sb = 0; bpar ^= 1u; }
+            if (SSE) {
+              // A_hi . B_lo: the chunk's low-order weights arrive in the next ring slot
+              tcw_wait(b_full_u + sb * 8, bpar, 4, it, a.no_trap);
+              tc_fence_after();
+              const uint64_t dbl = dB + (uint64_t)(sb * (BSLOT >> 4));
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) umma_f16(d_tmem, da + (uint64_t)(ks * 256), dbl + (uint64_t)(ks * bstep16), idesc, 1);
+                umma_commit(a_free_u + slot * 8);
+                umma_commit(b_free_u + sb * 8);
+                if (j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
+              }
+              __syncwarp();
+              if (++sb == NB) { sb = 0; bpar ^= 1u; }
+            }
           }
         }
         if (!overlap && has_next) layer0(it + 1);
@@ -457,21 +521,20 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
     __syncwarp();
   } else if (warp == TCW_CTHREADS / 32 + 1) {
     // =============================== weight streamer ===============================================================
+    // walks the issuer's chunk sequence: [SSE: the lo image of layer 0 before every tile's layer-0 MMAs], then per layer
+    // >= 1 its chunks in order (SSE: hi chunk, lo chunk, hi chunk, ... -- stored interleaved, so the walk is linear)
     {
-      const int total = my_tiles * NL * NCH;
       const bool prof = a.prof != nullptr && blockIdx.x == 0;
       long long pw = 0, plat = 0;
-      int s = 0;
+      int s = 0, g = 0;
       uint32_t fpar = 1u;      // parity 1 on the first pass: "the phase before the first one", complete on a fresh barrier
-      for (int g = 0; g < total; ++g) {
+      auto put = [&](const uint8_t* src, uint32_t bytes) {
         const long long c0 = prof ? clock64() : 0;
         tcw_wait(smem_u32(&s_b_free[s]), fpar, 6, g, a.no_trap);
         if (prof) pw += clock64() - c0;
-        const int l = 1 + (g / NCH) % NL, j = g % NCH;
-        const uint32_t bytes = (uint32_t)((l == NL ? TCW_NOUT : BC) * 32 * KS);
         if (elect_one()) {
           mbar_expect_tx(smem_u32(&s_b_full[s]), bytes);
-          bulk_g2s(bring_u + s * BSLOT, a.blk + H->off_b[l] + (size_t)j * bytes, bytes, smem_u32(&s_b_full[s]));
+          bulk_g2s(bring_u + s * BSLOT, src, bytes, smem_u32(&s_b_full[s]));
         }
         __syncwarp();
         if (prof && a.prof_lat) {
@@ -480,8 +543,27 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           plat += clock64() - c1;
         }
         if (++s == NB) { s = 0; fpar ^= 1u; }
+        ++g;
+      };
+      auto layer0_lo = [&]() {
+        for (int i = 0; i < nch0; ++i) {
+          const int nks = (nk16 - i * KS) < KS ? (nk16 - i * KS) : KS;
+          put(a.blk + H->off_b0lo + (size_t)i * BSLOT, (uint32_t)(nks * BSTEP));
+        }
+      };
+      if (SSE && my_tiles > 0) layer0_lo();
+      for (int it = 0; it < my_tiles; ++it) {
+        const bool has_next = it + 1 < my_tiles;
+        for (int l = 1; l <= NL; ++l) {
+          const bool outl = l == NL;
+          if (SSE && outl && overlap && has_next) layer0_lo();
+          const uint32_t bytes = (uint32_t)((outl ? TCW_NOUT : BC) * 32 * KS);
+          const int nsub = (SSE ? 2 : 1) * NCH;
+          for (int c = 0; c < nsub; ++c) put(a.blk + H->off_b[l] + (size_t)c * bytes, bytes);
+        }
+        if (SSE && !overlap && has_next) layer0_lo();
       }
-      if (prof && (tid & 31) == 0) { a.prof[4] = pw; a.prof[5] = plat; a.prof[6] = total; }
+      if (prof && (tid & 31) == 0) { a.prof[4] = pw; a.prof[5] = plat; a.prof[6] = g; }
     }
     __syncwarp();
   } else {
@@ -571,6 +653,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
       }
     };
     uint32_t ph_acc = 0u;        // bit p: phase parity of s_acc_full[p]; bit 2: s_out_full
+    double sse_local = 0.0;      // SSE mode
     const bool prof = a.prof != nullptr && blockIdx.x == 0 && (tid & 127) == 0;   // one lane per warpgroup
     long long pacc = 0, pslot = 0, pstage = 0, pout = 0;
     const long long c_start = prof ? clock64() : 0;
@@ -666,8 +749,15 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             const float z = fmaf(tmem_ld1(tmem_row + (uint32_t)(((NL - 1) & 1) * BC + c)), scale, bo[c]);
             if (gy < net.row1 && gx < net.W) {
               const float y = sigmoidf_rn(z);
-              const int res = (int)rintf(y * net.qmax);
-              a.out[((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx] = (uint16_t)((mctr[q] << net.K) + (uint32_t)res);
+              const size_t off = ((size_t)c * net.buf_rows + (gy - net.buf_row0)) * net.W + gx;
+              if (SSE) {
+                const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+                const float d = y - __fdiv_rn((float)code, net.qmax);
+                sse_local += (double)(d * d);
+              } else {
+                const int res = (int)rintf(y * net.qmax);
+                a.out[off] = (uint16_t)((mctr[q] << net.K) + (uint32_t)res);
+              }
             }
           }
         }
@@ -679,6 +769,26 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
     if (prof) {
       long long* o = a.prof + 8 + 8 * wg;
       o[0] = pacc; o[1] = pslot; o[2] = pstage; o[3] = pout; o[4] = clock64() - c_start;
+    }
+    if (SSE) {
+      // deterministic: lanes -> warp -> CTA partial -> the last CTA sums the partials in index order
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sse_local += __shfl_xor_sync(0xffffffffu, sse_local, off);
+      if ((tid & 31) == 0) s_red[tid >> 5] = sse_local;
+      bar_compute();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < TCW_CTHREADS / 32; ++i) sum += s_red[i];
+        a.partials[blockIdx.x] = sum;
+        __threadfence();
+        if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {
+          __threadfence();
+          double tot = 0.0;
+          for (unsigned int i = 0; i < gridDim.x; ++i) tot += ((volatile double*)a.partials)[i];
+          *a.sse_out = tot;
+          *a.counter = 0u;
+        }
+      }
     }
   }
 
@@ -695,19 +805,19 @@ size_t g_wblk_bytes[64] = {0};
 
 using KernW = void (*)(const TcwArgs);
 
-template <bool FAST, int BC, int APW, int NB>
+template <bool FAST, int BC, int APW, int NB, bool SSE = false>
 KernW pick_wide(const Net& n) {
-  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3, APW, NB>;
-  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2, APW, NB>;
-  return tcw_decode_kernel<FAST, BC, 0, 0, APW, NB>;
+  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3, APW, NB, SSE>;
+  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2, APW, NB, SSE>;
+  return tcw_decode_kernel<FAST, BC, 0, 0, APW, NB, SSE>;
 }
 
 // ring geometries built: (APW, NB) = (1, 3) [what fits at bc 256 / D 3], (1, 4), (2, 6) [bc 128]
-template <bool FAST, int BC>
+template <bool FAST, int BC, bool SSE = false>
 KernW pick_ring(const Net& n, int apw, int nb) {
-  if (apw == 1 && nb == 3) return pick_wide<FAST, BC, 1, 3>(n);
-  if (apw == 1 && nb == 4) return pick_wide<FAST, BC, 1, 4>(n);
-  if (apw == 2 && nb == 6) return pick_wide<FAST, BC, 2, 6>(n);
+  if (apw == 1 && nb == 3) return pick_wide<FAST, BC, 1, 3, SSE>(n);
+  if (apw == 1 && nb == 4) return pick_wide<FAST, BC, 1, 4, SSE>(n);
+  if (apw == 2 && nb == 6) return pick_wide<FAST, BC, 2, 6, SSE>(n);
   return nullptr;
 }
 
@@ -823,6 +933,65 @@ int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out
     CUDA_TRY(cudaMemcpyToSymbol(g_tcw_dbg, h16, sizeof h16));
   }
   if (exact_flag_out) *exact_flag_out = reinterpret_cast<const int*>(blk);   // TcwHeader::exact is the first word
+  return LBDRN_OK;
+}
+
+// Full-scene squared error on the wide tensor-core kernel (per-epoch evaluation of bc 128 / 256 training, encode.py:105-108):
+// fp32 weights -> hi + lo fp16 operands (tcw_prep_kernel with the wlo layout), polynomial sine, deterministic reduction.
+int tcw_eval_sse(const Net& n, const void* msb, const void* lsb, const float* params, double* sse_out, cudaStream_t st) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
+  TcwHeader h;
+  tcw_plan(n, h, true);
+  {
+    std::lock_guard<std::mutex> lk(tcw_mu());
+    if (g_wblk_bytes[dev] < (size_t)h.total) {
+      if (g_wblk[dev]) CUDA_TRY(cudaFree(g_wblk[dev]));
+      g_wblk[dev] = nullptr; g_wblk_bytes[dev] = 0;
+      CUDA_TRY(cudaMalloc(&g_wblk[dev], (size_t)h.total));
+      g_wblk_bytes[dev] = (size_t)h.total;
+    }
+  }
+  uint8_t* blk = g_wblk[dev];
+  Scratch* sc = nullptr;
+  int rc = get_scratch(n.P, sc);
+  if (rc) return rc;
+  tcw_prep_kernel<<<1, 1024, 0, st>>>(n, h, params, blk);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  TcwArgs a;
+  memset(&a, 0, sizeof a);
+  a.net = n; a.msb = msb; a.lsb = lsb; a.blk = blk;
+  a.partials = sc->partials; a.counter = sc->counter; a.sse_out = sse_out;
+  a.res_bytes = h.res_bytes;
+  a.tiles_x = (n.W + TC_TW - 1) / TC_TW;
+  a.n_tiles = a.tiles_x * ((n.row1 - n.row0 + TC_TH - 1) / TC_TH);
+  a.no_trap = getenv("LBDRN_DEBUG") != nullptr;
+  int apw = 0, nb = 0;
+  if (!tcw_pick_ring(n, h, apw, nb)) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core evaluation: operand rings do not fit");
+  const size_t smem = tcw_smem_bytes(n, h, apw, nb);
+  KernW kern = n.bc == 256 ? pick_ring<false, 256, true>(n, apw, nb) : pick_ring<false, 128, true>(n, apw, nb);
+  if (!kern) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core evaluation: ring geometry %dx%d is not built", apw, nb);
+  int sms = 0, max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem > (size_t)max_smem) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core evaluation needs %zu B of shared memory", smem);
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = sms < a.n_tiles ? sms : a.n_tiles;
+  kern<<<grid, TCW_THREADS, smem, st>>>(a);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (a.no_trap) {
+    int h16[16];
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpyFromSymbol(h16, g_tcw_dbg, sizeof h16));
+    if (h16[0])
+      fprintf(stderr, "[lbdrn] wide tc evaluation: first timeout kind %d where %d block %d thread %d; counts by kind 1..6: %d %d %d %d %d %d\n",
+              h16[0], h16[1], h16[2], h16[3], h16[9], h16[10], h16[11], h16[12], h16[13], h16[14]);
+    memset(h16, 0, sizeof h16);
+    CUDA_TRY(cudaMemcpyToSymbol(g_tcw_dbg, h16, sizeof h16));
+  }
   return LBDRN_OK;
 }
 

@@ -361,11 +361,11 @@ def predict_image(base, flat_params, D, bc, nl, flags=None, relu=False, w0=30.0,
     return y
 
 
-def eval_mse(scene, flat_params_dev, D, bc, nl, flags=None, relu=False, w0=30.0, tab=None):
+def eval_mse(scene, flat_params_dev, D, bc, nl, flags=None, relu=False, w0=30.0, tab=None, path="auto"):
     """Full-scene MSE of the network against the LSB labels (encode.py:105-108 / LBDRNperformance.py:18-21)."""
     flags, lib = _flags(flags), cabi.load()
     dev = scene.msb.device
-    d = scene.desc(D, bc, nl, flags, relu, w0)
+    d = scene.desc(D, bc, nl, flags, relu, w0, path=_PATHS[path])
     if tab is None:
         tab = _tab_tensor(scene.H, scene.W, flags, dev)
     sse = torch.zeros(1, dtype=torch.float64, device=dev)

@@ -90,3 +90,31 @@ def test_wide_falls_back_to_fp32_kernel_for_inexact_weights():
     msb, _ = O.split_msb_lsb(img, 5)
     ref = O.decode_image(msb, O.unflatten_params(flat, 196, 256, 4, 2), 5, 3)
     _check(F.decode_image(msb, flat, 5, 3, 256, 2, flags=F.Flags(), path="tensor"), ref, "inexact/tensor")
+
+
+@pytest.mark.parametrize("bc,D,shape", [(256, 3, (4, 203, 317)), (256, 3, (4, 1024, 1024)), (256, 2, (4, 300, 500)),
+                                        (128, 2, (4, 150, 131)), (128, 3, (4, 257, 513))])
+def test_wide_tensor_evaluation_matches_the_fp32_kernel(bc, D, shape):
+    """lbdrn_eval_sse at bc 128 / 256 (the per-epoch full-scene MSE of config-3 training, encode.py:105-108) on the wide
+    tcgen05 kernel with fp32 weights -- not fp16-exact, so every product also takes the low-order weight operand -- against
+    the fp32 kernel (path "precise") on the same weights; and deterministic (three runs, identical bits)."""
+    from synth_scene import make_scene
+    from LBDRNmodel import LBDRNModel
+    C, H, W = shape
+    img = make_scene(C, H, W, 12, seed=bc + D + W)
+    scene = F.DeviceScene.from_image(img, 5)
+    torch.manual_seed(bc + D)
+    model = LBDRNModel(C * (2 * D + 1) ** 2, bc, C, 2)
+    flat = model.flat_params().cuda()                       # full fp32 weights: low mantissa bits set
+    want = F.eval_mse(scene, flat, D, bc, 2, flags=F.Flags(), path="precise")
+    got = [F.eval_mse(scene, flat, D, bc, 2, flags=F.Flags()) for _ in range(3)]
+    assert got[0] == got[1] == got[2]
+    assert abs(got[0] - want) <= 2e-5 * want, (got[0], want)
+    # and against the oracle's forward on a crop-sized scene (float64 accumulation of the same squared errors)
+    if H * W <= 203 * 317:
+        msb, lsb = O.split_msb_lsb(img, 5)
+        params = O.unflatten_params(model.flat_params().numpy(), C * (2 * D + 1) ** 2, bc, C, 2)
+        X = torch.from_numpy(O.features(msb, D, O.Flags()))
+        y = O.forward(params, X).numpy().astype(np.float64)
+        ref = float(((y - O.labels(lsb).astype(np.float64)) ** 2).mean())
+        assert abs(got[0] - ref) <= 2e-5 * ref, (got[0], ref)
