@@ -17,6 +17,12 @@
  *   - return value: 0 (LBDRN_OK) or a negative LBDRN_E_* code; the message of the last failure on the
  *     calling thread is available from lbdrn_last_error().  No exception crosses the boundary.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns LBDRN_E_CUDA.
+ *   - concurrency: lbdrn_decode / lbdrn_predict / lbdrn_eval_sse keep a small per-device scratch (packed weights, the
+ *     partials of the squared-error reduction, a ring of TMA descriptors) that is NOT keyed by stream: on one device,
+ *     queue these calls on ONE stream at a time (a LbdrnTrain handle owns its own state and may run on another stream
+ *     concurrently -- FusedTrainer trains on one stream and evaluates on a second one).
+ *   - hidden widths: the kernels are built for bc = 32, 64, 128, 256; any other width returns LBDRN_E_UNSUPPORTED
+ *     (the .bin header can describe any power of two: such streams are refused, not decoded wrongly).
  */
 #ifndef LBDRN_H_
 #define LBDRN_H_

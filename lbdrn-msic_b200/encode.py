@@ -102,7 +102,8 @@ def build_parser():
     p.add_argument('-o', '--output_dir', default='outputs', type=str, help='output dir')
     p.add_argument('-sr', '--split_ratio', type=int, default=1, help='tile size (default: 1)')
     p.add_argument('-K', '--K', type=int, default=5, help=' (default: 5)')
-    p.add_argument('-bc', '--base_channel', type=int, default=64, help='base channel (default: 64)')
+    p.add_argument('-bc', '--base_channel', type=int, default=64, choices=[32, 64, 128, 256],
+                   help='base channel (default: 64); the fused kernels are built for 32 / 64 / 128 / 256')
     p.add_argument('-nl', '--num_layers', type=int, default=2, help='Number of layers (default: 2)')
     p.add_argument('-D', '--D', type=int, default=2, help='#neighbors (2D+1)^2')
     p.add_argument('-prec', '--precision', type=int, default=16, help=' (default: 16)')
