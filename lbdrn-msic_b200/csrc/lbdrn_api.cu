@@ -241,6 +241,10 @@ int launch_train(LbdrnTrain* t, TrainArgs& a, cudaStream_t st) {
   a.beta1 = t->cfg.beta1; a.beta2 = t->cfg.beta2;
   a.omb1 = (float)(1.0 - t->cfg.beta1); a.omb2 = (float)(1.0 - t->cfg.beta2);
   a.beta2f = (float)t->cfg.beta2; a.eps = (float)t->cfg.eps;
+  if (t->plan.tcx) {        // the streamed variant reads the hidden weights from the global image from its first step on
+    launch_tcx_wimg(t->net, t->params, t->wimg, st);
+    CUDA_TRY(cudaGetLastError());
+  }
   return train_fp32_launch(t->plan, a, st);
 }
 

@@ -45,12 +45,14 @@ struct TrainPlan {
   bool wsmem = true;
   size_t wimg_bytes = 0;              // h2: bytes of the global image of the split weight operands
   bool h2 = false;                    // fp16 hi+lo split operands + ldmatrix variant selected
+  bool tcx = false;                   // streamed tcgen05 variant (bc 256): the global weight image is (re)built before every launch
   int grid = 0, dimpad = 0, pstride = 0;
   int pf_off = 0, pf_stride = 0;      // TMA neighbourhood boxes: offset inside dynamic smem, bytes per pixel (0: not planned)
 };
 struct TrainArgs;
 int train_fp32_plan(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& plan);
 int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st);
+void launch_tcx_wimg(const Net& n, const float* params, uint16_t* wimg, cudaStream_t st);
 void launch_interleave_u8(const void* planes, int C, size_t npix, uint32_t* out, int sms, cudaStream_t st);
 void launch_adam_apply(const Net& n, const float* grad, float* params, float* wpack, float* m, float* v, float omb1,
                        float omb2, float beta2, float eps, float step_size, float bc2_sqrt, cudaStream_t st);

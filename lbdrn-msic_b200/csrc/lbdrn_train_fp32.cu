@@ -92,6 +92,25 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
       t.wimg_bytes = wimg;
     }
   }
+  // streamed tcgen05 variant (MMA = 4) for bc 256: transposed GEMMs with M = 128 units, 32-pixel chunks, hidden weights
+  // streamed from the global operand image (LBDRN_TRAIN_TF32=1 keeps the 3xTF32 warp-level kernel for A/B)
+  if constexpr (kMma && TM == 2 && BC == 256) {
+    const int KP0 = round16(n.dim_in), L = n.nl;
+    const size_t xfl = (size_t)t.dimpad * kTrainLDP * 4 > 32768 ? (size_t)t.dimpad * kTrainLDP : 8192;
+    const size_t fl = xfl + 2 * (size_t)CP * kTrainLDP + (size_t)round4(L * BC + n.C * BC + n.C);
+    const size_t wimg = ((size_t)2 * KP0 * BC + (size_t)(L - 1) * 2 * BC * BC + (size_t)2 * 16 * BC) * 2;
+    const size_t imgs = (size_t)2 * 16 * BC * 2 + (size_t)2 * (KP0 + 8) * kTrainNPIX * 2 + (size_t)L * 2 * (BC + 8) * kTrainNPIX * 2 +
+                        (size_t)L * 2 * BC * kTrainNPIX * 2 + (size_t)2 * 16 * kTrainNPIX * 2;
+    const size_t tx = fl * sizeof(float) + 128 + imgs;
+    if (mma && getenv("LBDRN_TRAIN_TF32") == nullptr && KP0 + 8 <= 256 && n.C <= 8 && tx <= (size_t)max_smem &&
+        fits((void*)train_fp32_kernel<BC, CP, false, kTT, TM, 4>, tx)) {
+      t.wsmem = false; t.smem = tx;
+      t.pf_off = 0; t.pf_stride = 0;
+      t.kernel = (void*)train_fp32_kernel<BC, CP, false, kTT, TM, 4>;
+      t.h2 = true; t.tcx = true;
+      t.wimg_bytes = wimg;
+    }
+  }
   void* k_with = mma ? (void*)train_fp32_kernel<BC, CP, true, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, true, kTT, TM>;
   void* k_without = mma ? (void*)train_fp32_kernel<BC, CP, false, kTT, TM, kMma> : (void*)train_fp32_kernel<BC, CP, false, kTT, TM>;
   if (t.h2) {
@@ -189,6 +208,43 @@ static __global__ void interleave_u8_kernel(const uint8_t* __restrict__ planes, 
       out[i] = w;
     }
   }
+}
+
+// Global operand image of the streamed tcgen05 variant from the master parameters (before every launch; the Adam phase keeps
+// it current inside a launch): per hidden layer [hi Kp*BC | lo Kp*BC] halves with rows = BC, then W_o as a 16-row image.
+static __global__ void tcx_wimg_kernel(Net net, const float* __restrict__ params, uint16_t* __restrict__ wimg) {
+  const int BC = net.bc, KP0 = round16(net.dim_in), L = net.nl;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < net.P; i += gridDim.x * blockDim.x) {
+    uint32_t img = 0u;
+    bool done = false;
+    for (int l = 0; l < L && !done; ++l) {
+      const int K = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, o = i - net.woff[l];
+      if (o >= 0 && o < K * BC) {
+        const int u = o / K, k = o - u * K;
+        uint16_t hi, lo;
+        split_h1(params[i] * kWScale, hi, lo);
+        const uint32_t e = img + (uint32_t)(img_off(BC, u, k) >> 1);
+        wimg[e] = hi;
+        wimg[e + (uint32_t)Kp * BC] = lo;
+        done = true;
+      }
+      img += 2u * (uint32_t)Kp * BC;
+    }
+    const int oo = i - net.woff[L];
+    if (!done && oo >= 0 && oo < net.C * BC) {
+      const int c = oo / BC, u = oo - c * BC;
+      uint16_t hi, lo;
+      split_h1(params[i] * kWScale, hi, lo);
+      const uint32_t e = img + (uint32_t)(img_off(16, c, u) >> 1);
+      wimg[e] = hi;
+      wimg[e + 16u * BC] = lo;
+    }
+  }
+}
+
+void launch_tcx_wimg(const Net& n, const float* params, uint16_t* wimg, cudaStream_t st) {
+  tcx_wimg_kernel<<<(n.P + 255) / 256, 256, 0, st>>>(n, params, wimg);
+  ++g_launches;
 }
 
 void launch_interleave_u8(const void* planes, int C, size_t npix, uint32_t* out, int sms, cudaStream_t st) {

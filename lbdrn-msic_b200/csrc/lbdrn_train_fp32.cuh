@@ -154,6 +154,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Split grid barrier on a monotonic counter: arrive (ONE thread, after a __syncthreads() that orders the CTA's writes before
 // its fence -- the same cumulativity cooperative_groups' grid.sync() relies on) ... independent work ... wait (one thread
@@ -566,14 +569,17 @@ __device__ __forceinline__ void grad_weight_nt_t(const float* __restrict__ G, co
 // memory); MMA = 0: FFMA.
 template <int BC, int CP, bool WSMEM, int THREADS, int TM, int MMA = 0>
 __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs a) {
-  static_assert(!MMA || (THREADS == 512 && BC % 32 == 0 && (TM == 4 || (MMA == 1 && TM == 2 && BC % 64 == 0))),
-                "MMA paths: 16 warps, 64-pixel chunks (3xTF32 also 32-pixel chunks: bc 256)");
-  static_assert(MMA < 2 || TM == 4, "fp16-split and tcgen05 paths: 64-pixel chunks");
+  static_assert(!MMA || (THREADS == 512 && BC % 32 == 0 && (TM == 4 || ((MMA == 1 || MMA == 4) && TM == 2 && BC % 64 == 0))),
+                "MMA paths: 16 warps, 64-pixel chunks (3xTF32 and streamed tcgen05 also 32-pixel chunks: bc 256)");
+  static_assert((MMA != 2 && MMA != 3) || TM == 4, "fp16-split and resident tcgen05 paths: 64-pixel chunks");
+  static_assert(MMA != 4 || (!WSMEM && TM == 2 && BC % 128 == 0), "streamed tcgen05 path: 32-pixel chunks, weights from the global image");
   constexpr int PT = train_npix(TM) / 16, NGW = 16 / PT;      // MMA = 1: pixel tiles per chunk, unit groups (warp = (tile, group))
   static_assert(MMA != 2 || (WSMEM && BC % 64 == 0), "fp16-split path: weights in shared memory, unit tiles in pairs");
   static_assert(MMA != 3 || (WSMEM && BC == 64), "tcgen05 path: M = 64 chunk GEMMs, everything resident in shared memory");
   constexpr bool H2 = MMA == 2;
   constexpr bool TC5 = MMA == 3;          // chunk GEMMs on tcgen05 (M = 64, accumulators in TMEM), see the TC5 block below
+  constexpr bool TCX = MMA == 4;          // wide layers on tcgen05: transposed GEMMs (M = 128 units, N = 32 pixels), weights
+                                          // streamed K step by K step from the global operand image, see the TCX block below
   constexpr int NPIX = train_npix(TM), LDP = train_ldp(TM), US = THREADS / 128, TN = BC / 8 / US;
   constexpr int VEC = TN >= 4 ? 4 : TN;
   static_assert(TN >= 1 && BC % (8 * US) == 0, "unit split does not divide bc");
@@ -590,12 +596,15 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   // H2: Hbuf holds the fp32 output of the LAST hidden layer only (output layer and its gradients read it); a layer's slot
   // of Gbuf is BC*kLDH floats: act' in fp32 [BC][LDP], overwritten in place by the scaled dz as [hi [BC][kLDH] | lo [BC][kLDH]]
   constexpr int GSZ = H2 ? BC * kLDH : BC * LDP;
-  float* Hbuf = X + (size_t)a.dimpad * LDP;                     // [L][BC][LDP]    hidden outputs
-  float* Gbuf = Hbuf + (size_t)(TC5 ? 0 : (H2 ? 1 : L)) * BC * LDP;   // [L][GSZ]  act' then dz
-  float* dZo = Gbuf + (size_t)L * GSZ;                          // [CP][LDP]       output-layer dz
-  float* Tl = dZo + (TC5 ? 0 : CP * LDP);                       // [CP][LDP]       labels
+  // TCX: the feature staging X shares its 32 KB with the two-stage weight ring (the gather is over before a GEMM starts)
+  constexpr int TX_RING = 2 * 16384;
+  const size_t x_floats = TCX ? (size_t)((a.dimpad * LDP * 4 > TX_RING ? a.dimpad * LDP * 4 : TX_RING) / 4) : (size_t)a.dimpad * LDP;
+  float* Hbuf = X + x_floats;                                   // [L][BC][LDP]    hidden outputs
+  float* Gbuf = Hbuf + (size_t)((TC5 || TCX) ? 0 : (H2 ? 1 : L)) * BC * LDP;   // [L][GSZ]  act' then dz
+  float* dZo = Gbuf + (size_t)(TCX ? 0 : L) * GSZ;              // [CP][LDP]       output-layer dz
+  float* Tl = dZo + ((TC5 || TCX) ? 0 : CP * LDP);              // [CP][LDP]       labels
   float* Pp = Tl + CP * LDP;                                    // [US][CP][LDP]   output-layer partial sums per unit split
-  float* wsm = Pp + (TC5 ? 0 : US * CP * LDP);                  // packed weights [P] (+pad) then natural hidden l>=1
+  float* wsm = Pp + (TC5 ? 0 : (TCX ? CP * LDP : US * CP * LDP));   // packed weights [P] (+pad) then natural hidden l>=1 (TCX: the Pp slot holds the fp32 dz_o)
   float* wnat_sm = wsm + round4(P);
   // H2: wsm = [biases of the hidden layers L*BC | W_o C*BC | b_o C] in fp32; behind it the split 16-bit operand arrays
   const int KP0 = round16(net.dim_in);                          // layer-0 contraction length, zero-padded to k = 16 steps
@@ -627,6 +636,33 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   // TMEM columns: two forward / dh accumulators, then the weight-gradient accumulators
   constexpr uint32_t T5_DWO = 2 * BC + 16, T5_DW0 = 2 * BC + 32;
   auto t5_dwcol = [&](int l) { return T5_DW0 + (l == 0 ? 0u : (uint32_t)(KP0 + 8) + (uint32_t)(l - 1) * (BC + 8)); };
+  // ---- TCX: operand images with NPIX = 32 rows behind the fp32 part (same element rule, rows = 32); W_o as a 16-row image
+  //   [hi | lo]; X split [hi (KP0+8)*32 | lo]; h_l [hi (BC+8)*32 | lo] for every hidden layer; per layer one region that holds
+  //   act' as fp32 [32][BC] until the backward pass overwrites it with the scaled dz_l image [hi BC*32 | lo]; output dz image.
+  //   The hidden weights are NOT resident: a.wimg holds their images (rows = BC) and the GEMMs stream K steps of them.
+  const uint32_t tx_base = (smem_u32(h2base) + 127u) & ~127u;
+  const uint32_t tx_wobytes = 16u * BC * 2u;                                    // one half of the W_o image
+  const uint32_t tx_wo = tx_base, tx_x = tx_wo + 2u * tx_wobytes;
+  const uint32_t tx_xbytes = (uint32_t)(KP0 + 8) * NPIX * 2u, tx_hbytes = (uint32_t)(BC + 8) * NPIX * 2u;
+  const uint32_t tx_h0 = tx_x + 2u * tx_xbytes;
+  auto tx_h = [&](int l) { return tx_h0 + (uint32_t)l * 2u * tx_hbytes; };
+  const uint32_t tx_dzbytes = (uint32_t)BC * NPIX * 2u;
+  auto tx_dz = [&](int l) { return tx_h0 + (uint32_t)L * 2u * tx_hbytes + (uint32_t)l * 2u * tx_dzbytes; };
+  const uint32_t tx_dzo = tx_dz(L), tx_dzobytes = 16u * NPIX * 2u, tx_end = tx_dzo + 2u * tx_dzobytes;
+  auto tx_g = [&](int l) {                                                       // act' of layer l, fp32 [NPIX][BC], in dz_l's region
+    return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem4) + (tx_dz(l) - smem_u32(smem4)));
+  };
+  // global image: per hidden layer [hi Kp*BC | lo Kp*BC] halves (rows = BC), then W_o [hi 16*BC | lo]
+  auto tx_wimg = [&](int l) -> const uint8_t* {                                  // hi half of layer l (l == L: W_o)
+    size_t h = 0;
+    for (int i = 0; i < l; ++i) h += 2u * (size_t)(i == 0 ? KP0 : BC) * BC;
+    return reinterpret_cast<const uint8_t*>(a.wimg) + 2u * h;
+  };
+  // TMEM columns: two slots of BC/128 x 32 (transposed z / dh: units in lanes, pixels in columns), output accumulator,
+  // W_o gradient (BC/128 x 16), then one weight-gradient pass at a time (128 units x (K + 8) columns)
+  constexpr uint32_t TX_SLOT = (BC / 128) * 32, TX_ZO = 2 * TX_SLOT, TX_DWO = TX_ZO + 16, TX_DWP = TX_DWO + (BC / 128) * 16;
+  __shared__ __align__(8) uint64_t s_tx_free[4];                // TCX: "the MMAs that read ring stage s have retired"
+  uint32_t tx_fpar = 0u;                                        // bit s: parity of the next wait on s_tx_free[s]
   __shared__ __align__(8) uint64_t s_t5_mbar;
   __shared__ uint32_t s_t5_tmem;
   __shared__ float s_t5_inv[kMaxLayers];                        // TC5: 1 / scale of dz_l (read-out of the gradient accumulators)
@@ -639,8 +675,8 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   __shared__ float s_adam[2];
 
   const float* w = WSMEM ? wsm : a.wpack;
-  const float* wo_p = (H2 || TC5) ? wsm + L * BC : w + net.woff[L];   // output layer W_o [C][BC] and b_o [C]
-  const float* bo_p = (H2 || TC5) ? wsm + L * BC + C * BC : w + net.boff[L];
+  const float* wo_p = (H2 || TC5 || TCX) ? wsm + L * BC : w + net.woff[L];   // output layer W_o [C][BC] and b_o [C]
+  const float* bo_p = (H2 || TC5 || TCX) ? wsm + L * BC + C * BC : w + net.boff[L];
   // natural (untransposed) W_l for hidden layers l>=1, used as the k-major B operand of dh = W^T dz
   auto wnat = [&](int l) -> const float* {
     return WSMEM ? (wnat_sm + (size_t)(l - 1) * BC * BC) : (a.params + net.woff[l]);
@@ -667,6 +703,29 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     for (int i = tid; i < (L + 1) * NPIX; i += THREADS) {
       const int which = i / NPIX, pp = i - which * NPIX;
       const uint32_t blk = which == 0 ? t5_x + (uint32_t)KP0 * NPIX * 2u : t5_h(which - 1) + (uint32_t)BC * NPIX * 2u;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(blk + 16u * pp), "h"((uint16_t)0x3c00) : "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    t5_tmem = s_t5_tmem;
+  }
+  if constexpr (TCX) {
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_t5_tmem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+      mbar_init(smem_u32(&s_t5_mbar), 1);
+      for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_tx_free[i]), 1);
+    }
+    for (uint32_t o = tx_base + 16u * tid; o < tx_end; o += 16u * THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(o), "r"(0u) : "memory");
+    __syncthreads();
+    for (int i = tid; i < (L + 1) * NPIX; i += THREADS) {       // constant blocks: element 0 of each pixel's 16-byte row = 1.0
+      const int which = i / NPIX, pp = i - which * NPIX;
+      const uint32_t blk = which == 0 ? tx_x + (uint32_t)KP0 * NPIX * 2u : tx_h(which - 1) + (uint32_t)BC * NPIX * 2u;
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(blk + 16u * pp), "h"((uint16_t)0x3c00) : "memory");
     }
     fence_async_smem();
@@ -1012,6 +1071,19 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     }
   };
 
+  auto tx_split_x = [&]() {       // TCX: features -> split operand image with 32 rows (a warp: 8 pixels x 4 feature pairs)
+    for (int i = tid; i < KP0 * (NPIX / 2); i += THREADS) {
+      const int kp = i & 3, pp = ((i >> 2) & 7) + 8 * ((i >> 5) & 3), k = 8 * (i >> 7) + 2 * kp;
+      const float x0 = k < net.dim_in ? X[(size_t)k * LDP + pp] : 0.f;
+      const float x1 = k + 1 < net.dim_in ? X[(size_t)(k + 1) * LDP + pp] : 0.f;
+      uint32_t hi, lo;
+      split_h2(x0, x1, hi, lo);
+      const uint32_t o = (uint32_t)img_off(NPIX, pp, k);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tx_x + o), "r"(hi) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tx_x + tx_xbytes + o), "r"(lo) : "memory");
+    }
+  };
+
   for (int s = 0; s < a.n_steps; ++s) {
     if (tid == 0) s_sse = 0.f;
     prefetch_index(s + 1);
@@ -1041,6 +1113,21 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     LBDRN_PHASE(7)    // wait for the Adam phase of every CTA (second barrier of the previous step)
     if (il) prefetch_l2_il(); else prefetch_l2();
     // ---- (re)load weights ----------------------------------------------------------------------------
+    if constexpr (TCX) {
+      // fp32 part (hidden biases, W_o, b_o) and the 16-row W_o image; the hidden weights stay in the global image
+      const int nlite = L * BC + C * BC + C;
+      for (int i = tid; i < nlite; i += THREADS) {
+        const int nb = L * BC, nwo = C * BC;
+        const int src = i < nb ? net.boff[i / BC] + i % BC : (i < nb + nwo ? net.woff[L] + (i - nb) : net.boff[L] + (i - nb - nwo));
+        wsm[i] = __ldcg(a.params + src);
+      }
+      const uint8_t* wo_img = tx_wimg(L);
+      for (int i = tid; i < (int)(2u * tx_wobytes >> 4); i += THREADS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tx_wo + 16u * i), "l"(wo_img + 16 * (size_t)i) : "memory");
+      cp_async_commit();
+      cp_async_wait_group<0>();
+      fence_async_smem();
+    }
     if (H2 || TC5) {
       const bool from_image = s > 0 && a.wimg != nullptr;           // the Adam phase of step s-1 wrote every weight's halves
       // fp32 part (hidden biases, output layer): requested FIRST (behind 49 KB of copies per SM its round trip tripled),
@@ -1193,6 +1280,11 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
       }
       if (TC5) {
         t5_split_x();
+        fence_async_smem();
+        __syncthreads();
+      }
+      if (TCX) {
+        tx_split_x();
         fence_async_smem();
         __syncthreads();
       }
@@ -1568,6 +1660,361 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           }
         }
         tc_fence_before();       // the accumulators are read: the next chunk / step may overwrite them after its barrier
+        first = false;
+        LBDRN_PHASE(4)   // backward (remainder)
+        continue;
+      }
+
+      if constexpr (TCX) {
+        // ============ chunk forward + backward on tcgen05 for wide layers (bc 256): TRANSPOSED GEMMs ========================
+        // z^T[unit][pixel] = W . x^T: the weights are the A operand (M = 128 units per block, full tensor rate), the 32-pixel
+        // activation / gradient images the B operand (N = 32), so accumulators are 32 columns per block and all 16 warps own
+        // accumulator rows: thread (sub-partition sp, block mb, pixel half ph) <-> unit u = 128 mb + 32 sp + lane, 16 pixels.
+        // Hidden weights (475 KB as hi + lo at D = 3) cannot be resident: every GEMM that contracts with them streams one K
+        // step (16 KB: hi 8 KB | lo 8 KB) at a time from the global image into a two-stage ring with per-thread cp.async and
+        // issues its MMAs as the stages land; dh = W^T dz reads the same image transposed (the stage is gathered as 16-row
+        // pieces and consumed through an MN-major descriptor).  Products are hi*hi + hi*lo + lo*hi in fp32 as in MMA = 3.
+        constexpr int NB128 = BC / 128;
+        const int sp = warp & 3, qd = warp >> 2, mb = qd / 2 % NB128, ph = qd & 1;
+        const int un = 128 * mb + 32 * sp + lane;                       // this thread's unit (accumulator row)
+        const uint32_t tm_lane = t5_tmem + ((uint32_t)(32 * sp) << 16);
+        const uint32_t mbar = smem_u32(&s_t5_mbar);
+        const uint32_t ring = smem_u32(smem4);
+        constexpr uint32_t STG = 16384u, HALF = 8192u;
+        static_assert(BC == 256, "stage geometry (one 16-byte piece per thread and half) is written for bc = 256");
+        auto tx_wait = [&]() {
+          mbar_wait(mbar, t5_phase, 8, (int)blockIdx.x);
+          t5_phase ^= 1u;
+          tc_fence_after();
+        };
+        auto mma3x = [&](uint32_t d_col, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, uint32_t acc) {
+          umma_f16(t5_tmem + d_col, a_lo, b_hi, idesc, acc);        // small terms first
+          umma_f16(t5_tmem + d_col, a_hi, b_lo, idesc, 1u);
+          umma_f16(t5_tmem + d_col, a_hi, b_hi, idesc, 1u);
+        };
+        // D[slot][unit][pixel] = sum_k W-stage[unit][k] * B-image[pixel][k], nk K steps; TRANSPOSED: the stage holds 16 rows
+        // (= K step) x BC columns of the weight image, i.e. W^T, read MN-major.  Ends with a commit to the chunk barrier.
+        auto stream_gemm = [&](int nk, const uint8_t* w_hi, uint32_t w_half, bool transposed, uint32_t b_img, uint32_t b_half,
+                               uint32_t d_col) {
+          auto load_stage = [&](int ks, uint32_t stg) {
+            // forward: K step ks of the K-major image = BC*32 contiguous bytes; transposed: rows 16 ks .. +15 of every 8-column
+            // group (BC/8 pieces of 256 bytes); either way thread tid moves bytes [16 tid, 16 tid + 16) of each half
+            const size_t src = transposed ? ((size_t)(tid >> 4) * BC + 16 * ks + (tid & 15)) * 16 : (size_t)ks * (BC * 32) + 16 * (size_t)tid;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg + 16u * tid), "l"(w_hi + src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg + HALF + 16u * tid), "l"(w_hi + w_half + src) : "memory");
+            cp_async_commit();
+          };
+          const uint32_t idesc = umma_idesc_f16_major(128, NPIX, transposed ? 1 : 0, 0);
+          // four stages: two over the feature staging buffer, two over the image of the LAST hidden layer's output, which is
+          // dead while a streamed GEMM runs (written by the last forward epilogue after its GEMM, last read by dW_o, which
+          // the caller waits for before the transposed stream starts)
+          auto stage_addr = [&](int st) { return st < 2 ? ring + (uint32_t)st * STG : tx_h(L - 1) + (uint32_t)(st - 2) * STG; };
+          constexpr int NS = 4;
+          for (int p = 0; p < NS && p < nk; ++p) load_stage(p, stage_addr(p));      // every stage is free at the start
+          for (int ks = 0; ks < nk; ++ks) {
+            const int st = ks & (NS - 1);
+            // K step ks + 2 goes into the stage K step ks - 2 used: its MMAs were committed two iterations ago, so this wait
+            // does not stall, and the copy has two iterations (> the L2 latency) to land
+            if (ks >= 2 && ks + 2 < nk) {
+              const int sr = (ks + 2) & (NS - 1);
+              mbar_wait(smem_u32(&s_tx_free[sr]), (tx_fpar >> sr) & 1u, 10, (int)blockIdx.x);
+              tx_fpar ^= 1u << sr;
+              load_stage(ks + 2, stage_addr(sr));
+            }
+            // groups that may stay in flight behind K step ks: those of ks + 1, ks + 2 (the first two iterations: stricter)
+            if (ks + 2 < nk) cp_async_wait_group<2>();
+            else if (ks + 1 < nk) cp_async_wait_group<1>();
+            else cp_async_wait_group<0>();
+            fence_async_smem();
+            __syncthreads();
+            if (warp == 0) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t sa = stage_addr(st);
+#pragma unroll
+                for (int b = 0; b < NB128; ++b) {
+                  const uint64_t a_hi = transposed ? umma_desc(sa + (uint32_t)b * 4096u, 128u, 256u) : umma_desc(sa + (uint32_t)b * 2048u, BC * 16u, 128u);
+                  const uint64_t a_lo = transposed ? umma_desc(sa + HALF + (uint32_t)b * 4096u, 128u, 256u)
+                                                   : umma_desc(sa + HALF + (uint32_t)b * 2048u, BC * 16u, 128u);
+                  mma3x(d_col + 32u * b, a_hi, a_lo, img_desc(b_img, NPIX, 0, ks), img_desc(b_img + b_half, NPIX, 0, ks), idesc, ks > 0);
+                }
+                if (ks + NS < nk) umma_commit(smem_u32(&s_tx_free[st]));   // refilled with K step ks + NS at iteration ks + 2
+                if (ks + 1 == nk) umma_commit(mbar);
+              }
+              __syncwarp();
+            }
+          }
+        };
+        // ---- forward (LBDRNmodel.py:79-82) ----------------------------------------------------------------------------------
+        for (int l = 0; l < L; ++l) {
+          const int Kp = l == 0 ? KP0 : BC;
+          stream_gemm(Kp >> 4, tx_wimg(l), (uint32_t)Kp * BC * 2u, false, l == 0 ? tx_x : tx_h(l - 1), l == 0 ? tx_xbytes : tx_hbytes,
+                      (uint32_t)(l & 1) * TX_SLOT);
+          tx_wait();
+          LBDRN_PHASE(15)   // fwd: GEMMs
+          float acc[16];
+          tmem_ld16(tm_lane + (uint32_t)(l & 1) * TX_SLOT + 32u * mb + 16u * ph, acc);
+          float* Gl = tx_g(l);
+          const float bias = wsm[l * BC + un];
+          const uint32_t o_hi = tx_h(l), o_lo = o_hi + tx_hbytes;
+          float amax = 0.f;
+          float hv[16], gv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float z = acc[i] * kWInv + bias;
+            if (net.relu) {
+              hv[i] = fmaxf(z, 0.f);
+              gv[i] = z > 0.f ? 1.f : 0.f;
+            } else {
+              const float arg = net.w0 * z;
+              float sn, cs;
+              sincos_cw_core(arg, sn, cs);
+              amax = fmaxf(amax, fabsf(arg));
+              hv[i] = sn;
+              gv[i] = cs * net.w0;
+            }
+          }
+          if (__builtin_expect(amax > 48000.0f, 0)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float arg = net.w0 * (acc[i] * kWInv + bias);
+              if (fabsf(arg) > 48000.0f) { hv[i] = sin_slow(arg); gv[i] = cos_slow(arg) * net.w0; }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int pixel = 16 * ph + i;
+            Gl[pixel * BC + un] = gv[i];                                // lanes = consecutive units: conflict-free
+            uint16_t hi, lo;
+            split_h1(hv[i], hi, lo);
+            const uint32_t o = (uint32_t)img_off(NPIX, pixel, un);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(o_hi + o), "h"(hi) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(o_lo + o), "h"(lo) : "memory");
+          }
+          fence_async_smem();
+          tc_fence_before();
+          __syncthreads();
+          LBDRN_PHASE(16)   // fwd: bias + sine / cosine + stores
+        }
+        LBDRN_PHASE(2)
+        // ---- output layer + loss (LBDRNloss.py:9) on the tensor core: z_o[pixel][c] = h_L . W_o^T, M = 64 (rows >= 32 unused),
+        // N = 16 (rows >= C of the W_o image are zero) ---------------------------------------------------------------------------
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t idesc = umma_idesc_f16_major(64, 16, 0, 0);
+            for (int ks = 0; ks < (BC >> 4); ++ks)
+              mma3x(TX_ZO, img_desc(tx_h(L - 1), NPIX, 0, ks), img_desc(tx_h(L - 1) + tx_hbytes, NPIX, 0, ks),
+                    img_desc(tx_wo, 16, 0, ks), img_desc(tx_wo + tx_wobytes, 16, 0, ks), idesc, ks > 0);
+            umma_commit(mbar);
+          }
+          __syncwarp();
+        }
+        tx_wait();
+        const float inv_o = gscale * (1.0f / 65536.0f);
+        float sse = 0.f;
+        float* const dZo5 = Pp;                                          // fp32 dz_o [CP][LDP] (the Pp slot of this variant)
+        if (warp < 2) {                                                  // M = 64 accumulator: pixels 16 sp + g, + 8; bands 2t, 2t + 1
+          const int g = lane >> 2, t = lane & 3;
+          uint32_t r[4];
+          tmem_ld16x256_x1(tm_lane + TX_ZO, r);
+          tmem_ld_wait4(r);
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int pixel = 16 * sp + g + 8 * e2;
+            const bool ok = s_valid[pixel] != 0;
+            float v[2] = {0.f, 0.f};
+#pragma unroll
+            for (int e1 = 0; e1 < 2; ++e1) {
+              const int c = 2 * t + e1;
+              if (c < C) {
+                const float y = sigmoidf_rn(__uint_as_float(r[2 * e2 + e1]) * kWInv + bo_p[c]);
+                const float d = y - Tl[c * LDP + pixel];
+                const float qq = (1.0f - y) * y;
+                dZo5[c * LDP + pixel] = ok ? (gscale * d) * qq : 0.f;
+                if (ok) { v[e1] = (d * qq) * 65536.0f; sse += d * d; }
+              }
+            }
+            uint32_t hi, lo;
+            split_h2(v[0], v[1], hi, lo);
+            const uint32_t o = (uint32_t)img_off(NPIX, pixel, 2 * t);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(tx_dzo + o), "r"(hi) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(tx_dzo + tx_dzobytes + o), "r"(lo) : "memory");
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
+        if (lane == 0) s_red[warp] = sse;
+        if (tid < kMaxLayers) s_dzmax[tid] = 0u;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          float tsum = 0.f;
+          for (int i = 0; i < THREADS / 32; ++i) tsum += s_red[i];
+          s_sse += tsum;
+        }
+        if (tid < C) {
+          const float gsum = row_sum<NPIX>(dZo5 + tid * LDP);
+          float* dd = mypart + net.boff[L] + tid;
+          *dd = first ? gsum : *dd + gsum;
+        }
+        LBDRN_PHASE(3)   // output layer + loss
+        // ---- backward: dW_o^T = h_L^T . dz_o first (small; it must have read h_L's image before the transposed stream reuses
+        // that region as ring stages), then dh_L^T = W_o^T . dz_o^T (W_o image read MN-major, K = 16 bands); ONE commit for both:
+        // two arrivals on the same barrier in quick succession could both land before a slow thread has observed the first,
+        // and a parity wait that misses a phase never returns
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t id1 = umma_idesc_f16_major(128, NPIX, 1, 0), id2 = umma_idesc_f16_major(128, 16, 1, 1);
+            for (int ks = 0; ks < (NPIX >> 4); ++ks)
+#pragma unroll
+              for (int b = 0; b < NB128; ++b)
+                mma3x(TX_DWO + 16u * b, umma_desc(tx_h(L - 1) + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u),
+                      umma_desc(tx_h(L - 1) + tx_hbytes + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u),
+                      img_desc(tx_dzo, NPIX, 1, ks), img_desc(tx_dzo + tx_dzobytes, NPIX, 1, ks), id2, ks > 0);
+#pragma unroll
+            for (int b = 0; b < NB128; ++b)
+              mma3x((uint32_t)((L - 1) & 1) * TX_SLOT + 32u * b, umma_desc(tx_wo + (uint32_t)b * 4096u, 128u, 256u),
+                    umma_desc(tx_wo + tx_wobytes + (uint32_t)b * 4096u, 128u, 256u), img_desc(tx_dzo, NPIX, 0, 0),
+                    img_desc(tx_dzo + tx_dzobytes, NPIX, 0, 0), id1, 0u);
+            umma_commit(mbar);
+          }
+          __syncwarp();
+        }
+        float inv_next = inv_o;
+        for (int l = L - 1; l >= 0; --l) {
+          tx_wait();
+          float acc[16];
+          tmem_ld16(tm_lane + (uint32_t)(l & 1) * TX_SLOT + 32u * mb + 16u * ph, acc);
+          const float* Gl = tx_g(l);
+          const float sc = kWInv * inv_next;
+          float dz[16], mx = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            dz[i] = (acc[i] * sc) * Gl[(16 * ph + i) * BC + un];
+            mx = fmaxf(mx, fabsf(dz[i]));
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+          if (lane == 0) atomicMax(&s_dzmax[l], __float_as_uint(mx));
+          tc_fence_before();
+          __syncthreads();                                               // every act' of the layer has been read: overwrite
+          LBDRN_PHASE(8)    // bwd: dh * act' + chunk maximum
+          float S, inv;
+          dz_scale(s_dzmax[l], S, inv);
+          const uint32_t o_hi = tx_dz(l), o_lo = o_hi + tx_dzbytes;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            uint16_t hi, lo;
+            split_h1(dz[i] * S, hi, lo);
+            const uint32_t o = (uint32_t)img_off(NPIX, 16 * ph + i, un);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(o_hi + o), "h"(hi) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(o_lo + o), "h"(lo) : "memory");
+          }
+          if (tid == 0) s_t5_inv[l] = inv;
+          fence_async_smem();
+          __syncthreads();
+          LBDRN_PHASE(9 + 2 * (l > 0 ? 1 : 0))     // bwd: dz image
+          if (l > 0)      // dh_{l-1}^T = W_l^T . dz_l^T: the weight image streamed transposed
+            stream_gemm(BC >> 4, tx_wimg(l), (uint32_t)BC * BC * 2u, true, tx_dz(l), tx_dzbytes, (uint32_t)((l - 1) & 1) * TX_SLOT);
+          inv_next = inv;
+        }
+        // ---- weight gradients: per layer and block of 128 units one pass [dW_l | db_l]^T-free form: D[unit][k] = dz_l^T . [in_l | 1]
+        // (both images read MN-major, contraction over the 32 pixels), accumulated in TMEM columns TX_DWP.., read out with the
+        // 16-lane shape so that a warp store covers 8 rows x 32 contiguous bytes -------------------------------------------------
+        {
+          const int g = lane >> 2, t = lane & 3;
+          for (int l = L - 1; l >= 0; --l) {
+            // N of an M = 128 instruction is a multiple of 16 and at most 256: K + 8 columns are rounded up (the extra columns
+            // multiply whatever follows the constant block and are never read) or, beyond 256, split into 256 + 16
+            const int Kin = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, ncol = Kp + 8;
+            const int n1 = ncol <= 256 ? (ncol + 15) & ~15 : 256, n2 = ncol <= 256 ? 0 : (ncol - 256 + 15) & ~15;
+            const uint32_t in_img = l == 0 ? tx_x : tx_h(l - 1), in_half = l == 0 ? tx_xbytes : tx_hbytes;
+            const float inv = s_t5_inv[l];
+            float* dst = mypart + net.woff[l];
+            const bool pair_ok = (Kin & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+            for (int b = 0; b < NB128; ++b) {
+              if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint32_t idw1 = umma_idesc_f16_major(128, n1, 1, 1), idw2 = umma_idesc_f16_major(128, n2 ? n2 : 16, 1, 1);
+                  for (int ks = 0; ks < (NPIX >> 4); ++ks) {
+                    const uint64_t a_hi = umma_desc(tx_dz(l) + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u);
+                    const uint64_t a_lo = umma_desc(tx_dz(l) + tx_dzbytes + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u);
+                    mma3x(TX_DWP, a_hi, a_lo, img_desc(in_img, NPIX, 1, ks), img_desc(in_img + in_half, NPIX, 1, ks), idw1, ks > 0);
+                    if (n2)     // columns 256 ..: 32 column groups further into the images
+                      mma3x(TX_DWP + 256u, a_hi, a_lo, img_desc(in_img + 32u * NPIX * 16u, NPIX, 1, ks),
+                            img_desc(in_img + in_half + 32u * NPIX * 16u, NPIX, 1, ks), idw2, ks > 0);
+                  }
+                  umma_commit(mbar);
+                }
+                __syncwarp();
+              }
+              tx_wait();
+              // warp (sp, qd): units 128 b + 32 sp + 16 h + g (+8), column tiles tt = qd, qd + 4, ... (the 16-lane load shape: a
+              // warp store covers 8 rows x 32 contiguous bytes = 8 full sectors).  A later chunk of the same step ADDS to what this
+              // thread stored for the first one with reductions that return nothing (red.global.add.v2.f32; the same thread owns
+              // the address in every chunk, so the additions happen in program order and the sum stays deterministic).
+              // Measured (cycles for the passes of both chunks of a step): this 74k; row-per-thread loads with 16-byte stores /
+              // reductions 85k (a warp instruction then touches 32 lines); loading the first chunk's values ahead of the
+              // accumulator loads, adding and storing 125k.
+              const int ntile = ncol >> 3;
+              for (int h = 0; h < 2; ++h) {
+                for (int tt0 = qd; tt0 < ntile; tt0 += 16) {
+                  uint32_t r[4][4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (tt0 + 4 * j < ntile) tmem_ld16x256_x1(tm_lane + ((uint32_t)(16 * h) << 16) + TX_DWP + 8u * (tt0 + 4 * j), r[j]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) tmem_ld_wait4(r[j]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int tt = tt0 + 4 * j, q = 8 * tt + 2 * t;
+                    if (tt >= ntile) continue;
+#pragma unroll
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                      const int u = 128 * b + 32 * sp + 16 * h + g + 8 * e2;
+                      const float v0 = __uint_as_float(r[j][2 * e2]) * inv, v1 = __uint_as_float(r[j][2 * e2 + 1]) * inv;
+                      if (q == Kp) {                                     // the constant block's column: bias gradient
+                        float* dd = mypart + net.boff[l] + u;
+                        if (first) *dd = v0; else atomicAdd(dd, v0);
+                      } else if (pair_ok && q + 1 < Kin) {
+                        float* d2 = dst + (size_t)u * Kin + q;
+                        if (first) *reinterpret_cast<float2*>(d2) = make_float2(v0, v1);
+                        else asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d2), "f"(v0), "f"(v1) : "memory");
+                      } else {
+                        if (q < Kin) { float* d1 = dst + (size_t)u * Kin + q; if (first) *d1 = v0; else atomicAdd(d1, v0); }
+                        if (q + 1 < Kin) { float* d1 = dst + (size_t)u * Kin + q + 1; if (first) *d1 = v1; else atomicAdd(d1, v1); }
+                      }
+                    }
+                  }
+                }
+              }
+              tc_fence_before();
+              __syncthreads();                                           // the pass' columns are read: the next pass may overwrite
+            }
+          }
+          // W_o gradient (issued long ago, complete by any later commit): D[unit][c]
+          if (qd < NB128) {
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[4];
+              tmem_ld16x256_x1(tm_lane + ((uint32_t)(16 * h) << 16) + TX_DWO + 16u * qd, r);
+              tmem_ld_wait4(r);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int u = 128 * qd + 32 * sp + 16 * h + g + (e >> 1) * 8, c = 2 * t + (e & 1);
+                if (c < C) {
+                  float* d1 = mypart + net.woff[L] + c * BC + u;
+                  const float v = __uint_as_float(r[e]) * inv_o;
+                  if (first) *d1 = v; else atomicAdd(d1, v);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
         first = false;
         LBDRN_PHASE(4)   // backward (remainder)
         continue;
@@ -2032,8 +2479,8 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     const int n_act = min((int)gridDim.x, n_chunks);
     {
       // Every partial row is read as whole 128-byte lines (8 lanes x float4 = 32 consecutive parameters of one row) and ALL
-      // loads of the phase are in flight at once: the CTA owns `per_cta` float4 columns; 12 warps = 3 column blocks of 8 x
-      // 16 row groups, a thread sums rows rg, rg + 16, ... (8 loads at 128 rows) of its column, the 16 row-group sums of a
+      // loads of the phase are in flight at once: the CTA owns `per_cta` float4 columns; 16 warps = 4 column blocks of 8 x
+      // 16 row groups, a thread sums rows rg, rg + 16, ... (10 loads: up to 160 rows) of its column, the 16 row-group sums of a
       // column meet in shared memory (over the feature buffer, dead here) and thread (column, component) adds them in a fixed
       // order and owns that parameter's Adam update.  History: 4 lanes per parameter with 32-bit loads touched four lines per
       // warp instruction and used a quarter of each (7.3k cycles, bound by the L1 wavefront queue); 3 warps x 2 batches of 16
@@ -2041,17 +2488,17 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
       const int n4 = (P + 4) >> 2;                                    // float4 columns of a partial row (P + 1 floats)
       const int per_cta = (((n4 + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;   // multiple of 8: whole lines
       const size_t ps4 = (size_t)(a.pstride >> 2);
-      constexpr int RW = THREADS >= 384 ? 12 : 3;                     // loader warps (3 column blocks x RW / 3 groups of 4 row groups)
-      constexpr int NRG = 4 * (RW / 3);                               // row groups
-      static_assert(THREADS / 32 >= RW && THREADS >= 96, "reduction layout needs 12 (or 3) warps");
-      float4* const rbuf = reinterpret_cast<float4*>(smem4);          // [NRG][24]
+      constexpr int NCB = 4, RW = 16, NRG = 16, NCOL = 8 * NCB;       // 4 column blocks of 8 x 4 groups of 4 row groups = 16 warps
+      constexpr int NLD = 10;                                         // rows per thread in one batch: 160 rows (grids up to 148)
+      static_assert(THREADS / 32 >= RW, "reduction layout needs 16 warps");
+      float4* const rbuf = reinterpret_cast<float4*>(smem4);          // [NRG][NCOL]
       const int r_lane = tid & 31, r_warp = tid >> 5;
-      const int cblk = r_warp % 3, rg = (r_warp / 3) * 4 + (r_lane >> 3);
+      const int cblk = r_warp % NCB, rg = (r_warp / NCB) * 4 + (r_lane >> 3);
       const bool loader = r_warp < RW;
-      for (int cb = 0; cb < per_cta; cb += 24) {
+      for (int cb = 0; cb < per_cta; cb += NCOL) {
         // owner of (column cb + tid / 4, component tid % 4): its parameter's state is requested first
         const int oc = cb + (tid >> 2), i = 4 * (blockIdx.x * per_cta + oc) + (tid & 3);
-        const bool in = tid < 96 && oc < per_cta && i <= P;
+        const bool in = tid < 4 * NCOL && oc < per_cta && i <= P;
         const bool upd = in && a.mode != TRAIN_GRAD_ONLY && i < P;
         float p_old = 0.f, m_old = 0.f, v_old = 0.f;
         if (upd) { p_old = __ldcg(a.params + i); m_old = __ldcg(a.m + i); v_old = __ldcg(a.v + i); }
@@ -2061,31 +2508,31 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           if (col < per_cta && i4 < n4) {
             // plain loads: ordered after the other CTAs' stores by the acquire in gbar_wait + the CTA barrier behind it
             const float4* pp = reinterpret_cast<const float4*>(a.partial) + i4;
-            float4 v[8];
+            float4 v[NLD];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NLD; ++j) {
               const int r = rg + NRG * j;
               v[j] = r < n_act ? pp[(size_t)r * ps4] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            acc.x = ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
-            acc.y = ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
-            acc.z = ((v[0].z + v[1].z) + (v[2].z + v[3].z)) + ((v[4].z + v[5].z) + (v[6].z + v[7].z));
-            acc.w = ((v[0].w + v[1].w) + (v[2].w + v[3].w)) + ((v[4].w + v[5].w) + (v[6].w + v[7].w));
-            for (int r = rg + NRG * 8; r < n_act; r += NRG) {          // more rows than 8 per group
+            acc.x = (((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x))) + (v[8].x + v[9].x);
+            acc.y = (((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y))) + (v[8].y + v[9].y);
+            acc.z = (((v[0].z + v[1].z) + (v[2].z + v[3].z)) + ((v[4].z + v[5].z) + (v[6].z + v[7].z))) + (v[8].z + v[9].z);
+            acc.w = (((v[0].w + v[1].w) + (v[2].w + v[3].w)) + ((v[4].w + v[5].w) + (v[6].w + v[7].w))) + (v[8].w + v[9].w);
+            for (int r = rg + NRG * NLD; r < n_act; r += NRG) {        // more rows than NLD per group
               const float4 t4 = pp[(size_t)r * ps4];
               acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
             }
           }
-          rbuf[rg * 24 + 8 * cblk + (r_lane & 7)] = acc;
+          rbuf[rg * NCOL + 8 * cblk + (r_lane & 7)] = acc;
         }
         __syncthreads();
         LBDRN_PHASE(17)   // reduce: row loads + exchange
         float g = 0.f;
-        if (tid < 96) {
+        if (tid < 4 * NCOL) {
           const float* rb = reinterpret_cast<const float*>(rbuf) + tid;       // column tid / 4, component tid % 4
           float t[NRG];
 #pragma unroll
-          for (int q = 0; q < NRG; ++q) t[q] = rb[q * 96];
+          for (int q = 0; q < NRG; ++q) t[q] = rb[q * 4 * NCOL];
 #pragma unroll
           for (int w = 1; w < NRG; w <<= 1)
 #pragma unroll
@@ -2102,7 +2549,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             float p = p_old, m = m_old, v = v_old;
             adam_update(p, m, v, g, a.omb1, a.omb2, a.beta2f, a.eps, s_adam[0], s_adam[1]);
             a.params[i] = p; a.m[i] = m; a.v[i] = v;
-            if (TC5) {
+            if (TC5 || TCX) {
               if (a.wimg != nullptr) {
                 uint32_t img = 0u;                                    // halves before layer l's block
                 bool done = false;
@@ -2118,6 +2565,17 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
                     done = true;
                   }
                   img += 2u * (uint32_t)Kp * BC;
+                }
+                if (TCX && !done) {
+                  const int oo = i - net.woff[L];
+                  if (oo >= 0 && oo < C * BC) {                       // W_o image, 16 rows
+                    const int c = oo / BC, u = oo - c * BC;
+                    uint16_t hi, lo;
+                    split_h1(p * kWScale, hi, lo);
+                    const uint32_t e = img + (uint32_t)(img_off(16, c, u) >> 1);
+                    a.wimg[e] = hi;
+                    a.wimg[e + 16u * BC] = lo;
+                  }
                 }
               }
             } else if (H2) {
@@ -2141,7 +2599,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             }
           }
         }
-        if (cb + 24 < per_cta) __syncthreads();      // the exchange buffer is reused by the next column block
+        if (cb + NCOL < per_cta) __syncthreads();    // the exchange buffer is reused by the next column block
       }
     }
     LBDRN_PHASE(6)   // reduce + Adam
@@ -2150,7 +2608,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
     if (tid == 0) gbar_arrive(a.gbar + 1);   // second barrier, arrive; the wait is at the head of the next step
     LBDRN_PHASE(20)  // fence + arrive 2
   }
-  if constexpr (TC5) {
+  if constexpr (TC5 || TCX) {
     tc_fence_before();
     __syncthreads();
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t5_tmem), "r"(512) : "memory");
