@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   // W_o gradient (BC/128 x 16), then one weight-gradient pass at a time (128 units x (K + 8) columns)
   constexpr uint32_t TX_SLOT = (BC / 128) * 32, TX_ZO = 2 * TX_SLOT, TX_DWO = TX_ZO + 16, TX_DWP = TX_DWO + (BC / 128) * 16;
   __shared__ __align__(8) uint64_t s_tx_free[4];                // TCX: "the MMAs that read ring stage s have retired"
+  __shared__ float s_txdb[TCX ? 2 : 1][TCX ? BC : 1];           // TCX: bias-gradient sums of the two pixel halves
   uint32_t tx_fpar = 0u;                                        // bit s: parity of the next wait on s_tx_free[s]
   __shared__ __align__(8) uint64_t s_t5_mbar;
   __shared__ uint32_t s_t5_tmem;
@@ -1896,11 +1897,19 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             dz[i] = (acc[i] * sc) * Gl[(16 * ph + i) * BC + un];
             mx = fmaxf(mx, fabsf(dz[i]));
           }
+          // db_l[u] = sum over the chunk's pixels of dz_l: this thread's 16 pixels in a fixed order, the two halves below
+          s_txdb[ph][un] = (((dz[0] + dz[1]) + (dz[2] + dz[3])) + ((dz[4] + dz[5]) + (dz[6] + dz[7]))) +
+                           (((dz[8] + dz[9]) + (dz[10] + dz[11])) + ((dz[12] + dz[13]) + (dz[14] + dz[15])));
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
           if (lane == 0) atomicMax(&s_dzmax[l], __float_as_uint(mx));
           tc_fence_before();
           __syncthreads();                                               // every act' of the layer has been read: overwrite
+          if (tid < BC) {
+            const float dbv = s_txdb[0][tid] + s_txdb[1][tid];
+            float* dd = mypart + net.boff[l] + tid;
+            if (first) *dd = dbv; else atomicAdd(dd, dbv);
+          }
           LBDRN_PHASE(8)    // bwd: dh * act' + chunk maximum
           float S, inv;
           dz_scale(s_dzmax[l], S, inv);
@@ -1921,74 +1930,56 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             stream_gemm(BC >> 4, tx_wimg(l), (uint32_t)BC * BC * 2u, true, tx_dz(l), tx_dzbytes, (uint32_t)((l - 1) & 1) * TX_SLOT);
           inv_next = inv;
         }
-        // ---- weight gradients: per layer and block of 128 units one pass [dW_l | db_l]^T-free form: D[unit][k] = dz_l^T . [in_l | 1]
-        // (both images read MN-major, contraction over the 32 pixels), accumulated in TMEM columns TX_DWP.., read out with the
-        // 16-lane shape so that a warp store covers 8 rows x 32 contiguous bytes -------------------------------------------------
+        // ---- weight gradients: per layer and block of 128 INPUT features one pass D[k][unit] = in_l^T . dz_l (both images read
+        // MN-major, contraction over the chunk's 32 pixels, N = all BC units) into TMEM columns TX_DWP..; rows beyond the layer's
+        // K multiply whatever follows the image and are never read.  Thread <-> input feature k (the accumulator row), so a warp
+        // store writes 32 consecutive k of one unit's gradient row: 128 contiguous bytes (the [unit][k] orientation wrote 8 rows
+        // x 32 bytes per instruction: 9k cycles per pass, bound by L1 wavefronts) ---------------------------------------------
         {
           const int g = lane >> 2, t = lane & 3;
           for (int l = L - 1; l >= 0; --l) {
-            // N of an M = 128 instruction is a multiple of 16 and at most 256: K + 8 columns are rounded up (the extra columns
-            // multiply whatever follows the constant block and are never read) or, beyond 256, split into 256 + 16
-            const int Kin = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, ncol = Kp + 8;
-            const int n1 = ncol <= 256 ? (ncol + 15) & ~15 : 256, n2 = ncol <= 256 ? 0 : (ncol - 256 + 15) & ~15;
+            const int Kin = l == 0 ? net.dim_in : BC, Kp = l == 0 ? KP0 : BC, nblk = (Kp + 127) >> 7;
             const uint32_t in_img = l == 0 ? tx_x : tx_h(l - 1), in_half = l == 0 ? tx_xbytes : tx_hbytes;
             const float inv = s_t5_inv[l];
             float* dst = mypart + net.woff[l];
-            const bool pair_ok = (Kin & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
-            for (int b = 0; b < NB128; ++b) {
+            for (int b = 0; b < nblk; ++b) {
               if (warp == 0) {
                 tc_fence_after();
                 if (elect_one()) {
-                  const uint32_t idw1 = umma_idesc_f16_major(128, n1, 1, 1), idw2 = umma_idesc_f16_major(128, n2 ? n2 : 16, 1, 1);
-                  for (int ks = 0; ks < (NPIX >> 4); ++ks) {
-                    const uint64_t a_hi = umma_desc(tx_dz(l) + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u);
-                    const uint64_t a_lo = umma_desc(tx_dz(l) + tx_dzbytes + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u);
-                    mma3x(TX_DWP, a_hi, a_lo, img_desc(in_img, NPIX, 1, ks), img_desc(in_img + in_half, NPIX, 1, ks), idw1, ks > 0);
-                    if (n2)     // columns 256 ..: 32 column groups further into the images
-                      mma3x(TX_DWP + 256u, a_hi, a_lo, img_desc(in_img + 32u * NPIX * 16u, NPIX, 1, ks),
-                            img_desc(in_img + in_half + 32u * NPIX * 16u, NPIX, 1, ks), idw2, ks > 0);
-                  }
+                  const uint32_t idw = umma_idesc_f16_major(128, BC, 1, 1);
+                  for (int ks = 0; ks < (NPIX >> 4); ++ks)
+                    mma3x(TX_DWP, umma_desc(in_img + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u),
+                          umma_desc(in_img + in_half + (uint32_t)b * (16u * NPIX * 16u) + (uint32_t)ks * 256u, 128u, NPIX * 16u),
+                          img_desc(tx_dz(l), NPIX, 1, ks), img_desc(tx_dz(l) + tx_dzbytes, NPIX, 1, ks), idw, ks > 0);
                   umma_commit(mbar);
                 }
                 __syncwarp();
               }
               tx_wait();
-              // warp (sp, qd): units 128 b + 32 sp + 16 h + g (+8), column tiles tt = qd, qd + 4, ... (the 16-lane load shape: a
-              // warp store covers 8 rows x 32 contiguous bytes = 8 full sectors).  A later chunk of the same step ADDS to what this
-              // thread stored for the first one with reductions that return nothing (red.global.add.v2.f32; the same thread owns
-              // the address in every chunk, so the additions happen in program order and the sum stays deterministic).
-              // Measured (cycles for the passes of both chunks of a step): this 74k; row-per-thread loads with 16-byte stores /
-              // reductions 85k (a warp instruction then touches 32 lines); loading the first chunk's values ahead of the
-              // accumulator loads, adding and storing 125k.
-              const int ntile = ncol >> 3;
-              for (int h = 0; h < 2; ++h) {
-                for (int tt0 = qd; tt0 < ntile; tt0 += 16) {
-                  uint32_t r[4][4];
+              // warp (sp, qd): k = 128 b + 32 sp + lane, units 64 qd .. + 63.  A later chunk of the same step ADDS to what this
+              // thread stored for the first one with reductions that return nothing (the same thread owns the address in
+              // every chunk, so the additions happen in program order and the sum stays deterministic)
+              const int k = 128 * b + 32 * sp + lane;
+              float* dk = dst + k;
+#pragma unroll 1
+              for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16_issue(tm_lane + TX_DWP + 64u * qd + c0, r0);
+                tmem_ld16_issue(tm_lane + TX_DWP + 64u * qd + c0 + 16u, r1);
+                tmem_ld16_wait(r0);
+                tmem_ld16_wait(r1);
+                if (k < Kin) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (tt0 + 4 * j < ntile) tmem_ld16x256_x1(tm_lane + ((uint32_t)(16 * h) << 16) + TX_DWP + 8u * (tt0 + 4 * j), r[j]);
+                  for (int j = 0; j < 16; ++j) {
+                    float* d1 = dk + (size_t)(64 * qd + c0 + j) * Kin;
+                    const float v = __uint_as_float(r0[j]) * inv;
+                    if (first) *d1 = v; else atomicAdd(d1, v);
+                  }
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) tmem_ld_wait4(r[j]);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const int tt = tt0 + 4 * j, q = 8 * tt + 2 * t;
-                    if (tt >= ntile) continue;
-#pragma unroll
-                    for (int e2 = 0; e2 < 2; ++e2) {
-                      const int u = 128 * b + 32 * sp + 16 * h + g + 8 * e2;
-                      const float v0 = __uint_as_float(r[j][2 * e2]) * inv, v1 = __uint_as_float(r[j][2 * e2 + 1]) * inv;
-                      if (q == Kp) {                                     // the constant block's column: bias gradient
-                        float* dd = mypart + net.boff[l] + u;
-                        if (first) *dd = v0; else atomicAdd(dd, v0);
-                      } else if (pair_ok && q + 1 < Kin) {
-                        float* d2 = dst + (size_t)u * Kin + q;
-                        if (first) *reinterpret_cast<float2*>(d2) = make_float2(v0, v1);
-                        else asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d2), "f"(v0), "f"(v1) : "memory");
-                      } else {
-                        if (q < Kin) { float* d1 = dst + (size_t)u * Kin + q; if (first) *d1 = v0; else atomicAdd(d1, v0); }
-                        if (q + 1 < Kin) { float* d1 = dst + (size_t)u * Kin + q + 1; if (first) *d1 = v1; else atomicAdd(d1, v1); }
-                      }
-                    }
+                  for (int j = 0; j < 16; ++j) {
+                    float* d1 = dk + (size_t)(64 * qd + c0 + 16 + j) * Kin;
+                    const float v = __uint_as_float(r1[j]) * inv;
+                    if (first) *d1 = v; else atomicAdd(d1, v);
                   }
                 }
               }
