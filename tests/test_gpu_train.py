@@ -446,3 +446,35 @@ def test_tcgen05_m64_images_serve_forward_and_backward_views():
             rw = raw.cpu().numpy()
             lanes = [int(np.argmin(np.abs(rw - ref[i][None, :]).sum(1))) for i in (0, 1, 8, 15, 16, 17, 32, 48, 63)]
             raise AssertionError((N, Kc, a_mn, b_mn, float(np.abs(got - ref).max()), "raw lanes of rows 0,1,8,15,16,17,32,48,63:", lanes))
+
+
+@pytest.mark.parametrize("variant", ["default", "tf32"])
+def test_bc256_two_chunks_per_cta_follow_the_oracle(variant, monkeypatch):
+    """BASELINE config 3 (D=3 bc256 nl2) with bs=8192 on a 4x100x93 scene: 256 chunks of 32 pixels on at most 148 CTAs, so
+    most CTAs take TWO chunks of a step and add the second chunk's gradients to the first's (reductions without a return
+    value in the streamed tcgen05 kernel, read-modify-write in the 3xTF32 kernel) -- per-step losses, per-epoch MSE (wide
+    tensor-core evaluation with low-order weight operands) and best epoch against the oracle's loop on the same seed; the
+    run repeated must give identical bits."""
+    from synth_scene import make_scene
+    if variant == "tf32":
+        monkeypatch.setenv("LBDRN_TRAIN_TF32", "1")
+    K, D, bc, nl, bs, epochs = 5, 3, 256, 2, 8192, 2
+    img = make_scene(4, 100, 93, bits=12, seed=11)
+    msb, lsb = O.split_msb_lsb(img, K)
+    torch.manual_seed(77)
+    ref = O.train(msb, lsb, D, bc, nl, 1e-3, bs, epochs)
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(77)
+        model = LBDRNModel(4 * (2 * D + 1) ** 2, bc, 4, nl)
+        scene = F.DeviceScene.from_image(img, K)
+        tr = F.FusedTrainer(model, scene, D, 1e-3, bs, epochs, flags=F.Flags())
+        runs.append(tr.run())
+        tr.close()
+    res = runs[0]
+    got, want = np.array(res["losses"]), np.array(ref["losses"])
+    assert got.shape == want.shape == (epochs * 2,)
+    assert np.max(np.abs(got - want) / want) < 2e-4, (got, want)
+    assert np.allclose(res["val_mse"], ref["mses"], rtol=2e-4)
+    assert res["best_epoch"] == ref["best_epoch"]
+    assert runs[0]["losses"] == runs[1]["losses"] and torch.equal(runs[0]["params"], runs[1]["params"])
