@@ -543,6 +543,20 @@ def run_ours(args):
                 other.append({"config": "configs[2] ENCODE: D=3 bc256 nl2, bs 8192, 2 epochs timed (incl. per-epoch evaluation)",
                               "s_per_2_epochs": s3, "s_per_scene_10_epochs_extrapolated": s3 * 5,
                               "us_per_step_incl_eval": s3 / len(r3["losses"]) * 1e6, "final_val_mse": r3["val_mse"][-1]})
+                # config 4 encode (README.md:57: USE_COORDINATES + EMBEDDING, USE_COLORS off: dim_in 50), two epochs timed
+                torch.manual_seed(19920517)
+                fl4 = F.Flags(use_coordinates=True, embedding=True, use_colors=False)
+                tr4 = F.FusedTrainer(LBDRNModel(fl4.dim_in(C_, D_), BC, C_, NL), scene, D_, 1e-3, 8192, 2, flags=fl4, sampler="device")
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r4 = tr4.run()
+                torch.cuda.synchronize()
+                s4 = time.perf_counter() - t0
+                tr4.close()
+                other.append({"config": "configs[3] ENCODE: USE_COORDINATES+EMBEDDING, USE_COLORS off (dim_in 50), bc64 nl2, bs 8192, "
+                                        "2 epochs timed (incl. per-epoch evaluation)",
+                              "s_per_2_epochs": s4, "s_per_scene_10_epochs_extrapolated": s4 * 5,
+                              "us_per_step_incl_eval": s4 / len(r4["losses"]) * 1e6, "final_val_mse": r4["val_mse"][-1]})
 
         # configs[4]: 8-band 16-bit 16384 x 16384 GF-6-shaped scene, decode sharded as row stripes over the N ranks (strong
         # scaling: the scene is fixed, every rank takes 16384/N rows + D-row halos), and one configs[1] scene split the same way

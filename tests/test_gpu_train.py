@@ -478,3 +478,38 @@ def test_bc256_two_chunks_per_cta_follow_the_oracle(variant, monkeypatch):
     assert np.allclose(res["val_mse"], ref["mses"], rtol=2e-4)
     assert res["best_epoch"] == ref["best_epoch"]
     assert runs[0]["losses"] == runs[1]["losses"] and torch.equal(runs[0]["params"], runs[1]["params"])
+
+
+@pytest.mark.parametrize("C,D,bc,bits", [(8, 2, 256, 12), (4, 2, 256, 12), (3, 3, 256, 12), (8, 2, 64, 12), (2, 1, 64, 12)])
+def test_gradients_match_autograd_on_other_shapes(C, D, bc, bits):
+    """lbdrn_train_grad against torch autograd on shapes the fixtures do not cover: 8 bands at bc 256 (streamed tcgen05 kernel
+    with the 8-band output layer), D = 2 at bc 256, 3 bands, 8 bands at bc 64 (warp-level kernel: the resident tcgen05 images
+    do not fit), 2 bands / D = 1 (resident tcgen05 kernel with a 32-wide first layer)."""
+    from synth_scene import make_scene
+    img = make_scene(C, 72, 80, bits=bits, seed=C + D + bc)
+    K = 5
+    scene = F.DeviceScene.from_image(img, K)
+    torch.manual_seed(C * 100 + D)
+    dim_in = C * (2 * D + 1) ** 2
+    model = LBDRNModel(dim_in, bc, C, 2)
+    lib = cabi.load()
+    tr = F.FusedTrainer(model, scene, D, 1e-3, 512, 1, flags=F.Flags())
+    tr.begin()
+    N = 72 * 80
+    msb, lsb = O.split_msb_lsb(img, K)
+    X = torch.from_numpy(O.features(msb, D, O.Flags()))
+    T = torch.from_numpy(O.labels(lsb))
+    for nb in (512, 77):
+        idx = torch.randperm(N)[:nb]
+        g = torch.zeros(model.flat_params().numel() + 1, device="cuda")
+        cabi.check(lib.lbdrn_train_grad(tr.handle, cabi.ptr(scene.msb), cabi.ptr(scene.lsb), cabi.ptr(tr.tab),
+                                        cabi.ptr(idx.cuda()), nb, nb, cabi.ptr(g), cabi.stream_ptr()))
+        params = [p.clone().requires_grad_(True) for p in model.state_dict().values()]
+        loss = torch.nn.functional.mse_loss(O.forward(params, X[idx]), T[idx])
+        loss.backward()
+        ref = torch.cat([p.grad.reshape(-1) for p in params])
+        got = g.cpu()
+        assert got[-1].item() / (nb * C) == pytest.approx(loss.item(), rel=2e-5)
+        scale = ref.abs().max().item()
+        assert (got[:-1] - ref).abs().max().item() < 2e-5 * scale + 1e-9, (nb, (got[:-1] - ref).abs().max().item(), scale)
+    tr.close()
