@@ -351,7 +351,7 @@ def run_ours(args):
     base_host = scene.msb.cpu().pin_memory()
     outs_host = [torch.empty((C_, SIDE, SIDE), dtype=torch.uint16).pin_memory() for _ in range(2)]
     params_host = params.cpu()
-    e2e_steps = max(4, min(args.steps, 8))
+    e2e_steps = max(8, min(2 * args.steps, 32))     # a stream of scenes: the pipeline's fill / drain (about one scene) is amortised
     if world == 1:
         streamer = F.StreamedDecoder(C_, SIDE, SIDE, base_host.dtype, K_, D_, BC, NL, params_host, flags=fl)
         submit = lambda i: streamer.submit(base_host, outs_host[i % 2])
