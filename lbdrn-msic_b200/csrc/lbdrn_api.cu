@@ -349,12 +349,10 @@ int32_t lbdrn_decode(const LbdrnDesc* d, const void* msb_dev, const float* param
     int fast = d->path == LBDRN_PATH_TENSOR_FASTSIN2 ? 2 : (d->path == LBDRN_PATH_TENSOR_FASTSIN ? 1 : 0);
     if (d->path == LBDRN_PATH_AUTO) fast = n.K <= kAutoMufuMaxK ? 2 : (n.K <= 8 ? 1 : 0);
     if (tcw_ok) {
-      // bc 128/256: the wide kernel decodes iff the weights are fp16-exact after scaling; the fp32 kernel queued behind
-      // it reads the same device flag and exits at once in that case (and does the work otherwise)
+      // bc 128/256: two sibling launches of the wide kernel -- fp16-exact weights, or hi + lo weight operands -- and the
+      // exactness flag decides ON THE DEVICE which of them decodes the scene (the other exits at once)
       const int* exact_flag = nullptr;
-      rc = tcw_decode(n, msb_dev, params_dev, out_dev, fast != 0, &exact_flag, (cudaStream_t)stream);
-      if (rc) return rc;
-      return run_infer<MODE_DECODE>(d, msb_dev, nullptr, params_dev, coord_tab_dev, out_dev, nullptr, stream, exact_flag);
+      return tcw_decode(n, msb_dev, params_dev, out_dev, fast != 0, &exact_flag, (cudaStream_t)stream);
     }
     return tc_decode(n, msb_dev, params_dev, coord_tab_dev, out_dev, fast, (cudaStream_t)stream);
   }

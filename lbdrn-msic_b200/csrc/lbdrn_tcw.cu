@@ -20,8 +20,10 @@
 //   * the output layer (bc x C) is one more streamed layer with N padded to 16, so every epilogue is the same code
 //     (sine -> hi/lo split -> operand chunk); the last one reads C accumulator columns: sigmoid -> round -> (m<<K)+r.
 //   * TMEM: two accumulators of bc columns, ping-pong by layer parity (512 columns at bc 256).
-// Weights that are not fp16-exact after scaling (-prec 32 streams): the kernel exits at once and the fp32 kernel
-// launched behind it (skip_flag = !exact) does the work -- decided on the device, no host sync.
+// Weights that are not fp16-exact after scaling (-prec 32 streams; the fp32 weights evaluated during training): MODE 2 / MODE 1
+// of the same kernel take the low-order weight operand W 2^s - hi in every product (layer 0's lo image and the interleaved
+// hi | lo chunks of the streamed layers go through the same B ring).  lbdrn_decode queues the exact-weights launch and its
+// MODE 2 sibling; the exactness flag decides on the device which of them decodes (the other exits at once), no host sync.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -335,8 +337,13 @@ __device__ __forceinline__ void produce_l0_static(const __half* __restrict__ pme
 // NOT fp16-exact (the fp32 weights of the epoch just trained): every product also takes the low-order weight operand,
 // A.(B_hi + B_lo) -- layer 0: one more MMA per K step against the streamed lo image; layers >= 1: A_hi.B_lo next to
 // A_hi.B_hi + A_lo.B_hi (the lo chunk follows its hi chunk through the same ring).
-template <bool FAST, int BC, int CC, int DD, int APW, int NB, bool SSE = false>
+// MODE 0: decode with fp16-exact weights (exits at once otherwise); MODE 1: squared error with low-order weight operands
+// (evaluation during training); MODE 2: decode with low-order weight operands (-prec 32 streams; exits at once when the
+// weights ARE exact: the MODE 0 launch queued in front of it has decoded the scene).
+template <bool FAST, int BC, int CC, int DD, int APW, int NB, int MODE = 0>
 __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArgs a) {
+  constexpr bool WLO = MODE != 0, SSE = MODE == 1;
+  if (MODE == 2 && reinterpret_cast<const TcwHeader*>(a.blk)->exact) return;
   constexpr int KS = TCW_KS;
   constexpr int NCH = BC / (16 * KS);                // operand chunks per streamed layer
   constexpr int BSTEP = BC * 32;                     // one K step of a hidden-layer operand (bc rows x 16 K x 2 B)
@@ -368,7 +375,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
   }
   __syncthreads();
   const TcwHeader* H = reinterpret_cast<const TcwHeader*>(sW);
-  if (!SSE && !H->exact) return;                           // the fp32 kernel queued behind this launch decodes the scene
+  if (!WLO && !H->exact) return;                           // the MODE 2 launch queued behind this one decodes the scene
   const int k1 = H->k1, k1pad = H->k1pad, NL = H->nl;
   const int nk16 = k1pad / 16, nch0 = (nk16 + KS - 1) / KS;     // layer 0: K steps, chunks
   const bool overlap = (NL & 1) == 0;
@@ -440,13 +447,13 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
             for (int ks = 0; ks < KS && i * KS + ks < nk16; ++ks)
               umma_f16(tmem, dA + (uint64_t)(slot * (TCW_ASLOT >> 4) + ks * 256),
                        dB0 + (uint64_t)((i * KS + ks) * (BSTEP >> 4)), idesc_h, (i | ks) > 0);
-            if (!SSE) {
+            if (!WLO) {
               umma_commit(a_free_u + slot * 8);
               if (i + 1 == nch0) umma_commit(smem_u32(&s_acc_full[0]));
             }
           }
           __syncwarp();
-          if (SSE) {
+          if (WLO) {
             // the same chunk against the low-order weights, streamed through the B ring
             tcw_wait(b_full_u + sb * 8, bpar, 4, it, a.no_trap);
             tc_fence_after();
@@ -489,13 +496,13 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
                 umma_f16(d_tmem, da + (uint64_t)(ks * 256), db + (uint64_t)(ks * bstep16), idesc, (j | ks) > 0);    // hi half
                 umma_f16(d_tmem, da + (uint64_t)((TCW_AHALF >> 4) + ks * 256), db + (uint64_t)(ks * bstep16), idesc, 1);  // lo
               }
-              if (!SSE) umma_commit(a_free_u + slot * 8);
+              if (!WLO) umma_commit(a_free_u + slot * 8);
               umma_commit(b_free_u + sb * 8);
-              if (!SSE && j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
+              if (!WLO && j + 1 == NCH) umma_commit(outl ? smem_u32(&s_out_full) : smem_u32(&s_acc_full[l & 1]));
             }
             __syncwarp();
             if (++sb == NB) { sb = 0; bpar ^= 1u; }
-            if (SSE) {
+            if (WLO) {
               // A_hi . B_lo: the chunk's low-order weights arrive in the next ring slot
               tcw_wait(b_full_u + sb * 8, bpar, 4, it, a.no_trap);
               tc_fence_after();
@@ -551,17 +558,17 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tcw_decode_kernel(const TcwArg
           put(a.blk + H->off_b0lo + (size_t)i * BSLOT, (uint32_t)(nks * BSTEP));
         }
       };
-      if (SSE && my_tiles > 0) layer0_lo();
+      if (WLO && my_tiles > 0) layer0_lo();
       for (int it = 0; it < my_tiles; ++it) {
         const bool has_next = it + 1 < my_tiles;
         for (int l = 1; l <= NL; ++l) {
           const bool outl = l == NL;
-          if (SSE && outl && overlap && has_next) layer0_lo();
+          if (WLO && outl && overlap && has_next) layer0_lo();
           const uint32_t bytes = (uint32_t)((outl ? TCW_NOUT : BC) * 32 * KS);
-          const int nsub = (SSE ? 2 : 1) * NCH;
+          const int nsub = (WLO ? 2 : 1) * NCH;
           for (int c = 0; c < nsub; ++c) put(a.blk + H->off_b[l] + (size_t)c * bytes, bytes);
         }
-        if (SSE && !overlap && has_next) layer0_lo();
+        if (WLO && !overlap && has_next) layer0_lo();
       }
       if (prof && (tid & 31) == 0) { a.prof[4] = pw; a.prof[5] = plat; a.prof[6] = g; }
     }
@@ -805,19 +812,19 @@ size_t g_wblk_bytes[64] = {0};
 
 using KernW = void (*)(const TcwArgs);
 
-template <bool FAST, int BC, int APW, int NB, bool SSE = false>
+template <bool FAST, int BC, int APW, int NB, int MODE = 0>
 KernW pick_wide(const Net& n) {
-  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3, APW, NB, SSE>;
-  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2, APW, NB, SSE>;
-  return tcw_decode_kernel<FAST, BC, 0, 0, APW, NB, SSE>;
+  if (n.C == 4 && n.D == 3) return tcw_decode_kernel<FAST, BC, 4, 3, APW, NB, MODE>;
+  if (n.C == 4 && n.D == 2) return tcw_decode_kernel<FAST, BC, 4, 2, APW, NB, MODE>;
+  return tcw_decode_kernel<FAST, BC, 0, 0, APW, NB, MODE>;
 }
 
 // ring geometries built: (APW, NB) = (1, 3) [what fits at bc 256 / D 3], (1, 4), (2, 6) [bc 128]
-template <bool FAST, int BC, bool SSE = false>
+template <bool FAST, int BC, int MODE = 0>
 KernW pick_ring(const Net& n, int apw, int nb) {
-  if (apw == 1 && nb == 3) return pick_wide<FAST, BC, 1, 3, SSE>(n);
-  if (apw == 1 && nb == 4) return pick_wide<FAST, BC, 1, 4, SSE>(n);
-  if (apw == 2 && nb == 6) return pick_wide<FAST, BC, 2, 6, SSE>(n);
+  if (apw == 1 && nb == 3) return pick_wide<FAST, BC, 1, 3, MODE>(n);
+  if (apw == 1 && nb == 4) return pick_wide<FAST, BC, 1, 4, MODE>(n);
+  if (apw == 2 && nb == 6) return pick_wide<FAST, BC, 2, 6, MODE>(n);
   return nullptr;
 }
 
@@ -861,20 +868,23 @@ int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
-  TcwHeader h;
+  TcwHeader h, hw;
   tcw_plan(n, h);
+  tcw_plan(n, hw, true);                       // second block: low-order weight operands for streams that are not fp16-exact
+  const size_t off_w = (size_t)align_up(h.total, 256), need = off_w + (size_t)hw.total;
   {
     std::lock_guard<std::mutex> lk(tcw_mu());
-    if (g_wblk_bytes[dev] < (size_t)h.total) {
+    if (g_wblk_bytes[dev] < need) {
       if (g_wblk[dev]) CUDA_TRY(cudaFree(g_wblk[dev]));
       g_wblk[dev] = nullptr; g_wblk_bytes[dev] = 0;
-      CUDA_TRY(cudaMalloc(&g_wblk[dev], (size_t)h.total));
-      g_wblk_bytes[dev] = (size_t)h.total;
+      CUDA_TRY(cudaMalloc(&g_wblk[dev], need));
+      g_wblk_bytes[dev] = need;
     }
   }
   uint8_t* blk = g_wblk[dev];
   tcw_prep_kernel<<<1, 1024, 0, st>>>(n, h, params, blk);
-  ++g_launches;
+  tcw_prep_kernel<<<1, 1024, 0, st>>>(n, hw, params, blk + off_w);
+  g_launches += 2;
   CUDA_TRY(cudaGetLastError());
   TcwArgs a;
   memset(&a, 0, sizeof a);
@@ -932,7 +942,21 @@ int tcw_decode(const Net& n, const void* msb, const float* params, uint16_t* out
     memset(h16, 0, sizeof h16);
     CUDA_TRY(cudaMemcpyToSymbol(g_tcw_dbg, h16, sizeof h16));
   }
-  if (exact_flag_out) *exact_flag_out = reinterpret_cast<const int*>(blk);   // TcwHeader::exact is the first word
+  // weights that are not fp16-exact after scaling (-prec 32 streams): the launch above exited at once; this one multiplies
+  // with hi + lo weight operands (polynomial sine) -- and exits at once in the common, exact case.  Decided on the device.
+  {
+    TcwArgs aw = a;
+    aw.blk = blk + off_w;
+    aw.res_bytes = hw.res_bytes;
+    aw.prof = nullptr;
+    KernW kw = n.bc == 256 ? pick_ring<false, 256, 2>(n, apw, nb) : pick_ring<false, 128, 2>(n, apw, nb);
+    if (!kw) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core decode: ring geometry %dx%d is not built", apw, nb);
+    CUDA_TRY(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kw<<<grid, TCW_THREADS, smem, st>>>(aw);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (exact_flag_out) *exact_flag_out = nullptr;          // nothing is left for an fp32 kernel
   return LBDRN_OK;
 }
 
@@ -942,18 +966,20 @@ int tcw_eval_sse(const Net& n, const void* msb, const void* lsb, const float* pa
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(LBDRN_E_UNSUPPORTED, "device ordinal %d", dev);
-  TcwHeader h;
+  TcwHeader h, hx;
   tcw_plan(n, h, true);
+  tcw_plan(n, hx);
+  const size_t off_w = (size_t)align_up(hx.total, 256), need = off_w + (size_t)h.total;   // same size and placement as tcw_decode
   {
     std::lock_guard<std::mutex> lk(tcw_mu());
-    if (g_wblk_bytes[dev] < (size_t)h.total) {
+    if (g_wblk_bytes[dev] < need) {
       if (g_wblk[dev]) CUDA_TRY(cudaFree(g_wblk[dev]));
       g_wblk[dev] = nullptr; g_wblk_bytes[dev] = 0;
-      CUDA_TRY(cudaMalloc(&g_wblk[dev], (size_t)h.total));
-      g_wblk_bytes[dev] = (size_t)h.total;
+      CUDA_TRY(cudaMalloc(&g_wblk[dev], need));
+      g_wblk_bytes[dev] = need;
     }
   }
-  uint8_t* blk = g_wblk[dev];
+  uint8_t* blk = g_wblk[dev] + off_w;
   Scratch* sc = nullptr;
   int rc = get_scratch(n.P, sc);
   if (rc) return rc;
@@ -971,7 +997,7 @@ int tcw_eval_sse(const Net& n, const void* msb, const void* lsb, const float* pa
   int apw = 0, nb = 0;
   if (!tcw_pick_ring(n, h, apw, nb)) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core evaluation: operand rings do not fit");
   const size_t smem = tcw_smem_bytes(n, h, apw, nb);
-  KernW kern = n.bc == 256 ? pick_ring<false, 256, true>(n, apw, nb) : pick_ring<false, 128, true>(n, apw, nb);
+  KernW kern = n.bc == 256 ? pick_ring<false, 256, 1>(n, apw, nb) : pick_ring<false, 128, 1>(n, apw, nb);
   if (!kern) return fail(LBDRN_E_UNSUPPORTED, "wide tensor-core evaluation: ring geometry %dx%d is not built", apw, nb);
   int sms = 0, max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -118,3 +118,25 @@ def test_wide_tensor_evaluation_matches_the_fp32_kernel(bc, D, shape):
         y = O.forward(params, X).numpy().astype(np.float64)
         ref = float(((y - O.labels(lsb).astype(np.float64)) ** 2).mean())
         assert abs(got[0] - ref) <= 2e-5 * ref, (got[0], ref)
+
+
+@pytest.mark.parametrize("bc,D,shape", [(256, 3, (4, 203, 317)), (128, 2, (4, 150, 131))])
+def test_wide_tensor_decode_of_full_precision_weights(bc, D, shape):
+    """A stream whose weights are NOT fp16-exact after scaling (what `-prec 32` produces; encode.py:129) at bc 128 / 256: the
+    exact-weights launch exits on the device and its sibling with hi + lo weight operands decodes the scene on the tensor
+    cores (no fp32 kernel behind it any more); bar as for every decode test, against the oracle on the same weights."""
+    from synth_scene import make_scene
+    from LBDRNmodel import LBDRNModel
+    C, H, W = shape
+    K = 5
+    img = make_scene(C, H, W, 12, seed=bc + 7 * D)
+    msb, _ = O.split_msb_lsb(img, K)
+    torch.manual_seed(bc + D)
+    model = LBDRNModel(C * (2 * D + 1) ** 2, bc, C, 2)
+    flat = model.flat_params().numpy()                      # full fp32 mantissas
+    lib = cabi.load()
+    before = lib.lbdrn_launch_count()
+    out = F.decode_image(msb, flat, K, D, bc, 2, flags=F.Flags(), path="auto")
+    ref = O.decode_image(msb, O.unflatten_params(flat, C * (2 * D + 1) ** 2, bc, C, 2), K, D)
+    _check(out, ref, f"bc{bc} D{D} full-precision weights")
+    assert lib.lbdrn_launch_count() - before == 4           # two operand preparations + the two sibling launches, nothing else
