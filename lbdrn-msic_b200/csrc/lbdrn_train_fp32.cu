@@ -76,14 +76,15 @@ int plan_t(const Net& n, int batch_size, int sms, int max_smem, TrainPlan& t) {
   // fits: it overrides the MMA = 2 selection above (LBDRN_TRAIN_H2=1 keeps the warp-level kernel for A/B).
   if constexpr (kMma && TM == 4 && BC == 64) {
     const int KP0 = round16(n.dim_in), L = n.nl;
-    const size_t fl = (size_t)t.dimpad * kTrainLDP + (size_t)L * BC * kTrainLDP + (size_t)CP * kTrainLDP +
-                      (size_t)round4(L * BC + n.C * BC + n.C);
+    // (the feature staging buffer shares the bytes of the hidden-output / dz images: it must fit there)
+    const size_t fl = (size_t)L * BC * kTrainLDP + (size_t)CP * kTrainLDP + (size_t)round4(L * BC + n.C * BC + n.C);
+    const bool x_fits = (size_t)t.dimpad * kTrainLDP * 4 <= (size_t)L * 2 * (BC + 8) * kTrainNPIX * 2 + (size_t)L * 2 * BC * kTrainNPIX * 2;
     const size_t wimg = ((size_t)2 * KP0 * BC + (size_t)(L - 1) * 2 * BC * BC) * 2;
     const size_t imgs = wimg + (size_t)2 * (KP0 + 8) * kTrainNPIX * 2 + (size_t)L * 2 * (BC + 8) * kTrainNPIX * 2 +
                         (size_t)L * 2 * BC * kTrainNPIX * 2 + (size_t)2 * 16 * kTrainNPIX * 2;
     const size_t t5 = fl * sizeof(float) + 128 + imgs;
     const int tmem_cols = 2 * BC + 32 + (KP0 + 8) + (L - 1) * (BC + 8);
-    if (mma && getenv("LBDRN_TRAIN_TF32") == nullptr && getenv("LBDRN_TRAIN_H2") == nullptr && tmem_cols <= 512 &&
+    if (mma && getenv("LBDRN_TRAIN_TF32") == nullptr && getenv("LBDRN_TRAIN_H2") == nullptr && tmem_cols <= 512 && x_fits &&
         n.C <= 8 && KP0 + 8 <= 256 && t5 <= (size_t)max_smem && fits((void*)train_fp32_kernel<BC, CP, true, kTT, TM, 3>, t5)) {
       t.wsmem = true; t.smem = t5;
       t.pf_off = 0; t.pf_stride = 0;     // (the optional TMA landing boxes belong to the warp-level kernels)

@@ -598,7 +598,10 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   constexpr int GSZ = H2 ? BC * kLDH : BC * LDP;
   // TCX: the feature staging X shares its 32 KB with the two-stage weight ring (the gather is over before a GEMM starts)
   constexpr int TX_RING = 2 * 16384;
-  const size_t x_floats = TCX ? (size_t)((a.dimpad * LDP * 4 > TX_RING ? a.dimpad * LDP * 4 : TX_RING) / 4) : (size_t)a.dimpad * LDP;
+  // TC5: X lives over the images of the hidden outputs and the dz's (all dead between the end of a chunk and its first
+  // epilogue): no bytes of its own (41 KB at dim_in 150 -- what lets coordinates + colours fit the tcgen05 variant)
+  const size_t x_floats = TCX ? (size_t)((a.dimpad * LDP * 4 > TX_RING ? a.dimpad * LDP * 4 : TX_RING) / 4)
+                              : (TC5 ? (size_t)0 : (size_t)a.dimpad * LDP);
   float* Hbuf = X + x_floats;                                   // [L][BC][LDP]    hidden outputs
   float* Gbuf = Hbuf + (size_t)((TC5 || TCX) ? 0 : (H2 ? 1 : L)) * BC * LDP;   // [L][GSZ]  act' then dz
   float* dZo = Gbuf + (size_t)(TCX ? 0 : L) * GSZ;              // [CP][LDP]       output-layer dz
@@ -629,6 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   const uint32_t t5_dzbytes = (uint32_t)BC * NPIX * 2u;
   auto t5_dz = [&](int l) { return t5_h0 + (uint32_t)L * 2u * t5_hbytes + (uint32_t)l * 2u * t5_dzbytes; };
   const uint32_t t5_dzo = t5_dz(L), t5_dzobytes = 16u * NPIX * 2u;
+  if (TC5) X = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem4) + (t5_h0 - smem_u32(smem4)));
   // fp32 scratch of the output layer, over the (not yet written) dz_0 image: partial sums per column group, then dz_o
   float* const Pp5 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem4) + (t5_dz(0) - smem_u32(smem4)));   // [4][CP][LDP]
   float* const dZo5 = Pp5 + 4 * CP * LDP;                                                                          // [CP][LDP]
@@ -1304,6 +1308,15 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
         const int sp = warp & 3, cg = warp >> 2, g = lane >> 2, t = lane & 3;
         const uint32_t tm_lane = t5_tmem + ((uint32_t)(32 * sp) << 16);
         const uint32_t mbar = smem_u32(&s_t5_mbar);
+        // the feature staging X shares its bytes with the hidden-output / dz images: put back the constant blocks behind the
+        // hidden outputs (1, 0, .., 0 per pixel in hi; zero in lo) that X's rows ran over.  Every reader of X is past the CTA
+        // barrier in front of this block; the first reader of a constant block is a weight-gradient GEMM, several fenced
+        // barriers from here.
+        for (int i = tid; i < 2 * L * NPIX; i += THREADS) {
+          const int l = i / (2 * NPIX), r = i - l * 2 * NPIX, half = r / NPIX, pp = r - half * NPIX;
+          const uint32_t addr = t5_h(l) + (uint32_t)half * t5_hbytes + (uint32_t)BC * NPIX * 2u + 16u * pp;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(addr), "r"(half == 0 ? 0x00003c00u : 0u), "r"(0u) : "memory");
+        }
         auto mma3 = [&](uint32_t d_col, uint32_t a_img, uint32_t a_half, int a_rows, int a_mn, uint32_t b_img, uint32_t b_half,
                         int b_rows, int b_mn, int N, int ksteps) {
           const uint32_t idesc = umma_idesc_f16_major(64, N, a_mn, b_mn);
@@ -1591,15 +1604,21 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             const float inv = s_t5_inv[0];
             float* dst = mypart + net.woff[0];
             const bool pair_ok = (net.dim_in & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int e2 = 0; e2 < 2; ++e2) {
-                const int u = 16 * sp + g + 8 * e2, q = 32 * cg + 8 * j + 2 * t;
-                const float v0 = __uint_as_float(r0[4 * j + 2 * e2]) * inv, v1 = __uint_as_float(r0[4 * j + 2 * e2 + 1]) * inv;
-                if (q == KP0) put_bias(0, u, v0);                  // the constant block's column: bias gradient
-                else put_pair(dst, net.dim_in, pair_ok, u, q, v0, v1);
+            for (int base = 0; base < KP0 + 8; base += 128) {      // first layers wider than 120 inputs: further rounds of 128 columns
+              if (base > 0) {
+                tmem_ld16x256_x4(tm_lane + t5_dwcol(0) + (uint32_t)base + 32u * cg, r0);
+                tmem_ld_wait16(r0);
               }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                  const int u = 16 * sp + g + 8 * e2, q = base + 32 * cg + 8 * j + 2 * t;
+                  const float v0 = __uint_as_float(r0[4 * j + 2 * e2]) * inv, v1 = __uint_as_float(r0[4 * j + 2 * e2 + 1]) * inv;
+                  if (q == KP0) put_bias(0, u, v0);                // the constant block's column: bias gradient
+                  else put_pair(dst, net.dim_in, pair_ok, u, q, v0, v1);
+                }
+            }
           }
           if (L > 1) {
             const float inv = s_t5_inv[1];
