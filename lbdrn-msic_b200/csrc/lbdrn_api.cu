@@ -500,11 +500,11 @@ int32_t lbdrn_train_steps(LbdrnTrain* t, const void* msb_dev, const void* lsb_de
     a.adam_tab = dst;
   }
   {
-    // Band-interleaved copies of the planes (uint8, <= 4 bands, 5x5 colour windows: the configurations the kernel's
-    // neighbourhood prefetch is specialised for), rebuilt before every launch -- the caller owns the planes and may have
-    // changed them; 2 x (C + 4) bytes per pixel of HBM traffic, ~0.3 ms at 8192^2 against ~200 ms per epoch.
+    // Band-interleaved copies of the planes (uint8, <= 4 bands, colour windows of 3, 5 or 7: the neighbourhood prefetch
+    // of the 5x5 kernels and the chunk gather of the others read one word per pixel instead of one byte per band),
+    // rebuilt before every launch -- the caller owns the planes and may have changed them; 2 x (C + 4) bytes per pixel of HBM traffic, ~0.3 ms at 8192^2 against ~200 ms per epoch.
     const Net& n = t->net;
-    const bool eligible = !n.msb_u16 && !n.lsb_u16 && n.C <= 4 && n.n == 5 && n.nco == 0 && n.ncol != 0 &&
+    const bool eligible = !n.msb_u16 && !n.lsb_u16 && n.C <= 4 && (n.n == 3 || n.n == 5 || n.n == 7) && n.nco == 0 && n.ncol != 0 &&
                           getenv("LBDRN_TRAIN_CHW") == nullptr && !t->plan.pf_stride;
     const size_t npix = (size_t)n.buf_rows * n.W;
     if (eligible && !t->i_failed && t->i_npix < npix) {

@@ -173,11 +173,11 @@ int train_fp32_launch(const TrainPlan& plan, TrainArgs& a, cudaStream_t st) {
     long long h[24];
     CUDA_TRY(cudaMemcpyAsync(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    static const char* names[22] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "wait1", "reduce+adam", "wait2",
+    static const char* names[24] = {"reload", "gather", "fwd_barriers", "out+loss", "bwd_rest", "wait1", "reduce+adam", "wait2",
                                     "bwd_out", "bwd_dh0", "bwd_dW0", "bwd_dh1", "bwd_dW1", "pf_commit", "pf_issue", "fwd_gemm",
-                                    "fwd_act", "red_batches", "red_tail", "red_sync", "arrive2", "head"};
+                                    "fwd_act", "red_batches", "red_tail", "red_sync", "arrive2", "head", "g_coords", "g_rows"};
     fprintf(stderr, "[lbdrn] train phases (cycles/step on CTA 0, %d steps, grid %d x %d thr):", a.n_steps, plan.grid, kTT);
-    for (int i = 0; i < 22; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
+    for (int i = 0; i < 24; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] / (a.n_steps > 0 ? a.n_steps : 1));
     fprintf(stderr, "\n");
   }
   return LBDRN_OK;

@@ -12,6 +12,7 @@
 // scene): the budget is the two grid barriers, the L2 round trips of the reduction and of the weight reload, not flops.
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "lbdrn_common.cuh"
 #include "lbdrn_umma.cuh"
@@ -503,6 +504,48 @@ __device__ __forceinline__ void gather_row(const void* msb, int u16, size_t rowo
   for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? __fdiv_rn((float)raw[dx], maxv) - ctr : 0.f;
 }
 
+// The same row read as aligned 8-byte words (two for 8-bit planes, three for 16-bit ones) and shifted into place.
+// Rows that touch the left/right border (reflection) or the ends of the buffer take the element-wise path.
+template <int N_, int kTrainLDP>
+__device__ __forceinline__ void gather_row_wide(const void* msb, size_t total_bytes, int u16, size_t rowoff, int gx,
+                                                const Net& net, float maxv, const float* quot, float ctr, bool ok,
+                                                float* d) {
+  constexpr int D_ = N_ / 2;
+  static_assert(N_ <= 8, "a row must fit the shifted words");
+  const uintptr_t base = (uintptr_t)msb;
+  const uintptr_t p = base + ((rowoff + (size_t)(gx - D_)) << u16);
+  const uintptr_t a0 = p & ~(uintptr_t)7;
+  const int sh = (int)(p & 7) * 8;
+  const bool fast = gx >= D_ && gx + D_ < net.W && a0 >= base && a0 + (u16 ? 24 : 16) <= base + total_bytes;
+  uint32_t raw[N_];
+  if (fast) {
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a0);
+    const unsigned long long q0 = __ldg(q), q1 = __ldg(q + 1);
+    const unsigned long long r0 = sh ? (q0 >> sh) | (q1 << (64 - sh)) : q0;
+    if (!u16) {
+#pragma unroll
+      for (int dx = 0; dx < N_; ++dx) raw[dx] = (uint32_t)(r0 >> (8 * dx)) & 0xffu;
+    } else {
+      const unsigned long long q2 = __ldg(q + 2);
+      const unsigned long long r1 = sh ? (q1 >> sh) | (q2 << (64 - sh)) : q1;
+#pragma unroll
+      for (int dx = 0; dx < N_; ++dx)
+        raw[dx] = (uint32_t)((dx < 4 ? r0 : r1) >> (16 * (dx & 3))) & 0xffffu;
+    }
+  } else {
+#pragma unroll
+    for (int dx = 0; dx < N_; ++dx) raw[dx] = load_msb_int(msb, u16, rowoff + reflect_clamp(gx + dx - D_, net.W));
+  }
+  // 8-bit planes: the quotient comes from the 256-entry table (49 divisions per pixel and band were the gather's cost)
+  if (!u16) {
+#pragma unroll
+    for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? quot[raw[dx]] - ctr : 0.f;
+  } else {
+#pragma unroll
+    for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * kTrainLDP] = ok ? __fdiv_rn((float)raw[dx], maxv) - ctr : 0.f;
+  }
+}
+
 // out[r][q] (+)= sum_p G[r][p] * A[q][p] for r < BC, q < Kin (dst = natural [BC][Kin] gradient block).
 // Thread (trow = tid%16, tcol = tid/16) owns rows trow + 16x (x<4) and columns tcol + CT*y (y<4, CT = THREADS/16):
 // a 4x4 register tile with 16 independent FFMA chains; per 4-pixel step 4 + (#valid y) LDS.128 feed 16*(#valid y)*4/4 FFMAs.
@@ -767,6 +810,8 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
                           !net.msb_u16 && !net.lsb_u16;
   uint32_t pf_w[3][2], pf_aux = 0u;          // [row][word]; aux: label code (even thread) or centre byte (odd thread)
   bool pf_have = false;
+  long long gp_idx = 0, gp_pos = -1;                 // generic gather: permutation entry loaded one chunk ahead
+  __shared__ uint32_t s_ctrw[NPIX];                  // generic gather, interleaved planes: the pixel's own word (centres)
   int pf_state = 0;                          // 1: aligned words in registers, 2: window bytes already extracted (border
                                              // pixel: reflected per-byte loads), 3: padding lane (beyond the batch)
   int pf_gy = 0, pf_gx = 0;                  // pixel the registers belong to
@@ -786,7 +831,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   bool pf_none = true;                       // this CTA has no chunk in the next step (uniform)
   __shared__ int s_ny[NPIX], s_nx[NPIX];     // next step's pixel coordinates (one division per pixel, not per thread)
   __shared__ float s_quot[256];
-  if (pf_enabled)
+  if (!net.msb_u16)                          // value / max for every 8-bit value: one correctly rounded division each, once
     for (int i = tid; i < 256; i += THREADS) s_quot[i] = __fdiv_rn((float)i, maxv);
   const size_t pf_total = (size_t)C * net.buf_rows * net.W;     // bytes in the MSB buffer
   const bool idx32 = (long long)net.H * net.W < (1ll << 31);
@@ -918,6 +963,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
   // loads -- 11 requests per pixel (5 rows x 2 + labels) + 4 centre words instead of ~48, and a third of the DRAM sectors.
   // Thread share = tid / NPIX: shares 0-4 own window row dy = share (8 words + the centre word), share 5 the labels.
   const bool il = pf_enabled && a.imsb != nullptr && !tma_on;
+  const bool gil = a.imsb != nullptr && net.ncol != 0 && net.nco == 0 && (n == 3 || n == 5 || n == 7);   // generic gather from the interleaved copies
   // registers shared with the CHW variant: pf_w[3][2] + il_w6, il_w7 = the aligned 32 bytes holding the row (border pixel: the
   // 5 words, packed); pf_aux = centre pixel (rows != D) or label word (share 5)
   uint32_t il_w6 = 0u, il_w7 = 0u;
@@ -1219,13 +1265,74 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
       const bool staged = early && ch == (int)blockIdx.x;            // committed before the barrier wait above
       if (!staged) {
       if (tid < NPIX) {
-        long long idx = tid < nvalid ? a.perm[b0 + (long long)ch * NPIX + tid] : 0;
-        int y = (int)(idx / net.W);
+        const long long pos = b0 + (long long)ch * NPIX + tid;
+        long long idx = 0;
+        if (tid < nvalid) idx = gp_pos == pos ? gp_idx : a.perm[pos];
+        int y, x;
+        if (idx32) { y = (int)((unsigned)idx / (unsigned)net.W); x = (int)((unsigned)idx - (unsigned)y * (unsigned)net.W); }
+        else { y = (int)(idx / net.W); x = (int)(idx - (long long)y * net.W); }
         s_py[tid] = y;
-        s_px[tid] = (int)(idx - (long long)y * net.W);
+        s_px[tid] = x;
         s_valid[tid] = tid < nvalid;
+        // the entry this thread needs next (this CTA's next chunk, or its first chunk of the next batch): the
+        // load has a whole chunk of arithmetic to land under
+        const bool more = ch + (int)gridDim.x < n_chunks;
+        gp_pos = more ? pos + (long long)gridDim.x * NPIX
+                      : (a.mode == TRAIN_FUSED ? b0 + a.bs + (long long)blockIdx.x * NPIX + tid : -1);
+        if (gp_pos >= 0 && gp_pos < a.n_perm && (more || gp_pos < b0 + 2ll * a.bs)) gp_idx = a.perm[gp_pos];
+        else gp_pos = -1;
+        if (gil) {
+          // interleaved planes: the pixel's own word holds the centre of every band, its LSB word every label
+          const size_t off = (size_t)(y - net.buf_row0) * net.W + x;
+          const uint32_t lw = a.ilsb[off];
+          s_ctrw[tid] = a.imsb[off];
+          for (int c = 0; c < C; ++c) Tl[c * LDP + tid] = __fdiv_rn((float)((lw >> (8 * c)) & 255u), net.qmax);
+        }
       }
       __syncthreads();
+      LBDRN_PHASE(22)  // pixel coordinates of the chunk
+      if (gil) {
+        // thread = (pixel, window row): the row of ALL bands is n consecutive words = two or three aligned 16-byte loads
+        // (the gather is bound by L1 wavefronts: one request per lane and row instead of one per lane, band and row)
+        auto gather_il = [&](auto nc) {
+          constexpr int N_ = decltype(nc)::value;
+          constexpr int D_ = N_ / 2;
+          for (int it = tid; it < NPIX * N_; it += THREADS) {
+            const int pp = it & (NPIX - 1), dy = it / NPIX;
+            const int gy = s_py[pp], gx = s_px[pp];
+            const bool ok = s_valid[pp] != 0;
+            const uint32_t* row = a.imsb + (size_t)(reflect_clamp(gy + dy - D_, net.H) - net.buf_row0) * net.W;
+            uint32_t v[N_];
+            if (gx >= D_ && gx + D_ < net.W) {
+              const uint32_t* p0 = row + (gx - D_);
+              const int o = (int)((reinterpret_cast<uintptr_t>(p0) >> 2) & 3);
+              const uint4* q = reinterpret_cast<const uint4*>(p0 - o);
+              const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+              uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
+              if (o + N_ > 8) q2 = __ldg(q + 2);
+              const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+              for (int dx = 0; dx < N_; ++dx)
+                v[dx] = o == 0 ? w[dx] : o == 1 ? w[dx + 1] : o == 2 ? w[dx + 2] : w[dx + 3];
+            } else {
+#pragma unroll
+              for (int dx = 0; dx < N_; ++dx) v[dx] = row[reflect_clamp(gx + dx - D_, net.W)];
+            }
+            const uint32_t cw = net.relative ? s_ctrw[pp] : 0u;
+            for (int c = 0; c < C; ++c) {
+              const float ctr = net.relative ? s_quot[(cw >> (8 * c)) & 255u] : 0.f;
+              float* d = X + pp + (size_t)(net.nco + (c * N_ + dy) * N_) * LDP;
+#pragma unroll
+              for (int dx = 0; dx < N_; ++dx) d[(size_t)dx * LDP] = ok ? s_quot[(v[dx] >> (8 * c)) & 255u] - ctr : 0.f;
+            }
+          }
+        };
+        switch (n) {
+          case 3: gather_il(std::integral_constant<int, 3>{}); break;
+          case 5: gather_il(std::integral_constant<int, 5>{}); break;
+          default: gather_il(std::integral_constant<int, 7>{}); break;
+        }
+      } else
       {
         // thread = (pixel, share); a share takes (band, window-row) items straight from the resident planes
         constexpr int NSH = THREADS / NPIX;
@@ -1242,6 +1349,42 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           }
         }
         const int n_items = net.ncol ? C * n : C;
+        // usual window sizes: a thread takes a band (or half of its rows when there are shares to spare) and reads
+        // each window row as two or three aligned 8-byte words: the gather is bound by L1 wavefronts (every lane of
+        // a load hits another sector), so fewer, wider requests are what shortens it
+        auto gather_n = [&](auto nc) {
+          constexpr int N_ = decltype(nc)::value;
+          constexpr int D_ = N_ / 2;
+          const int RG = NSH >= 2 * C ? 2 : 1;
+          const int rows_per = (N_ + RG - 1) / RG;
+          for (int it = share; it < C * RG; it += NSH) {
+            const int c = it / RG, g = it - c * RG;
+            const size_t plane = (size_t)c * net.buf_rows;
+            const size_t off = (plane + (gy - net.buf_row0)) * net.W + gx;
+            if (g == 0) {
+              const uint32_t code = net.lsb_u16 ? (uint32_t)((const uint16_t*)a.lsb)[off] : (uint32_t)((const uint8_t*)a.lsb)[off];
+              Tl[c * LDP + pp] = __fdiv_rn((float)code, net.qmax);          // label = LSB/(2^K-1)
+            }
+            float ctr = 0.f;
+            if (net.relative) ctr = net.msb_u16 ? load_msb_norm(a.msb, 1, off, maxv) : s_quot[((const uint8_t*)a.msb)[off]];
+            const int dy0 = g * rows_per, dy1 = min(N_, dy0 + rows_per);
+#pragma unroll
+            for (int dy = 0; dy < N_; ++dy) {
+              if (dy < dy0 || dy >= dy1) continue;
+              const size_t rowoff = (plane + (reflect_clamp(gy + dy - D_, net.H) - net.buf_row0)) * net.W;
+              gather_row_wide<N_, LDP>(a.msb, pf_total << net.msb_u16, net.msb_u16, rowoff, gx, net, maxv, s_quot, ctr, ok,
+                                       dst + (size_t)(net.nco + (c * N_ + dy) * N_) * LDP);
+            }
+          }
+        };
+        bool batched = net.ncol != 0;
+        switch (net.ncol ? n : 0) {
+          case 3: gather_n(std::integral_constant<int, 3>{}); break;
+          case 5: gather_n(std::integral_constant<int, 5>{}); break;
+          case 7: gather_n(std::integral_constant<int, 7>{}); break;
+          default: batched = false;
+        }
+        if (!batched)
         for (int it = share; it < n_items; it += NSH) {
           const int c = net.ncol ? it / n : it, dy = net.ncol ? it - c * n : 0;
           const size_t plane = (size_t)c * net.buf_rows;
@@ -1269,6 +1412,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
         }
       }
       __syncthreads();
+      LBDRN_PHASE(23)  // labels, centres, window rows
       if (H2) {
         // features -> split 16-bit operand arrays (rows >= dim_in are the zero padding of the last k = 16 step)
         for (int i = tid; i < KP0 * (NPIX / 2); i += THREADS) {

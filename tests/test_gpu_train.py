@@ -513,3 +513,29 @@ def test_gradients_match_autograd_on_other_shapes(C, D, bc, bits):
         scale = ref.abs().max().item()
         assert (got[:-1] - ref).abs().max().item() < 2e-5 * scale + 1e-9, (nb, (got[:-1] - ref).abs().max().item(), scale)
     tr.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,D,bc", [(4, 3, 256), (3, 1, 64), (4, 1, 32), (2, 3, 128)])
+def test_interleaved_chunk_gather_is_the_plane_gather(C, D, bc, monkeypatch):
+    """Windows of 3 and 7 take the generic chunk gather.  With 8-bit planes of at most four bands it reads the
+    band-interleaved copies (one word per pixel: a window row of all bands is two or three aligned 16-byte loads); with
+    LBDRN_TRAIN_CHW set it reads the caller's planes (aligned 8-byte words per band and row).  Both must build the same
+    features bit for bit, borders (reflection) and every alignment of a row included: a 61x53 scene, identical losses
+    and parameters after two epochs."""
+    from synth_scene import make_scene
+    K, nl, bs, epochs = 5, 2, 1024, 2
+    img = make_scene(C, 61, 53, bits=12, seed=5)
+    runs = []
+    for chw in (False, True):
+        if chw:
+            monkeypatch.setenv("LBDRN_TRAIN_CHW", "1")
+        torch.manual_seed(9)
+        model = LBDRNModel(C * (2 * D + 1) ** 2, bc, C, nl)
+        scene = F.DeviceScene.from_image(img, K)
+        tr = F.FusedTrainer(model, scene, D, 1e-3, bs, epochs, flags=F.Flags())
+        runs.append(tr.run())
+        tr.close()
+    assert runs[0]["losses"] == runs[1]["losses"]
+    assert torch.equal(runs[0]["params"], runs[1]["params"])
+    assert all(np.isfinite(runs[0]["losses"]))
