@@ -539,3 +539,30 @@ def test_interleaved_chunk_gather_is_the_plane_gather(C, D, bc, monkeypatch):
     assert runs[0]["losses"] == runs[1]["losses"]
     assert torch.equal(runs[0]["params"], runs[1]["params"])
     assert all(np.isfinite(runs[0]["losses"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,bc", [(1, 64), (3, 64), (3, 256)])
+def test_sixteen_bit_odd_width_chunk_gather_follows_the_oracle(D, bc):
+    """16-bit MSB planes (a 16-bit scene at K=5 keeps 11 MSBs) are gathered from the caller's planes: a window row of
+    3 or 7 uint16 is read as three aligned 8-byte words and shifted into place.  A 45x37 scene makes every row start
+    at a different alignment and a quarter of the pixels touch a reflected border; per-step losses, per-epoch MSE and
+    the best epoch against the oracle's loop on the same seed."""
+    from synth_scene import make_scene
+    K, nl, bs, epochs = 5, 2, 512, 2
+    img = make_scene(4, 45, 37, bits=16, seed=3)
+    msb, lsb = O.split_msb_lsb(img, K)
+    assert msb.dtype == np.uint16 or int(msb.max()) > 255
+    torch.manual_seed(31)
+    ref = O.train(msb, lsb, D, bc, nl, 1e-3, bs, epochs)
+    torch.manual_seed(31)
+    model = LBDRNModel(4 * (2 * D + 1) ** 2, bc, 4, nl)
+    scene = F.DeviceScene.from_image(img, K)
+    tr = F.FusedTrainer(model, scene, D, 1e-3, bs, epochs, flags=F.Flags())
+    res = tr.run()
+    tr.close()
+    got, want = np.array(res["losses"]), np.array(ref["losses"])
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want) / want) < 2e-4, (got, want)
+    assert np.allclose(res["val_mse"], ref["mses"], rtol=2e-4)
+    assert res["best_epoch"] == ref["best_epoch"]
