@@ -1271,6 +1271,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
         int y, x;
         if (idx32) { y = (int)((unsigned)idx / (unsigned)net.W); x = (int)((unsigned)idx - (unsigned)y * (unsigned)net.W); }
         else { y = (int)(idx / net.W); x = (int)(idx - (long long)y * net.W); }
+        if (tid >= nvalid) { y = net.row0; x = 0; }      // padding lane of a partial chunk: a pixel that is inside the buffer
         s_py[tid] = y;
         s_px[tid] = x;
         s_valid[tid] = tid < nvalid;
@@ -1283,9 +1284,14 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
         else gp_pos = -1;
         if (gil) {
           // interleaved planes: the pixel's own word holds the centre of every band, its LSB word every label
-          const size_t off = (size_t)(y - net.buf_row0) * net.W + x;
-          const uint32_t lw = a.ilsb[off];
-          s_ctrw[tid] = a.imsb[off];
+          // (padding lanes of a partial chunk read nothing: row 0 need not be inside the plane buffer)
+          uint32_t lw = 0u, cw = 0u;
+          if (tid < nvalid) {
+            const size_t off = (size_t)(y - net.buf_row0) * net.W + x;
+            lw = a.ilsb[off];
+            cw = a.imsb[off];
+          }
+          s_ctrw[tid] = cw;
           for (int c = 0; c < C; ++c) Tl[c * LDP + tid] = __fdiv_rn((float)((lw >> (8 * c)) & 255u), net.qmax);
         }
       }
@@ -1303,7 +1309,10 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             const bool ok = s_valid[pp] != 0;
             const uint32_t* row = a.imsb + (size_t)(reflect_clamp(gy + dy - D_, net.H) - net.buf_row0) * net.W;
             uint32_t v[N_];
-            if (gx >= D_ && gx + D_ < net.W) {
+            if (!ok) {
+#pragma unroll
+              for (int dx = 0; dx < N_; ++dx) v[dx] = 0u;
+            } else if (gx >= D_ && gx + D_ < net.W) {
               const uint32_t* p0 = row + (gx - D_);
               const int o = (int)((reinterpret_cast<uintptr_t>(p0) >> 2) & 3);
               const uint4* q = reinterpret_cast<const uint4*>(p0 - o);
@@ -1359,6 +1368,14 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
           const int rows_per = (N_ + RG - 1) / RG;
           for (int it = share; it < C * RG; it += NSH) {
             const int c = it / RG, g = it - c * RG;
+            const int dy0 = g * rows_per, dy1 = min(N_, dy0 + rows_per);
+            if (!ok) {                       // padding lane of a partial chunk: zeros, no loads
+              if (g == 0) Tl[c * LDP + pp] = 0.f;
+              for (int dy = dy0; dy < dy1; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < N_; ++dx) dst[(size_t)(net.nco + (c * N_ + dy) * N_ + dx) * LDP] = 0.f;
+              continue;
+            }
             const size_t plane = (size_t)c * net.buf_rows;
             const size_t off = (plane + (gy - net.buf_row0)) * net.W + gx;
             if (g == 0) {
@@ -1367,7 +1384,6 @@ __global__ void __launch_bounds__(THREADS, 1) train_fp32_kernel(const TrainArgs 
             }
             float ctr = 0.f;
             if (net.relative) ctr = net.msb_u16 ? load_msb_norm(a.msb, 1, off, maxv) : s_quot[((const uint8_t*)a.msb)[off]];
-            const int dy0 = g * rows_per, dy1 = min(N_, dy0 + rows_per);
 #pragma unroll
             for (int dy = 0; dy < N_; ++dy) {
               if (dy < dy0 || dy >= dy1) continue;
