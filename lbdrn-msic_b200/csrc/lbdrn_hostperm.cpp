@@ -12,6 +12,8 @@
 // misses overlap.  Bit-exactness against torch.randperm is pinned by tests/test_host_logic.py (CPU test, several n and
 // seeds); larger n (torch switches to a 64-bit inside-out variant there) are left to torch itself.
 #include <stdint.h>
+#include <stdlib.h>
+#include <sys/mman.h>
 
 #include <random>
 
@@ -23,6 +25,13 @@ template <typename T>
 int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host) {
   if (n < 0 || (n > 0 && out_host == nullptr)) return LBDRN_E_INVALID;
   if (n >= (int64_t)(UINT32_MAX / 20)) return LBDRN_E_UNSUPPORTED;     // torch's other branch (random64, inside-out)
+  // every swap is a TLB miss as well on 4 KB pages (65 k pages for an 8192^2 scene): ask for huge pages before the first
+  // touch of the (usually fresh) buffer; advisory -- the call failing or the pages having been touched changes nothing
+  {
+    constexpr uintptr_t HP = (uintptr_t)2 << 20;
+    const uintptr_t b = ((uintptr_t)out_host + HP - 1) & ~(HP - 1), e = ((uintptr_t)(out_host + n)) & ~(HP - 1);
+    if (e > b && getenv("LBDRN_NO_THP") == nullptr) (void)madvise((void*)b, (size_t)(e - b), MADV_HUGEPAGE);
+  }
   for (int64_t i = 0; i < n; ++i) out_host[i] = (T)i;
   if (n < 2) return LBDRN_OK;
   std::mt19937 eng((uint32_t)(seed & 0xffffffffu));
