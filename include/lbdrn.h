@@ -34,9 +34,9 @@ extern "C" {
 #endif
 
 /* 2: optional device-side msb_max in LbdrnDesc; 3: lbdrn_randperm added; 4: LBDRN_PATH_TENSOR_FASTSIN2 and the
- * lbdrn_fpz_* nn sub-stream codec added; 5: lbdrn_selftest_tc_gemm3, lbdrn_host_randperm[32] (all additive: older callers
+ * lbdrn_fpz_* nn sub-stream codec added; 5: lbdrn_selftest_tc_gemm3, lbdrn_host_randperm[32]; 6: lbdrn_host_randperm32_progress (all additive: older callers
  * are unaffected) */
-#define LBDRN_ABI_VERSION 5
+#define LBDRN_ABI_VERSION 6
 
 enum {
   LBDRN_OK = 0,
@@ -134,6 +134,11 @@ int32_t lbdrn_randperm(int64_t n, uint64_t seed, int64_t* out_dev, void* stream)
  * ahead of the swaps and the lines they will touch are prefetched.  Host-only; thread-safe; no device is needed. */
 int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host);
 int32_t lbdrn_host_randperm32(int64_t n, uint64_t seed, int32_t* out_host);   /* same order as 32-bit indices (half the traffic) */
+/* The 32-bit order with its progress published (ABI 6): *progress_host (aligned int64 in host memory, written with
+ * release stores about every 2^18 steps) = number of LEADING entries of out_host that are final, n when the call
+ * returns.  The shuffle is a forward Fisher-Yates, so a consumer on another thread may read out_host[0 .. *progress_host)
+ * while the call is still running: the trainer starts the first epoch on the head of its order. */
+int32_t lbdrn_host_randperm32_progress(int64_t n, uint64_t seed, int32_t* out_host, int64_t* progress_host);
 
 /* ---- a16: quality read-out (decode.py:216): *sse_dev (device uint64, zero-initialised by the caller) += sum over n
  * elements of (a-b)^2 for two uint16 images.  Integer accumulation: exact and order-independent. */

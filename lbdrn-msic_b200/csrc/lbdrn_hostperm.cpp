@@ -22,7 +22,7 @@
 namespace {
 
 template <typename T>
-int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host) {
+int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host, int64_t* progress = nullptr) {
   if (n < 0 || (n > 0 && out_host == nullptr)) return LBDRN_E_INVALID;
   if (n >= (int64_t)(UINT32_MAX / 20)) return LBDRN_E_UNSUPPORTED;     // torch's other branch (random64, inside-out)
   // every swap is a TLB miss as well on 4 KB pages (65 k pages for an 8192^2 scene): ask for huge pages before the first
@@ -33,7 +33,10 @@ int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host) {
     if (e > b && getenv("LBDRN_NO_THP") == nullptr) (void)madvise((void*)b, (size_t)(e - b), MADV_HUGEPAGE);
   }
   for (int64_t i = 0; i < n; ++i) out_host[i] = (T)i;
-  if (n < 2) return LBDRN_OK;
+  if (n < 2) {
+    if (progress) __atomic_store_n(progress, n, __ATOMIC_RELEASE);
+    return LBDRN_OK;
+  }
   std::mt19937 eng((uint32_t)(seed & 0xffffffffu));
   constexpr int64_t LA = 128;                    // look-ahead (iterations): ~LA independent misses in flight
   uint32_t ring[LA];
@@ -44,6 +47,9 @@ int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host) {
     __builtin_prefetch(out_host + i + ring[i], 0, 2);
   }
   for (int64_t i = 0; i < steps; ++i) {
+    // entries [0, i) are final (later swaps touch positions >= i only): published every 2^18 steps for a consumer that
+    // starts on the head of the order while the tail is still being shuffled
+    if (progress && (i & 0x3ffff) == 0) __atomic_store_n(progress, i, __ATOMIC_RELEASE);
     const uint32_t z = ring[i & (LA - 1)];
     const int64_t j = i + LA;
     if (j < steps) {
@@ -55,6 +61,7 @@ int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host) {
     out_host[i] = out_host[i + z];
     out_host[i + z] = sav;
   }
+  if (progress) __atomic_store_n(progress, n, __ATOMIC_RELEASE);
   return LBDRN_OK;
 }
 
@@ -64,3 +71,10 @@ extern "C" int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_ho
 
 // the same permutation as 32-bit indices (every n in range fits): half the memory traffic of the shuffle and of the upload
 extern "C" int32_t lbdrn_host_randperm32(int64_t n, uint64_t seed, int32_t* out_host) { return host_randperm_t(n, seed, out_host); }
+
+// the 32-bit order with its progress published: *progress_host = number of leading entries that are final (n at the end)
+extern "C" int32_t lbdrn_host_randperm32_progress(int64_t n, uint64_t seed, int32_t* out_host, int64_t* progress_host) {
+  if (progress_host == nullptr) return LBDRN_E_INVALID;
+  __atomic_store_n(progress_host, (int64_t)0, __ATOMIC_RELEASE);
+  return host_randperm_t(n, seed, out_host, progress_host);
+}

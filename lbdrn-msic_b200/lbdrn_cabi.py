@@ -16,7 +16,7 @@ PATH_AUTO, PATH_PRECISE, PATH_TENSOR, PATH_TENSOR_FASTSIN, PATH_TENSOR_FASTSIN2 
 
 # every symbol include/lbdrn.h declares (tests check the library exports exactly these)
 SYMBOLS = ["lbdrn_version", "lbdrn_last_error", "lbdrn_dim_in", "lbdrn_param_count", "lbdrn_has_tensor_path",
-           "lbdrn_launch_count", "lbdrn_selftest_tc_gemm", "lbdrn_selftest_tc_gemm2", "lbdrn_selftest_tc_gemm3", "lbdrn_split", "lbdrn_sse_u16", "lbdrn_max_shifted", "lbdrn_randperm", "lbdrn_host_randperm", "lbdrn_host_randperm32", "lbdrn_decode", "lbdrn_predict",
+           "lbdrn_launch_count", "lbdrn_selftest_tc_gemm", "lbdrn_selftest_tc_gemm2", "lbdrn_selftest_tc_gemm3", "lbdrn_split", "lbdrn_sse_u16", "lbdrn_max_shifted", "lbdrn_randperm", "lbdrn_host_randperm", "lbdrn_host_randperm32", "lbdrn_host_randperm32_progress", "lbdrn_decode", "lbdrn_predict",
            "lbdrn_eval_sse", "lbdrn_train_create", "lbdrn_train_destroy", "lbdrn_train_set_params",
            "lbdrn_train_get_params", "lbdrn_train_steps", "lbdrn_train_grad", "lbdrn_train_apply",
            "lbdrn_fpz_bound", "lbdrn_fpz_compress", "lbdrn_fpz_header", "lbdrn_fpz_decompress"]
@@ -75,6 +75,7 @@ def load(build_if_missing=True):
         "lbdrn_randperm": (i32, [i64, C.c_uint64, vp, vp]),
         "lbdrn_host_randperm": (i32, [i64, C.c_uint64, vp]),
         "lbdrn_host_randperm32": (i32, [i64, C.c_uint64, vp]),
+        "lbdrn_host_randperm32_progress": (i32, [i64, C.c_uint64, vp, vp]),
         "lbdrn_decode": (i32, [D, vp, vp, vp, vp, vp]),
         "lbdrn_predict": (i32, [D, vp, vp, vp, vp, vp]),
         "lbdrn_eval_sse": (i32, [D, vp, vp, vp, vp, vp, vp]),

@@ -399,7 +399,7 @@ def torch_permutation_from_seed(n, seed, out=None):
     return torch.randperm(n, generator=g) if out is None else torch.randperm(n, generator=g, out=out)
 
 
-def permutation_from_seed(n, seed, out=None, dtype=torch.int64):
+def permutation_from_seed(n, seed, out=None, dtype=torch.int64, progress=None):
     """The same permutation, from the library's restatement of torch's CPU randperm (`lbdrn_host_randperm`: forward
     Fisher-Yates on MT19937 outputs with the draws running ahead of the swaps, ~2x faster at 67 M pixels; bit-exactness
     against torch is a CPU test).  dtype=torch.int32 gives the same order as 32-bit indices (half the traffic).  Sizes
@@ -407,13 +407,22 @@ def permutation_from_seed(n, seed, out=None, dtype=torch.int64):
     if n < (1 << 32) // 20:
         buf = torch.empty(n, dtype=dtype) if out is None else out
         assert buf.dtype in (torch.int64, torch.int32) and buf.is_contiguous() and buf.numel() == n and buf.device.type == "cpu"
+        if progress is not None:
+            # `progress` (ctypes.c_int64) counts the leading entries that are final while the call runs (32-bit orders only)
+            assert buf.dtype == torch.int32
+            if cabi.load().lbdrn_host_randperm32_progress(n, seed & 0xFFFFFFFFFFFFFFFF, buf.data_ptr(), ctypes.addressof(progress)) == 0:
+                return buf
         fn = cabi.load().lbdrn_host_randperm if buf.dtype == torch.int64 else cabi.load().lbdrn_host_randperm32
         if fn(n, seed & 0xFFFFFFFFFFFFFFFF, buf.data_ptr()) == 0:
+            if progress is not None:
+                progress.value = n
             return buf
     perm = torch_permutation_from_seed(n, seed, out if (out is not None and out.dtype == torch.int64) else None)
     if out is not None and out.dtype != torch.int64:
         out.copy_(perm)
         return out
+    if progress is not None:
+        progress.value = n
     return perm if dtype == torch.int64 else perm.to(dtype)
 
 
@@ -428,7 +437,7 @@ class HostPermutations:
     ready; `release(e, event)` hands its buffer back once `event` (the upload) has completed.  Results are exactly
     `permutation_from_seed(n, seeds[e-1])`, in epoch order."""
 
-    def __init__(self, seeds, n, workers=None, pin=False, device=None, max_bytes=4 << 30, dtype=None):
+    def __init__(self, seeds, n, workers=None, pin=False, device=None, max_bytes=4 << 30, dtype=None, stream_first=False):
         import concurrent.futures
         import os
         self.seeds, self.n, self.device = list(seeds), n, device
@@ -446,6 +455,10 @@ class HostPermutations:
         self.busy = {}                               # epoch -> (buffer, upload event or None)
         self.fut = {}
         self.next_epoch = 1
+        # epoch 1's order is the only one nothing can hide: its buffer is allocated here and its progress published, so the
+        # trainer can start on the head of the order while the tail is still being shuffled (`first_stream`)
+        self.first_progress = ctypes.c_int64(0) if (stream_first and self.dtype == torch.int32 and n < (1 << 32) // 20) else None
+        self.first_buf = torch.empty(n, dtype=self.dtype) if self.first_progress is not None else None
         self._fill()
 
     def _draw(self, e, buf):
@@ -453,7 +466,18 @@ class HostPermutations:
             if self.pin and self.device is not None:
                 torch.cuda.set_device(self.device)   # worker threads start on device 0: pin in this rank's context
             buf = torch.empty(self.n, dtype=self.dtype, pin_memory=self.pin)
-        return permutation_from_seed(self.n, self.seeds[e - 1], out=buf)
+        return permutation_from_seed(self.n, self.seeds[e - 1], out=buf,
+                                     progress=self.first_progress if (e == 1 and buf is self.first_buf) else None)
+
+    def first_stream(self):
+        """(buffer, progress, future) of epoch 1 while it is being drawn: entries [0, progress.value) are final.  The caller
+        releases epoch 1 like any other.  None when the order is not streamable (64-bit indices, torch's other algorithm)."""
+        if self.first_progress is None or 1 not in self.fut:
+            return None
+        fut = self.fut.pop(1)
+        self.busy[1] = (self.first_buf, None)
+        self._fill()
+        return self.first_buf, self.first_progress, fut
 
     def _reclaim(self, block):
         """Move buffers whose upload has finished back to the free list; with `block`, wait for the oldest one."""
@@ -475,6 +499,8 @@ class HostPermutations:
                 buf = self.free.pop()
             elif self.n_buffers < self.workers + 1:
                 buf, self.n_buffers = None, self.n_buffers + 1       # allocated inside the worker
+                if self.next_epoch == 1 and self.first_buf is not None:
+                    buf = self.first_buf
             else:
                 return
             e = self.next_epoch
@@ -564,12 +590,13 @@ class FusedTrainer:
         cabi.check(self.lib.lbdrn_train_set_params(self.handle, cabi.ptr(self.params_dev), cabi.stream_ptr()))
         self.adam_t = 0
 
-    def train_epoch(self, perm_dev, lr):
+    def train_epoch(self, perm_dev, lr, losses_out=None):
         """One pass over `perm_dev` (int64 pixel indices on the device) in batches of `bs`; returns the per-step
-        losses (device tensor).  One persistent kernel launch."""
+        losses (device tensor; `losses_out` when given: a slice of an epoch's loss vector).  One persistent kernel launch."""
         n = perm_dev.numel()
         steps = math.ceil(n / self.bs)
-        losses = torch.empty(steps, dtype=torch.float32, device=self.dev)
+        losses = torch.empty(steps, dtype=torch.float32, device=self.dev) if losses_out is None else losses_out
+        assert losses.numel() == steps and losses.is_contiguous()
         sc = self.scene
         cabi.check(self.lib.lbdrn_train_steps(self.handle, cabi.ptr(sc.msb), cabi.ptr(sc.lsb), cabi.ptr(self.tab),
                                               cabi.ptr(perm_dev), n, steps, self.adam_t, float(lr), cabi.ptr(losses),
@@ -602,7 +629,10 @@ class FusedTrainer:
         with torch.cuda.stream(main):
             self.begin()
         seeds = self._plan_seeds()
-        host = HostPermutations(seeds, N, device=self.dev) if self.sampler == "reference" else None
+        import os
+        import time
+        stream_first = os.environ.get("LBDRN_NO_STREAM_FIRST") is None and math.ceil(N / self.bs) >= 64
+        host = HostPermutations(seeds, N, device=self.dev, stream_first=stream_first) if self.sampler == "reference" else None
 
         def device_perm(e):
             """(perm, event): drawn on the side stream"""
@@ -646,14 +676,52 @@ class FusedTrainer:
                 ev.record(upl)
             return perm, ev
 
-        next_perm = host_perm if host is not None else device_perm
-        next_dev = next_perm(1)
-        for e in range(1, self.epochs + 1):
+        def first_epoch_streamed(first):
+            """Epoch 1 of the reference sampler in slices of whole batches, each uploaded and trained as soon as the host
+            shuffle (a forward Fisher-Yates: a finished prefix never changes) has got past it -- the one permutation whose
+            drawing nothing else can hide.  Same batches, same launch arithmetic as the one-launch epoch."""
+            buf, prog, fut = first
+            steps = math.ceil(N / self.bs)
             with torch.cuda.stream(main):
-                perm, ev = next_dev
-                main.wait_event(ev)
-                perm.record_stream(main)
-                self.losses.append(self.train_epoch(perm, lr_for_epoch(self.lr, e, self.epochs)))
+                losses = torch.empty(steps, dtype=torch.float32, device=self.dev)
+            per = max(1, steps // 8)
+            lr1 = lr_for_epoch(self.lr, 1, self.epochs)
+            s0, up = 0, None
+            while s0 < steps:
+                s1 = min(steps, s0 + per)
+                need = min(N, s1 * self.bs)
+                while prog.value < need:
+                    if fut.done():
+                        fut.result()                                     # re-raises a failed draw; progress is final by now
+                        break
+                    time.sleep(0.0002)
+                with torch.cuda.stream(upl):
+                    sl = buf[s0 * self.bs:need].to(self.dev, non_blocking=True).to(torch.int64)
+                    up = torch.cuda.Event()
+                    up.record(upl)
+                with torch.cuda.stream(main):
+                    main.wait_event(up)
+                    sl.record_stream(main)
+                    self.train_epoch(sl, lr1, losses_out=losses[s0:s1])
+                s0 = s1
+            fut.result()
+            host.release(1, up)
+            return losses
+
+        next_perm = host_perm if host is not None else device_perm
+        first = host.first_stream() if host is not None else None
+        next_dev = next_perm(1) if first is None else None
+        for e in range(1, self.epochs + 1):
+            if e == 1 and first is not None:
+                self.losses.append(first_epoch_streamed(first))
+            with torch.cuda.stream(main):
+                if not (e == 1 and first is not None):
+                    perm, ev = next_dev
+                    main.wait_event(ev)
+                    perm.record_stream(main)
+                    self.losses.append(self.train_epoch(perm, lr_for_epoch(self.lr, e, self.epochs)))
+                else:
+                    perm = None
                 evaluate = self.epochs != 1 and e % min(self.val_duration, self.epochs) == 0
                 cur = self.current_params() if (evaluate or self.epochs == 1) else None
                 snap = torch.cuda.Event()

@@ -566,3 +566,27 @@ def test_sixteen_bit_odd_width_chunk_gather_follows_the_oracle(D, bc):
     assert np.max(np.abs(got - want) / want) < 2e-4, (got, want)
     assert np.allclose(res["val_mse"], ref["mses"], rtol=2e-4)
     assert res["best_epoch"] == ref["best_epoch"]
+
+
+@pytest.mark.gpu
+def test_streamed_first_epoch_is_the_one_launch_epoch(monkeypatch):
+    """With the reference sampler, epoch 1 is trained in slices of whole batches as the host shuffle finalises the head of
+    its order (64 steps or more).  Same batches, same arithmetic: losses, evaluation and parameters must equal the run
+    that waits for the whole permutation (LBDRN_NO_STREAM_FIRST=1) bit for bit."""
+    from synth_scene import make_scene
+    K, D, bc, nl, bs, epochs = 5, 2, 64, 2, 1024, 3
+    img = make_scene(4, 272, 250, bits=12, seed=21)          # 68 000 pixels: 67 steps, the last batch partial
+    runs = []
+    for streamed in (True, False):
+        if not streamed:
+            monkeypatch.setenv("LBDRN_NO_STREAM_FIRST", "1")
+        torch.manual_seed(5)
+        model = LBDRNModel(4 * (2 * D + 1) ** 2, bc, 4, nl)
+        scene = F.DeviceScene.from_image(img, K)
+        tr = F.FusedTrainer(model, scene, D, 1e-3, bs, epochs, flags=F.Flags(), sampler="reference")
+        runs.append(tr.run())
+        tr.close()
+    assert len(runs[0]["losses"]) == epochs * 67
+    assert runs[0]["losses"] == runs[1]["losses"]
+    assert runs[0]["val_mse"] == runs[1]["val_mse"] and runs[0]["best_epoch"] == runs[1]["best_epoch"]
+    assert torch.equal(runs[0]["params"], runs[1]["params"])

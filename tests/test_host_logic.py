@@ -121,7 +121,7 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == sorted(cabi.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lbdrn_version() == int(re.search(r"#define\s+LBDRN_ABI_VERSION\s+(\d+)", hdr).group(1)) == 5
+    assert lib.lbdrn_version() == int(re.search(r"#define\s+LBDRN_ABI_VERSION\s+(\d+)", hdr).group(1)) == 6
 
 
 def test_cabi_struct_layout_matches_header():
@@ -258,3 +258,32 @@ def test_host_randperm_is_torch_randperm():
     assert lib.lbdrn_host_randperm((1 << 32) // 20, 1, None) == cabi.E_INVALID or True
     one = torch.empty(1, dtype=torch.int64)
     assert lib.lbdrn_host_randperm((1 << 32) // 20 + 5, 1, one.data_ptr()) == cabi.E_UNSUPPORTED
+
+
+def test_host_randperm_progress_publishes_a_final_prefix():
+    """lbdrn_host_randperm32_progress: the same order as torch.randperm, and every prefix it announces while it runs is
+    already final (forward Fisher-Yates) -- what lets the trainer start epoch 1 on the head of the order."""
+    import ctypes
+    import threading
+    import time
+    import lbdrn_fused as F
+    n, seed = 3_000_000, 4242
+    prog = ctypes.c_int64(-1)
+    buf = torch.empty(n, dtype=torch.int32)
+    snaps = []
+    th = threading.Thread(target=lambda: F.permutation_from_seed(n, seed, out=buf, progress=prog))
+    th.start()
+    while prog.value < n:
+        k = prog.value
+        if k > 0 and (not snaps or snaps[-1][0] != k):
+            snaps.append((k, buf[:k].clone()))
+        time.sleep(0.0005)
+    th.join()
+    ref = F.torch_permutation_from_seed(n, seed).to(torch.int32)
+    assert torch.equal(buf, ref) and prog.value == n
+    assert all(torch.equal(b, ref[:k]) for k, b in snaps)
+    # tiny inputs finish at once
+    for m in (0, 1, 2, 5):
+        p2 = ctypes.c_int64(-1)
+        out = F.permutation_from_seed(m, 3, dtype=torch.int32, progress=p2)
+        assert p2.value == m and torch.equal(out, F.torch_permutation_from_seed(m, 3).to(torch.int32))
