@@ -433,6 +433,10 @@ def run_ours(args):
                 enc_s = float(t.item())
             return enc_s, res, enc_clk.summary()
 
+        # the first encode of a process also pays the lazy load of the training / evaluation modules and the first device
+        # allocations (0.05-0.2 s): timed and reported as `first_run_s_per_scene`; `s_per_scene` is the second, like the
+        # decode leg's warm-up steps (a scheduler encodes many scenes per process)
+        cold_s, _, _ = run_encode(args.sampler)
         enc_s, res, enc_clocks = run_encode(args.sampler)
         n_steps = len(res["losses"])
         flop = SIDE * SIDE * args.encode_epochs * (TRAIN_FLOP_PER_PX + FLOP_PER_PX)
@@ -441,6 +445,7 @@ def run_ours(args):
                   "us_per_step_incl_eval": enc_s / n_steps * 1e6, "sampler": args.sampler,
                   "final_val_mse": res["val_mse"][-1] if res["val_mse"] else None, "best_epoch": res["best_epoch"],
                   "tensor_roofline_frac": flop / enc_s / 1e12 / pk["bf16_sustained"], "clocks": enc_clocks,
+                  "first_run_s_per_scene": cold_s,
                   "excludes": "GDAL read/write, JPEG-2000 base layer, fpzip (host, unchanged)"}
         if world == 1 and not args.no_extra:
             # the parity-pinned mode of encode.py's default (--sampler reference: the DataLoader's own permutations, drawn on
@@ -451,8 +456,8 @@ def run_ours(args):
             encode[f"{other}_sampler_final_val_mse"] = o_res["val_mse"][-1] if o_res["val_mse"] else None
             encode["sampler_note"] = ("device: lbdrn_randperm orders (quality pinned per seed against the oracle trained on the same "
                                       "orders, tests/test_gpu_train.py::test_device_sampler_encode_quality_is_pinned); reference: "
-                                      "the reference DataLoader's exact batches (host randperm, ~3 s per 67 M pixels per epoch, "
-                                      "drawn by up to 8 threads ahead of the device)")
+                                      "the reference DataLoader's exact batches (torch's CPU randperm restated natively, drawn by host threads "
+                                      "ahead of the device; epoch 1 trained in slices as its order is finalised)")
 
     # ---- encode, data-parallel mode (N > 1): every rank holds the SAME scene and takes 1/N of each batch; one NCCL
     # all-reduce of the P+1 gradient floats per step (lbdrn_dist.DataParallelTrainer).  Reported as measured next to the
