@@ -15,7 +15,10 @@
 #include <stdlib.h>
 #include <sys/mman.h>
 
+#include <atomic>
 #include <random>
+#include <thread>
+#include <vector>
 
 #include "../../include/lbdrn.h"
 
@@ -65,6 +68,51 @@ int32_t host_randperm_t(int64_t n, uint64_t seed, T* out_host, int64_t* progress
   return LBDRN_OK;
 }
 
+// The same shuffle with the draws on a second thread (the order nothing can hide -- epoch 1's -- is worth two cores): the
+// generator and its n - i remainders run in a producer that stays up to kBlocks blocks ahead in a ring; this thread only
+// swaps (and prefetches kLA swaps ahead inside the blocks already produced).  Same draws in the same order: same output.
+template <typename T>
+int32_t host_randperm_two_threads(int64_t n, uint64_t seed, T* out_host, int64_t* progress) {
+  constexpr int64_t kBS = 1 << 16, kBlocks = 16, kMask = kBS * kBlocks - 1, kLA = 128;
+  {
+    constexpr uintptr_t HP = (uintptr_t)2 << 20;
+    const uintptr_t b = ((uintptr_t)out_host + HP - 1) & ~(HP - 1), e = ((uintptr_t)(out_host + n)) & ~(HP - 1);
+    if (e > b && getenv("LBDRN_NO_THP") == nullptr) (void)madvise((void*)b, (size_t)(e - b), MADV_HUGEPAGE);
+  }
+  const int64_t steps = n - 1, nblk = (steps + kBS - 1) / kBS;
+  std::vector<uint32_t> ring((size_t)(kBS * kBlocks));
+  std::atomic<int64_t> produced{0}, consumed{0};
+  std::thread producer([&]() {
+    std::mt19937 eng((uint32_t)(seed & 0xffffffffu));
+    for (int64_t blk = 0; blk < nblk; ++blk) {
+      while (blk - consumed.load(std::memory_order_acquire) >= kBlocks) std::this_thread::yield();
+      const int64_t i0 = blk * kBS, i1 = i0 + kBS < steps ? i0 + kBS : steps;
+      uint32_t* z = ring.data() + (i0 & kMask);
+      for (int64_t i = i0; i < i1; ++i) z[i - i0] = (uint32_t)eng() % (uint32_t)(n - i);
+      produced.store(blk + 1, std::memory_order_release);
+    }
+  });
+  for (int64_t i = 0; i < n; ++i) out_host[i] = (T)i;        // under the producer's first blocks
+  for (int64_t blk = 0; blk < nblk; ++blk) {
+    const int64_t want = blk + 2 < nblk ? blk + 2 : nblk;     // this block and the one the look-ahead reaches into
+    while (produced.load(std::memory_order_acquire) < want) std::this_thread::yield();
+    const int64_t i0 = blk * kBS, i1 = i0 + kBS < steps ? i0 + kBS : steps;
+    for (int64_t i = i0; i < i1; ++i) {
+      if ((i & 0x3ffff) == 0) __atomic_store_n(progress, i, __ATOMIC_RELEASE);
+      const int64_t j = i + kLA;
+      if (j < steps) __builtin_prefetch(out_host + j + ring[(size_t)(j & kMask)], 0, 2);
+      const uint32_t z = ring[(size_t)(i & kMask)];
+      const T sav = out_host[i];
+      out_host[i] = out_host[i + z];
+      out_host[i + z] = sav;
+    }
+    consumed.store(blk + 1, std::memory_order_release);
+  }
+  producer.join();
+  __atomic_store_n(progress, n, __ATOMIC_RELEASE);
+  return LBDRN_OK;
+}
+
 }  // namespace
 
 extern "C" int32_t lbdrn_host_randperm(int64_t n, uint64_t seed, int64_t* out_host) { return host_randperm_t(n, seed, out_host); }
@@ -76,5 +124,8 @@ extern "C" int32_t lbdrn_host_randperm32(int64_t n, uint64_t seed, int32_t* out_
 extern "C" int32_t lbdrn_host_randperm32_progress(int64_t n, uint64_t seed, int32_t* out_host, int64_t* progress_host) {
   if (progress_host == nullptr) return LBDRN_E_INVALID;
   __atomic_store_n(progress_host, (int64_t)0, __ATOMIC_RELEASE);
+  if (n >= ((int64_t)1 << 22) && n < (int64_t)(UINT32_MAX / 20) && out_host != nullptr && getenv("LBDRN_PERM_ONE_THREAD") == nullptr &&
+      std::thread::hardware_concurrency() >= 4)
+    return host_randperm_two_threads(n, seed, out_host, progress_host);
   return host_randperm_t(n, seed, out_host, progress_host);
 }

@@ -260,14 +260,18 @@ def test_host_randperm_is_torch_randperm():
     assert lib.lbdrn_host_randperm((1 << 32) // 20 + 5, 1, one.data_ptr()) == cabi.E_UNSUPPORTED
 
 
-def test_host_randperm_progress_publishes_a_final_prefix():
+@pytest.mark.parametrize("n,one_thread", [(3_000_000, False), (5_000_000, False), (5_000_000, True)])
+def test_host_randperm_progress_publishes_a_final_prefix(n, one_thread, monkeypatch):
     """lbdrn_host_randperm32_progress: the same order as torch.randperm, and every prefix it announces while it runs is
-    already final (forward Fisher-Yates) -- what lets the trainer start epoch 1 on the head of the order."""
+    already final (forward Fisher-Yates) -- what lets the trainer start epoch 1 on the head of the order.  From 2^22
+    entries on the draws run on a second thread (ring of blocks ahead of the swaps); LBDRN_PERM_ONE_THREAD keeps one."""
     import ctypes
     import threading
     import time
     import lbdrn_fused as F
-    n, seed = 3_000_000, 4242
+    if one_thread:
+        monkeypatch.setenv("LBDRN_PERM_ONE_THREAD", "1")
+    seed = 4242
     prog = ctypes.c_int64(-1)
     buf = torch.empty(n, dtype=torch.int32)
     snaps = []
